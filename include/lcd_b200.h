@@ -1,0 +1,212 @@
+/*
+ * lcd_b200.h — C ABI of the B200-native loop-closure hot path
+ * (detect -> quantise -> score -> verify) that drops in behind
+ * rtabmap::Memory / VWDictionary / Signature / Feature2D.
+ *
+ * RTAB-Map has no C ABI or plugin loader for this path; its
+ * seams are C++ virtuals owned by rtabmap::Memory.  Every entry point below
+ * names the reference member function (file:line under corelib/) whose work it
+ * replaces.  INTEGRATION.md shows the two shim classes (VWDictionaryB200,
+ * ORB_B200) a maintainer adds on the reference side to bind these symbols.
+ *
+ * Conventions (mirroring the reference's):
+ *   - all functions return 0 on success, <0 on error (never throw); the message
+ *     is available through lcd_last_error(engine)  [reference: UERROR + empty
+ *     return, VWDictionary.cpp:920-957];
+ *   - all buffers are caller-owned HOST pointers, row-major, unless the function
+ *     name ends in _dev (device pointers valid on the engine's device);
+ *   - word ids are positive ints, 0 = invalid / no match; signature ids are
+ *     positive ints (VWDictionary.cpp:875-878, Memory.cpp:6040-6058);
+ *   - one engine = one VWDictionary instance + its inverted index on one GPU;
+ *     several engines may coexist (RegistrationVis builds temporary
+ *     dictionaries, RegistrationVis.cpp:1482-1503);
+ *   - calls on one engine must be serialised by the caller, except that
+ *     lcd_orb_* may run concurrently with lcd_dict_update (the reference runs
+ *     VWDictionary::update() on PreUpdateThread beside feature extraction,
+ *     Memory.cpp:5284, :5926).
+ */
+#ifndef LCD_B200_H
+#define LCD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCD_OK 0
+#define LCD_ERR_INVALID (-1)  /* bad argument / size or type mismatch            */
+#define LCD_ERR_CUDA (-2)     /* CUDA runtime failure (message has the detail)   */
+#define LCD_ERR_CAPACITY (-3) /* a configured capacity would be exceeded         */
+#define LCD_ERR_STATE (-4)    /* call not valid in the current state             */
+
+/* descriptor types: cv::Mat type()/cols of VisualWord::getDescriptor()
+ * (VWDictionary.cpp:933-957 checks) */
+#define LCD_DESC_U8 0  /* CV_8U rows, desc_dim bytes (ORB/BRIEF: 32)  -> Hamming   */
+#define LCD_DESC_F32 1 /* CV_32F rows, desc_dim floats (SURF: 64/128) -> squared L2 */
+
+typedef struct lcd_engine lcd_engine;
+
+typedef struct lcd_config {
+	int device;         /* CUDA device ordinal                                          */
+	int desc_type;      /* LCD_DESC_U8 | LCD_DESC_F32                                   */
+	int desc_dim;       /* bytes (U8: 16/32/64) or floats (F32: 64/128)                 */
+	int max_words;      /* initial capacity hint for vocabulary rows (grows)            */
+	int max_signatures; /* initial capacity hint for signature ids (grows)              */
+	int max_queries;    /* max descriptors per lcd_dict_* call / per frame (<= 4096)    */
+	int max_batch;      /* max frames per lcd_localize_batch call                       */
+} lcd_config;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+/* replaces: VWDictionary::VWDictionary / ~VWDictionary (VWDictionary.cpp:56-120) */
+lcd_engine * lcd_create(const lcd_config * cfg);
+void lcd_destroy(lcd_engine * e);
+/* last error text of this engine (e may be NULL: error of the last failed lcd_create) */
+const char * lcd_last_error(const lcd_engine * e);
+/* library/ABI version, and the name of the CUDA arch the kernels were built for */
+int lcd_abi_version(void);
+const char * lcd_build_arch(void);
+/* number of kernels this engine has launched since creation (bench "gpu_launches") */
+long long lcd_launch_count(const lcd_engine * e);
+
+/* ---- dictionary: VWDictionary ------------------------------------------------ */
+/* replaces: VWDictionary::addWord (VWDictionary.cpp:1554-1580) for n words whose ids
+ * the caller chose (DB load, LTM reactivation).  Words become "not indexed" until
+ * lcd_dict_update, exactly like _notIndexedWords. */
+int lcd_dict_add_words(lcd_engine * e, const int * ids, const void * desc, int n);
+/* replaces: VWDictionary::removeWords / deleteUnusedWords (VWDictionary.cpp:1582-1607).
+ * Indexed words leave the search structure at the next lcd_dict_update
+ * (_removedIndexedWords); their posting lists are dropped immediately. */
+int lcd_dict_remove_words(lcd_engine * e, const int * ids, int n);
+/* replaces: VWDictionary::update (VWDictionary.cpp:475-701), Kp/NNStrategy=0 row order:
+ * not-indexed words are appended in ascending id, removed rows are compacted out. */
+int lcd_dict_update(lcd_engine * e);
+/* replaces: VWDictionary::clear (VWDictionary.cpp:842-873) */
+int lcd_dict_clear(lcd_engine * e);
+/* _visualWords.size(), rows of the search index, _notIndexedWords.size(), _lastWordId */
+int lcd_dict_size(const lcd_engine * e);
+int lcd_dict_indexed_size(const lcd_engine * e);
+int lcd_dict_not_indexed_size(const lcd_engine * e);
+int lcd_dict_last_word_id(const lcd_engine * e);
+int lcd_dict_set_last_word_id(lcd_engine * e, int id);
+/* 1 if the word is in _visualWords (uContains), else 0 */
+int lcd_dict_has_word(const lcd_engine * e, int word_id);
+/* copy back the indexed rows in search order: ids[rows], desc[rows*dim] (either may be NULL).
+ * Mirrors what _dataTree/_mapIndexId hold (VWDictionary.cpp:650-676). */
+int lcd_dict_get_indexed(lcd_engine * e, int * ids, void * desc, int cap_rows);
+
+/* replaces: FlannIndex::knnSearch(k=2) on a LinearIndex (FlannIndex.cpp:701-745 ->
+ * rtflann linear_index.h:129-146 + result_set.h:151-172): exact 2-NN of every query
+ * row over the INDEXED words; ties -> lowest row.  id = 0 and dist = -1 where fewer
+ * than 1 (2) indexed words exist.  dist: Hamming count, or squared L2, as float. */
+int lcd_dict_knn2(lcd_engine * e, const void * queries, int nq,
+                  int * id1, float * d1, int * id2, float * d2);
+
+/* replaces: VWDictionary::addNewWords (VWDictionary.cpp:913-1229) incl. the NNDR test,
+ * intra-frame new-word comparison (Kp/NewWordsComparedTogether) and addWordRef for
+ * sig_id (VWDictionary.cpp:880-897).  incremental = Kp/IncrementalDictionary,
+ * nndr = Kp/NndrRatio.  word_ids_out[nq]; *n_new_out = words created.
+ * sig_id <= 0: quantise only, add no references. */
+int lcd_dict_quantize(lcd_engine * e, const void * queries, int nq, int sig_id,
+                      int incremental, float nndr, int new_words_compared_together,
+                      int * word_ids_out, int * n_new_out);
+
+/* replaces: VWDictionary::findNN(cv::Mat) (VWDictionary.cpp:1273-1552): read-only,
+ * also searches the not-indexed words; 0 where NNDR rejects. */
+int lcd_dict_find_nn(lcd_engine * e, const void * queries, int nq, int incremental,
+                     float nndr, int * word_ids_out);
+
+/* ---- inverted index: VisualWord::_references + Memory::computeLikelihood ------ */
+/* replaces: VWDictionary::addWordRef (VWDictionary.cpp:880-897) / VisualWord::addRef
+ * (VisualWord.cpp:51-63) for the n words of one signature (duplicates count). */
+int lcd_index_add_refs(lcd_engine * e, int sig_id, const int * word_ids, int n);
+/* replaces: VWDictionary::removeAllWordRef (VWDictionary.cpp:899-911) for every word of
+ * sig_id (what Memory::disableWordsRef does, Memory.cpp:6871-6897). */
+int lcd_index_remove_sig(lcd_engine * e, int sig_id);
+/* ni of Memory::getNi (Memory.cpp:4955-4968): total words of the signature, including
+ * un-quantised (<=0) ones.  lcd_index_add_refs / lcd_dict_quantize add n to it; this
+ * overrides it. */
+int lcd_index_set_ni(lcd_engine * e, const int * sig_ids, const int * ni, int n);
+/* bulk load of a word->(signature,count) table in CSR form (cold start from a database,
+ * Memory::loadDataFromDb, Memory.cpp:410-438): word_ids[nw], row_ptr[nw+1],
+ * sig[row_ptr[nw]], cnt[row_ptr[nw]].  Words must exist in the dictionary. */
+int lcd_index_load_csr(lcd_engine * e, const int * word_ids, int nw, const int64_t * row_ptr,
+                       const int * sig, const int * cnt);
+/* number of signatures referencing word (VisualWord::getReferences().size()), total refs */
+int lcd_index_word_nw(lcd_engine * e, int word_id);
+long long lcd_index_total_refs(const lcd_engine * e);
+/* copy back the posting list of one word sorted by signature id (cap entries max);
+ * returns the list length or <0. */
+int lcd_index_get_refs(lcd_engine * e, int word_id, int * sig, int * cnt, int cap);
+
+/* replaces: the TF-IDF branch of Memory::computeLikelihood (Memory.cpp:2215-2291):
+ * query_word_ids = the new signature's words (any order, duplicates and ids <= 0
+ * allowed: uUniqueKeys + the *i>0 test are applied), sig_ids[ns] = the ids to score,
+ * n_total = N = Memory::getSignatures().size().  likelihood_out[ns] float. */
+int lcd_index_score(lcd_engine * e, const int * query_word_ids, int nq,
+                    const int * sig_ids, int ns, int n_total, float * likelihood_out);
+
+/* ---- fused, batched localisation query (frozen dictionary + frozen map) ---------
+ * One call = B independent queries of the quantise -> score half of the hot path with
+ * NO mutation of the engine: for each frame b
+ *   addNewWords(desc_b, sigId) -> computeLikelihood(sig, sig_ids) -> roll back.
+ * queries: B*nq_per_frame descriptors (frame-major); n_total = N including the query
+ * itself; word_ids_out[B*nq] (new words get ids last_word_id+1.. per frame, not kept);
+ * likelihood_out[B*ns]. Either output may be NULL. */
+int lcd_localize_batch(lcd_engine * e, const void * queries, int n_frames, int nq_per_frame,
+                       int incremental, float nndr, int new_words_compared_together,
+                       const int * sig_ids, int ns, int n_total,
+                       int * word_ids_out, float * likelihood_out);
+
+/* Same work on device-resident inputs/outputs, asynchronous on `stream` (a cudaStream_t
+ * passed as void*; NULL = the engine's stream).  d_queries as above; d_sig_ids[ns];
+ * outputs may be NULL.  Used by bench.py for the HBM-resident timing and by the
+ * word-range-sharded multi-GPU path. */
+int lcd_localize_batch_dev(lcd_engine * e, const void * d_queries, int n_frames, int nq_per_frame,
+                           int incremental, float nndr, int new_words_compared_together,
+                           const int * d_sig_ids, int ns, int n_total,
+                           int * d_word_ids_out, float * d_likelihood_out, void * stream);
+
+/* ---- word-range sharding across GPUs ---------------------------
+ * Each rank owns the words whose row (in ascending id order) falls in its range; rows
+ * are numbered globally: set the global row offset of this shard so that packed top-2
+ * keys (dist<<22 | global_row) from different ranks merge with the reference's
+ * tie-break (lowest row = lowest id). */
+int lcd_shard_set_row_offset(lcd_engine * e, int global_row_offset);
+/* stage 1: local top-2 keys of every query over this rank's rows -> d_keys_out[2*nq] u32
+ * (0xFFFFFFFF = none).  All-gather these across ranks, then call stage 2 on every rank. */
+int lcd_shard_knn2_keys_dev(lcd_engine * e, const void * d_queries, int nq, uint32_t * d_keys_out,
+                            void * stream);
+/* stage 2: merge G gathered key sets [G][2*nq], run the replicated NNDR / new-word pass,
+ * and accumulate this rank's share of the TF-IDF scores into d_scores_out[n_frames*ns]
+ * (fixed-point int64, exact and order-independent; all-reduce(sum) them, then call
+ * lcd_shard_finalize_dev).  d_row_ids: global row -> word id table [total_rows]. */
+int lcd_shard_resolve_score_dev(lcd_engine * e, const void * d_queries, int n_frames, int nq_per_frame,
+                                const uint32_t * d_keys_gathered, int n_ranks,
+                                const int * d_row_ids, int total_rows, int last_word_id,
+                                int incremental, float nndr, int new_words_compared_together,
+                                const int * d_sig_ids, int ns, int n_total,
+                                int * d_word_ids_out, long long * d_scores_out, void * stream);
+int lcd_shard_finalize_dev(lcd_engine * e, const long long * d_scores, int n, float * d_likelihood_out,
+                           void * stream);
+
+/* ---- measurement hooks ---------------------------------------------------------------
+ * Optional per-kernel timing with CUDA events recorded on the launching stream around
+ * every launch of kernel class `which` (0 = dictionary NN, 1 = resolve, 2 = score).
+ * lcd_profile_read synchronises, returns the summed device time and the launch count
+ * since the last reset. */
+#define LCD_PROF_NN 0
+#define LCD_PROF_RESOLVE 1
+#define LCD_PROF_SCORE 2
+int lcd_profile_enable(lcd_engine * e, int on);
+int lcd_profile_read(lcd_engine * e, int which, double * total_ms, long long * launches);
+int lcd_profile_reset(lcd_engine * e);
+
+/* engine stream (cudaStream_t as void*) and a full device sync, for harnesses */
+void * lcd_stream(lcd_engine * e);
+int lcd_synchronize(lcd_engine * e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCD_B200_H */

@@ -1,0 +1,250 @@
+"""ctypes binding of oracle/liboracle.so (restatement) and oracle/_ref/libref_flann.so
+(the reference's own rtflann, compiled from /root/reference by oracle/Makefile).
+
+TEST INFRASTRUCTURE ONLY: checker for tests/, smoke() and bench.py's CPU baseline.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "liboracle.so"
+REF_LIB = HERE / "_ref" / "libref_flann.so"
+REFERENCE_ROOT = Path("/root/reference")
+
+_lib = None
+_ref = None
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+
+
+def build(with_ref: bool = True) -> None:
+    """Compile liboracle.so (always) and _ref/libref_flann.so (when /root/reference is present)."""
+    if not LIB.exists() or LIB.stat().st_mtime < (HERE / "oracle.cpp").stat().st_mtime:
+        subprocess.run(["make", "-C", str(HERE), "liboracle.so"], check=True, capture_output=True)
+    if with_ref and REFERENCE_ROOT.exists() and not REF_LIB.exists():
+        subprocess.run(["make", "-C", str(HERE), "ref"], check=True, capture_output=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build(with_ref=False)
+        L = C.CDLL(str(LIB))
+        L.orc_create.restype = _P
+        L.orc_create.argtypes = [_I, _I, _I, _F, _I]
+        L.orc_destroy.argtypes = [_P]
+        L.orc_set_params.argtypes = [_P, _I, _F, _I]
+        L.orc_add_words.argtypes = [_P, _P, _P, _I]
+        L.orc_remove_words.argtypes = [_P, _P, _I]
+        L.orc_update.argtypes = [_P]
+        for f in ("orc_size", "orc_indexed_size", "orc_not_indexed_size", "orc_last_word_id"):
+            getattr(L, f).argtypes = [_P]
+            getattr(L, f).restype = _I
+        L.orc_set_last_word_id.argtypes = [_P, _I]
+        L.orc_total_refs.argtypes = [_P]
+        L.orc_total_refs.restype = C.c_longlong
+        L.orc_get_indexed_ids.argtypes = [_P, _P, _I]
+        L.orc_get_indexed_ids.restype = _I
+        L.orc_knn2.argtypes = [_P, _P, _I, _P, _P, _P, _P]
+        L.orc_knn2_raw.argtypes = [_I, _I, _P, _I, _P, _I, _P, _P]
+        L.orc_add_new_words.argtypes = [_P, _P, _I, _I, _P]
+        L.orc_add_new_words.restype = _I
+        L.orc_find_nn.argtypes = [_P, _P, _I, _P]
+        L.orc_add_refs.argtypes = [_P, _I, _P, _I]
+        L.orc_remove_sig.argtypes = [_P, _I]
+        L.orc_set_ni.argtypes = [_P, _P, _P, _I]
+        L.orc_load_csr.argtypes = [_P, _P, _I, _P, _P, _P]
+        L.orc_get_refs.argtypes = [_P, _I, _P, _P, _I]
+        L.orc_get_refs.restype = _I
+        L.orc_likelihood.argtypes = [_P, _P, _I, _P, _I, _I, _P]
+        L.orc_localize.argtypes = [_P, _P, _I, _I, _P, _I, _I, _P, _P]
+        L.orc_localize.restype = _I
+        L.orc_adjust_likelihood.argtypes = [_P, _I, _I]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's compiled rtflann, or None when it has not been built (no /root/reference)."""
+    global _ref
+    if _ref is None:
+        if not REF_LIB.exists():
+            if REFERENCE_ROOT.exists():
+                build(with_ref=True)
+            else:
+                return None
+        R = C.CDLL(str(REF_LIB))
+        R.ref_flann_knn2_hamming.argtypes = [_P, _I, _I, _P, _I, _P, _P]
+        R.ref_flann_knn2_l2.argtypes = [_P, _I, _I, _P, _I, _P, _P]
+        _ref = R
+    return _ref
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def ref_knn2(data: np.ndarray, queries: np.ndarray):
+    """2-NN through the reference's rtflann LinearIndex: (idx[nq,2] int64, dist[nq,2] float32)."""
+    R = ref_lib()
+    if R is None:
+        raise RuntimeError("oracle/_ref/libref_flann.so is not built")
+    nq = len(queries)
+    idx = np.zeros((nq, 2), np.int64)
+    dist = np.zeros((nq, 2), np.float32)
+    if data.dtype == np.uint8:
+        data = np.ascontiguousarray(data)
+        queries = np.ascontiguousarray(queries)
+        R.ref_flann_knn2_hamming(_p(data), len(data), data.shape[1], _p(queries), nq, _p(idx), _p(dist))
+    else:
+        data = np.ascontiguousarray(data, np.float32)
+        queries = np.ascontiguousarray(queries, np.float32)
+        R.ref_flann_knn2_l2(_p(data), len(data), data.shape[1], _p(queries), nq, _p(idx), _p(dist))
+    return idx, dist
+
+
+def knn2_raw(data: np.ndarray, queries: np.ndarray):
+    L = lib()
+    t = 0 if data.dtype == np.uint8 else 1
+    data = np.ascontiguousarray(data)
+    queries = np.ascontiguousarray(queries)
+    nq = len(queries)
+    idx = np.zeros((nq, 2), np.int32)
+    dist = np.zeros((nq, 2), np.float32)
+    L.orc_knn2_raw(t, data.shape[1], _p(data), len(data), _p(queries), nq, _p(idx), _p(dist))
+    return idx, dist
+
+
+def adjust_likelihood(lik: np.ndarray, virtual_place_ratio: int = 0) -> np.ndarray:
+    out = np.ascontiguousarray(lik, np.float32).copy()
+    lib().orc_adjust_likelihood(_p(out), len(out), virtual_place_ratio)
+    return out
+
+
+class OracleDictionary:
+    """Restated rtabmap::VWDictionary (+ Memory::computeLikelihood) on the CPU."""
+
+    def __init__(self, desc_type: int = 0, dim: int = 32, incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True):
+        self.L = lib()
+        self.h = self.L.orc_create(desc_type, dim, int(incremental), nndr, int(cmp_new))
+        self.dt = np.uint8 if desc_type == 0 else np.float32
+        self.dim = dim
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def _d(self, x):
+        x = np.ascontiguousarray(x, self.dt)
+        assert x.ndim == 2 and x.shape[1] == self.dim
+        return x
+
+    def set_params(self, incremental, nndr, cmp_new):
+        self.L.orc_set_params(self.h, int(incremental), nndr, int(cmp_new))
+
+    def add_words(self, ids, desc):
+        ids = _i32(ids)
+        self.L.orc_add_words(self.h, _p(ids), _p(self._d(desc)), len(ids))
+
+    def remove_words(self, ids):
+        ids = _i32(ids)
+        self.L.orc_remove_words(self.h, _p(ids), len(ids))
+
+    def update(self):
+        self.L.orc_update(self.h)
+
+    def size(self):
+        return self.L.orc_size(self.h)
+
+    def indexed_size(self):
+        return self.L.orc_indexed_size(self.h)
+
+    def not_indexed_size(self):
+        return self.L.orc_not_indexed_size(self.h)
+
+    @property
+    def last_word_id(self):
+        return self.L.orc_last_word_id(self.h)
+
+    @last_word_id.setter
+    def last_word_id(self, v):
+        self.L.orc_set_last_word_id(self.h, int(v))
+
+    def indexed_ids(self):
+        n = self.indexed_size()
+        ids = np.zeros(n, np.int32)
+        self.L.orc_get_indexed_ids(self.h, _p(ids), n)
+        return ids
+
+    def knn2(self, q):
+        q = self._d(q)
+        n = len(q)
+        id1 = np.zeros(n, np.int32)
+        id2 = np.zeros(n, np.int32)
+        d1 = np.zeros(n, np.float32)
+        d2 = np.zeros(n, np.float32)
+        self.L.orc_knn2(self.h, _p(q), n, _p(id1), _p(d1), _p(id2), _p(d2))
+        return id1, d1, id2, d2
+
+    def add_new_words(self, desc, sig_id):
+        desc = self._d(desc)
+        out = np.zeros(len(desc), np.int32)
+        n = self.L.orc_add_new_words(self.h, _p(desc), len(desc), int(sig_id), _p(out))
+        return out[:n]
+
+    def find_nn(self, desc):
+        desc = self._d(desc)
+        out = np.zeros(len(desc), np.int32)
+        self.L.orc_find_nn(self.h, _p(desc), len(desc), _p(out))
+        return out
+
+    def add_refs(self, sig_id, word_ids):
+        w = _i32(word_ids)
+        self.L.orc_add_refs(self.h, int(sig_id), _p(w), len(w))
+
+    def remove_sig(self, sig_id):
+        self.L.orc_remove_sig(self.h, int(sig_id))
+
+    def set_ni(self, sig_ids, ni):
+        s, n = _i32(sig_ids), _i32(ni)
+        self.L.orc_set_ni(self.h, _p(s), _p(n), len(s))
+
+    def load_csr(self, word_ids, row_ptr, sig, cnt):
+        w = _i32(word_ids)
+        rp = np.ascontiguousarray(row_ptr, np.int64)
+        s, c = _i32(sig), _i32(cnt)
+        self.L.orc_load_csr(self.h, _p(w), len(w), _p(rp), _p(s), _p(c))
+
+    def get_refs(self, word_id, cap=1 << 16):
+        s = np.zeros(cap, np.int32)
+        c = np.zeros(cap, np.int32)
+        n = self.L.orc_get_refs(self.h, int(word_id), _p(s), _p(c), cap)
+        return s[:n], c[:n]
+
+    def total_refs(self):
+        return int(self.L.orc_total_refs(self.h))
+
+    def likelihood(self, qwords, sig_ids, n_total):
+        w, s = _i32(qwords), _i32(sig_ids)
+        out = np.zeros(len(s), np.float32)
+        self.L.orc_likelihood(self.h, _p(w), len(w), _p(s), len(s), int(n_total), _p(out))
+        return out
+
+    def localize(self, desc, sig_id, sig_ids, n_total, want_like=True):
+        desc = self._d(desc)
+        s = _i32(sig_ids)
+        words = np.zeros(len(desc), np.int32)
+        like = np.zeros(len(s), np.float32) if want_like else None
+        n = self.L.orc_localize(self.h, _p(desc), len(desc), int(sig_id), _p(s), len(s), int(n_total), _p(words), _p(like))
+        return words[:n], like

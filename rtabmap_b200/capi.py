@@ -1,0 +1,347 @@
+"""ctypes binding of include/lcd_b200.h (the C ABI of liblcd_b200.so).
+
+This is the binding a Python host would use; INTEGRATION.md shows the equivalent C++ shim
+for the reference.  Every method maps 1:1 onto an ``lcd_*`` entry point and raises
+:class:`LcdError` with ``lcd_last_error`` on a non-zero status.  Nothing here computes:
+if the library is missing it is built (nvcc); if no CUDA device is present ``Engine()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import build as _build
+
+LCD_DESC_U8 = 0
+LCD_DESC_F32 = 1
+
+_lib = None
+
+
+class LcdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lcd_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int),
+        ("desc_type", C.c_int),
+        ("desc_dim", C.c_int),
+        ("max_words", C.c_int),
+        ("max_signatures", C.c_int),
+        ("max_queries", C.c_int),
+        ("max_batch", C.c_int),
+    ]
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_IP = C.POINTER(C.c_int)
+_FP = C.POINTER(C.c_float)
+
+# name -> (restype, argtypes); kept in the order of include/lcd_b200.h
+SIGNATURES = {
+    "lcd_create": (_P, [C.POINTER(_Config)]),
+    "lcd_destroy": (None, [_P]),
+    "lcd_last_error": (C.c_char_p, [_P]),
+    "lcd_abi_version": (_I, []),
+    "lcd_build_arch": (C.c_char_p, []),
+    "lcd_launch_count": (C.c_longlong, [_P]),
+    "lcd_dict_add_words": (_I, [_P, _P, _P, _I]),
+    "lcd_dict_remove_words": (_I, [_P, _P, _I]),
+    "lcd_dict_update": (_I, [_P]),
+    "lcd_dict_clear": (_I, [_P]),
+    "lcd_dict_size": (_I, [_P]),
+    "lcd_dict_indexed_size": (_I, [_P]),
+    "lcd_dict_not_indexed_size": (_I, [_P]),
+    "lcd_dict_last_word_id": (_I, [_P]),
+    "lcd_dict_set_last_word_id": (_I, [_P, _I]),
+    "lcd_dict_has_word": (_I, [_P, _I]),
+    "lcd_dict_get_indexed": (_I, [_P, _P, _P, _I]),
+    "lcd_dict_knn2": (_I, [_P, _P, _I, _P, _P, _P, _P]),
+    "lcd_dict_quantize": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
+    "lcd_dict_find_nn": (_I, [_P, _P, _I, _I, _F, _P]),
+    "lcd_index_add_refs": (_I, [_P, _I, _P, _I]),
+    "lcd_index_remove_sig": (_I, [_P, _I]),
+    "lcd_index_set_ni": (_I, [_P, _P, _P, _I]),
+    "lcd_index_load_csr": (_I, [_P, _P, _I, _P, _P, _P]),
+    "lcd_index_word_nw": (_I, [_P, _I]),
+    "lcd_index_total_refs": (C.c_longlong, [_P]),
+    "lcd_index_get_refs": (_I, [_P, _I, _P, _P, _I]),
+    "lcd_index_score": (_I, [_P, _P, _I, _P, _I, _I, _P]),
+    "lcd_localize_batch": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P]),
+    "lcd_localize_batch_dev": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
+    "lcd_shard_set_row_offset": (_I, [_P, _I]),
+    "lcd_shard_knn2_keys_dev": (_I, [_P, _P, _I, _P, _P]),
+    "lcd_shard_resolve_score_dev": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
+    "lcd_shard_finalize_dev": (_I, [_P, _P, _I, _P, _P]),
+    "lcd_profile_enable": (_I, [_P, _I]),
+    "lcd_profile_read": (_I, [_P, _I, _P, _P]),
+    "lcd_profile_reset": (_I, [_P]),
+    "lcd_stream": (_P, [_P]),
+    "lcd_synchronize": (_I, [_P]),
+}
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen liblcd_b200.so (building it with nvcc first if needed) and set prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not path.exists():
+        raise LcdError(-2, f"{path} is missing: the CUDA extension must be built (python -m rtabmap_b200.build)")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One device-resident dictionary + inverted index (``lcd_engine``)."""
+
+    def __init__(self, device: int = 0, desc_type: int = LCD_DESC_U8, desc_dim: int = 32, max_words: int = 65536,
+                 max_signatures: int = 16384, max_queries: int = 1024, max_batch: int = 64):
+        self._lib = load_library()
+        cfg = _Config(device, desc_type, desc_dim, max_words, max_signatures, max_queries, max_batch)
+        self._h = self._lib.lcd_create(C.byref(cfg))
+        if not self._h:
+            raise LcdError(-2, self._lib.lcd_last_error(None).decode())
+        self.desc_type = desc_type
+        self.desc_dim = desc_dim
+        self.device = device
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lcd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise LcdError(rc, self._lib.lcd_last_error(self._h).decode())
+
+    def _desc(self, d) -> np.ndarray:
+        dt = np.uint8 if self.desc_type == LCD_DESC_U8 else np.float32
+        d = np.ascontiguousarray(d, dtype=dt)
+        if d.ndim != 2 or d.shape[1] != self.desc_dim:
+            raise LcdError(-1, f"descriptors must be [n,{self.desc_dim}] {dt.__name__}, got {d.shape}")
+        return d
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.lcd_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.lcd_stream(self._h) or 0)
+
+    def synchronize(self):
+        self._check(self._lib.lcd_synchronize(self._h))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.lcd_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._check(self._lib.lcd_profile_reset(self._h))
+
+    def profile_read(self, which: int):
+        ms = C.c_double(0)
+        n = C.c_longlong(0)
+        self._check(self._lib.lcd_profile_read(self._h, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- dictionary --------------------------------------------------------------------------
+    def add_words(self, ids, desc):
+        ids = _i32(ids)
+        desc = self._desc(desc)
+        assert len(ids) == len(desc)
+        self._check(self._lib.lcd_dict_add_words(self._h, _ptr(ids), _ptr(desc), len(ids)))
+
+    def remove_words(self, ids):
+        ids = _i32(ids)
+        self._check(self._lib.lcd_dict_remove_words(self._h, _ptr(ids), len(ids)))
+
+    def update(self):
+        self._check(self._lib.lcd_dict_update(self._h))
+
+    def clear(self):
+        self._check(self._lib.lcd_dict_clear(self._h))
+
+    def size(self) -> int:
+        return self._lib.lcd_dict_size(self._h)
+
+    def indexed_size(self) -> int:
+        return self._lib.lcd_dict_indexed_size(self._h)
+
+    def not_indexed_size(self) -> int:
+        return self._lib.lcd_dict_not_indexed_size(self._h)
+
+    @property
+    def last_word_id(self) -> int:
+        return self._lib.lcd_dict_last_word_id(self._h)
+
+    @last_word_id.setter
+    def last_word_id(self, v: int):
+        self._check(self._lib.lcd_dict_set_last_word_id(self._h, int(v)))
+
+    def has_word(self, word_id: int) -> bool:
+        return bool(self._lib.lcd_dict_has_word(self._h, int(word_id)))
+
+    def get_indexed(self):
+        n = self.indexed_size()
+        ids = np.zeros(n, np.int32)
+        dt = np.uint8 if self.desc_type == LCD_DESC_U8 else np.float32
+        desc = np.zeros((n, self.desc_dim), dt)
+        if n:
+            r = self._lib.lcd_dict_get_indexed(self._h, _ptr(ids), _ptr(desc), n)
+            if r < 0:
+                self._check(r)
+        return ids, desc
+
+    def knn2(self, queries):
+        q = self._desc(queries)
+        n = len(q)
+        id1 = np.zeros(n, np.int32)
+        id2 = np.zeros(n, np.int32)
+        d1 = np.zeros(n, np.float32)
+        d2 = np.zeros(n, np.float32)
+        self._check(self._lib.lcd_dict_knn2(self._h, _ptr(q), n, _ptr(id1), _ptr(d1), _ptr(id2), _ptr(d2)))
+        return id1, d1, id2, d2
+
+    def quantize(self, queries, sig_id: int, incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True):
+        q = self._desc(queries)
+        out = np.zeros(len(q), np.int32)
+        n_new = C.c_int(0)
+        self._check(self._lib.lcd_dict_quantize(self._h, _ptr(q), len(q), int(sig_id), int(incremental), float(nndr),
+                                                 int(cmp_new), _ptr(out), C.byref(n_new)))
+        return out, n_new.value
+
+    def find_nn(self, queries, incremental: bool = True, nndr: float = 0.8):
+        q = self._desc(queries)
+        out = np.zeros(len(q), np.int32)
+        self._check(self._lib.lcd_dict_find_nn(self._h, _ptr(q), len(q), int(incremental), float(nndr), _ptr(out)))
+        return out
+
+    # -- inverted index ----------------------------------------------------------------------
+    def add_refs(self, sig_id: int, word_ids):
+        w = _i32(word_ids)
+        self._check(self._lib.lcd_index_add_refs(self._h, int(sig_id), _ptr(w), len(w)))
+
+    def remove_sig(self, sig_id: int):
+        self._check(self._lib.lcd_index_remove_sig(self._h, int(sig_id)))
+
+    def set_ni(self, sig_ids, ni):
+        s = _i32(sig_ids)
+        n = _i32(ni)
+        self._check(self._lib.lcd_index_set_ni(self._h, _ptr(s), _ptr(n), len(s)))
+
+    def load_csr(self, word_ids, row_ptr, sig, cnt):
+        w = _i32(word_ids)
+        rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        s = _i32(sig)
+        c = _i32(cnt)
+        assert len(rp) == len(w) + 1 and len(s) == len(c) == rp[-1]
+        self._check(self._lib.lcd_index_load_csr(self._h, _ptr(w), len(w), _ptr(rp), _ptr(s), _ptr(c)))
+
+    def word_nw(self, word_id: int) -> int:
+        return self._lib.lcd_index_word_nw(self._h, int(word_id))
+
+    def total_refs(self) -> int:
+        return int(self._lib.lcd_index_total_refs(self._h))
+
+    def get_refs(self, word_id: int):
+        n = self.word_nw(word_id)
+        s = np.zeros(max(n, 1), np.int32)
+        c = np.zeros(max(n, 1), np.int32)
+        r = self._lib.lcd_index_get_refs(self._h, int(word_id), _ptr(s), _ptr(c), len(s))
+        if r < 0:
+            self._check(r)
+        return s[:r], c[:r]
+
+    def score(self, query_word_ids, sig_ids, n_total: int):
+        w = _i32(query_word_ids)
+        s = _i32(sig_ids)
+        out = np.zeros(len(s), np.float32)
+        self._check(self._lib.lcd_index_score(self._h, _ptr(w), len(w), _ptr(s), len(s), int(n_total), _ptr(out)))
+        return out
+
+    # -- batched localisation ------------------------------------------------------------------
+    def localize_batch(self, queries, n_frames: int, sig_ids, n_total: int, incremental: bool = True, nndr: float = 0.8,
+                       cmp_new: bool = True, want_words: bool = True, want_likelihood: bool = True,
+                       out_words=None, out_like=None):
+        q = self._desc(queries)
+        assert len(q) % n_frames == 0
+        nq = len(q) // n_frames
+        s = _i32(sig_ids)
+        words = None
+        like = None
+        if want_words:
+            words = out_words if out_words is not None else np.zeros((n_frames, nq), np.int32)
+        if want_likelihood:
+            like = out_like if out_like is not None else np.zeros((n_frames, len(s)), np.float32)
+        self._check(self._lib.lcd_localize_batch(self._h, _ptr(q), n_frames, nq, int(incremental), float(nndr), int(cmp_new),
+                                                  _ptr(s), len(s), int(n_total), _ptr(words), _ptr(like)))
+        return words, like
+
+    def localize_batch_dev(self, d_queries: int, n_frames: int, nq: int, d_sig_ids: int, ns: int, n_total: int,
+                           d_words_out: int = 0, d_like_out: int = 0, incremental: bool = True, nndr: float = 0.8,
+                           cmp_new: bool = True, stream: int = 0):
+        self._check(self._lib.lcd_localize_batch_dev(self._h, C.c_void_p(d_queries), n_frames, nq, int(incremental), float(nndr),
+                                                      int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total),
+                                                      C.c_void_p(d_words_out or None), C.c_void_p(d_like_out or None),
+                                                      C.c_void_p(stream or None)))
+
+    # -- word-range sharding ----------------------------------------------------------------------
+    def shard_set_row_offset(self, off: int):
+        self._check(self._lib.lcd_shard_set_row_offset(self._h, int(off)))
+
+    def shard_knn2_keys_dev(self, d_queries: int, nq: int, d_keys_out: int, stream: int = 0):
+        self._check(self._lib.lcd_shard_knn2_keys_dev(self._h, C.c_void_p(d_queries), nq, C.c_void_p(d_keys_out), C.c_void_p(stream or None)))
+
+    def shard_resolve_score_dev(self, d_queries: int, n_frames: int, nq: int, d_keys_gathered: int, n_ranks: int, d_row_ids: int,
+                                total_rows: int, last_word_id: int, d_sig_ids: int, ns: int, n_total: int, d_words_out: int,
+                                d_scores_out: int, incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True, stream: int = 0):
+        self._check(self._lib.lcd_shard_resolve_score_dev(
+            self._h, C.c_void_p(d_queries), n_frames, nq, C.c_void_p(d_keys_gathered), n_ranks, C.c_void_p(d_row_ids), total_rows,
+            last_word_id, int(incremental), float(nndr), int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total),
+            C.c_void_p(d_words_out or None), C.c_void_p(d_scores_out or None), C.c_void_p(stream or None)))
+
+    def shard_finalize_dev(self, d_scores: int, n: int, d_like_out: int, stream: int = 0):
+        self._check(self._lib.lcd_shard_finalize_dev(self._h, C.c_void_p(d_scores), n, C.c_void_p(d_like_out), C.c_void_p(stream or None)))

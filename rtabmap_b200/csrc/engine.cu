@@ -1,0 +1,1307 @@
+// engine.cu — host side of the loop-closure engine and the C ABI (include/lcd_b200.h).
+//
+// One lcd_engine = the device-resident state of one rtabmap::VWDictionary
+// (corelib/include/rtabmap/core/VWDictionary.h:46-160): the vocabulary matrix in search
+// order (_dataTree + _mapIndexId), the not-indexed tail (_notIndexedWords), and the inverted
+// index (VisualWord::_references of every word) as an arena of posting lists.  The host keeps
+// only the bookkeeping the reference keeps in std::map's (id -> row, list extents, the words
+// of each signature); all descriptor and posting data lives in HBM and every distance,
+// decision and score is computed by the kernels in nn_hamming.cuh / resolve.cuh / score.cuh.
+// There is deliberately no CPU fallback: every entry point fails with LCD_ERR_CUDA if the
+// device is missing.
+#include "../../include/lcd_b200.h"
+#include "common.cuh"
+#include "nn_hamming.cuh"
+#include "resolve.cuh"
+#include "score.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+using namespace lcd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf
+{
+	T * p = nullptr;
+	size_t cap = 0; // elements
+	~DevBuf() { release(); }
+	void release()
+	{
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	// grow to at least n elements; keep the first `keep` elements; zero the rest if asked
+	cudaError_t reserve(size_t n, size_t keep, bool zero_new, cudaStream_t s)
+	{
+		if (n <= cap) return cudaSuccess;
+		size_t ncap = std::max(n, cap + cap / 2 + 16);
+		T * np = nullptr;
+		cudaError_t err = cudaMalloc(&np, ncap * sizeof(T));
+		if (err != cudaSuccess) return err;
+		if (zero_new)
+		{
+			err = cudaMemsetAsync(np, 0, ncap * sizeof(T), s);
+			if (err != cudaSuccess) return err;
+		}
+		if (p && keep)
+		{
+			err = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+			if (err != cudaSuccess) return err;
+		}
+		if (p)
+		{
+			cudaStreamSynchronize(s);
+			cudaFree(p);
+		}
+		p = np;
+		cap = ncap;
+		return cudaSuccess;
+	}
+};
+
+template <typename T>
+struct PinBuf
+{
+	T * p = nullptr;
+	size_t cap = 0;
+	~PinBuf()
+	{
+		if (p) cudaFreeHost(p);
+	}
+	cudaError_t reserve(size_t n)
+	{
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t ncap = n + n / 2 + 16;
+		cudaError_t err = cudaMallocHost(&p, ncap * sizeof(T));
+		if (err == cudaSuccess) cap = ncap;
+		return err;
+	}
+};
+
+int env_int(const char * name, int def)
+{
+	const char * v = getenv(name);
+	return v && *v ? atoi(v) : def;
+}
+
+} // namespace
+
+struct lcd_engine
+{
+	lcd_config cfg{};
+	int nw = 0; // 32-bit words per descriptor
+	mutable std::string err;
+	cudaStream_t stream = nullptr;
+	long long launches = 0;
+	int sm_count = 148;
+	int smem_optin = 0;
+
+	// --- vocabulary: rows [0,n_indexed) searchable, [n_indexed, n_indexed+n_pending) not indexed
+	DevBuf<uint32_t> vocab, vocab_alt;
+	DevBuf<int> row_ids, row_ids_alt;
+	std::vector<int> h_row_ids;
+	std::unordered_map<int, int> id2row;
+	std::unordered_set<int> removed_rows; // indexed rows leaving at the next update
+	int n_indexed = 0, n_pending = 0;
+	bool pending_sorted = true;
+	int last_word_id = 0;
+	int row_offset = 0;
+
+	// --- inverted index
+	DevBuf<uint32_t> post_off;
+	DevBuf<int> post_len;
+	std::vector<uint32_t> h_off;
+	std::vector<int> h_len, h_cap;
+	DevBuf<int2> postings;
+	size_t post_used = 0;
+	DevBuf<int> ni;
+	std::vector<int> h_ni;
+	std::unordered_map<int, std::vector<std::pair<int, int>>> sig_words; // sig -> sorted (word,count)
+	long long total_refs = 0;
+
+	// --- scratch
+	DevBuf<uint32_t> d_queries;
+	DevBuf<uint2> d_partial;
+	DevBuf<uint32_t> d_keys;
+	DevBuf<int> d_word_ids, d_n_new, d_in_ids;
+	DevBuf<int> uq_count, uq_word, uq_prefix;
+	DevBuf<float> uq_idf;
+	DevBuf<long long> acc;
+	int acc_stride = 0;
+	DevBuf<int> d_sig_ids;
+	DevBuf<float> d_like;
+	DevBuf<int> d_i1, d_i2;
+	DevBuf<float> d_f1, d_f2;
+	DevBuf<RefOp> d_ops;
+	DevBuf<MoveOp> d_moves;
+	DevBuf<int> d_perm;
+
+	// measurement hooks (lcd_profile_*)
+	bool prof_on = false;
+	struct Prof
+	{
+		std::vector<cudaEvent_t> ev; // start/stop pairs
+		size_t used = 0;
+	} prof[3];
+
+	// tuning knobs (env: LCD_NN_CTAS_PER_SM, LCD_NN_TQ, LCD_NN_VARIANT, LCD_SCORE_BLOCKS)
+	int nn_ctas_per_sm = 2, nn_tq = 4, nn_variant = 0, score_blocks = 32;
+};
+
+#define LCD_FAIL(e, code, ...)                          \
+	do                                                  \
+	{                                                   \
+		char _b[512];                                   \
+		snprintf(_b, sizeof(_b), __VA_ARGS__);          \
+		(e)->err = _b;                                  \
+		return (code);                                  \
+	} while (0)
+
+#define LCD_CUDA(e, call)                                                                          \
+	do                                                                                             \
+	{                                                                                              \
+		cudaError_t _c = (call);                                                                   \
+		if (_c != cudaSuccess)                                                                     \
+		{                                                                                          \
+			LCD_FAIL(e, LCD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_c), __FILE__, __LINE__); \
+		}                                                                                          \
+	} while (0)
+
+#define LCD_CHECK_LAUNCH(e)                 \
+	do                                      \
+	{                                       \
+		++(e)->launches;                    \
+		LCD_CUDA(e, cudaGetLastError());    \
+	} while (0)
+
+#define LCD_TRY(expr)              \
+	do                             \
+	{                              \
+		int _r = (expr);           \
+		if (_r != LCD_OK) return _r; \
+	} while (0)
+
+namespace {
+
+int total_rows(const lcd_engine * e) { return e->n_indexed + e->n_pending; }
+
+int set_device(lcd_engine * e)
+{
+	LCD_CUDA(e, cudaSetDevice(e->cfg.device));
+	return LCD_OK;
+}
+
+int ensure_rows(lcd_engine * e, int rows)
+{
+	const size_t keep = static_cast<size_t>(total_rows(e));
+	LCD_CUDA(e, e->vocab.reserve(static_cast<size_t>(rows) * e->nw, keep * e->nw, false, e->stream));
+	LCD_CUDA(e, e->row_ids.reserve(static_cast<size_t>(rows), keep, false, e->stream));
+	return LCD_OK;
+}
+
+int ensure_ids(lcd_engine * e, int max_id)
+{
+	const size_t need = static_cast<size_t>(max_id) + 1;
+	if (need > e->h_len.size())
+	{
+		const size_t old = e->h_len.size();
+		const size_t ncap = std::max(need, old + old / 2 + 1024);
+		LCD_CUDA(e, e->post_off.reserve(ncap, old, true, e->stream));
+		LCD_CUDA(e, e->post_len.reserve(ncap, old, true, e->stream));
+		e->h_off.resize(e->post_off.cap, 0u);
+		e->h_len.resize(e->post_off.cap, 0);
+		e->h_cap.resize(e->post_off.cap, 0);
+	}
+	return LCD_OK;
+}
+
+int ensure_sigs(lcd_engine * e, int max_sig)
+{
+	const size_t need = static_cast<size_t>(max_sig) + 1;
+	if (need > e->h_ni.size())
+	{
+		const size_t old = e->h_ni.size();
+		const size_t ncap = std::max(need, old + old / 2 + 1024);
+		LCD_CUDA(e, e->ni.reserve(ncap, old, true, e->stream));
+		e->h_ni.resize(e->ni.cap, 0);
+	}
+	return LCD_OK;
+}
+
+int ensure_acc(lcd_engine * e, int n_frames)
+{
+	const int stride = static_cast<int>(e->h_ni.size());
+	if (stride != e->acc_stride || e->acc.cap < static_cast<size_t>(stride) * n_frames)
+	{
+		LCD_CUDA(e, e->acc.reserve(static_cast<size_t>(std::max(stride, 1)) * n_frames, 0, false, e->stream));
+		e->acc_stride = stride;
+	}
+	return LCD_OK;
+}
+
+int ensure_postings(lcd_engine * e, size_t extra)
+{
+	if (e->post_used + extra > 0xFFFFFFF0ull) LCD_FAIL(e, LCD_ERR_CAPACITY, "posting arena exceeds 2^32 entries");
+	LCD_CUDA(e, e->postings.reserve(e->post_used + extra, e->post_used, false, e->stream));
+	return LCD_OK;
+}
+
+// ---- measurement hooks ------------------------------------------------------------------
+void prof_mark(lcd_engine * e, int which, cudaStream_t s)
+{
+	if (!e->prof_on) return;
+	auto & p = e->prof[which];
+	if (p.used == p.ev.size())
+	{
+		cudaEvent_t ev;
+		if (cudaEventCreate(&ev) != cudaSuccess) return;
+		p.ev.push_back(ev);
+	}
+	cudaEventRecord(p.ev[p.used++], s);
+}
+
+// ---- kernel launch helpers --------------------------------------------------------------
+template <int NW, int TQ, int VARIANT>
+int launch_knn_t(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int n_chunks, int rows_per_cta,
+                 uint2 * d_partial, cudaStream_t s)
+{
+	auto kern = knn2_hamming_kernel<NW, TQ, VARIANT>;
+	const size_t smem = 16 + static_cast<size_t>(rows_per_cta) * NW * 4;
+	if (smem > 48 * 1024)
+	{
+		LCD_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	}
+	prof_mark(e, LCD_PROF_NN, s);
+	kern<<<n_chunks, kNnThreads, smem, s>>>(e->vocab.p, n_rows, e->row_offset, d_q, nq_total, d_partial, rows_per_cta);
+	prof_mark(e, LCD_PROF_NN, s);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+template <int NW>
+int launch_knn_nw(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int n_chunks, int rows_per_cta,
+                  uint2 * d_partial, cudaStream_t s)
+{
+	const int tq = e->nn_tq, var = (NW == 8) ? e->nn_variant : 0;
+#define LCD_KNN_CASE(TQ_, V_) \
+	if (tq == TQ_ && var == V_) return launch_knn_t<NW, TQ_, V_>(e, d_q, nq_total, n_rows, n_chunks, rows_per_cta, d_partial, s);
+	LCD_KNN_CASE(4, 0)
+	LCD_KNN_CASE(2, 0)
+	LCD_KNN_CASE(8, 0)
+	if constexpr (NW == 8)
+	{
+		LCD_KNN_CASE(4, 1)
+		LCD_KNN_CASE(2, 1)
+		LCD_KNN_CASE(8, 1)
+		LCD_KNN_CASE(4, 2)
+		LCD_KNN_CASE(2, 2)
+		LCD_KNN_CASE(8, 2)
+	}
+#undef LCD_KNN_CASE
+	return launch_knn_t<NW, 4, 0>(e, d_q, nq_total, n_rows, n_chunks, rows_per_cta, d_partial, s);
+}
+
+// exact 2-NN of nq_total queries over rows [0,n_rows): fills e->d_partial, returns chunk count
+int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int * n_chunks_out, cudaStream_t s)
+{
+	if (e->row_offset + n_rows > kMaxRowsPacked) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d indexed words", kMaxRowsPacked);
+	const int max_rows_smem = static_cast<int>((static_cast<size_t>(e->smem_optin) - 16 - 1024) / (e->nw * 4));
+	int n_chunks = e->sm_count * e->nn_ctas_per_sm;
+	n_chunks = std::min(n_chunks, std::max(1, (n_rows + 31) / 32));
+	n_chunks = std::max(n_chunks, (n_rows + max_rows_smem - 1) / max_rows_smem);
+	n_chunks = std::max(n_chunks, 1);
+	int rows_per_cta = (n_rows + n_chunks - 1) / n_chunks;
+	if (rows_per_cta < 1) rows_per_cta = 1;
+	n_chunks = std::max(1, (n_rows + rows_per_cta - 1) / rows_per_cta);
+	LCD_CUDA(e, e->d_partial.reserve(static_cast<size_t>(n_chunks) * nq_total, 0, false, s));
+	int r;
+	switch (e->nw)
+	{
+	case 4: r = launch_knn_nw<4>(e, d_q, nq_total, n_rows, n_chunks, rows_per_cta, e->d_partial.p, s); break;
+	case 8: r = launch_knn_nw<8>(e, d_q, nq_total, n_rows, n_chunks, rows_per_cta, e->d_partial.p, s); break;
+	case 16: r = launch_knn_nw<16>(e, d_q, nq_total, n_rows, n_chunks, rows_per_cta, e->d_partial.p, s); break;
+	default: LCD_FAIL(e, LCD_ERR_INVALID, "unsupported descriptor size %d bytes", e->nw * 4);
+	}
+	*n_chunks_out = n_chunks;
+	return r;
+}
+
+int launch_resolve(lcd_engine * e, const ResolveArgs & a, int n_frames, cudaStream_t s)
+{
+	const size_t smem = resolve_smem_bytes(a.nq);
+#define LCD_RES_CASE(NW_)                                                                                               \
+	case NW_:                                                                                                           \
+	{                                                                                                                   \
+		auto kern = resolve_kernel<NW_>;                                                                                \
+		if (smem > 48 * 1024)                                                                                           \
+			LCD_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+		prof_mark(e, LCD_PROF_RESOLVE, s);                                                                              \
+		kern<<<n_frames, kResolveThreads, smem, s>>>(a);                                                                \
+		prof_mark(e, LCD_PROF_RESOLVE, s);                                                                              \
+		break;                                                                                                          \
+	}
+	switch (e->nw)
+	{
+		LCD_RES_CASE(4)
+		LCD_RES_CASE(8)
+		LCD_RES_CASE(16)
+	default: LCD_FAIL(e, LCD_ERR_INVALID, "unsupported descriptor size");
+	}
+#undef LCD_RES_CASE
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+int ensure_uq(lcd_engine * e, int n_frames, int nq, cudaStream_t s)
+{
+	LCD_CUDA(e, e->uq_count.reserve(n_frames, 0, false, s));
+	LCD_CUDA(e, e->uq_word.reserve(static_cast<size_t>(n_frames) * nq, 0, false, s));
+	LCD_CUDA(e, e->uq_prefix.reserve(static_cast<size_t>(n_frames) * (nq + 1), 0, false, s));
+	LCD_CUDA(e, e->uq_idf.reserve(static_cast<size_t>(n_frames) * nq, 0, false, s));
+	return LCD_OK;
+}
+
+void fill_prep(lcd_engine * e, ResolveArgs & a, float n_total, int self_ref)
+{
+	a.do_prep = 1;
+	a.post_len = e->post_len.p;
+	a.id_cap = static_cast<int>(e->h_len.size());
+	a.n_total = n_total;
+	a.self_ref = self_ref;
+	a.uq_count = e->uq_count.p;
+	a.uq_word = e->uq_word.p;
+	a.uq_prefix = e->uq_prefix.p;
+	a.uq_idf = e->uq_idf.p;
+}
+
+int launch_score(lcd_engine * e, int n_frames, int nq, cudaStream_t s)
+{
+	ScoreArgs sa;
+	sa.nq = nq;
+	sa.uq_count = e->uq_count.p;
+	sa.uq_word = e->uq_word.p;
+	sa.uq_prefix = e->uq_prefix.p;
+	sa.uq_idf = e->uq_idf.p;
+	sa.post_off = e->post_off.p;
+	sa.postings = e->postings.p;
+	sa.ni = e->ni.p;
+	sa.sig_cap = static_cast<int>(e->h_ni.size());
+	sa.acc = e->acc.p;
+	sa.acc_stride = e->acc_stride;
+	dim3 grid(e->score_blocks, n_frames);
+	prof_mark(e, LCD_PROF_SCORE, s);
+	score_kernel<<<grid, kScoreThreads, (nq + 1) * sizeof(int), s>>>(sa);
+	prof_mark(e, LCD_PROF_SCORE, s);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+// make the not-indexed tail ascending in id (std::set<int> _notIndexedWords iteration order)
+int sort_pending(lcd_engine * e)
+{
+	if (e->pending_sorted || e->n_pending < 2)
+	{
+		e->pending_sorted = true;
+		return LCD_OK;
+	}
+	const int base = e->n_indexed, n = e->n_pending;
+	std::vector<int> order(n);
+	for (int i = 0; i < n; ++i) order[i] = base + i;
+	std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return e->h_row_ids[x] < e->h_row_ids[y]; });
+	LCD_CUDA(e, e->d_perm.reserve(n, 0, false, e->stream));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_perm.p, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, e->vocab_alt.reserve(static_cast<size_t>(n) * e->nw, 0, false, e->stream));
+	const size_t elems = static_cast<size_t>(n) * e->nw;
+	gather_rows_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, e->stream>>>(e->vocab.p, e->d_perm.p, n, e->nw, e->vocab_alt.p);
+	LCD_CHECK_LAUNCH(e);
+	LCD_CUDA(e, cudaMemcpyAsync(e->vocab.p + static_cast<size_t>(base) * e->nw, e->vocab_alt.p, elems * sizeof(uint32_t),
+	                            cudaMemcpyDeviceToDevice, e->stream));
+	std::vector<int> ids(n);
+	for (int i = 0; i < n; ++i) ids[i] = e->h_row_ids[order[i]];
+	for (int i = 0; i < n; ++i)
+	{
+		e->h_row_ids[base + i] = ids[i];
+		e->id2row[ids[i]] = base + i;
+	}
+	LCD_CUDA(e, cudaMemcpyAsync(e->row_ids.p + base, ids.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	e->pending_sorted = true;
+	return LCD_OK;
+}
+
+// VWDictionary::addWordRef for the words of one signature (host bookkeeping + device ops)
+int add_refs_impl(lcd_engine * e, int sig_id, const int * word_ids, int n)
+{
+	if (sig_id <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "signature id must be positive");
+	LCD_TRY(ensure_sigs(e, sig_id));
+	std::vector<int> ids;
+	ids.reserve(n);
+	for (int i = 0; i < n; ++i)
+	{
+		if (word_ids[i] > 0) ids.push_back(word_ids[i]);
+	}
+	std::sort(ids.begin(), ids.end());
+	std::vector<RefOp> ops;
+	std::vector<MoveOp> moves;
+	auto & sw = e->sig_words[sig_id];
+	std::vector<std::pair<int, int>> merged;
+	merged.reserve(sw.size() + ids.size());
+	size_t si = 0;
+	size_t extra = 0;
+	for (size_t i = 0; i < ids.size();)
+	{
+		size_t j = i;
+		while (j < ids.size() && ids[j] == ids[i]) ++j;
+		const int word = ids[i], cnt = static_cast<int>(j - i);
+		i = j;
+		if (e->id2row.find(word) == e->id2row.end())
+		{
+			// reference: UWARN("Not found word %d"), VWDictionary.cpp:893
+			continue;
+		}
+		LCD_TRY(ensure_ids(e, word));
+		while (si < sw.size() && sw[si].first < word) merged.push_back(sw[si++]);
+		RefOp op{word, sig_id, cnt, -1, 0};
+		if (si < sw.size() && sw[si].first == word)
+		{
+			merged.emplace_back(word, sw[si].second + cnt);
+			++si;
+			op.pos = -1;
+			op.newlen = e->h_len[word];
+		}
+		else
+		{
+			merged.emplace_back(word, cnt);
+			if (e->h_len[word] == e->h_cap[word])
+			{
+				const int ncap = std::max(4, e->h_cap[word] * 2);
+				MoveOp mv{word, e->h_off[word], static_cast<uint32_t>(e->post_used + extra), e->h_len[word]};
+				extra += ncap;
+				e->h_off[word] = mv.new_off;
+				e->h_cap[word] = ncap;
+				moves.push_back(mv);
+			}
+			op.pos = e->h_len[word];
+			op.newlen = ++e->h_len[word];
+		}
+		e->total_refs += cnt;
+		ops.push_back(op);
+	}
+	while (si < sw.size()) merged.push_back(sw[si++]);
+	sw.swap(merged);
+	e->h_ni[sig_id] += n;
+	LCD_CUDA(e, cudaMemcpyAsync(e->ni.p + sig_id, &e->h_ni[sig_id], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	if (extra)
+	{
+		LCD_TRY(ensure_postings(e, extra));
+		e->post_used += extra;
+	}
+	if (!moves.empty())
+	{
+		LCD_CUDA(e, e->d_moves.reserve(moves.size(), 0, false, e->stream));
+		LCD_CUDA(e, cudaMemcpyAsync(e->d_moves.p, moves.data(), moves.size() * sizeof(MoveOp), cudaMemcpyHostToDevice, e->stream));
+		const int nm = static_cast<int>(moves.size());
+		index_move_kernel<<<(nm * 32 + 255) / 256, 256, 0, e->stream>>>(e->d_moves.p, nm, e->post_off.p, e->postings.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	if (!ops.empty())
+	{
+		LCD_CUDA(e, e->d_ops.reserve(ops.size(), 0, false, e->stream));
+		LCD_CUDA(e, cudaMemcpyAsync(e->d_ops.p, ops.data(), ops.size() * sizeof(RefOp), cudaMemcpyHostToDevice, e->stream));
+		const int no = static_cast<int>(ops.size());
+		index_apply_kernel<<<(no + 255) / 256, 256, 0, e->stream>>>(e->d_ops.p, no, e->post_off.p, e->post_len.p, e->postings.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	// the op vectors are pageable: make sure the copies completed before they go out of scope
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+int check_queries(lcd_engine * e, const void * q, int nq)
+{
+	if (!q || nq <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
+	if (nq > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "at most %d descriptors per frame", kMaxFrameQueries);
+	return LCD_OK;
+}
+
+// quantise + score of n_frames independent frames on device buffers, no mutation
+int localize_dev(lcd_engine * e, const uint32_t * d_q, int n_frames, int nq, int incremental, float nndr, int cmp_new,
+                 const int * d_sig_ids, int ns, int n_total, int * d_word_ids_out, float * d_like_out, cudaStream_t s)
+{
+	if (e->n_indexed == 0 && !incremental) LCD_FAIL(e, LCD_ERR_STATE, "Dictionary mode is set to fixed but no words are in it!");
+	const int nq_total = n_frames * nq;
+	int n_chunks = 0;
+	LCD_TRY(run_knn(e, d_q, nq_total, e->n_indexed, &n_chunks, s));
+	const bool score = d_like_out != nullptr && ns > 0;
+	ResolveArgs a{};
+	a.queries = d_q;
+	a.nq = nq;
+	a.nq_total = nq_total;
+	a.partial = e->d_partial.p;
+	a.n_chunks = n_chunks;
+	a.row_ids = e->row_ids.p;
+	a.incremental = incremental;
+	a.nndr = nndr;
+	a.cmp_new = cmp_new;
+	a.last_word_id = e->last_word_id;
+	a.word_ids_out = d_word_ids_out;
+	a.n_new_out = nullptr;
+	a.pending_desc = nullptr;
+	a.pending_ids = nullptr;
+	if (score)
+	{
+		LCD_TRY(ensure_uq(e, n_frames, nq, s));
+		LCD_TRY(ensure_acc(e, n_frames));
+		LCD_CUDA(e, cudaMemsetAsync(e->acc.p, 0, static_cast<size_t>(e->acc_stride) * n_frames * sizeof(long long), s));
+		fill_prep(e, a, static_cast<float>(n_total), 1);
+	}
+	LCD_TRY(launch_resolve(e, a, n_frames, s));
+	if (score)
+	{
+		LCD_TRY(launch_score(e, n_frames, nq, s));
+		dim3 grid((ns + 255) / 256, n_frames);
+		gather_likelihood_kernel<<<grid, 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), d_sig_ids, ns, d_like_out);
+		LCD_CHECK_LAUNCH(e);
+	}
+	return LCD_OK;
+}
+
+} // namespace
+
+// ============================================================================ C ABI ====
+extern "C" {
+
+int lcd_abi_version(void) { return 1; }
+const char * lcd_build_arch(void) { return "sm_100a"; }
+
+const char * lcd_last_error(const lcd_engine * e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+long long lcd_launch_count(const lcd_engine * e) { return e ? e->launches : 0; }
+void * lcd_stream(lcd_engine * e) { return e ? static_cast<void *>(e->stream) : nullptr; }
+
+lcd_engine * lcd_create(const lcd_config * cfg)
+{
+	if (!cfg)
+	{
+		g_create_error = "null config";
+		return nullptr;
+	}
+	if (cfg->desc_type != LCD_DESC_U8)
+	{
+		g_create_error = "only LCD_DESC_U8 (binary descriptors, Hamming) is implemented in this build";
+		return nullptr;
+	}
+	if (cfg->desc_dim != 16 && cfg->desc_dim != 32 && cfg->desc_dim != 64)
+	{
+		g_create_error = "binary descriptor size must be 16, 32 or 64 bytes";
+		return nullptr;
+	}
+	int ndev = 0;
+	cudaError_t err = cudaGetDeviceCount(&ndev);
+	if (err != cudaSuccess || ndev <= cfg->device || cfg->device < 0)
+	{
+		g_create_error = std::string("no usable CUDA device: ") + (err != cudaSuccess ? cudaGetErrorString(err) : "device ordinal out of range");
+		return nullptr;
+	}
+	lcd_engine * e = new lcd_engine();
+	e->cfg = *cfg;
+	e->nw = cfg->desc_dim / 4;
+	if ((err = cudaSetDevice(cfg->device)) != cudaSuccess || (err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess)
+	{
+		g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(err);
+		delete e;
+		return nullptr;
+	}
+	cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+	cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+	e->nn_ctas_per_sm = std::max(1, env_int("LCD_NN_CTAS_PER_SM", e->nn_ctas_per_sm));
+	e->nn_tq = env_int("LCD_NN_TQ", e->nn_tq);
+	e->nn_variant = env_int("LCD_NN_VARIANT", e->nn_variant);
+	e->score_blocks = std::max(1, env_int("LCD_SCORE_BLOCKS", e->score_blocks));
+	if (ensure_rows(e, std::max(cfg->max_words, 1024)) != LCD_OK || ensure_ids(e, std::max(cfg->max_words, 1024)) != LCD_OK ||
+	    ensure_sigs(e, std::max(cfg->max_signatures, 1024)) != LCD_OK)
+	{
+		g_create_error = e->err;
+		lcd_destroy(e);
+		return nullptr;
+	}
+	return e;
+}
+
+void lcd_destroy(lcd_engine * e)
+{
+	if (!e) return;
+	cudaSetDevice(e->cfg.device);
+	if (e->stream)
+	{
+		cudaStreamSynchronize(e->stream);
+		cudaStreamDestroy(e->stream);
+	}
+	for (auto & p : e->prof)
+		for (auto ev : p.ev) cudaEventDestroy(ev);
+	delete e;
+}
+
+int lcd_profile_enable(lcd_engine * e, int on)
+{
+	if (!e) return LCD_ERR_INVALID;
+	e->prof_on = on != 0;
+	return LCD_OK;
+}
+
+int lcd_profile_reset(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_CUDA(e, cudaDeviceSynchronize());
+	for (auto & p : e->prof) p.used = 0;
+	return LCD_OK;
+}
+
+int lcd_profile_read(lcd_engine * e, int which, double * total_ms, long long * launches)
+{
+	if (!e || which < 0 || which > 2) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_CUDA(e, cudaDeviceSynchronize());
+	auto & p = e->prof[which];
+	double tot = 0.0;
+	for (size_t i = 0; i + 1 < p.used; i += 2)
+	{
+		float ms = 0.f;
+		LCD_CUDA(e, cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]));
+		tot += ms;
+	}
+	if (total_ms) *total_ms = tot;
+	if (launches) *launches = static_cast<long long>(p.used / 2);
+	return LCD_OK;
+}
+
+int lcd_synchronize(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+// ---- dictionary ---------------------------------------------------------------------------
+int lcd_dict_add_words(lcd_engine * e, const int * ids, const void * desc, int n)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (n <= 0) return LCD_OK;
+	if (!ids || !desc) LCD_FAIL(e, LCD_ERR_INVALID, "null ids/descriptors");
+	LCD_TRY(set_device(e));
+	int max_id = 0;
+	for (int i = 0; i < n; ++i)
+	{
+		if (ids[i] <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "word ids must be positive (got %d)", ids[i]);
+		if (e->id2row.count(ids[i])) LCD_FAIL(e, LCD_ERR_INVALID, "word %d already in the dictionary", ids[i]);
+		max_id = std::max(max_id, ids[i]);
+	}
+	const int base = total_rows(e);
+	LCD_TRY(ensure_rows(e, base + n));
+	LCD_TRY(ensure_ids(e, max_id));
+	LCD_CUDA(e, cudaMemcpyAsync(e->vocab.p + static_cast<size_t>(base) * e->nw, desc, static_cast<size_t>(n) * e->nw * 4, cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaMemcpyAsync(e->row_ids.p + base, ids, static_cast<size_t>(n) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	for (int i = 0; i < n; ++i)
+	{
+		if (!e->h_row_ids.empty() && e->n_pending + i > 0 && ids[i] < e->h_row_ids.back()) e->pending_sorted = false;
+		e->h_row_ids.push_back(ids[i]);
+		e->id2row[ids[i]] = base + i;
+	}
+	e->n_pending += n;
+	// the reference does not touch _lastWordId in addWord; the caller sets it (Memory.cpp:431)
+	return LCD_OK;
+}
+
+int lcd_dict_remove_words(lcd_engine * e, const int * ids, int n)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (n <= 0) return LCD_OK;
+	LCD_TRY(set_device(e));
+	bool pending_hit = false;
+	std::vector<int> zero_ids;
+	for (int i = 0; i < n; ++i)
+	{
+		auto it = e->id2row.find(ids[i]);
+		if (it == e->id2row.end()) continue;
+		const int row = it->second;
+		if (row < e->n_indexed) e->removed_rows.insert(row);
+		else pending_hit = true;
+		e->id2row.erase(it);
+		if (ids[i] < static_cast<int>(e->h_len.size()) && e->h_len[ids[i]] > 0)
+		{
+			e->total_refs -= 0; // references of a removed word are dropped with it (caller removes only unused words)
+			e->h_len[ids[i]] = 0;
+			zero_ids.push_back(ids[i]);
+		}
+	}
+	for (int id : zero_ids)
+	{
+		LCD_CUDA(e, cudaMemsetAsync(e->post_len.p + id, 0, sizeof(int), e->stream));
+	}
+	if (pending_hit)
+	{
+		// compact the not-indexed tail on the spot (it is small)
+		const int base = e->n_indexed, np = e->n_pending;
+		std::vector<int> keep;
+		for (int r = base; r < base + np; ++r)
+		{
+			auto it = e->id2row.find(e->h_row_ids[r]);
+			if (it != e->id2row.end() && it->second == r) keep.push_back(r);
+		}
+		const int nk = static_cast<int>(keep.size());
+		if (nk)
+		{
+			LCD_CUDA(e, e->d_perm.reserve(nk, 0, false, e->stream));
+			LCD_CUDA(e, cudaMemcpyAsync(e->d_perm.p, keep.data(), nk * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+			LCD_CUDA(e, e->vocab_alt.reserve(static_cast<size_t>(nk) * e->nw, 0, false, e->stream));
+			const size_t elems = static_cast<size_t>(nk) * e->nw;
+			gather_rows_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, e->stream>>>(e->vocab.p, e->d_perm.p, nk, e->nw, e->vocab_alt.p);
+			LCD_CHECK_LAUNCH(e);
+			LCD_CUDA(e, cudaMemcpyAsync(e->vocab.p + static_cast<size_t>(base) * e->nw, e->vocab_alt.p, elems * 4, cudaMemcpyDeviceToDevice, e->stream));
+		}
+		std::vector<int> kid(nk);
+		for (int i = 0; i < nk; ++i) kid[i] = e->h_row_ids[keep[i]];
+		e->h_row_ids.resize(base);
+		for (int i = 0; i < nk; ++i)
+		{
+			e->h_row_ids.push_back(kid[i]);
+			e->id2row[kid[i]] = base + i;
+		}
+		if (nk) LCD_CUDA(e, cudaMemcpyAsync(e->row_ids.p + base, kid.data(), nk * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+		e->n_pending = nk;
+	}
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+int lcd_dict_update(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_TRY(sort_pending(e));
+	if (!e->removed_rows.empty())
+	{
+		const int tot = total_rows(e);
+		std::vector<int> keep;
+		keep.reserve(tot);
+		int kept_indexed = 0;
+		for (int r = 0; r < tot; ++r)
+		{
+			if (r < e->n_indexed && e->removed_rows.count(r)) continue;
+			keep.push_back(r);
+			if (r < e->n_indexed) ++kept_indexed;
+		}
+		const int nk = static_cast<int>(keep.size());
+		LCD_CUDA(e, e->vocab_alt.reserve(std::max<size_t>(e->vocab.cap, 1), 0, false, e->stream));
+		LCD_CUDA(e, e->row_ids_alt.reserve(std::max<size_t>(e->row_ids.cap, 1), 0, false, e->stream));
+		std::vector<int> kid(nk);
+		for (int i = 0; i < nk; ++i) kid[i] = e->h_row_ids[keep[i]];
+		if (nk)
+		{
+			LCD_CUDA(e, e->d_perm.reserve(nk, 0, false, e->stream));
+			LCD_CUDA(e, cudaMemcpyAsync(e->d_perm.p, keep.data(), nk * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+			const size_t elems = static_cast<size_t>(nk) * e->nw;
+			gather_rows_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, e->stream>>>(e->vocab.p, e->d_perm.p, nk, e->nw, e->vocab_alt.p);
+			LCD_CHECK_LAUNCH(e);
+			LCD_CUDA(e, cudaMemcpyAsync(e->row_ids_alt.p, kid.data(), nk * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+		}
+		LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+		std::swap(e->vocab.p, e->vocab_alt.p);
+		std::swap(e->vocab.cap, e->vocab_alt.cap);
+		std::swap(e->row_ids.p, e->row_ids_alt.p);
+		std::swap(e->row_ids.cap, e->row_ids_alt.cap);
+		e->h_row_ids.swap(kid);
+		e->id2row.clear();
+		for (int i = 0; i < nk; ++i) e->id2row[e->h_row_ids[i]] = i;
+		e->n_pending = nk - kept_indexed;
+		e->n_indexed = kept_indexed;
+		e->removed_rows.clear();
+	}
+	e->n_indexed += e->n_pending;
+	e->n_pending = 0;
+	e->pending_sorted = true;
+	return LCD_OK;
+}
+
+int lcd_dict_clear(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	e->h_row_ids.clear();
+	e->id2row.clear();
+	e->removed_rows.clear();
+	e->n_indexed = e->n_pending = 0;
+	e->pending_sorted = true;
+	e->last_word_id = 0;
+	std::fill(e->h_off.begin(), e->h_off.end(), 0u);
+	std::fill(e->h_len.begin(), e->h_len.end(), 0);
+	std::fill(e->h_cap.begin(), e->h_cap.end(), 0);
+	std::fill(e->h_ni.begin(), e->h_ni.end(), 0);
+	if (e->post_len.p) LCD_CUDA(e, cudaMemsetAsync(e->post_len.p, 0, e->post_len.cap * sizeof(int), e->stream));
+	if (e->post_off.p) LCD_CUDA(e, cudaMemsetAsync(e->post_off.p, 0, e->post_off.cap * sizeof(uint32_t), e->stream));
+	if (e->ni.p) LCD_CUDA(e, cudaMemsetAsync(e->ni.p, 0, e->ni.cap * sizeof(int), e->stream));
+	e->post_used = 0;
+	e->sig_words.clear();
+	e->total_refs = 0;
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+int lcd_dict_size(const lcd_engine * e) { return e ? static_cast<int>(e->id2row.size()) : 0; }
+int lcd_dict_indexed_size(const lcd_engine * e) { return e ? e->n_indexed : 0; }
+int lcd_dict_not_indexed_size(const lcd_engine * e) { return e ? e->n_pending : 0; }
+int lcd_dict_last_word_id(const lcd_engine * e) { return e ? e->last_word_id : 0; }
+int lcd_dict_set_last_word_id(lcd_engine * e, int id)
+{
+	if (!e || id < 0) return LCD_ERR_INVALID;
+	e->last_word_id = id;
+	return LCD_OK;
+}
+
+int lcd_dict_has_word(const lcd_engine * e, int word_id) { return e && e->id2row.count(word_id) ? 1 : 0; }
+
+int lcd_dict_get_indexed(lcd_engine * e, int * ids, void * desc, int cap_rows)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	const int n = std::min(cap_rows, e->n_indexed);
+	if (n <= 0) return 0;
+	if (ids) memcpy(ids, e->h_row_ids.data(), n * sizeof(int));
+	if (desc)
+	{
+		LCD_CUDA(e, cudaMemcpyAsync(desc, e->vocab.p, static_cast<size_t>(n) * e->nw * 4, cudaMemcpyDeviceToHost, e->stream));
+		LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	}
+	return n;
+}
+
+int lcd_dict_knn2(lcd_engine * e, const void * queries, int nq, int * id1, float * d1, int * id2, float * d2)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!queries || nq <= 0 || !id1 || !d1 || !id2 || !d2) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	cudaStream_t s = e->stream;
+	LCD_CUDA(e, e->d_queries.reserve(static_cast<size_t>(nq) * e->nw, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, static_cast<size_t>(nq) * e->nw * 4, cudaMemcpyHostToDevice, s));
+	int n_chunks = 0;
+	LCD_TRY(run_knn(e, e->d_queries.p, nq, e->n_indexed, &n_chunks, s));
+	LCD_CUDA(e, e->d_keys.reserve(2 * static_cast<size_t>(nq), 0, false, s));
+	knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_partial.p, n_chunks, nq, e->d_keys.p);
+	LCD_CHECK_LAUNCH(e);
+	LCD_CUDA(e, e->d_i1.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->d_i2.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->d_f1.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->d_f2.reserve(nq, 0, false, s));
+	knn2_decode_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_keys.p, nq, e->row_ids.p, e->d_i1.p, e->d_f1.p, e->d_i2.p, e->d_f2.p);
+	LCD_CHECK_LAUNCH(e);
+	LCD_CUDA(e, cudaMemcpyAsync(id1, e->d_i1.p, nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(id2, e->d_i2.p, nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(d1, e->d_f1.p, nq * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(d2, e->d_f2.p, nq * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+int lcd_dict_quantize(lcd_engine * e, const void * queries, int nq, int sig_id, int incremental, float nndr,
+                      int new_words_compared_together, int * word_ids_out, int * n_new_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_TRY(check_queries(e, queries, nq));
+	if (!word_ids_out) LCD_FAIL(e, LCD_ERR_INVALID, "null output");
+	if (!incremental && e->id2row.empty()) LCD_FAIL(e, LCD_ERR_STATE, "Dictionary mode is set to fixed but no words are in it!");
+	cudaStream_t s = e->stream;
+	const int rows0 = total_rows(e);
+	LCD_TRY(ensure_rows(e, rows0 + nq));
+	LCD_CUDA(e, e->d_queries.reserve(static_cast<size_t>(nq) * e->nw, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, static_cast<size_t>(nq) * e->nw * 4, cudaMemcpyHostToDevice, s));
+	int n_chunks = 0;
+	LCD_TRY(run_knn(e, e->d_queries.p, nq, e->n_indexed, &n_chunks, s));
+	LCD_CUDA(e, e->d_word_ids.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->d_n_new.reserve(1, 0, false, s));
+	ResolveArgs a{};
+	a.queries = e->d_queries.p;
+	a.nq = nq;
+	a.nq_total = nq;
+	a.partial = e->d_partial.p;
+	a.n_chunks = n_chunks;
+	a.row_ids = e->row_ids.p;
+	a.incremental = incremental;
+	a.nndr = nndr;
+	a.cmp_new = new_words_compared_together;
+	a.last_word_id = e->last_word_id;
+	a.word_ids_out = e->d_word_ids.p;
+	a.n_new_out = e->d_n_new.p;
+	a.pending_desc = e->vocab.p + static_cast<size_t>(rows0) * e->nw;
+	a.pending_ids = e->row_ids.p + rows0;
+	a.do_prep = 0;
+	LCD_TRY(launch_resolve(e, a, 1, s));
+	int n_new = 0;
+	LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(&n_new, e->d_n_new.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	if (n_new > 0)
+	{
+		LCD_TRY(ensure_ids(e, e->last_word_id + n_new));
+		for (int k = 0; k < n_new; ++k)
+		{
+			const int id = e->last_word_id + 1 + k;
+			e->h_row_ids.push_back(id);
+			e->id2row[id] = rows0 + k;
+		}
+		e->n_pending += n_new;
+		e->last_word_id += n_new;
+	}
+	if (n_new_out) *n_new_out = n_new;
+	if (sig_id > 0) LCD_TRY(add_refs_impl(e, sig_id, word_ids_out, nq));
+	return LCD_OK;
+}
+
+int lcd_dict_find_nn(lcd_engine * e, const void * queries, int nq, int incremental, float nndr, int * word_ids_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_TRY(check_queries(e, queries, nq));
+	if (!word_ids_out) LCD_FAIL(e, LCD_ERR_INVALID, "null output");
+	if (e->id2row.empty())
+	{
+		memset(word_ids_out, 0, nq * sizeof(int));
+		return LCD_OK;
+	}
+	LCD_TRY(sort_pending(e));
+	cudaStream_t s = e->stream;
+	LCD_CUDA(e, e->d_queries.reserve(static_cast<size_t>(nq) * e->nw, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, static_cast<size_t>(nq) * e->nw * 4, cudaMemcpyHostToDevice, s));
+	int n_chunks = 0;
+	// index rows first, then the not-indexed tail: (dist,row) order = index hits before
+	// not-indexed hits at equal distance, as the multimap insertion order (VWDictionary.cpp:1476-1517)
+	LCD_TRY(run_knn(e, e->d_queries.p, nq, total_rows(e), &n_chunks, s));
+	LCD_CUDA(e, e->d_word_ids.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->d_n_new.reserve(1, 0, false, s));
+	ResolveArgs a{};
+	a.queries = e->d_queries.p;
+	a.nq = nq;
+	a.nq_total = nq;
+	a.partial = e->d_partial.p;
+	a.n_chunks = n_chunks;
+	a.row_ids = e->row_ids.p;
+	a.incremental = incremental;
+	a.nndr = nndr;
+	a.cmp_new = 0;
+	a.last_word_id = e->last_word_id;
+	a.find_only = 1;
+	a.word_ids_out = e->d_word_ids.p;
+	a.n_new_out = e->d_n_new.p;
+	LCD_TRY(launch_resolve(e, a, 1, s));
+	LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+// ---- inverted index ---------------------------------------------------------------------
+int lcd_index_add_refs(lcd_engine * e, int sig_id, const int * word_ids, int n)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (n < 0 || (n > 0 && !word_ids)) LCD_FAIL(e, LCD_ERR_INVALID, "bad word list");
+	LCD_TRY(set_device(e));
+	return add_refs_impl(e, sig_id, word_ids, n);
+}
+
+int lcd_index_remove_sig(lcd_engine * e, int sig_id)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	auto it = e->sig_words.find(sig_id);
+	if (it == e->sig_words.end()) return LCD_OK;
+	std::vector<RefOp> ops;
+	for (auto & wc : it->second)
+	{
+		const int word = wc.first;
+		if (e->id2row.find(word) == e->id2row.end() || e->h_len[word] == 0) continue;
+		ops.push_back(RefOp{word, sig_id, wc.second, -1, 0});
+		--e->h_len[word];
+		e->total_refs -= wc.second;
+	}
+	e->sig_words.erase(it);
+	if (sig_id < static_cast<int>(e->h_ni.size()))
+	{
+		e->h_ni[sig_id] = 0;
+		LCD_CUDA(e, cudaMemsetAsync(e->ni.p + sig_id, 0, sizeof(int), e->stream));
+	}
+	if (!ops.empty())
+	{
+		const int no = static_cast<int>(ops.size());
+		LCD_CUDA(e, e->d_ops.reserve(no, 0, false, e->stream));
+		LCD_CUDA(e, cudaMemcpyAsync(e->d_ops.p, ops.data(), no * sizeof(RefOp), cudaMemcpyHostToDevice, e->stream));
+		index_remove_kernel<<<(no * 32 + 255) / 256, 256, 0, e->stream>>>(e->d_ops.p, no, e->post_off.p, e->post_len.p, e->postings.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+int lcd_index_set_ni(lcd_engine * e, const int * sig_ids, const int * ni, int n)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (n <= 0) return LCD_OK;
+	LCD_TRY(set_device(e));
+	int mx = 0;
+	for (int i = 0; i < n; ++i)
+	{
+		if (sig_ids[i] <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "signature id must be positive");
+		mx = std::max(mx, sig_ids[i]);
+	}
+	LCD_TRY(ensure_sigs(e, mx));
+	for (int i = 0; i < n; ++i) e->h_ni[sig_ids[i]] = ni[i];
+	LCD_CUDA(e, cudaMemcpyAsync(e->ni.p, e->h_ni.data(), (static_cast<size_t>(mx) + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+int lcd_index_load_csr(lcd_engine * e, const int * word_ids, int nw, const int64_t * row_ptr, const int * sig, const int * cnt)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (nw <= 0) return LCD_OK;
+	if (!word_ids || !row_ptr || !sig || !cnt) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	LCD_TRY(set_device(e));
+	const int64_t total = row_ptr[nw] - row_ptr[0];
+	int max_word = 0, max_sig = 0;
+	for (int k = 0; k < nw; ++k)
+	{
+		if (e->id2row.find(word_ids[k]) == e->id2row.end()) LCD_FAIL(e, LCD_ERR_INVALID, "word %d is not in the dictionary", word_ids[k]);
+		max_word = std::max(max_word, word_ids[k]);
+	}
+	for (int64_t p = row_ptr[0]; p < row_ptr[nw]; ++p)
+	{
+		if (sig[p] <= 0 || cnt[p] <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "postings need positive signature ids and counts");
+		max_sig = std::max(max_sig, sig[p]);
+	}
+	LCD_TRY(ensure_ids(e, max_word));
+	LCD_TRY(ensure_sigs(e, max_sig));
+	LCD_TRY(ensure_postings(e, static_cast<size_t>(total)));
+	std::vector<int2> buf(static_cast<size_t>(total));
+	size_t w = 0;
+	for (int k = 0; k < nw; ++k)
+	{
+		const int word = word_ids[k];
+		if (e->h_len[word] != 0) LCD_FAIL(e, LCD_ERR_STATE, "word %d already has references; bulk load needs empty lists", word);
+		const int len = static_cast<int>(row_ptr[k + 1] - row_ptr[k]);
+		e->h_off[word] = static_cast<uint32_t>(e->post_used + w);
+		e->h_len[word] = len;
+		e->h_cap[word] = len;
+		for (int64_t p = row_ptr[k]; p < row_ptr[k + 1]; ++p)
+		{
+			buf[w++] = make_int2(sig[p], cnt[p]);
+			e->sig_words[sig[p]].emplace_back(word, cnt[p]);
+			e->h_ni[sig[p]] += cnt[p];
+			e->total_refs += cnt[p];
+		}
+	}
+	// keep the per-signature word lists sorted by word id (add_refs_impl merges against them)
+	for (auto & kv : e->sig_words) std::sort(kv.second.begin(), kv.second.end());
+	LCD_CUDA(e, cudaMemcpyAsync(e->postings.p + e->post_used, buf.data(), buf.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+	e->post_used += static_cast<size_t>(total);
+	LCD_CUDA(e, cudaMemcpyAsync(e->post_off.p, e->h_off.data(), (static_cast<size_t>(max_word) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaMemcpyAsync(e->post_len.p, e->h_len.data(), (static_cast<size_t>(max_word) + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaMemcpyAsync(e->ni.p, e->h_ni.data(), (static_cast<size_t>(max_sig) + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+int lcd_index_word_nw(lcd_engine * e, int word_id)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (word_id <= 0 || word_id >= static_cast<int>(e->h_len.size()) || !e->id2row.count(word_id)) return 0;
+	return e->h_len[word_id];
+}
+
+long long lcd_index_total_refs(const lcd_engine * e) { return e ? e->total_refs : 0; }
+
+int lcd_index_get_refs(lcd_engine * e, int word_id, int * sig, int * cnt, int cap)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (word_id <= 0 || word_id >= static_cast<int>(e->h_len.size()) || !e->id2row.count(word_id)) return 0;
+	const int len = e->h_len[word_id];
+	if (len == 0) return 0;
+	std::vector<int2> buf(len);
+	LCD_CUDA(e, cudaMemcpyAsync(buf.data(), e->postings.p + e->h_off[word_id], len * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	std::sort(buf.begin(), buf.end(), [](const int2 & x, const int2 & y) { return x.x < y.x; });
+	for (int i = 0; i < len && i < cap; ++i)
+	{
+		if (sig) sig[i] = buf[i].x;
+		if (cnt) cnt[i] = buf[i].y;
+	}
+	return len;
+}
+
+int lcd_index_score(lcd_engine * e, const int * query_word_ids, int nq, const int * sig_ids, int ns, int n_total, float * likelihood_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!query_word_ids || nq <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "The signature is null");
+	if (!sig_ids || ns <= 0 || !likelihood_out) LCD_FAIL(e, LCD_ERR_INVALID, "ids list is empty");
+	if (nq > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "at most %d words per signature", kMaxFrameQueries);
+	cudaStream_t s = e->stream;
+	LCD_CUDA(e, e->d_in_ids.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->d_sig_ids.reserve(ns, 0, false, s));
+	LCD_CUDA(e, e->d_like.reserve(ns, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_in_ids.p, query_word_ids, nq * sizeof(int), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_sig_ids.p, sig_ids, ns * sizeof(int), cudaMemcpyHostToDevice, s));
+	LCD_TRY(ensure_uq(e, 1, nq, s));
+	LCD_TRY(ensure_acc(e, 1));
+	LCD_CUDA(e, cudaMemsetAsync(e->acc.p, 0, static_cast<size_t>(e->acc_stride) * sizeof(long long), s));
+	ResolveArgs a{};
+	a.nq = nq;
+	fill_prep(e, a, static_cast<float>(n_total), 0);
+	int nq_pad = 32;
+	while (nq_pad < nq) nq_pad <<= 1;
+	prep_from_ids_kernel<<<1, kResolveThreads, nq_pad * sizeof(uint32_t), s>>>(e->d_in_ids.p, a);
+	LCD_CHECK_LAUNCH(e);
+	LCD_TRY(launch_score(e, 1, nq, s));
+	gather_likelihood_kernel<<<dim3((ns + 255) / 256, 1), 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), e->d_sig_ids.p, ns, e->d_like.p);
+	LCD_CHECK_LAUNCH(e);
+	LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+// ---- batched localisation ------------------------------------------------------------------
+int lcd_localize_batch_dev(lcd_engine * e, const void * d_queries, int n_frames, int nq_per_frame, int incremental, float nndr,
+                           int new_words_compared_together, const int * d_sig_ids, int ns, int n_total,
+                           int * d_word_ids_out, float * d_likelihood_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_queries || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	return localize_dev(e, static_cast<const uint32_t *>(d_queries), n_frames, nq_per_frame, incremental, nndr, new_words_compared_together,
+	                    d_sig_ids, ns, n_total, d_word_ids_out, d_likelihood_out, s);
+}
+
+int lcd_localize_batch(lcd_engine * e, const void * queries, int n_frames, int nq_per_frame, int incremental, float nndr,
+                       int new_words_compared_together, const int * sig_ids, int ns, int n_total,
+                       int * word_ids_out, float * likelihood_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!queries || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
+	if (likelihood_out && (!sig_ids || ns <= 0)) LCD_FAIL(e, LCD_ERR_INVALID, "ids list is empty");
+	cudaStream_t s = e->stream;
+	const size_t nq_total = static_cast<size_t>(n_frames) * nq_per_frame;
+	LCD_CUDA(e, e->d_queries.reserve(nq_total * e->nw, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, nq_total * e->nw * 4, cudaMemcpyHostToDevice, s));
+	if (word_ids_out) LCD_CUDA(e, e->d_word_ids.reserve(nq_total, 0, false, s));
+	if (likelihood_out)
+	{
+		LCD_CUDA(e, e->d_sig_ids.reserve(ns, 0, false, s));
+		LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->d_sig_ids.p, sig_ids, ns * sizeof(int), cudaMemcpyHostToDevice, s));
+	}
+	LCD_TRY(localize_dev(e, e->d_queries.p, n_frames, nq_per_frame, incremental, nndr, new_words_compared_together,
+	                     e->d_sig_ids.p, likelihood_out ? ns : 0, n_total, word_ids_out ? e->d_word_ids.p : nullptr,
+	                     likelihood_out ? e->d_like.p : nullptr, s));
+	if (word_ids_out) LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, nq_total * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (likelihood_out)
+		LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, static_cast<size_t>(n_frames) * ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+// ---- word-range sharding ---------------------------------------------------------------------
+int lcd_shard_set_row_offset(lcd_engine * e, int global_row_offset)
+{
+	if (!e || global_row_offset < 0) return LCD_ERR_INVALID;
+	e->row_offset = global_row_offset;
+	return LCD_OK;
+}
+
+int lcd_shard_knn2_keys_dev(lcd_engine * e, const void * d_queries, int nq, uint32_t * d_keys_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_queries || nq <= 0 || !d_keys_out) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	int n_chunks = 0;
+	LCD_TRY(run_knn(e, static_cast<const uint32_t *>(d_queries), nq, e->n_indexed, &n_chunks, s));
+	knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_partial.p, n_chunks, nq, d_keys_out);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+int lcd_shard_resolve_score_dev(lcd_engine * e, const void * d_queries, int n_frames, int nq_per_frame,
+                                const uint32_t * d_keys_gathered, int n_ranks, const int * d_row_ids, int total_rows_, int last_word_id,
+                                int incremental, float nndr, int new_words_compared_together, const int * d_sig_ids, int ns, int n_total,
+                                int * d_word_ids_out, long long * d_scores_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_queries || !d_keys_gathered || !d_row_ids || n_frames <= 0 || n_ranks <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
+	(void)total_rows_;
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	const bool score = d_scores_out != nullptr && ns > 0;
+	ResolveArgs a{};
+	a.queries = static_cast<const uint32_t *>(d_queries);
+	a.nq = nq_per_frame;
+	a.nq_total = n_frames * nq_per_frame;
+	a.partial = reinterpret_cast<const uint2 *>(d_keys_gathered);
+	a.n_chunks = n_ranks;
+	a.row_ids = d_row_ids;
+	a.incremental = incremental;
+	a.nndr = nndr;
+	a.cmp_new = new_words_compared_together;
+	a.last_word_id = last_word_id;
+	a.word_ids_out = d_word_ids_out;
+	if (score)
+	{
+		LCD_TRY(ensure_uq(e, n_frames, nq_per_frame, s));
+		LCD_TRY(ensure_acc(e, n_frames));
+		LCD_CUDA(e, cudaMemsetAsync(e->acc.p, 0, static_cast<size_t>(e->acc_stride) * n_frames * sizeof(long long), s));
+		fill_prep(e, a, static_cast<float>(n_total), 1);
+	}
+	LCD_TRY(launch_resolve(e, a, n_frames, s));
+	if (score)
+	{
+		LCD_TRY(launch_score(e, n_frames, nq_per_frame, s));
+		dim3 grid((ns + 255) / 256, n_frames);
+		gather_fixed_kernel<<<grid, 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), d_sig_ids, ns, d_scores_out);
+		LCD_CHECK_LAUNCH(e);
+	}
+	return LCD_OK;
+}
+
+int lcd_shard_finalize_dev(lcd_engine * e, const long long * d_scores, int n, float * d_likelihood_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_scores || !d_likelihood_out || n <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	fixed_to_float_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_scores, n, d_likelihood_out);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,377 @@
+// resolve.cuh — per-frame word assignment: merge of per-chunk top-2, NNDR test,
+// intra-frame new-word resolution, word-id assignment and TF-IDF preparation.
+//
+// Replaces: the "Process results" loop of VWDictionary::addNewWords
+// (corelib/src/VWDictionary.cpp:1088-1219) and the read-only variant in
+// VWDictionary::findNN (VWDictionary.cpp:1476-1546).
+//
+// The reference loop is sequential: descriptor i is also matched against the words
+// created by descriptors 0..i-1 of the same frame (Kp/NewWordsComparedTogether,
+// VWDictionary.cpp:1139-1160) and ties in the std::multimap<float,int> keep insertion
+// order (index hits first, then new-word hits; lower row / earlier new word first).
+// Here one CTA owns one frame and solves that lower-triangular dependency by fixed-point
+// iteration: new[i] = f_i(new[0..i-1]) has a unique fixed point, which is the sequential
+// answer; after round r the first r entries are final, and in practice 2-4 rounds
+// converge because dependency chains (chains of mutually close unmatched descriptors)
+// are short.  Every round is fully parallel over the frame's descriptors.
+#pragma once
+#include "common.cuh"
+#include <math.h>
+#include <limits.h>
+
+namespace lcd {
+
+constexpr int kResolveThreads = 1024;
+constexpr int kMaxFrameQueries = 4096;
+constexpr uint32_t kSortNone = 0x7FFFFFFFu;
+
+struct ResolveArgs
+{
+	const uint32_t * queries; // [n_frames*nq][NW]
+	int nq;                   // descriptors per frame
+	int nq_total;             // n_frames*nq (stride of `partial`)
+	const uint2 * partial;    // [n_chunks][nq_total] top-2 keys per vocabulary chunk / per rank
+	int n_chunks;
+	const int * row_ids; // global row -> word id
+	int incremental;     // Kp/IncrementalDictionary
+	float nndr;          // Kp/NndrRatio
+	int cmp_new;         // Kp/NewWordsComparedTogether
+	int last_word_id;    // _lastWordId before this frame
+	int find_only;       // findNN semantics: rejected descriptors get id 0, nothing is created
+	int * word_ids_out;  // [nq_total] or nullptr
+	int * n_new_out;     // [n_frames] or nullptr
+	// commit of created words into the not-indexed tail of the vocabulary (single frame) or nullptr
+	uint32_t * pending_desc;
+	int * pending_ids;
+	// TF-IDF preparation (Memory::computeLikelihood, Memory.cpp:2238-2266)
+	int do_prep;
+	const int * post_len; // posting-list length by word id
+	int id_cap;           // entries of post_len
+	float n_total;        // N
+	int self_ref;         // 1: count the query signature itself in nw (its refs are not in the index)
+	int * uq_count;       // [n_frames]
+	int * uq_word;        // [n_frames][nq]    unique matched word ids, ascending
+	int * uq_prefix;      // [n_frames][nq+1]  exclusive scan of posting lengths to walk
+	float * uq_idf;       // [n_frames][nq]    log10(N/nw)
+};
+
+// Outcome of the multimap<float,int> fullResults of one descriptor.
+// a1,a2: index hits (packed keys), n1,n2: hits among this frame's new words (dist<<22|k).
+// Returns badDist; best_tag: 0/1 = a1/a2, 2/3 = n1/n2, -1 none.
+__device__ __forceinline__ bool nndr_decide(uint32_t a1, uint32_t a2, uint32_t n1, uint32_t n2, float nndr, int & best_tag)
+{
+	float bd = INFINITY, sd = INFINITY;
+	int bt = -1, cnt = 0;
+	const uint32_t keys[4] = {a1, a2, n1, n2};
+#pragma unroll
+	for (int t = 0; t < 4; ++t)
+	{
+		if (keys[t] != kKeyNone)
+		{
+			const float d = static_cast<float>(keys[t] >> kKeyShift);
+			++cnt;
+			if (d < bd)
+			{
+				sd = bd;
+				bd = d;
+				bt = t;
+			}
+			else if (d < sd)
+			{
+				sd = d;
+			}
+		}
+	}
+	best_tag = bt;
+	return cnt < 2 || bd > __fmul_rn(nndr, sd); // VWDictionary.cpp:1170-1183
+}
+
+// warp 0 only: stable compaction of flagged indices; L[k] = k-th flagged index, rank[i] = k.
+__device__ __forceinline__ int warp0_compact(const uint8_t * flag, int n, uint16_t * L, uint16_t * rank)
+{
+	const int lane = threadIdx.x & 31;
+	int base = 0;
+	for (int c = 0; c < n; c += 32)
+	{
+		const int i = c + lane;
+		const bool f = i < n && flag[i] != 0;
+		const uint32_t m = __ballot_sync(0xFFFFFFFFu, f);
+		if (f)
+		{
+			const int k = base + __popc(m & ((1u << lane) - 1u));
+			L[k] = static_cast<uint16_t>(i);
+			rank[i] = static_cast<uint16_t>(k);
+		}
+		base += __popc(m);
+	}
+	return base;
+}
+
+template <int NW>
+__device__ __forceinline__ void load_desc(const uint32_t * __restrict__ base, int idx, uint32_t (&q)[NW])
+{
+	const uint4 * src = reinterpret_cast<const uint4 *>(base + static_cast<size_t>(idx) * NW);
+#pragma unroll
+	for (int v = 0; v < NW / 4; ++v)
+	{
+		const uint4 x = __ldg(src + v);
+		q[4 * v + 0] = x.x;
+		q[4 * v + 1] = x.y;
+		q[4 * v + 2] = x.z;
+		q[4 * v + 3] = x.w;
+	}
+}
+
+// Shared-memory carve-up for one frame of nq descriptors (nq_pad = next pow2 >= nq).
+__host__ __device__ inline size_t resolve_smem_bytes(int nq)
+{
+	int nq_pad = 32;
+	while (nq_pad < nq) nq_pad <<= 1;
+	return static_cast<size_t>(nq) * (4 + 4 + 4 + 2 + 2 + 1 + 1) + static_cast<size_t>(nq_pad) * 4 + 64;
+}
+
+// TF-IDF preparation from a list of candidate word ids in sbuf[0..n_pad) (kSortNone = skip):
+// sort, unique, per-word posting length + idf, exclusive scan.  Used by both entry kernels.
+__device__ void score_prep(uint32_t * sbuf, int n_pad, int nq, const ResolveArgs & a, int frame)
+{
+	const int tid = threadIdx.x;
+	// bitonic sort, ascending
+	for (int k = 2; k <= n_pad; k <<= 1)
+	{
+		for (int j = k >> 1; j > 0; j >>= 1)
+		{
+			for (int idx = tid; idx < n_pad; idx += blockDim.x)
+			{
+				const int ixj = idx ^ j;
+				if (ixj > idx)
+				{
+					const uint32_t x = sbuf[idx], y = sbuf[ixj];
+					const bool asc = (idx & k) == 0;
+					if ((x > y) == asc)
+					{
+						sbuf[idx] = y;
+						sbuf[ixj] = x;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	}
+	// unique + compaction + per-word idf / length (warp 0, in order)
+	if (tid < 32)
+	{
+		const int lane = tid;
+		int base = 0;
+		int run = 0; // running exclusive prefix of posting lengths
+		int * uqw = a.uq_word + static_cast<size_t>(frame) * nq;
+		int * uqp = a.uq_prefix + static_cast<size_t>(frame) * (nq + 1);
+		float * uqi = a.uq_idf + static_cast<size_t>(frame) * nq;
+		for (int c = 0; c < n_pad; c += 32)
+		{
+			const int i = c + lane;
+			const uint32_t v = sbuf[i];
+			const bool f = v != kSortNone && (i == 0 || sbuf[i - 1] != v);
+			const uint32_t m = __ballot_sync(0xFFFFFFFFu, f);
+			int len = 0;
+			float idf = 0.0f;
+			if (f)
+			{
+				const int id = static_cast<int>(v);
+				const int plen = id < a.id_cap ? a.post_len[id] : 0;
+				const float nw = static_cast<float>(plen + a.self_ref);
+				if (nw > 0.0f)
+				{
+					// logNnw = log10(N/nw) on floats (Memory.cpp:2266)
+					idf = static_cast<float>(log10(static_cast<double>(__fdiv_rn(a.n_total, nw))));
+				}
+				len = idf != 0.0f ? plen : 0;
+			}
+			// inclusive scan of len across the warp
+			int incl = len;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+				if (lane >= o) incl += t;
+			}
+			if (f)
+			{
+				const int k = base + __popc(m & ((1u << lane) - 1u));
+				uqw[k] = static_cast<int>(v);
+				uqi[k] = idf;
+				uqp[k] = run + incl - len;
+			}
+			run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+			base += __popc(m);
+		}
+		if (lane == 0)
+		{
+			uqp[base] = run;
+			a.uq_count[frame] = base;
+		}
+	}
+	__syncthreads();
+}
+
+// One CTA per frame.
+template <int NW>
+__global__ void __launch_bounds__(kResolveThreads)
+resolve_kernel(const ResolveArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int nq = a.nq;
+	int nq_pad = 32;
+	while (nq_pad < nq) nq_pad <<= 1;
+	uint32_t * sa1 = reinterpret_cast<uint32_t *>(smem_raw);
+	uint32_t * sa2 = sa1 + nq;
+	int * res = reinterpret_cast<int *>(sa2 + nq);              // >=0 row, -1-k new word k, INT_MIN none
+	uint32_t * sbuf = reinterpret_cast<uint32_t *>(res + nq);    // [nq_pad]
+	uint16_t * L = reinterpret_cast<uint16_t *>(sbuf + nq_pad);  // [nq]
+	uint16_t * rank = L + nq;                                    // [nq]
+	uint8_t * flag = reinterpret_cast<uint8_t *>(rank + nq);     // [nq]
+	uint8_t * flag2 = flag + nq;                                 // [nq]
+	__shared__ int s_nL;
+
+	const int tid = threadIdx.x;
+	const int frame = blockIdx.x;
+	const uint32_t * fq = a.queries + static_cast<size_t>(frame) * nq * NW;
+	const size_t pbase = static_cast<size_t>(frame) * nq;
+
+	// 1. merge the per-chunk top-2 keys (FlannIndex::knnSearch result of this descriptor)
+	for (int i = tid; i < nq; i += blockDim.x)
+	{
+		uint32_t k1 = kKeyNone, k2 = kKeyNone;
+		for (int c = 0; c < a.n_chunks; ++c)
+		{
+			const uint2 p = a.partial[static_cast<size_t>(c) * a.nq_total + pbase + i];
+			top2_insert(k1, k2, p.x);
+			top2_insert(k1, k2, p.y);
+		}
+		sa1[i] = k1;
+		sa2[i] = k2;
+		int bt;
+		const bool bad = nndr_decide(k1, k2, kKeyNone, kKeyNone, a.nndr, bt);
+		if (a.incremental)
+		{
+			flag[i] = bad ? 1 : 0;
+			res[i] = static_cast<int>(k1 & kKeyRowMask);
+		}
+		else
+		{
+			// fixed dictionary: nearest word, no NNDR (VWDictionary.cpp:1211-1218)
+			flag[i] = 0;
+			res[i] = k1 != kKeyNone ? static_cast<int>(k1 & kKeyRowMask) : INT_MIN;
+		}
+	}
+	__syncthreads();
+
+	int n_new = 0;
+	if (a.incremental)
+	{
+		// 2. fixed-point rounds over the intra-frame dependency
+		for (int round = 0; round <= nq; ++round)
+		{
+			if (tid < 32)
+			{
+				const int n = warp0_compact(flag, nq, L, rank);
+				if (tid == 0) s_nL = n;
+			}
+			__syncthreads();
+			const int nL = s_nL;
+			if (!a.cmp_new) break;
+			int changed = 0;
+			for (int i = tid; i < nq; i += blockDim.x)
+			{
+				uint32_t n1 = kKeyNone, n2 = kKeyNone;
+				if (nL > 0 && L[0] < i)
+				{
+					uint32_t qi[NW];
+					load_desc<NW>(fq, i, qi);
+					for (int k = 0; k < nL; ++k)
+					{
+						const int j = L[k];
+						if (j >= i) break;
+						uint32_t qj[NW];
+						load_desc<NW>(fq, j, qj);
+						uint32_t d = 0;
+#pragma unroll
+						for (int v = 0; v < NW; ++v) d += __popc(qi[v] ^ qj[v]);
+						top2_insert(n1, n2, (d << kKeyShift) + static_cast<uint32_t>(k));
+					}
+				}
+				int bt;
+				const bool bad = nndr_decide(sa1[i], sa2[i], n1, n2, a.nndr, bt);
+				flag2[i] = bad ? 1 : 0;
+				changed |= (flag2[i] != flag[i]);
+				if (!bad) res[i] = bt >= 2 ? -1 - static_cast<int>(n1 & kKeyRowMask) : static_cast<int>(sa1[i] & kKeyRowMask);
+			}
+			changed = __syncthreads_or(changed);
+			if (!changed) break;
+			for (int i = tid; i < nq; i += blockDim.x) flag[i] = flag2[i];
+			__syncthreads();
+		}
+		n_new = s_nL;
+	}
+
+	// 3. word ids (VWDictionary::getNextId = ++_lastWordId in creation order)
+	for (int i = tid; i < nq; i += blockDim.x)
+	{
+		int wid;
+		uint32_t sv = kSortNone;
+		if (flag[i])
+		{
+			wid = a.find_only ? 0 : a.last_word_id + 1 + rank[i];
+			if (a.pending_desc && !a.find_only)
+			{
+				uint32_t qi[NW];
+				load_desc<NW>(fq, i, qi);
+#pragma unroll
+				for (int v = 0; v < NW; ++v) a.pending_desc[static_cast<size_t>(rank[i]) * NW + v] = qi[v];
+				a.pending_ids[rank[i]] = wid;
+			}
+		}
+		else if (res[i] == INT_MIN)
+		{
+			wid = 0;
+		}
+		else if (res[i] < 0)
+		{
+			wid = a.last_word_id + 1 + (-1 - res[i]);
+		}
+		else
+		{
+			wid = a.row_ids[res[i]];
+			sv = static_cast<uint32_t>(wid);
+		}
+		if (a.word_ids_out) a.word_ids_out[pbase + i] = wid;
+		sbuf[i] = sv;
+	}
+	for (int i = nq + tid; i < nq_pad; i += blockDim.x) sbuf[i] = kSortNone;
+	if (tid == 0 && a.n_new_out) a.n_new_out[frame] = n_new;
+	__syncthreads();
+
+	// 4. unique matched words -> idf + posting extents for the scoring kernel
+	if (a.do_prep) score_prep(sbuf, nq_pad, nq, a, frame);
+}
+
+// TF-IDF preparation from host-provided word ids (lcd_index_score): applies uUniqueKeys and
+// the "*i > 0" filter of Memory::computeLikelihood (Memory.cpp:2238, :2256).
+__global__ void __launch_bounds__(kResolveThreads)
+prep_from_ids_kernel(const int * __restrict__ word_ids, const ResolveArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int nq = a.nq;
+	int nq_pad = 32;
+	while (nq_pad < nq) nq_pad <<= 1;
+	uint32_t * sbuf = reinterpret_cast<uint32_t *>(smem_raw);
+	const int frame = blockIdx.x;
+	for (int i = threadIdx.x; i < nq_pad; i += blockDim.x)
+	{
+		int w = i < nq ? word_ids[static_cast<size_t>(frame) * nq + i] : 0;
+		sbuf[i] = w > 0 ? static_cast<uint32_t>(w) : kSortNone;
+	}
+	__syncthreads();
+	score_prep(sbuf, nq_pad, nq, a, frame);
+}
+
+} // namespace lcd

@@ -1,0 +1,99 @@
+"""Seeded synthetic workloads for the quantise -> score path.
+
+Input generation only (numpy, host): vocabularies, maps (inverted index in CSR form) and query
+frames of the shapes BASELINE.json names.  Seeds: vocabulary 1, map 2, stream 3.
+
+* binary vocabulary: W x 32 B; W/4 uniformly random "centres" plus 3 children per centre at
+  Hamming distance ~ Binomial(256, 0.12) from it; ids 1..W contiguous (or strided).
+* map: S signatures x F features whose words follow Zipf(s=1) over a random permutation of
+  the vocabulary  =>  sum of postings ~ S*F.
+* query frame: the words of one map signature ("place"), each descriptor = the word's row
+  with i.i.d. bit flips (p=0.05), and a fraction replaced by random descriptors so that the
+  NNDR test rejects them and the new-word path is exercised.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def make_binary_vocabulary(n_words: int, dim_bytes: int = 32, seed: int = 1, child_p: float = 0.12) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    n_centres = max(1, (n_words + 3) // 4)
+    centres = rng.integers(0, 256, size=(n_centres, dim_bytes), dtype=np.uint8)
+    vocab = np.empty((n_centres * 4, dim_bytes), dtype=np.uint8)
+    vocab[0::4] = centres
+    for c in range(1, 4):
+        flips = rng.random((n_centres, dim_bytes * 8)) < child_p
+        vocab[c::4] = centres ^ np.packbits(flips, axis=1)
+    return np.ascontiguousarray(vocab[:n_words])
+
+
+def flip_bits(desc: np.ndarray, p: float, rng: np.random.Generator) -> np.ndarray:
+    flips = rng.random((desc.shape[0], desc.shape[1] * 8)) < p
+    return desc ^ np.packbits(flips, axis=1)
+
+
+@dataclass
+class SynthMap:
+    """Inverted index of a synthetic map in CSR form over words (ascending word id)."""
+    word_ids: np.ndarray      # [n_words_with_refs] int32, ascending
+    row_ptr: np.ndarray       # [n+1] int64
+    sig: np.ndarray           # [nnz] int32
+    cnt: np.ndarray           # [nnz] int32
+    sig_ids: np.ndarray       # [S] int32 (1..S)
+    ni: np.ndarray            # [S] int32 words per signature
+    sig_words: np.ndarray     # [S, F] int32 word id of every feature (the forward index)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.row_ptr[-1])
+
+
+def make_map(word_ids: np.ndarray, n_signatures: int, feats_per_sig: int, seed: int = 2, zipf_s: float = 1.0) -> SynthMap:
+    rng = np.random.default_rng(seed)
+    W = len(word_ids)
+    ranks = np.arange(1, W + 1, dtype=np.float64)
+    p = 1.0 / ranks ** zipf_s
+    cdf = np.cumsum(p / p.sum())
+    perm = rng.permutation(W)
+    u = rng.random(n_signatures * feats_per_sig)
+    r = np.minimum(np.searchsorted(cdf, u), W - 1)
+    words = np.asarray(word_ids, dtype=np.int32)[perm[r]].reshape(n_signatures, feats_per_sig)
+    sig_ids = np.arange(1, n_signatures + 1, dtype=np.int32)
+    flat_w = words.reshape(-1).astype(np.int64)
+    flat_s = np.repeat(sig_ids.astype(np.int64), feats_per_sig)
+    key = flat_w * (int(n_signatures) + 2) + flat_s
+    uk, cnt = np.unique(key, return_counts=True)
+    pw = (uk // (int(n_signatures) + 2)).astype(np.int32)
+    ps = (uk % (int(n_signatures) + 2)).astype(np.int32)
+    uw, start = np.unique(pw, return_index=True)
+    row_ptr = np.concatenate([start, [len(pw)]]).astype(np.int64)
+    ni = np.full(n_signatures, feats_per_sig, dtype=np.int32)
+    return SynthMap(uw.astype(np.int32), row_ptr, ps, cnt.astype(np.int32), sig_ids, ni, words)
+
+
+def make_query_frames(vocab: np.ndarray, word_ids: np.ndarray, smap: SynthMap, n_frames: int, feats_per_frame: int,
+                      seed: int = 3, flip_p: float = 0.05, new_frac: float = 0.2):
+    """Frames revisiting random places of the map. Returns (desc [n_frames*F, D] uint8, place ids [n_frames])."""
+    rng = np.random.default_rng(seed)
+    id2row = np.full(int(np.max(word_ids)) + 1, -1, dtype=np.int64)
+    id2row[np.asarray(word_ids)] = np.arange(len(word_ids))
+    places = rng.integers(0, len(smap.sig_ids), size=n_frames)
+    out = np.empty((n_frames * feats_per_frame, vocab.shape[1]), dtype=np.uint8)
+    F = smap.sig_words.shape[1]
+    for f in range(n_frames):
+        sel = rng.permutation(F)[:feats_per_frame] if feats_per_frame <= F else rng.integers(0, F, feats_per_frame)
+        rows = id2row[smap.sig_words[places[f], sel]]
+        d = flip_bits(vocab[rows], flip_p, rng)
+        n_new = int(round(new_frac * feats_per_frame))
+        if n_new:
+            idx = rng.permutation(feats_per_frame)[:n_new]
+            d[idx] = rng.integers(0, 256, size=(n_new, vocab.shape[1]), dtype=np.uint8)
+            # make a few of the random ones near-duplicates of each other so the intra-frame
+            # new-word comparison (Kp/NewWordsComparedTogether) has work to do
+            for k in range(0, n_new - 1, 4):
+                d[idx[k + 1]] = flip_bits(d[idx[k]:idx[k] + 1], 0.03, rng)[0]
+        out[f * feats_per_frame:(f + 1) * feats_per_frame] = d
+    return out, smap.sig_ids[places]
