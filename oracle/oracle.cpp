@@ -558,6 +558,90 @@ int orc_localize(void * h, const void * desc, int n, int sig_id, const int * sig
 	return nout;
 }
 
+// Read-only form of orc_localize for the multi-threaded CPU baseline: the same decisions and the
+// same float arithmetic, but the words the frame would create live in local vectors and the query's
+// own reference is accounted for as nw = refs.size() + 1 instead of being inserted and rolled back.
+// tests/test_oracle_golden.py checks it against orc_localize.  Safe to call from many threads.
+int orc_localize_ro(void * h, const void * desc_, int n, const int * sig_ids, int ns, int n_total, int * out_words, float * out_like)
+{
+	const OracleDict & d = *(const OracleDict *)h;
+	const uint8_t * desc = (const uint8_t *)desc_;
+	const size_t rb = d.row_bytes();
+	const std::vector<const uint8_t *> rowptr = indexed_ptrs(d);
+	std::vector<const uint8_t *> newptr;
+	std::vector<int> newid;
+	std::vector<int> ids;
+	int next_id = d.last_id;
+	for (int i = 0; i < n; ++i)
+	{
+		const uint8_t * q = desc + (size_t)i * rb;
+		std::multimap<float, int> full;
+		if (!rowptr.empty())
+		{
+			Top2 t;
+			knn2_rows(d, rowptr, q, t);
+			for (int j = 0; j < 2; ++j)
+			{
+				if (t.idx[j] < 0) break;
+				full.insert(std::make_pair(t.d[j], d.rows[t.idx[j]]));
+			}
+		}
+		if (d.cmp_new && !newptr.empty())
+		{
+			Top2 t;
+			knn2_rows(d, newptr, q, t);
+			for (int j = 0; j < 2; ++j)
+			{
+				if (t.idx[j] < 0) break;
+				full.insert(std::make_pair(t.d[j], newid[t.idx[j]]));
+			}
+		}
+		Decision r = decide(d, full);
+		if (d.incremental && r.bad)
+		{
+			newptr.push_back(q);
+			newid.push_back(++next_id);
+			ids.push_back(next_id);
+		}
+		else if (!r.bad) ids.push_back(r.best_id);
+	}
+	if (out_words) memcpy(out_words, ids.data(), ids.size() * sizeof(int));
+	if (out_like)
+	{
+		std::map<int, float> lik;
+		for (int k = 0; k < ns; ++k) lik.insert(lik.end(), std::make_pair(sig_ids[k], 0.0f));
+		std::set<int> uniq(ids.begin(), ids.end());
+		const float N = (float)n_total;
+		for (int w : uniq)
+		{
+			if (w <= 0 || w > d.last_id) continue; // words created by this frame are referenced by it alone
+			auto it = d.words.find(w);
+			if (it == d.words.end()) continue;
+			const std::map<int, int> & refs = it->second.refs;
+			const float nw = (float)(refs.size() + 1);
+			const float logNnw = log10f(N / nw);
+			if (!logNnw) continue;
+			for (auto & r : refs)
+			{
+				auto li = lik.find(r.first);
+				if (li == lik.end()) continue;
+				const float nwi = (float)r.second;
+				auto nit = d.ni.find(r.first);
+				const float ni = nit != d.ni.end() ? (float)nit->second : 0.0f;
+				if (ni != 0)
+				{
+					volatile float num = nwi * logNnw;
+					volatile float term = num / ni;
+					volatile float acc = li->second + term;
+					li->second = acc;
+				}
+			}
+		}
+		for (int k = 0; k < ns; ++k) out_like[k] = lik[sig_ids[k]];
+	}
+	return (int)ids.size();
+}
+
 // Rtabmap::adjustLikelihood with Rtabmap/VirtualPlaceLikelihoodRatio = 0 or 1; element 0 is the virtual place
 void orc_adjust_likelihood(float * lik, int n, int virtual_place_ratio)
 {

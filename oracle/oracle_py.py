@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.orc_likelihood.argtypes = [_P, _P, _I, _P, _I, _I, _P]
         L.orc_localize.argtypes = [_P, _P, _I, _I, _P, _I, _I, _P, _P]
         L.orc_localize.restype = _I
+        L.orc_localize_ro.argtypes = [_P, _P, _I, _P, _I, _I, _P, _P]
+        L.orc_localize_ro.restype = _I
         L.orc_adjust_likelihood.argtypes = [_P, _I, _I]
         _lib = L
     return _lib
@@ -247,4 +249,13 @@ class OracleDictionary:
         words = np.zeros(len(desc), np.int32)
         like = np.zeros(len(s), np.float32) if want_like else None
         n = self.L.orc_localize(self.h, _p(desc), len(desc), int(sig_id), _p(s), len(s), int(n_total), _p(words), _p(like))
+        return words[:n], like
+
+    def localize_ro(self, desc, sig_ids, n_total, want_like=True):
+        """Thread-safe read-only variant of localize() (ctypes releases the GIL during the call)."""
+        desc = self._d(desc)
+        s = _i32(sig_ids)
+        words = np.zeros(len(desc), np.int32)
+        like = np.zeros(len(s), np.float32) if want_like else None
+        n = self.L.orc_localize_ro(self.h, _p(desc), len(desc), _p(s), len(s), int(n_total), _p(words), _p(like))
         return words[:n], like

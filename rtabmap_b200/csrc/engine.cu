@@ -161,7 +161,7 @@ struct lcd_engine
 	} prof[3];
 
 	// tuning knobs (env: LCD_NN_CTAS_PER_SM, LCD_NN_TQ, LCD_NN_VARIANT, LCD_SCORE_BLOCKS)
-	int nn_ctas_per_sm = 2, nn_tq = 4, nn_variant = 0, score_blocks = 32;
+	int nn_ctas_per_sm = 2, nn_tq = 8, nn_variant = 2, score_blocks = 32;
 };
 
 #define LCD_FAIL(e, code, ...)                          \

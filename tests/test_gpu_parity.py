@@ -152,7 +152,7 @@ def test_add_words_out_of_order_and_find_nn():
 
 # ---------------------------------------------------------------- scoring ----------------------
 def test_tfidf_golden_vector_on_gpu():
-    from tests.test_oracle_golden import GOLD, load_golden_into
+    from golden_util import GOLD, load_golden_into
 
     remap = lambda s: 1000 if s == -1 else s
     eng = Engine()

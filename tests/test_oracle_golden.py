@@ -2,32 +2,11 @@
 (archive/2010-LoopClosure/Tests/TestComputeLikelihood.m, fixture made by
 tests/golden/make_tfidf_golden.py), plus hand-checked cases of the sequential
 addNewWords semantics (VWDictionary.cpp:1088-1219)."""
-import json
-from pathlib import Path
-
 import numpy as np
 
 from oracle import oracle_py as orc
 
-GOLD = json.loads((Path(__file__).parent / "golden" / "tfidf_golden.json").read_text())
-
-
-def load_golden_into(d, remap):
-    """Feed the golden inverted index into a dictionary-like object (oracle or engine)."""
-    word_ids = sorted(int(w) for w in GOLD["words"])
-    desc = np.zeros((len(word_ids), 32), np.uint8)
-    desc[:, :4] = np.asarray(word_ids, dtype=np.uint32).view(np.uint8).reshape(-1, 4)
-    d.add_words(word_ids, desc)
-    d.update()
-    rp = [0]
-    sig, cnt = [], []
-    for w in word_ids:
-        for s, c in GOLD["words"][str(w)]:
-            sig.append(remap(s))
-            cnt.append(c)
-        rp.append(len(sig))
-    d.load_csr(word_ids, rp, sig, cnt)
-    d.set_ni([remap(s) for s in GOLD["sig_ids"]], GOLD["ni"])
+from golden_util import GOLD, load_golden_into
 
 
 def test_tfidf_golden_vector():
@@ -100,3 +79,23 @@ def test_adjust_likelihood_matches_formula():
     assert out[3] > 1.0 and np.isclose(out[3], (0.9 - (std - 1e-4)) / mean, rtol=1e-5)
     assert out[1] == 1.0 and out[4] == 1.0
     assert np.isclose(out[0], mean / std + 1.0, rtol=1e-5)
+
+
+def test_read_only_localisation_equals_insert_and_roll_back():
+    from rtabmap_b200 import synth
+
+    vocab = synth.make_binary_vocabulary(3000, 32, 1)
+    ids = np.arange(1, 3001, dtype=np.int32)
+    m = synth.make_map(ids, 200, 150)
+    d = orc.OracleDictionary()
+    d.add_words(ids, vocab)
+    d.last_word_id = 3000
+    d.update()
+    d.load_csr(m.word_ids, m.row_ptr, m.sig, m.cnt)
+    q, _ = synth.make_query_frames(vocab, ids, m, 3, 150)
+    for b in range(3):
+        f = q[b * 150:(b + 1) * 150]
+        w1, l1 = d.localize(f, 777, m.sig_ids, 201)
+        w2, l2 = d.localize_ro(f, m.sig_ids, 201)
+        assert np.array_equal(w1, w2) and np.array_equal(l1, l2)
+        assert d.size() == 3000 and d.last_word_id == 3000 and d.total_refs() == 200 * 150
