@@ -167,6 +167,45 @@ int lcd_localize_batch_dev(lcd_engine * e, const void * d_queries, int n_frames,
                            const int * d_sig_ids, int ns, int n_total,
                            int * d_word_ids_out, float * d_likelihood_out, void * stream);
 
+/* ---- geometric verification: Memory::computeTransform ----------------------------------
+ * Batched verification of n_pairs (FROM = old signature with 3-D points, TO = new signature with
+ * 2-D keypoints) hypotheses.  Buffers are [n_pairs][cap] row-major; n_from/n_to give the valid
+ * rows of each pair.  Single camera, identity local transform, rectified (no distortion). */
+typedef struct lcd_verify_params {
+	float nndr;            /* Vis/CorNNDR (0.8)                                             */
+	int min_inliers;       /* Vis/MinInliers (20)                                           */
+	int iterations;        /* Vis/Iterations (300, <= 320)                                  */
+	float reproj_error;    /* Vis/PnPReprojError (2): RANSAC compares the error with its square */
+	int refine_iterations; /* Vis/PnPRefineIterations (1)                                   */
+	float refine_sigma;    /* refineSigma of util3d::solvePnPRansac (3.0)                   */
+	double fx, fy, cx, cy; /* CameraModel::K() of the TO signature                          */
+} lcd_verify_params;
+
+typedef struct lcd_verify_result {
+	int ok;               /* 1: inliers >= min_inliers, transform valid                      */
+	int n_matches;        /* correspondences given to PnP                                    */
+	int n_inliers;
+	int iterations_run;   /* RANSAC iterations the sequential reference would have executed  */
+	double rvec[3];       /* PnP pose (object -> camera), Rodrigues vector                   */
+	double tvec[3];
+	float transform[12];  /* (localTransform * pnp)^-1 as rtabmap::Transform 3x4             */
+} lcd_verify_result;
+
+/* replaces: the global matching of RegistrationVis::computeTransformationImpl through a temporary
+ * VWDictionary (RegistrationVis.cpp:1482-1503), Vis/CorNNType 0/3: from_ids/to_ids[n_pairs*cap] word
+ * ids of every descriptor (ids start at 1 per pair). */
+int lcd_match_pairs(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const int * n_from,
+                    const void * desc_to, const int * n_to, float nndr, int * from_ids, int * to_ids);
+
+/* replaces: Memory::computeTransform -> RegistrationVis (global matching, RegistrationVis.cpp:1482-1546)
+ * -> util3d::estimateMotion3DTo2D (util3d_motion_estimation.cpp:59-289) -> util3d::solvePnPRansac
+ * (:843-990) -> cv3::solvePnPRansac (opencv/solvepnp.cpp:112-417).  xyz_from: NaN where a keypoint has
+ * no depth.  match_ids / inlier_ids [n_pairs*cap] (word ids, ascending / in inlier order) may be NULL. */
+int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const float * xyz_from,
+                     const int * n_from, const void * desc_to, const float * uv_to, const int * n_to,
+                     const lcd_verify_params * params, lcd_verify_result * results, int * match_ids,
+                     int * inlier_ids);
+
 /* ---- word-range sharding across GPUs ---------------------------
  * Each rank owns the words whose row (in ascending id order) falls in its range; rows
  * are numbered globally: set the global row offset of this shard so that packed top-2
@@ -192,12 +231,15 @@ int lcd_shard_finalize_dev(lcd_engine * e, const long long * d_scores, int n, fl
 
 /* ---- measurement hooks ---------------------------------------------------------------
  * Optional per-kernel timing with CUDA events recorded on the launching stream around
- * every launch of kernel class `which` (0 = dictionary NN, 1 = resolve, 2 = score).
+ * every launch of kernel class `which` (0 = dictionary NN, 1 = resolve, 2 = score, 3 = pair
+ * matching, 4 = PnP RANSAC).
  * lcd_profile_read synchronises, returns the summed device time and the launch count
  * since the last reset. */
 #define LCD_PROF_NN 0
 #define LCD_PROF_RESOLVE 1
 #define LCD_PROF_SCORE 2
+#define LCD_PROF_MATCH 3
+#define LCD_PROF_PNP 4
 int lcd_profile_enable(lcd_engine * e, int on);
 int lcd_profile_read(lcd_engine * e, int which, double * total_ms, long long * launches);
 int lcd_profile_reset(lcd_engine * e);

@@ -25,7 +25,8 @@ _F = C.c_float
 
 def build(with_ref: bool = True) -> None:
     """Compile liboracle.so (always) and _ref/libref_flann.so (when /root/reference is present)."""
-    if not LIB.exists() or LIB.stat().st_mtime < (HERE / "oracle.cpp").stat().st_mtime:
+    srcs = [HERE / "oracle.cpp", HERE / "oracle_verify.cpp", HERE / "pnp_math.h"]
+    if not LIB.exists() or LIB.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(HERE), "liboracle.so"], check=True, capture_output=True)
     if with_ref and REFERENCE_ROOT.exists() and not REF_LIB.exists():
         subprocess.run(["make", "-C", str(HERE), "ref"], check=True, capture_output=True)
@@ -259,3 +260,97 @@ class OracleDictionary:
         like = np.zeros(len(s), np.float32) if want_like else None
         n = self.L.orc_localize_ro(self.h, _p(desc), len(desc), _p(s), len(s), int(n_total), _p(words), _p(like))
         return words[:n], like
+
+
+# ---------------------------------------------------------------- verification stage (oracle_verify.cpp)
+def _vlib():
+    L = lib()
+    if not getattr(L, "_verify_ready", False):
+        L.orcv_solve_pnp_epnp.argtypes = [_P, _P, _I, _P, _P, _P]
+        L.orcv_solve_pnp_epnp.restype = _I
+        L.orcv_solve_pnp_iterative.argtypes = [_P, _P, _I, _P, _P, _P]
+        L.orcv_project.argtypes = [_P, _I, _P, _P, _P, _P]
+        L.orcv_rodrigues.argtypes = [_P, _P]
+        L.orcv_rodrigues_inv.argtypes = [_P, _P]
+        L.orcv_rng_draws.argtypes = [_I, _I, _P]
+        L.orcv_pnp_ransac.argtypes = [_P, _P, _I, _P, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P]
+        L.orcv_pnp_ransac.restype = _I
+        L.orcv_match_pair.argtypes = [_I, _I, _P, _I, _P, _I, _F, _P, _P]
+        L.orcv_verify_pair.argtypes = [_I, _I, _P, _P, _I, _P, _P, _I, _P, _F, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P]
+        L.orcv_verify_pair.restype = _I
+        L._verify_ready = True
+    return L
+
+
+def solve_pnp_epnp(X, uv, K4):
+    L = _vlib()
+    X = np.ascontiguousarray(X, np.float32)
+    uv = np.ascontiguousarray(uv, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    r = np.zeros(3)
+    t = np.zeros(3)
+    ok = L.orcv_solve_pnp_epnp(_p(X), _p(uv), len(X), _p(K4), _p(r), _p(t))
+    return bool(ok), r, t
+
+
+def solve_pnp_iterative(X, uv, K4, rvec0, tvec0):
+    L = _vlib()
+    X = np.ascontiguousarray(X, np.float32)
+    uv = np.ascontiguousarray(uv, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    r = np.array(rvec0, np.float64).copy()
+    t = np.array(tvec0, np.float64).copy()
+    L.orcv_solve_pnp_iterative(_p(X), _p(uv), len(X), _p(K4), _p(r), _p(t))
+    return r, t
+
+
+def pnp_ransac(X, uv, K4, iterations=300, reproj=2.0, min_inliers=20, refine_iterations=1, refine_sigma=3.0, guess=None):
+    """util3d::solvePnPRansac (cv3::solvePnPRansac + refinement): ok, rvec, tvec, inlier indices, iterations run."""
+    L = _vlib()
+    X = np.ascontiguousarray(X, np.float32)
+    uv = np.ascontiguousarray(uv, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    r = np.zeros(3)
+    t = np.zeros(3)
+    inl = np.zeros(len(X), np.int32)
+    n_inl = C.c_int(0)
+    it = C.c_int(0)
+    g = None if guess is None else np.ascontiguousarray(guess, np.float64)
+    ok = L.orcv_pnp_ransac(_p(X), _p(uv), len(X), _p(K4), iterations, reproj, min_inliers, refine_iterations, refine_sigma,
+                           _p(g), _p(r), _p(t), _p(inl), C.byref(n_inl), C.byref(it))
+    return bool(ok), r, t, inl[:n_inl.value].copy(), it.value
+
+
+def match_pair(desc_from, desc_to, nndr=0.8):
+    """RegistrationVis global matching through a temporary dictionary: (from word ids, to word ids)."""
+    L = _vlib()
+    t = 0 if desc_from.dtype == np.uint8 else 1
+    a = np.ascontiguousarray(desc_from)
+    b = np.ascontiguousarray(desc_to)
+    fi = np.zeros(max(len(a), 1), np.int32)
+    ti = np.zeros(max(len(b), 1), np.int32)
+    L.orcv_match_pair(t, a.shape[1], _p(a), len(a), _p(b), len(b), nndr, _p(fi), _p(ti))
+    return fi[:len(a)], ti[:len(b)]
+
+
+def verify_pair(desc_from, xyz_from, desc_to, uv_to, K4, nndr=0.8, min_inliers=20, iterations=300, reproj=2.0, refine_iterations=1):
+    """Memory::computeTransform for one pair (global matching + PnP RANSAC).  Returns a dict."""
+    L = _vlib()
+    t = 0 if desc_from.dtype == np.uint8 else 1
+    a = np.ascontiguousarray(desc_from)
+    b = np.ascontiguousarray(desc_to)
+    xa = np.ascontiguousarray(xyz_from, np.float32)
+    ub = np.ascontiguousarray(uv_to, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    cap = max(len(a), len(b), 1)
+    mids = np.zeros(cap, np.int32)
+    iids = np.zeros(cap, np.int32)
+    nm = C.c_int(0)
+    ni = C.c_int(0)
+    r = np.zeros(3)
+    tv = np.zeros(3)
+    T = np.zeros(12, np.float32)
+    ok = L.orcv_verify_pair(t, a.shape[1], _p(a), _p(xa), len(a), _p(b), _p(ub), len(b), _p(K4), nndr, min_inliers, iterations, reproj,
+                            refine_iterations, _p(mids), C.byref(nm), _p(iids), C.byref(ni), _p(r), _p(tv), _p(T))
+    return {"ok": bool(ok), "matches": mids[:nm.value].copy(), "inliers": iids[:ni.value].copy(), "rvec": r, "tvec": tv,
+            "transform": T.reshape(3, 4)}

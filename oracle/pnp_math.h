@@ -1,0 +1,317 @@
+// pnp_math.h — small dense fp64 linear algebra shared by the oracle's PnP restatement.
+// TEST INFRASTRUCTURE (oracle/): plain C++, no dependency on the product.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace orc_pnp {
+
+// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, n <= 12).
+// On return: w[k] eigenvalues in DESCENDING order, vt row k = the matching unit eigenvector
+// (the layout cvSVD(A, W, Ut, 0, CV_SVD_U_T) gives for a symmetric positive semi-definite A).
+inline void jacobi_eigen_desc(const double * a_in, int n, double * w, double * vt)
+{
+	double a[144], v[144];
+	memcpy(a, a_in, sizeof(double) * n * n);
+	for (int i = 0; i < n; ++i)
+		for (int j = 0; j < n; ++j) v[i * n + j] = i == j ? 1.0 : 0.0;
+	for (int sweep = 0; sweep < 64; ++sweep)
+	{
+		double off = 0.0;
+		for (int i = 0; i < n; ++i)
+			for (int j = i + 1; j < n; ++j) off += a[i * n + j] * a[i * n + j];
+		if (off < 1e-300) break;
+		for (int p = 0; p < n - 1; ++p)
+		{
+			for (int q = p + 1; q < n; ++q)
+			{
+				const double apq = a[p * n + q];
+				if (std::fabs(apq) < 1e-300) continue;
+				const double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+				const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+				const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+				for (int k = 0; k < n; ++k)
+				{
+					const double akp = a[k * n + p], akq = a[k * n + q];
+					a[k * n + p] = c * akp - s * akq;
+					a[k * n + q] = s * akp + c * akq;
+				}
+				for (int k = 0; k < n; ++k)
+				{
+					const double apk = a[p * n + k], aqk = a[q * n + k];
+					a[p * n + k] = c * apk - s * aqk;
+					a[q * n + k] = s * apk + c * aqk;
+				}
+				for (int k = 0; k < n; ++k)
+				{
+					const double vkp = v[k * n + p], vkq = v[k * n + q];
+					v[k * n + p] = c * vkp - s * vkq;
+					v[k * n + q] = s * vkp + c * vkq;
+				}
+			}
+		}
+	}
+	int order[12];
+	for (int i = 0; i < n; ++i) order[i] = i;
+	std::sort(order, order + n, [&](int x, int y) { return a[x * n + x] > a[y * n + y]; });
+	for (int k = 0; k < n; ++k)
+	{
+		w[k] = a[order[k] * n + order[k]];
+		for (int i = 0; i < n; ++i) vt[k * n + i] = v[i * n + order[k]];
+	}
+}
+
+// One-sided (Hestenes) Jacobi SVD exactly as OpenCV's internal JacobiSVDImpl_ (modules/core/src/lapack.cpp),
+// which cv::SVD / cvSVD use for matrices smaller than 25x25 even in LAPACK builds (hal_internal.cpp,
+// HAL_SVD_SMALL_MATRIX_THRESH).  At is n x m row-major and holds A^T on entry (row i = column i of A);
+// on return row i of At = i-th LEFT singular vector (unit), W = singular values descending, Vt (n x n,
+// may be null) = V^T.  EPnP's control points depend on the SIGN of these vectors, which is why the
+// iteration order, rotation formulas and the final selection sort are reproduced literally.
+inline void jacobi_svd_opencv(double * At, double * W, double * Vt, int m, int n)
+{
+	const double eps = 2.220446049250313e-16 * 10, minval = 2.2250738585072014e-308;
+	const int max_iter = std::max(m, 30);
+	for (int i = 0; i < n; ++i)
+	{
+		double sd = 0;
+		for (int k = 0; k < m; ++k) sd += At[i * m + k] * At[i * m + k];
+		W[i] = sd;
+		if (Vt)
+		{
+			for (int k = 0; k < n; ++k) Vt[i * n + k] = 0;
+			Vt[i * n + i] = 1;
+		}
+	}
+	for (int iter = 0; iter < max_iter; ++iter)
+	{
+		bool changed = false;
+		for (int i = 0; i < n - 1; ++i)
+			for (int j = i + 1; j < n; ++j)
+			{
+				double * Ai = At + i * m;
+				double * Aj = At + j * m;
+				double a = W[i], p = 0, b = W[j];
+				for (int k = 0; k < m; ++k) p += Ai[k] * Aj[k];
+				if (std::fabs(p) <= eps * std::sqrt(a * b)) continue;
+				p *= 2;
+				const double beta = a - b, gamma = hypot(p, beta);
+				double c, s;
+				if (beta < 0)
+				{
+					const double delta = (gamma - beta) * 0.5;
+					s = std::sqrt(delta / gamma);
+					c = p / (gamma * s * 2);
+				}
+				else
+				{
+					c = std::sqrt((gamma + beta) / (gamma * 2));
+					s = p / (gamma * c * 2);
+				}
+				a = b = 0;
+				for (int k = 0; k < m; ++k)
+				{
+					const double t0 = c * Ai[k] + s * Aj[k];
+					const double t1 = -s * Ai[k] + c * Aj[k];
+					Ai[k] = t0;
+					Aj[k] = t1;
+					a += t0 * t0;
+					b += t1 * t1;
+				}
+				W[i] = a;
+				W[j] = b;
+				changed = true;
+				if (Vt)
+				{
+					double * Vi = Vt + i * n;
+					double * Vj = Vt + j * n;
+					for (int k = 0; k < n; ++k)
+					{
+						const double t0 = c * Vi[k] + s * Vj[k];
+						const double t1 = -s * Vi[k] + c * Vj[k];
+						Vi[k] = t0;
+						Vj[k] = t1;
+					}
+				}
+			}
+		if (!changed) break;
+	}
+	for (int i = 0; i < n; ++i)
+	{
+		double sd = 0;
+		for (int k = 0; k < m; ++k) sd += At[i * m + k] * At[i * m + k];
+		W[i] = std::sqrt(sd);
+	}
+	for (int i = 0; i < n - 1; ++i)
+	{
+		int j = i;
+		for (int k = i + 1; k < n; ++k)
+			if (W[j] < W[k]) j = k;
+		if (i != j)
+		{
+			std::swap(W[i], W[j]);
+			for (int k = 0; k < m; ++k) std::swap(At[i * m + k], At[j * m + k]);
+			if (Vt)
+				for (int k = 0; k < n; ++k) std::swap(Vt[i * n + k], Vt[j * n + k]);
+		}
+	}
+	for (int i = 0; i < n; ++i)
+	{
+		// OpenCV fills rows whose singular value is <= DBL_MIN with random orthogonal vectors; exact
+		// rank deficiency does not occur on the noisy inputs of this path, so such rows are left as zeros.
+		const double s = W[i] > minval ? 1 / W[i] : 0.;
+		for (int k = 0; k < m; ++k) At[i * m + k] *= s;
+	}
+}
+
+// Least-squares solution of A x = b (A is m x n, row-major, m >= n <= 6) through the normal
+// equations' eigen-decomposition = the minimum-norm SVD solution cvSolve(..., CV_SVD) returns.
+inline void solve_ls(const double * A, const double * b, int m, int n, double * x)
+{
+	double ata[36], atb[6], w[6], vt[36];
+	for (int i = 0; i < n; ++i)
+	{
+		for (int j = 0; j < n; ++j)
+		{
+			double s = 0;
+			for (int k = 0; k < m; ++k) s += A[k * n + i] * A[k * n + j];
+			ata[i * n + j] = s;
+		}
+		double s = 0;
+		for (int k = 0; k < m; ++k) s += A[k * n + i] * b[k];
+		atb[i] = s;
+	}
+	jacobi_eigen_desc(ata, n, w, vt);
+	for (int i = 0; i < n; ++i) x[i] = 0;
+	const double tol = w[0] * 1e-14 * n;
+	for (int k = 0; k < n; ++k)
+	{
+		if (w[k] <= tol) continue;
+		double c = 0;
+		for (int i = 0; i < n; ++i) c += vt[k * n + i] * atb[i];
+		c /= w[k];
+		for (int i = 0; i < n; ++i) x[i] += c * vt[k * n + i];
+	}
+}
+
+// SVD of a 3x3 matrix M = U diag(w) V^T (row-major U and V, columns are singular vectors).
+inline void svd3(const double * M, double * U, double * w, double * V)
+{
+	double mtm[9], ew[3], vt[9];
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+		{
+			double s = 0;
+			for (int k = 0; k < 3; ++k) s += M[k * 3 + i] * M[k * 3 + j];
+			mtm[i * 3 + j] = s;
+		}
+	jacobi_eigen_desc(mtm, 3, ew, vt);
+	for (int k = 0; k < 3; ++k)
+	{
+		w[k] = std::sqrt(std::max(ew[k], 0.0));
+		for (int i = 0; i < 3; ++i) V[i * 3 + k] = vt[k * 3 + i];
+	}
+	// U columns = M v_k / w_k; complete the basis when a singular value vanishes
+	for (int k = 0; k < 3; ++k)
+	{
+		double u[3];
+		for (int i = 0; i < 3; ++i) u[i] = M[i * 3 + 0] * V[0 * 3 + k] + M[i * 3 + 1] * V[1 * 3 + k] + M[i * 3 + 2] * V[2 * 3 + k];
+		double nrm = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+		if (nrm > 1e-12 * (w[0] + 1e-300))
+			for (int i = 0; i < 3; ++i) U[i * 3 + k] = u[i] / nrm;
+		else
+		{
+			// cross product of the two previous columns (k == 2) keeps U orthonormal
+			const int a = (k + 1) % 3, b = (k + 2) % 3;
+			U[0 * 3 + k] = U[1 * 3 + a] * U[2 * 3 + b] - U[2 * 3 + a] * U[1 * 3 + b];
+			U[1 * 3 + k] = U[2 * 3 + a] * U[0 * 3 + b] - U[0 * 3 + a] * U[2 * 3 + b];
+			U[2 * 3 + k] = U[0 * 3 + a] * U[1 * 3 + b] - U[1 * 3 + a] * U[0 * 3 + b];
+		}
+	}
+}
+
+inline void mat3_inv(const double * m, double * inv)
+{
+	const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+	const double id = 1.0 / det;
+	inv[0] = (m[4] * m[8] - m[5] * m[7]) * id;
+	inv[1] = (m[2] * m[7] - m[1] * m[8]) * id;
+	inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+	inv[3] = (m[5] * m[6] - m[3] * m[8]) * id;
+	inv[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+	inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+	inv[6] = (m[3] * m[7] - m[4] * m[6]) * id;
+	inv[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+	inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+// cv::Rodrigues, vector -> matrix, optional jacobian J[3][9] = dR(k)/dr(i)
+inline void rodrigues_v2m(const double r[3], double R[9], double * J)
+{
+	const double theta = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+	if (theta < 2.220446049250313e-16)
+	{
+		for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+		if (J)
+		{
+			memset(J, 0, sizeof(double) * 27);
+			J[5] = J[15] = J[19] = -1;
+			J[7] = J[11] = J[21] = 1;
+		}
+		return;
+	}
+	const double c = std::cos(theta), s = std::sin(theta), c1 = 1.0 - c, itheta = 1.0 / theta;
+	const double rx = r[0] * itheta, ry = r[1] * itheta, rz = r[2] * itheta;
+	const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+	const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+	const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	for (int k = 0; k < 9; ++k) R[k] = c * I[k] + c1 * rrt[k] + s * r_x[k];
+	if (J)
+	{
+		const double drrt[27] = {rx + rx, ry, rz, ry, 0, 0, rz, 0, 0, 0, rx, 0, rx, ry + ry, rz, 0, rz, 0, 0, 0, rx, 0, 0, ry, rx, ry, rz + rz};
+		const double d_r_x[27] = {0, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 1, 0, 0, 0, -1, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0, 0};
+		for (int i = 0; i < 3; ++i)
+		{
+			const double ri = i == 0 ? rx : i == 1 ? ry : rz;
+			const double a0 = -s * ri, a1 = (s - 2 * c1 * itheta) * ri, a2 = c1 * itheta;
+			const double a3 = (c - s * itheta) * ri, a4 = s * itheta;
+			for (int k = 0; k < 9; ++k) J[i * 9 + k] = a0 * I[k] + a1 * rrt[k] + a2 * drrt[i * 9 + k] + a3 * r_x[k] + a4 * d_r_x[i * 9 + k];
+		}
+	}
+}
+
+// cv::Rodrigues, matrix -> vector (R is re-orthonormalised by SVD first, as OpenCV does)
+inline void rodrigues_m2v(const double Rin[9], double r[3])
+{
+	double U[9], w[3], V[9], R[9];
+	svd3(Rin, U, w, V);
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j) R[i * 3 + j] = U[i * 3 + 0] * V[j * 3 + 0] + U[i * 3 + 1] * V[j * 3 + 1] + U[i * 3 + 2] * V[j * 3 + 2];
+	double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+	const double s = std::sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+	double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+	c = c > 1. ? 1. : c < -1. ? -1. : c;
+	const double theta = std::acos(c);
+	if (s < 1e-5)
+	{
+		if (c > 0) { r[0] = r[1] = r[2] = 0; }
+		else
+		{
+			double t;
+			t = (R[0] + 1) * 0.5; rx = std::sqrt(std::max(t, 0.));
+			t = (R[4] + 1) * 0.5; ry = std::sqrt(std::max(t, 0.)) * (R[1] < 0 ? -1. : 1.);
+			t = (R[8] + 1) * 0.5; rz = std::sqrt(std::max(t, 0.)) * (R[2] < 0 ? -1. : 1.);
+			if (std::fabs(rx) < std::fabs(ry) && std::fabs(rx) < std::fabs(rz) && (R[5] > 0) != (ry * rz > 0)) rz = -rz;
+			const double k = theta / std::sqrt(rx * rx + ry * ry + rz * rz);
+			r[0] = rx * k; r[1] = ry * k; r[2] = rz * k;
+		}
+	}
+	else
+	{
+		const double vth = 1 / (2 * s) * theta;
+		r[0] = rx * vth; r[1] = ry * vth; r[2] = rz * vth;
+	}
+}
+
+} // namespace orc_pnp

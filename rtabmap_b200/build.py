@@ -16,11 +16,12 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "lib" / "liblcd_b200.so"
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "nn_hamming.cuh", "resolve.cuh", "score.cuh", "../../include/lcd_b200.h"]
+HEADERS = ["common.cuh", "nn_hamming.cuh", "resolve.cuh", "score.cuh", "verify.cuh", "pnp_device.cuh", "../../include/lcd_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",  # fp64 PnP code must round like the host oracle; the integer kernels do not care
     "-shared", "-Xcompiler", "-fPIC",
     "-diag-suppress", "1886",
 ]

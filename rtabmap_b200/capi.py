@@ -38,6 +38,34 @@ class _Config(C.Structure):
     ]
 
 
+class VerifyParams(C.Structure):
+    """lcd_verify_params (Vis/* parameters of the reference, corelib/include/rtabmap/core/Parameters.h:713-754)."""
+    _fields_ = [
+        ("nndr", C.c_float),
+        ("min_inliers", C.c_int),
+        ("iterations", C.c_int),
+        ("reproj_error", C.c_float),
+        ("refine_iterations", C.c_int),
+        ("refine_sigma", C.c_float),
+        ("fx", C.c_double),
+        ("fy", C.c_double),
+        ("cx", C.c_double),
+        ("cy", C.c_double),
+    ]
+
+
+class VerifyResult(C.Structure):
+    _fields_ = [
+        ("ok", C.c_int),
+        ("n_matches", C.c_int),
+        ("n_inliers", C.c_int),
+        ("iterations_run", C.c_int),
+        ("rvec", C.c_double * 3),
+        ("tvec", C.c_double * 3),
+        ("transform", C.c_float * 12),
+    ]
+
+
 def library_path() -> Path:
     return _build.LIB
 
@@ -80,6 +108,8 @@ SIGNATURES = {
     "lcd_index_score": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "lcd_localize_batch": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P]),
     "lcd_localize_batch_dev": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
+    "lcd_match_pairs": (_I, [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
+    "lcd_verify_batch": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lcd_shard_set_row_offset": (_I, [_P, _I]),
     "lcd_shard_knn2_keys_dev": (_I, [_P, _P, _I, _P, _P]),
     "lcd_shard_resolve_score_dev": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
@@ -327,6 +357,45 @@ class Engine:
                                                       int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total),
                                                       C.c_void_p(d_words_out or None), C.c_void_p(d_like_out or None),
                                                       C.c_void_p(stream or None)))
+
+    # -- geometric verification -----------------------------------------------------------------
+    def _pairs(self, desc_from, desc_to, n_from, n_to):
+        dt = np.uint8 if self.desc_type == LCD_DESC_U8 else np.float32
+        a = np.ascontiguousarray(desc_from, dtype=dt)
+        b = np.ascontiguousarray(desc_to, dtype=dt)
+        if a.ndim != 3 or a.shape != b.shape or a.shape[2] != self.desc_dim:
+            raise LcdError(-1, f"descriptors must be [n_pairs, cap, {self.desc_dim}]")
+        n_pairs, cap = a.shape[:2]
+        nf = _i32(n_from if n_from is not None else np.full(n_pairs, cap))
+        nt = _i32(n_to if n_to is not None else np.full(n_pairs, cap))
+        return a, b, nf, nt, n_pairs, cap
+
+    def match_pairs(self, desc_from, desc_to, n_from=None, n_to=None, nndr: float = 0.8):
+        a, b, nf, nt, n_pairs, cap = self._pairs(desc_from, desc_to, n_from, n_to)
+        fid = np.zeros((n_pairs, cap), np.int32)
+        tid = np.zeros((n_pairs, cap), np.int32)
+        self._check(self._lib.lcd_match_pairs(self._h, n_pairs, cap, _ptr(a), _ptr(nf), _ptr(b), _ptr(nt), float(nndr), _ptr(fid), _ptr(tid)))
+        return fid, tid
+
+    def verify_batch(self, desc_from, xyz_from, desc_to, uv_to, K4, n_from=None, n_to=None, nndr: float = 0.8, min_inliers: int = 20,
+                     iterations: int = 300, reproj_error: float = 2.0, refine_iterations: int = 1, refine_sigma: float = 3.0):
+        """Memory::computeTransform for a batch of (FROM, TO) pairs; returns a list of dicts."""
+        a, b, nf, nt, n_pairs, cap = self._pairs(desc_from, desc_to, n_from, n_to)
+        xyz = np.ascontiguousarray(xyz_from, np.float32).reshape(n_pairs, cap, 3)
+        uv = np.ascontiguousarray(uv_to, np.float32).reshape(n_pairs, cap, 2)
+        prm = VerifyParams(nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, *[float(k) for k in K4])
+        res = (VerifyResult * n_pairs)()
+        mids = np.zeros((n_pairs, cap), np.int32)
+        iids = np.zeros((n_pairs, cap), np.int32)
+        self._check(self._lib.lcd_verify_batch(self._h, n_pairs, cap, _ptr(a), _ptr(xyz), _ptr(nf), _ptr(b), _ptr(uv), _ptr(nt),
+                                                C.byref(prm), res, _ptr(mids), _ptr(iids)))
+        out = []
+        for i in range(n_pairs):
+            r = res[i]
+            out.append({"ok": bool(r.ok), "matches": mids[i, :r.n_matches].copy(), "inliers": iids[i, :r.n_inliers].copy(),
+                        "iterations_run": r.iterations_run, "rvec": np.array(r.rvec[:]), "tvec": np.array(r.tvec[:]),
+                        "transform": np.array(r.transform[:], np.float32).reshape(3, 4)})
+        return out
 
     # -- word-range sharding ----------------------------------------------------------------------
     def shard_set_row_offset(self, off: int):

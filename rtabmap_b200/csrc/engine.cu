@@ -14,6 +14,7 @@
 #include "nn_hamming.cuh"
 #include "resolve.cuh"
 #include "score.cuh"
+#include "verify.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -151,6 +152,11 @@ struct lcd_engine
 	DevBuf<RefOp> d_ops;
 	DevBuf<MoveOp> d_moves;
 	DevBuf<int> d_perm;
+	// verification scratch
+	DevBuf<uint32_t> v_df, v_dt;
+	DevBuf<float> v_xyz, v_uv, v_obj, v_img, v_T;
+	DevBuf<int> v_nf, v_nt, v_mid, v_mfrom, v_mto, v_nm, v_fid, v_tid, v_inl, v_ninl, v_iters, v_ok, v_inl_ids;
+	DevBuf<double> v_rvec, v_tvec;
 
 	// measurement hooks (lcd_profile_*)
 	bool prof_on = false;
@@ -158,7 +164,7 @@ struct lcd_engine
 	{
 		std::vector<cudaEvent_t> ev; // start/stop pairs
 		size_t used = 0;
-	} prof[3];
+	} prof[5];
 
 	// tuning knobs (env: LCD_NN_CTAS_PER_SM, LCD_NN_TQ, LCD_NN_VARIANT, LCD_SCORE_BLOCKS)
 	int nn_ctas_per_sm = 2, nn_tq = 8, nn_variant = 2, score_blocks = 32;
@@ -675,7 +681,7 @@ int lcd_profile_reset(lcd_engine * e)
 
 int lcd_profile_read(lcd_engine * e, int which, double * total_ms, long long * launches)
 {
-	if (!e || which < 0 || which > 2) return LCD_ERR_INVALID;
+	if (!e || which < 0 || which > 4) return LCD_ERR_INVALID;
 	LCD_TRY(set_device(e));
 	LCD_CUDA(e, cudaDeviceSynchronize());
 	auto & p = e->prof[which];
@@ -1227,6 +1233,190 @@ int lcd_localize_batch(lcd_engine * e, const void * queries, int n_frames, int n
 	if (likelihood_out)
 		LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, static_cast<size_t>(n_frames) * ns * sizeof(float), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+// ---- geometric verification ------------------------------------------------------------------
+static int verify_upload(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const float * xyz_from, const int * n_from,
+                         const void * desc_to, const float * uv_to, const int * n_to, cudaStream_t s)
+{
+	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	LCD_CUDA(e, e->v_df.reserve(rows * e->nw, 0, false, s));
+	LCD_CUDA(e, e->v_dt.reserve(rows * e->nw, 0, false, s));
+	LCD_CUDA(e, e->v_xyz.reserve(rows * 3, 0, false, s));
+	LCD_CUDA(e, e->v_uv.reserve(rows * 2, 0, false, s));
+	LCD_CUDA(e, e->v_nf.reserve(n_pairs, 0, false, s));
+	LCD_CUDA(e, e->v_nt.reserve(n_pairs, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->v_df.p, desc_from, rows * e->nw * 4, cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->v_dt.p, desc_to, rows * e->nw * 4, cudaMemcpyHostToDevice, s));
+	if (xyz_from) LCD_CUDA(e, cudaMemcpyAsync(e->v_xyz.p, xyz_from, rows * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	else LCD_CUDA(e, cudaMemsetAsync(e->v_xyz.p, 0, rows * 3 * sizeof(float), s));
+	if (uv_to) LCD_CUDA(e, cudaMemcpyAsync(e->v_uv.p, uv_to, rows * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+	else LCD_CUDA(e, cudaMemsetAsync(e->v_uv.p, 0, rows * 2 * sizeof(float), s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->v_nf.p, n_from, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->v_nt.p, n_to, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+	return LCD_OK;
+}
+
+static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool want_ids, cudaStream_t s)
+{
+	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	LCD_CUDA(e, e->v_obj.reserve(rows * 3, 0, false, s));
+	LCD_CUDA(e, e->v_img.reserve(rows * 2, 0, false, s));
+	LCD_CUDA(e, e->v_mid.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->v_mfrom.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->v_mto.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->v_nm.reserve(n_pairs, 0, false, s));
+	if (want_ids)
+	{
+		LCD_CUDA(e, e->v_fid.reserve(rows, 0, false, s));
+		LCD_CUDA(e, e->v_tid.reserve(rows, 0, false, s));
+	}
+	MatchArgs a{};
+	a.desc_from = e->v_df.p;
+	a.xyz_from = e->v_xyz.p;
+	a.n_from = e->v_nf.p;
+	a.desc_to = e->v_dt.p;
+	a.uv_to = e->v_uv.p;
+	a.n_to = e->v_nt.p;
+	a.cap = cap;
+	a.nndr = nndr;
+	a.obj = e->v_obj.p;
+	a.img = e->v_img.p;
+	a.match_id = e->v_mid.p;
+	a.match_from = e->v_mfrom.p;
+	a.match_to = e->v_mto.p;
+	a.n_match = e->v_nm.p;
+	a.from_ids = want_ids ? e->v_fid.p : nullptr;
+	a.to_ids = want_ids ? e->v_tid.p : nullptr;
+	const size_t smem = match_smem_bytes(cap, e->nw);
+	if (smem > static_cast<size_t>(e->smem_optin)) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap %d needs %zu B of shared memory", cap, smem);
+#define LCD_MATCH_CASE(NW_)                                                                                             \
+	case NW_:                                                                                                           \
+	{                                                                                                                   \
+		auto kern = pair_match_kernel<NW_>;                                                                             \
+		if (smem > 48 * 1024)                                                                                           \
+			LCD_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+		prof_mark(e, LCD_PROF_MATCH, s);                                                                                \
+		kern<<<n_pairs, kResolveThreads, smem, s>>>(a);                                                                 \
+		prof_mark(e, LCD_PROF_MATCH, s);                                                                                \
+		break;                                                                                                          \
+	}
+	switch (e->nw)
+	{
+		LCD_MATCH_CASE(4)
+		LCD_MATCH_CASE(8)
+		LCD_MATCH_CASE(16)
+	default: LCD_FAIL(e, LCD_ERR_INVALID, "unsupported descriptor size");
+	}
+#undef LCD_MATCH_CASE
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_params * p, cudaStream_t s)
+{
+	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	LCD_CUDA(e, e->v_rvec.reserve(n_pairs * 3, 0, false, s));
+	LCD_CUDA(e, e->v_tvec.reserve(n_pairs * 3, 0, false, s));
+	LCD_CUDA(e, e->v_inl.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->v_ninl.reserve(n_pairs, 0, false, s));
+	LCD_CUDA(e, e->v_iters.reserve(n_pairs, 0, false, s));
+	LCD_CUDA(e, e->v_ok.reserve(n_pairs, 0, false, s));
+	LCD_CUDA(e, e->v_T.reserve(n_pairs * 12, 0, false, s));
+	PnpArgs a{};
+	a.obj = e->v_obj.p;
+	a.img = e->v_img.p;
+	a.n_pts = e->v_nm.p;
+	a.cap = cap;
+	a.cam = CamK{p->fx, p->fy, p->cx, p->cy};
+	a.iterations = p->iterations;
+	a.reproj = p->reproj_error;
+	a.min_inliers = p->min_inliers;
+	a.refine_iterations = p->refine_iterations;
+	a.refine_sigma = p->refine_sigma;
+	a.rvec = e->v_rvec.p;
+	a.tvec = e->v_tvec.p;
+	a.inliers = e->v_inl.p;
+	a.n_inliers = e->v_ninl.p;
+	a.iters_run = e->v_iters.p;
+	a.ok = e->v_ok.p;
+	a.transform = e->v_T.p;
+	const size_t smem = pnp_smem_bytes(cap);
+	if (smem > static_cast<size_t>(e->smem_optin)) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap %d needs %zu B of shared memory", cap, smem);
+	if (smem > 48 * 1024)
+		LCD_CUDA(e, cudaFuncSetAttribute(pnp_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	prof_mark(e, LCD_PROF_PNP, s);
+	pnp_ransac_kernel<<<n_pairs, kVerifyThreads, smem, s>>>(a);
+	prof_mark(e, LCD_PROF_PNP, s);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+static int check_verify_args(lcd_engine * e, int n_pairs, int cap, const void * a, const void * b, const int * na, const int * nb)
+{
+	if (n_pairs <= 0 || cap <= 0 || !a || !b || !na || !nb) LCD_FAIL(e, LCD_ERR_INVALID, "null or empty verification input");
+	if (cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "at most %d features per signature", kMaxFrameQueries);
+	return LCD_OK;
+}
+
+int lcd_match_pairs(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const int * n_from, const void * desc_to,
+                    const int * n_to, float nndr, int * from_ids, int * to_ids)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_TRY(check_verify_args(e, n_pairs, cap, desc_from, desc_to, n_from, n_to));
+	cudaStream_t s = e->stream;
+	LCD_TRY(verify_upload(e, n_pairs, cap, desc_from, nullptr, n_from, desc_to, nullptr, n_to, s));
+	LCD_TRY(launch_match(e, n_pairs, cap, nndr, true, s));
+	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	if (from_ids) LCD_CUDA(e, cudaMemcpyAsync(from_ids, e->v_fid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (to_ids) LCD_CUDA(e, cudaMemcpyAsync(to_ids, e->v_tid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const float * xyz_from, const int * n_from,
+                     const void * desc_to, const float * uv_to, const int * n_to, const lcd_verify_params * params,
+                     lcd_verify_result * results, int * match_ids, int * inlier_ids)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_TRY(check_verify_args(e, n_pairs, cap, desc_from, desc_to, n_from, n_to));
+	if (!xyz_from || !uv_to || !params || !results) LCD_FAIL(e, LCD_ERR_INVALID, "null verification argument");
+	if (params->iterations > kMaxRansacIters) LCD_FAIL(e, LCD_ERR_CAPACITY, "Vis/Iterations > %d", kMaxRansacIters);
+	cudaStream_t s = e->stream;
+	LCD_TRY(verify_upload(e, n_pairs, cap, desc_from, xyz_from, n_from, desc_to, uv_to, n_to, s));
+	LCD_TRY(launch_match(e, n_pairs, cap, params->nndr, false, s));
+	LCD_TRY(launch_pnp(e, n_pairs, cap, params, s));
+	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	LCD_CUDA(e, e->v_inl_ids.reserve(rows, 0, false, s));
+	gather_by_index_kernel<<<dim3((cap + 255) / 256, n_pairs), 256, 0, s>>>(e->v_mid.p, e->v_inl.p, e->v_ninl.p, cap, e->v_inl_ids.p);
+	LCD_CHECK_LAUNCH(e);
+	std::vector<int> nm(n_pairs), ni(n_pairs), it(n_pairs), ok(n_pairs);
+	std::vector<double> rv(n_pairs * 3), tv(n_pairs * 3);
+	std::vector<float> T(n_pairs * 12);
+	LCD_CUDA(e, cudaMemcpyAsync(nm.data(), e->v_nm.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ni.data(), e->v_ninl.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(it.data(), e->v_iters.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ok.data(), e->v_ok.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(rv.data(), e->v_rvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(tv.data(), e->v_tvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(T.data(), e->v_T.p, n_pairs * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+	if (match_ids) LCD_CUDA(e, cudaMemcpyAsync(match_ids, e->v_mid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (inlier_ids) LCD_CUDA(e, cudaMemcpyAsync(inlier_ids, e->v_inl_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	for (int i = 0; i < n_pairs; ++i)
+	{
+		lcd_verify_result & r = results[i];
+		r.ok = ok[i];
+		r.n_matches = nm[i];
+		r.n_inliers = ni[i];
+		r.iterations_run = it[i];
+		memcpy(r.rvec, &rv[3 * i], 3 * sizeof(double));
+		memcpy(r.tvec, &tv[3 * i], 3 * sizeof(double));
+		memcpy(r.transform, &T[12 * i], 12 * sizeof(float));
+	}
 	return LCD_OK;
 }
 

@@ -213,6 +213,60 @@ __device__ void score_prep(uint32_t * sbuf, int n_pad, int nq, const ResolveArgs
 	__syncthreads();
 }
 
+// Fixed-point rounds of the intra-frame new-word dependency for ONE frame held by the calling CTA.
+// On entry sa1/sa2 hold each descriptor's two best index hits, flag[i] the decision made from them
+// alone and res[i] the row of the best index hit.  On return flag[i] = 1 for descriptors that create a
+// word (rank[i] = creation order), res[i] >= 0 = matched index row, res[i] = -1-k = matched the k-th word
+// created by this frame.  Returns the number of created words.  All threads of the CTA must call it.
+template <int NW>
+__device__ int resolve_rounds(const uint32_t * __restrict__ fq, int nq, const uint32_t * sa1, const uint32_t * sa2, int * res,
+                              uint16_t * L, uint16_t * rank, uint8_t * flag, uint8_t * flag2, int * s_nL, float nndr, int cmp_new)
+{
+	const int tid = threadIdx.x;
+	for (int round = 0; round <= nq; ++round)
+	{
+		if (tid < 32)
+		{
+			const int n = warp0_compact(flag, nq, L, rank);
+			if (tid == 0) *s_nL = n;
+		}
+		__syncthreads();
+		const int nL = *s_nL;
+		if (!cmp_new) break;
+		int changed = 0;
+		for (int i = tid; i < nq; i += blockDim.x)
+		{
+			uint32_t n1 = kKeyNone, n2 = kKeyNone;
+			if (nL > 0 && L[0] < i)
+			{
+				uint32_t qi[NW];
+				load_desc<NW>(fq, i, qi);
+				for (int k = 0; k < nL; ++k)
+				{
+					const int j = L[k];
+					if (j >= i) break;
+					uint32_t qj[NW];
+					load_desc<NW>(fq, j, qj);
+					uint32_t d = 0;
+#pragma unroll
+					for (int v = 0; v < NW; ++v) d += __popc(qi[v] ^ qj[v]);
+					top2_insert(n1, n2, (d << kKeyShift) + static_cast<uint32_t>(k));
+				}
+			}
+			int bt;
+			const bool bad = nndr_decide(sa1[i], sa2[i], n1, n2, nndr, bt);
+			flag2[i] = bad ? 1 : 0;
+			changed |= (flag2[i] != flag[i]);
+			if (!bad) res[i] = bt >= 2 ? -1 - static_cast<int>(n1 & kKeyRowMask) : static_cast<int>(sa1[i] & kKeyRowMask);
+		}
+		changed = __syncthreads_or(changed);
+		if (!changed) break;
+		for (int i = tid; i < nq; i += blockDim.x) flag[i] = flag2[i];
+		__syncthreads();
+	}
+	return *s_nL;
+}
+
 // One CTA per frame.
 template <int NW>
 __global__ void __launch_bounds__(kResolveThreads)
@@ -269,48 +323,7 @@ resolve_kernel(const ResolveArgs a)
 	if (a.incremental)
 	{
 		// 2. fixed-point rounds over the intra-frame dependency
-		for (int round = 0; round <= nq; ++round)
-		{
-			if (tid < 32)
-			{
-				const int n = warp0_compact(flag, nq, L, rank);
-				if (tid == 0) s_nL = n;
-			}
-			__syncthreads();
-			const int nL = s_nL;
-			if (!a.cmp_new) break;
-			int changed = 0;
-			for (int i = tid; i < nq; i += blockDim.x)
-			{
-				uint32_t n1 = kKeyNone, n2 = kKeyNone;
-				if (nL > 0 && L[0] < i)
-				{
-					uint32_t qi[NW];
-					load_desc<NW>(fq, i, qi);
-					for (int k = 0; k < nL; ++k)
-					{
-						const int j = L[k];
-						if (j >= i) break;
-						uint32_t qj[NW];
-						load_desc<NW>(fq, j, qj);
-						uint32_t d = 0;
-#pragma unroll
-						for (int v = 0; v < NW; ++v) d += __popc(qi[v] ^ qj[v]);
-						top2_insert(n1, n2, (d << kKeyShift) + static_cast<uint32_t>(k));
-					}
-				}
-				int bt;
-				const bool bad = nndr_decide(sa1[i], sa2[i], n1, n2, a.nndr, bt);
-				flag2[i] = bad ? 1 : 0;
-				changed |= (flag2[i] != flag[i]);
-				if (!bad) res[i] = bt >= 2 ? -1 - static_cast<int>(n1 & kKeyRowMask) : static_cast<int>(sa1[i] & kKeyRowMask);
-			}
-			changed = __syncthreads_or(changed);
-			if (!changed) break;
-			for (int i = tid; i < nq; i += blockDim.x) flag[i] = flag2[i];
-			__syncthreads();
-		}
-		n_new = s_nL;
+		n_new = resolve_rounds<NW>(fq, nq, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, a.cmp_new);
 	}
 
 	// 3. word ids (VWDictionary::getNextId = ++_lastWordId in creation order)

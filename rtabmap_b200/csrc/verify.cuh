@@ -1,0 +1,697 @@
+// verify.cuh — geometric verification of loop-closure hypotheses: descriptor matching of a
+// signature pair and PnP/RANSAC with refinement, batched one CTA per pair.
+//
+// Replaces, for Vis/CorNNType in {0,3} (exact matching), Vis/EstimationType=1 (PnP), single camera:
+//   pair_match_kernel  RegistrationVis::computeTransformationImpl global matching through a temporary
+//                      VWDictionary (corelib/src/RegistrationVis.cpp:1482-1546) and the correspondence
+//                      assembly of util3d::estimateMotion3DTo2D (util3d_motion_estimation.cpp:88-110)
+//   pnp_ransac_kernel  util3d::solvePnPRansac (util3d_motion_estimation.cpp:843-990) =
+//                      cv3::solvePnPRansac / RANSACPointSetRegistrator::run (opencv/solvepnp.cpp:112-417)
+//                      + the PCL-style refinement loop, and the pose -> Transform conversion (:121-154)
+//
+// RANSAC is sequential in the reference (adaptive iteration count, strict-best update) but its random
+// samples depend only on the point count (cv::RNG seeded with (uint64)-1 on every run), so all
+// Vis/Iterations hypotheses are evaluated in parallel (one thread each: EPnP on 6 points + inlier count
+// over all points) and one thread then replays the sequential best/niters bookkeeping over the counts.
+#pragma once
+#include "common.cuh"
+#include "pnp_device.cuh"
+#include "resolve.cuh"
+
+namespace lcd {
+
+constexpr int kVerifyThreads = 320; // >= Vis/Iterations hypotheses per pair, multiple of 32
+constexpr int kMaxRansacIters = 320;
+
+struct MatchArgs
+{
+	const uint32_t * desc_from; // [n_pairs][cap][NW]
+	const float * xyz_from;     // [n_pairs][cap][3]   NaN = no depth
+	const int * n_from;         // [n_pairs]
+	const uint32_t * desc_to;   // [n_pairs][cap][NW]
+	const float * uv_to;        // [n_pairs][cap][2]
+	const int * n_to;           // [n_pairs]
+	int cap;
+	float nndr; // Vis/CorNNDR
+	// outputs
+	float * obj;       // [n_pairs][cap][3]
+	float * img;       // [n_pairs][cap][2]
+	int * match_id;    // [n_pairs][cap]  word id of the correspondence (ascending)
+	int * match_from;  // [n_pairs][cap]  descriptor index in FROM
+	int * match_to;    // [n_pairs][cap]  descriptor index in TO
+	int * n_match;     // [n_pairs]
+	int * from_ids;    // [n_pairs][cap] or nullptr
+	int * to_ids;      // [n_pairs][cap] or nullptr
+};
+
+__host__ __device__ inline size_t match_smem_bytes(int cap, int nw)
+{
+	return static_cast<size_t>(cap) * (4 + 4 + 4 + 2 + 2 + 1 + 1 + 4 + 4 + 2 + 2) + static_cast<size_t>(cap) * nw * 4 + 128;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kResolveThreads)
+pair_match_kernel(const MatchArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int cap = a.cap;
+	uint32_t * dict = reinterpret_cast<uint32_t *>(smem_raw);             // [cap][NW]
+	uint32_t * sa1 = dict + static_cast<size_t>(cap) * NW;                // [cap]
+	uint32_t * sa2 = sa1 + cap;
+	int * res = reinterpret_cast<int *>(sa2 + cap);
+	int * cntF = res + cap;
+	int * cntT = cntF + cap;
+	uint16_t * L = reinterpret_cast<uint16_t *>(cntT + cap);
+	uint16_t * rank = L + cap;
+	uint16_t * idxF = rank + cap;
+	uint16_t * idxT = idxF + cap;
+	uint8_t * flag = reinterpret_cast<uint8_t *>(idxT + cap);
+	uint8_t * flag2 = flag + cap;
+	__shared__ int s_nL;
+
+	const int tid = threadIdx.x;
+	const int pair = blockIdx.x;
+	const int nf = min(a.n_from[pair], cap), nt = min(a.n_to[pair], cap);
+	const size_t base = static_cast<size_t>(pair) * cap;
+	const uint32_t * F = a.desc_from + base * NW;
+	const uint32_t * T = a.desc_to + base * NW;
+
+	// ---- FROM side: addNewWords(descriptorsFrom, 1) on an empty dictionary -------------------
+	for (int i = tid; i < nf; i += blockDim.x)
+	{
+		sa1[i] = kKeyNone;
+		sa2[i] = kKeyNone;
+		flag[i] = 1;
+		res[i] = 0;
+	}
+	__syncthreads();
+	int n_dict = 0;
+	if (nf > 0) n_dict = resolve_rounds<NW>(F, nf, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
+	__syncthreads();
+	for (int k = tid; k < n_dict; k += blockDim.x)
+	{
+		cntF[k] = 0;
+		cntT[k] = 0;
+		uint32_t q[NW];
+		load_desc<NW>(F, L[k], q);
+#pragma unroll
+		for (int v = 0; v < NW; ++v) dict[static_cast<size_t>(k) * NW + v] = q[v];
+	}
+	__syncthreads();
+	for (int i = tid; i < nf; i += blockDim.x)
+	{
+		const int k = flag[i] ? rank[i] : (-1 - res[i]);
+		atomicAdd(&cntF[k], 1);
+		idxF[k] = static_cast<uint16_t>(i);
+		if (a.from_ids) a.from_ids[base + i] = k + 1;
+	}
+	__syncthreads();
+
+	// ---- TO side: update(); addNewWords(descriptorsTo, 2) --------------------------------------
+	for (int j = tid; j < nt; j += blockDim.x)
+	{
+		uint32_t q[NW];
+		load_desc<NW>(T, j, q);
+		uint32_t k1 = kKeyNone, k2 = kKeyNone;
+		for (int k = 0; k < n_dict; ++k)
+		{
+			const uint4 * row = reinterpret_cast<const uint4 *>(dict + static_cast<size_t>(k) * NW);
+			uint32_t d = 0;
+#pragma unroll
+			for (int v = 0; v < NW / 4; ++v)
+			{
+				const uint4 x = row[v];
+				d += __popc(q[4 * v] ^ x.x) + __popc(q[4 * v + 1] ^ x.y) + __popc(q[4 * v + 2] ^ x.z) + __popc(q[4 * v + 3] ^ x.w);
+			}
+			top2_insert(k1, k2, (d << kKeyShift) + static_cast<uint32_t>(k));
+		}
+		sa1[j] = k1;
+		sa2[j] = k2;
+		int bt;
+		flag[j] = nndr_decide(k1, k2, kKeyNone, kKeyNone, a.nndr, bt) ? 1 : 0;
+		res[j] = static_cast<int>(k1 & kKeyRowMask);
+	}
+	__syncthreads();
+	if (nt > 0) resolve_rounds<NW>(T, nt, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
+	__syncthreads();
+	for (int j = tid; j < nt; j += blockDim.x)
+	{
+		int id;
+		if (flag[j]) id = n_dict + 1 + rank[j];
+		else if (res[j] >= 0)
+		{
+			id = res[j] + 1;
+			atomicAdd(&cntT[res[j]], 1);
+			idxT[res[j]] = static_cast<uint16_t>(j);
+		}
+		else id = n_dict + 1 + (-1 - res[j]);
+		if (a.to_ids) a.to_ids[base + j] = id;
+	}
+	__syncthreads();
+
+	// ---- correspondences: ids seen exactly once on each side, finite 3D, ascending id ------------
+	for (int k = tid; k < n_dict; k += blockDim.x)
+	{
+		bool ok = cntF[k] == 1 && cntT[k] == 1;
+		if (ok)
+		{
+			const float * p = a.xyz_from + (base + idxF[k]) * 3;
+			ok = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
+		}
+		flag[k] = ok ? 1 : 0;
+	}
+	__syncthreads();
+	if (tid < 32)
+	{
+		const int n = warp0_compact(flag, n_dict, L, rank);
+		if (tid == 0)
+		{
+			s_nL = n;
+			a.n_match[pair] = n;
+		}
+	}
+	__syncthreads();
+	const int nm = s_nL;
+	for (int m = tid; m < nm; m += blockDim.x)
+	{
+		const int k = L[m];
+		const int fi = idxF[k], ti = idxT[k];
+		const float * p = a.xyz_from + (base + fi) * 3;
+		const float * q = a.uv_to + (base + ti) * 2;
+		a.obj[(base + m) * 3 + 0] = p[0];
+		a.obj[(base + m) * 3 + 1] = p[1];
+		a.obj[(base + m) * 3 + 2] = p[2];
+		a.img[(base + m) * 2 + 0] = q[0];
+		a.img[(base + m) * 2 + 1] = q[1];
+		a.match_id[base + m] = k + 1;
+		a.match_from[base + m] = fi;
+		a.match_to[base + m] = ti;
+	}
+}
+
+// ------------------------------------------------------------------------------------ PnP RANSAC
+struct PnpArgs
+{
+	const float * obj;   // [n_pairs][cap][3]
+	const float * img;   // [n_pairs][cap][2]
+	const int * n_pts;   // [n_pairs]
+	int cap;
+	CamK cam;
+	int iterations;        // Vis/Iterations (<= kMaxRansacIters)
+	float reproj;          // Vis/PnPReprojError
+	int min_inliers;       // Vis/MinInliers
+	int refine_iterations; // Vis/PnPRefineIterations
+	float refine_sigma;    // 3.0
+	// outputs
+	double * rvec;      // [n_pairs][3]
+	double * tvec;      // [n_pairs][3]
+	int * inliers;      // [n_pairs][cap] indices into the correspondence list
+	int * n_inliers;    // [n_pairs]
+	int * iters_run;    // [n_pairs]
+	int * ok;           // [n_pairs] 1 = accepted (inliers >= min_inliers)
+	float * transform;  // [n_pairs][12] (localTransform * pnp)^-1, localTransform = identity
+};
+
+__host__ __device__ inline size_t pnp_smem_bytes(int cap)
+{
+	return static_cast<size_t>(cap) * (12 + 8 + 4 + 2 + 2 + 1) + kMaxRansacIters * (6 * 2 + 4 + 6 * 8) + (28 * 32 + 32) * 8 + 1024;
+}
+
+__device__ inline int ransac_update_num_iters(double p, double ep, int modelPoints, int maxIters)
+{
+	p = fmax(p, 0.);
+	p = fmin(p, 1.);
+	ep = fmax(ep, 0.);
+	ep = fmin(ep, 1.);
+	double num = fmax(1. - p, 2.2250738585072014e-308);
+	double denom = 1. - pow(1. - ep, static_cast<double>(modelPoints));
+	if (denom < 2.2250738585072014e-308) return 0;
+	num = log(num);
+	denom = log(denom);
+	return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : static_cast<int>(nearbyint(num / denom));
+}
+
+// block-wide sum of NV doubles per thread; result valid in all threads (via smem)
+template <int NV>
+__device__ inline void block_sum(double (&v)[NV], double * s_red /* [NV * 32] */, double * s_out /* [NV] */)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+	for (int k = 0; k < NV; ++k)
+	{
+		double x = v[k];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
+		if (lane == 0) s_red[k * 32 + warp] = x;
+	}
+	__syncthreads();
+	if (threadIdx.x < NV)
+	{
+		double x = 0;
+		for (int w = 0; w < nwarps; ++w) x += s_red[threadIdx.x * 32 + w];
+		s_out[threadIdx.x] = x;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < NV; ++k) v[k] = s_out[k];
+	__syncthreads();
+}
+
+struct LmState
+{
+	double param[6], prev[6], JtJ[36], JtErr[6];
+	double R[9], dRdr[27];
+	double prevErrNorm;
+	int lambdaLg10, iters, done, cont;
+};
+
+// LM step: param = prev - (JtJ with diag*(1+lambda))^-1 JtErr   (CvLevMarq::step)
+__device__ inline void lm_step(LmState & s)
+{
+	const double lambda = exp(s.lambdaLg10 * log(10.0));
+	double A[36], v[36], dx[6] = {0, 0, 0, 0, 0, 0};
+	int ord[6];
+	for (int i = 0; i < 36; ++i) A[i] = s.JtJ[i];
+	for (int i = 0; i < 6; ++i) A[i * 6 + i] *= 1.0 + lambda;
+	sym_eigen<6>(A, v, ord);
+	const double wmax = A[ord[0] * 6 + ord[0]];
+	for (int kk = 0; kk < 6; ++kk)
+	{
+		const int k = ord[kk];
+		const double w = A[k * 6 + k];
+		if (w <= 2.220446049250313e-16 * 6 * wmax) continue;
+		double c = 0;
+		for (int i = 0; i < 6; ++i) c += v[i * 6 + k] * s.JtErr[i];
+		c /= w;
+		for (int i = 0; i < 6; ++i) dx[i] += c * v[i * 6 + k];
+	}
+	for (int i = 0; i < 6; ++i) s.param[i] = s.prev[i] - dx[i];
+}
+
+// cv::solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess = true) on the points X[list[0..m)], cooperatively by the CTA.
+__device__ inline void lm_refine_block(const float * X, const float * uv, const uint16_t * list, int m, const CamK & cam, LmState & s,
+                                       double * s_red, double * s_out)
+{
+	const int tid = threadIdx.x;
+	if (tid == 0)
+	{
+		s.lambdaLg10 = -3;
+		s.iters = 0;
+		s.done = 0;
+		s.prevErrNorm = 1.7976931348623157e308;
+	}
+	__syncthreads();
+	for (;;)
+	{
+		if (tid == 0) rodrigues_v2m(s.param, s.R, s.dRdr);
+		__syncthreads();
+		// JtJ (upper 21) + JtErr (6) + |err|^2
+		double acc[28];
+#pragma unroll
+		for (int k = 0; k < 28; ++k) acc[k] = 0;
+		for (int p = tid; p < m; p += blockDim.x)
+		{
+			const float * P = X + 3 * list[p];
+			const double Xx = P[0], Xy = P[1], Xz = P[2];
+			const double x = s.R[0] * Xx + s.R[1] * Xy + s.R[2] * Xz + s.param[3];
+			const double y = s.R[3] * Xx + s.R[4] * Xy + s.R[5] * Xz + s.param[4];
+			double z = s.R[6] * Xx + s.R[7] * Xy + s.R[8] * Xz + s.param[5];
+			z = z ? 1. / z : 1;
+			const double xn = x * z, yn = y * z;
+			double j0[6], j1[6];
+			j0[3] = cam.fu * z;
+			j0[4] = 0;
+			j0[5] = -cam.fu * xn * z;
+			j1[3] = 0;
+			j1[4] = cam.fv * z;
+			j1[5] = -cam.fv * yn * z;
+			for (int k = 0; k < 3; ++k)
+			{
+				const double * d = s.dRdr + 9 * k;
+				const double dx = d[0] * Xx + d[1] * Xy + d[2] * Xz;
+				const double dy = d[3] * Xx + d[4] * Xy + d[5] * Xz;
+				const double dz = d[6] * Xx + d[7] * Xy + d[8] * Xz;
+				j0[k] = cam.fu * (dx * z - xn * z * dz);
+				j1[k] = cam.fv * (dy * z - yn * z * dz);
+			}
+			const double e0 = xn * cam.fu + cam.uc - static_cast<double>(uv[2 * list[p]]);
+			const double e1 = yn * cam.fv + cam.vc - static_cast<double>(uv[2 * list[p] + 1]);
+			int q = 0;
+#pragma unroll
+			for (int a = 0; a < 6; ++a)
+#pragma unroll
+				for (int b = a; b < 6; ++b) acc[q++] += j0[a] * j0[b] + j1[a] * j1[b];
+#pragma unroll
+			for (int a = 0; a < 6; ++a) acc[21 + a] += j0[a] * e0 + j1[a] * e1;
+			acc[27] += e0 * e0 + e1 * e1;
+		}
+		block_sum<28>(acc, s_red, s_out);
+		if (tid == 0)
+		{
+			int q = 0;
+			for (int a = 0; a < 6; ++a)
+				for (int b = a; b < 6; ++b)
+				{
+					s.JtJ[a * 6 + b] = acc[q];
+					s.JtJ[b * 6 + a] = acc[q];
+					++q;
+				}
+			for (int a = 0; a < 6; ++a)
+			{
+				s.JtErr[a] = acc[21 + a];
+				s.prev[a] = s.param[a];
+			}
+			lm_step(s);
+			if (s.iters == 0) s.prevErrNorm = sqrt(acc[27]);
+		}
+		__syncthreads();
+		// CHECK_ERR
+		for (;;)
+		{
+			if (tid == 0) rodrigues_v2m(s.param, s.R, nullptr);
+			__syncthreads();
+			double e[1] = {0};
+			for (int p = tid; p < m; p += blockDim.x)
+			{
+				double u, v;
+				project_point(s.R, s.param + 3, cam, X + 3 * list[p], u, v);
+				const double e0 = u - static_cast<double>(uv[2 * list[p]]), e1 = v - static_cast<double>(uv[2 * list[p] + 1]);
+				e[0] += e0 * e0 + e1 * e1;
+			}
+			block_sum<1>(e, s_red, s_out);
+			if (tid == 0)
+			{
+				const double errNorm = sqrt(e[0]);
+				s.cont = 0;
+				if (errNorm > s.prevErrNorm && ++s.lambdaLg10 <= 16)
+				{
+					lm_step(s);
+					s.cont = 1;
+				}
+				else
+				{
+					s.lambdaLg10 = max(s.lambdaLg10 - 1, -16);
+					double num = 0, den = 0;
+					for (int i = 0; i < 6; ++i)
+					{
+						num += (s.param[i] - s.prev[i]) * (s.param[i] - s.prev[i]);
+						den += s.prev[i] * s.prev[i];
+					}
+					if (++s.iters >= 20 || sqrt(num) < 1.1920928955078125e-07 * sqrt(den)) s.done = 1;
+					s.prevErrNorm = errNorm;
+				}
+			}
+			__syncthreads();
+			if (!s.cont) break;
+		}
+		if (s.done) break;
+	}
+}
+
+__global__ void __launch_bounds__(kVerifyThreads)
+pnp_ransac_kernel(const PnpArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int cap = a.cap;
+	double * h_rt = reinterpret_cast<double *>(smem_raw);                    // [kMaxRansacIters][6]
+	double * s_red = h_rt + kMaxRansacIters * 6;                             // [28*32]
+	double * s_out = s_red + 28 * 32;                                        // [32]
+	float * X = reinterpret_cast<float *>(s_out + 32);                       // [cap][3]
+	float * uv = X + static_cast<size_t>(cap) * 3;                           // [cap][2]
+	float * errs = uv + static_cast<size_t>(cap) * 2;                        // [cap]
+	int * cnt = reinterpret_cast<int *>(errs + cap);                         // [kMaxRansacIters]
+	uint16_t * sidx = reinterpret_cast<uint16_t *>(cnt + kMaxRansacIters);   // [kMaxRansacIters][6]
+	uint16_t * listA = sidx + kMaxRansacIters * 6;                           // [cap]
+	uint16_t * listB = listA + cap;                                          // [cap]
+	uint8_t * flag = reinterpret_cast<uint8_t *>(listB + cap);               // [cap]
+	__shared__ LmState lm;
+	__shared__ int s_best, s_iters_run, s_nA, s_nB, s_ctrl, s_sizes[64];
+	__shared__ float s_thr;
+
+	const int tid = threadIdx.x;
+	const int pair = blockIdx.x;
+	const int n = min(a.n_pts[pair], cap);
+	const size_t base = static_cast<size_t>(pair) * cap;
+	const CamK cam = a.cam;
+	const int iterations = min(max(a.iterations, 1), kMaxRansacIters);
+	const int min_inliers = max(a.min_inliers, 4);
+
+	if (tid < 3)
+	{
+		a.rvec[pair * 3 + tid] = 0;
+		a.tvec[pair * 3 + tid] = 0;
+	}
+	if (tid < 12) a.transform[pair * 12 + tid] = 0.f;
+	if (tid == 0)
+	{
+		a.n_inliers[pair] = 0;
+		a.iters_run[pair] = 0;
+		a.ok[pair] = 0;
+	}
+	// util3d::estimateMotion3DTo2D runs PnP only with >= Vis/MinInliers correspondences; RANSAC needs >= 6
+	if (n < a.min_inliers || n < 6) return;
+
+	for (int i = tid; i < n * 3; i += blockDim.x) X[i] = a.obj[base * 3 + i];
+	for (int i = tid; i < n * 2; i += blockDim.x) uv[i] = a.img[base * 2 + i];
+	if (tid == 0)
+	{
+		// RANSACPointSetRegistrator::getSubset with cv::RNG((uint64)-1): draws depend only on n
+		unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+		for (int it = 0; it < iterations; ++it)
+		{
+			for (int i = 0; i < 6;)
+			{
+				int idx_i;
+				for (;;)
+				{
+					state = static_cast<unsigned long long>(static_cast<unsigned>(state)) * 4164903690ull + static_cast<unsigned>(state >> 32);
+					idx_i = static_cast<int>(static_cast<unsigned>(state) % static_cast<unsigned>(n));
+					int j;
+					for (j = 0; j < i; ++j)
+						if (idx_i == sidx[it * 6 + j]) break;
+					if (j == i) break;
+				}
+				sidx[it * 6 + i] = static_cast<uint16_t>(idx_i);
+				++i;
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- every hypothesis in parallel: EPnP on its sample, then its inlier count ---------------
+	const float thr2 = static_cast<float>(static_cast<double>(a.reproj) * static_cast<double>(a.reproj));
+	for (int it = tid; it < iterations; it += blockDim.x)
+	{
+		int idx[6];
+		for (int k = 0; k < 6; ++k) idx[k] = (n == 6) ? k : sidx[it * 6 + k];
+		double rv[3], tv[3];
+		int c = -1;
+		if (solve_pnp_epnp6(X, uv, idx, cam, rv, tv))
+		{
+			double R[9];
+			rodrigues_v2m(rv, R, nullptr);
+			c = 0;
+			for (int i = 0; i < n; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
+			for (int k = 0; k < 3; ++k)
+			{
+				h_rt[it * 6 + k] = rv[k];
+				h_rt[it * 6 + 3 + k] = tv[k];
+			}
+		}
+		cnt[it] = c;
+	}
+	__syncthreads();
+
+	// ---- sequential bookkeeping of RANSACPointSetRegistrator::run (solvepnp.cpp:358-399) ---------
+	if (tid == 0)
+	{
+		int best = -1, maxGood = 0, it = 0;
+		if (n == 6)
+		{
+			if (cnt[0] >= 0) best = 0; // count == modelPoints: single model, every point an inlier
+		}
+		else
+		{
+			int niters = iterations;
+			for (it = 0; it < niters; ++it)
+			{
+				const int c = cnt[it];
+				if (c < 0) continue;
+				if (c > max(maxGood, 5))
+				{
+					best = it;
+					maxGood = c;
+					niters = ransac_update_num_iters(0.99, static_cast<double>(n - c) / n, 6, niters);
+				}
+			}
+		}
+		s_best = best;
+		s_iters_run = it;
+	}
+	__syncthreads();
+	const int best = s_best;
+	if (tid == 0) a.iters_run[pair] = s_iters_run;
+	if (best < 0) return; // rvec/tvec keep the (identity) guess
+
+	// ---- inliers of the best minimal-sample model ----------------------------------------------
+	if (tid < 6) lm.param[tid] = h_rt[best * 6 + tid];
+	__syncthreads();
+	if (tid == 0) rodrigues_v2m(lm.param, lm.R, nullptr);
+	__syncthreads();
+	for (int i = tid; i < n; i += blockDim.x)
+		flag[i] = (n == 6) ? 1 : (reproj_err(lm.R, lm.param + 3, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0);
+	__syncthreads();
+	if (tid < 32)
+	{
+		const int c = warp0_compact(flag, n, listA, listB /* scratch ranks */);
+		if (tid == 0) s_nA = c;
+	}
+	__syncthreads();
+	// listA = inliers (RANSAC).  From here on: prev = listA / new = listB as in util3d::solvePnPRansac.
+	uint16_t * prev = listA;
+	uint16_t * nw = listB;
+	int n_prev = s_nA, n_new = 0;
+	uint16_t * fin = prev; // list that ends up in `inliers`
+	int n_fin = n_prev;
+
+	if (n_prev >= min_inliers && a.refine_iterations > 0)
+	{
+		if (tid == 0)
+		{
+			s_thr = a.reproj;
+			s_ctrl = 0;
+		}
+		int refine_it = 0, n_sizes = 0;
+		bool inlier_changed = false;
+		__syncthreads();
+		for (;;) // do { ... } while (inlier_changed && ++refine_it < refineIterations)
+		{
+			bool leave = false;
+			lm_refine_block(X, uv, prev, n_prev, cam, lm, s_red, s_out);
+			if (tid == 0 && n_sizes < 64) s_sizes[n_sizes] = n_prev;
+			++n_sizes;
+			// computeReprojErrors under the refined model, threshold NOT squared (util3d_motion_estimation.cpp:829-837)
+			if (tid == 0) rodrigues_v2m(lm.param, lm.R, nullptr);
+			__syncthreads();
+			const float thr = s_thr;
+			for (int i = tid; i < n; i += blockDim.x)
+			{
+				const float e = reproj_err(lm.R, lm.param + 3, cam, X + 3 * i, uv + 2 * i);
+				errs[i] = e;
+				flag[i] = e <= thr ? 1 : 0;
+			}
+			__syncthreads();
+			if (tid < 32)
+			{
+				const int lane = tid;
+				int basec = 0;
+				for (int c0 = 0; c0 < n; c0 += 32)
+				{
+					const int i = c0 + lane;
+					const bool f = i < n && flag[i] != 0;
+					const uint32_t mk = __ballot_sync(0xFFFFFFFFu, f);
+					if (f) nw[basec + __popc(mk & ((1u << lane) - 1u))] = static_cast<uint16_t>(i);
+					basec += __popc(mk);
+				}
+				if (lane == 0) s_nB = basec;
+			}
+			__syncthreads();
+			n_new = s_nB;
+			if (n_new < min_inliers)
+			{
+				// "continue" of a do-while: falls to the loop condition with inlier_changed unchanged
+				++refine_it;
+				if (refine_it >= a.refine_iterations) leave = true;
+			}
+			else
+			{
+				if (tid == 0)
+				{
+					// uMean / uVariance over the new inliers' errors, sequential float arithmetic (UMath.h:419-431, :512-526)
+					float mean = 0.f;
+					for (int k = 0; k < n_new; ++k) mean += errs[nw[k]];
+					mean /= static_cast<float>(n_new);
+					float variance = 0.f;
+					if (n_new > 1)
+					{
+						float sum = 0.f;
+						for (int k = 0; k < n_new; ++k) sum += (errs[nw[k]] - mean) * (errs[nw[k]] - mean);
+						variance = sum / static_cast<float>(n_new - 1);
+					}
+					s_thr = fminf(a.reproj, a.refine_sigma * static_cast<float>(sqrt(static_cast<double>(variance))));
+					int changed = 0;
+					if (n_new != n_prev) changed = 1;
+					else
+						for (int k = 0; k < n_new; ++k)
+							if (prev[k] != nw[k])
+							{
+								changed = 1;
+								break;
+							}
+					s_ctrl = changed;
+				}
+				__syncthreads();
+				// std::swap(prev_inliers, new_inliers)
+				{
+					uint16_t * t = prev;
+					prev = nw;
+					nw = t;
+					const int tn = n_prev;
+					n_prev = n_new;
+					n_new = tn;
+				}
+				inlier_changed = s_ctrl != 0;
+				if (n_new != n_prev && n_sizes >= min_inliers && n_sizes >= 4 && n_sizes <= 64 &&
+				    s_sizes[n_sizes - 1] == s_sizes[n_sizes - 3] && s_sizes[n_sizes - 2] == s_sizes[n_sizes - 4])
+					leave = true; // oscillating
+				__syncthreads();
+			}
+			if (leave) break;
+			if (!(inlier_changed && ++refine_it < a.refine_iterations)) break;
+		}
+		// std::swap(inliers, new_inliers); rvec/tvec = refined model
+		fin = nw;
+		n_fin = n_new;
+	}
+	__syncthreads();
+
+	if (tid < 3)
+	{
+		a.rvec[pair * 3 + tid] = lm.param[tid];
+		a.tvec[pair * 3 + tid] = lm.param[3 + tid];
+	}
+	for (int k = tid; k < n_fin; k += blockDim.x) a.inliers[base + k] = fin[k];
+	if (tid == 0)
+	{
+		a.n_inliers[pair] = n_fin;
+		const int accepted = n_fin >= a.min_inliers ? 1 : 0;
+		a.ok[pair] = accepted;
+		if (accepted)
+		{
+			double R[9];
+			rodrigues_v2m(lm.param, R, nullptr);
+			float Rf[9], tf[3];
+			for (int i = 0; i < 9; ++i) Rf[i] = static_cast<float>(R[i]);
+			for (int i = 0; i < 3; ++i) tf[i] = static_cast<float>(lm.param[3 + i]);
+			float * T = a.transform + pair * 12;
+			for (int i = 0; i < 3; ++i)
+			{
+				for (int j = 0; j < 3; ++j) T[4 * i + j] = Rf[3 * j + i];
+				T[4 * i + 3] = -(Rf[0 + i] * tf[0] + Rf[3 + i] * tf[1] + Rf[6 + i] * tf[2]);
+			}
+		}
+	}
+}
+
+// out[pair][k] = values[pair][index[pair][k]] for k < count[pair]  (inlier word ids = matches[inliers[k]])
+__global__ void gather_by_index_kernel(const int * __restrict__ values, const int * __restrict__ index, const int * __restrict__ count,
+                                       int cap, int * __restrict__ out)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const int pair = blockIdx.y;
+	if (k >= cap) return;
+	const size_t base = static_cast<size_t>(pair) * cap;
+	out[base + k] = k < count[pair] ? values[base + index[base + k]] : 0;
+}
+
+} // namespace lcd
