@@ -8,7 +8,10 @@
 
 namespace orc_pnp {
 
-// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, n <= 12).
+// Cyclic two-sided Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, n <= 12).
+// Rotations annihilate a_pq exactly; a pair is skipped once |a_pq| <= eps*sqrt(|a_pp a_qq|) and the
+// iteration stops after a sweep without rotations (at most 30 sweeps).  The CUDA kernels use the same
+// sequence of operations (rtabmap_b200/csrc/pnp_device.cuh, sym_eigen).
 // On return: w[k] eigenvalues in DESCENDING order, vt row k = the matching unit eigenvector
 // (the layout cvSVD(A, W, Ut, 0, CV_SVD_U_T) gives for a symmetric positive semi-definite A).
 inline void jacobi_eigen_desc(const double * a_in, int n, double * w, double * vt)
@@ -17,32 +20,33 @@ inline void jacobi_eigen_desc(const double * a_in, int n, double * w, double * v
 	memcpy(a, a_in, sizeof(double) * n * n);
 	for (int i = 0; i < n; ++i)
 		for (int j = 0; j < n; ++j) v[i * n + j] = i == j ? 1.0 : 0.0;
-	for (int sweep = 0; sweep < 64; ++sweep)
+	for (int sweep = 0; sweep < 30; ++sweep)
 	{
-		double off = 0.0;
-		for (int i = 0; i < n; ++i)
-			for (int j = i + 1; j < n; ++j) off += a[i * n + j] * a[i * n + j];
-		if (off < 1e-300) break;
+		bool rotated = false;
 		for (int p = 0; p < n - 1; ++p)
 		{
 			for (int q = p + 1; q < n; ++q)
 			{
 				const double apq = a[p * n + q];
-				if (std::fabs(apq) < 1e-300) continue;
-				const double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+				const double app = a[p * n + p], aqq = a[q * n + q];
+				if (std::fabs(apq) <= 2.220446049250313e-16 * std::sqrt(std::fabs(app * aqq))) continue;
+				rotated = true;
+				const double theta = (aqq - app) / (2.0 * apq);
 				const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
 				const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+				a[p * n + p] = app - t * apq;
+				a[q * n + q] = aqq + t * apq;
+				a[p * n + q] = 0.0;
+				a[q * n + p] = 0.0;
 				for (int k = 0; k < n; ++k)
 				{
+					if (k == p || k == q) continue;
 					const double akp = a[k * n + p], akq = a[k * n + q];
-					a[k * n + p] = c * akp - s * akq;
-					a[k * n + q] = s * akp + c * akq;
-				}
-				for (int k = 0; k < n; ++k)
-				{
-					const double apk = a[p * n + k], aqk = a[q * n + k];
-					a[p * n + k] = c * apk - s * aqk;
-					a[q * n + k] = s * apk + c * aqk;
+					const double nkp = c * akp - s * akq, nkq = s * akp + c * akq;
+					a[k * n + p] = nkp;
+					a[p * n + k] = nkp;
+					a[k * n + q] = nkq;
+					a[q * n + k] = nkq;
 				}
 				for (int k = 0; k < n; ++k)
 				{
@@ -52,10 +56,19 @@ inline void jacobi_eigen_desc(const double * a_in, int n, double * w, double * v
 				}
 			}
 		}
+		if (!rotated) break;
 	}
 	int order[12];
 	for (int i = 0; i < n; ++i) order[i] = i;
-	std::sort(order, order + n, [&](int x, int y) { return a[x * n + x] > a[y * n + y]; });
+	for (int i = 0; i < n - 1; ++i) // selection sort, descending, stable
+	{
+		int j = i;
+		for (int k = i + 1; k < n; ++k)
+			if (a[order[k] * n + order[k]] > a[order[j] * n + order[j]]) j = k;
+		const int t = order[j];
+		for (int k = j; k > i; --k) order[k] = order[k - 1];
+		order[i] = t;
+	}
 	for (int k = 0; k < n; ++k)
 	{
 		w[k] = a[order[k] * n + order[k]];

@@ -106,38 +106,42 @@ __device__ inline void svd_rows_jacobi3(double * At, double * W)
 }
 
 // Cyclic two-sided Jacobi eigen-decomposition of a symmetric N x N matrix held in a[] (destroyed).
-// v[] receives the eigenvectors as COLUMNS; ord[] the column order of descending eigenvalue.
+// Rotations annihilate a_pq exactly; a pair is skipped once |a_pq| <= eps*sqrt(|a_pp a_qq|) and the
+// iteration stops after a sweep without rotations (<= 30 sweeps) — the same operation sequence as the
+// CPU oracle's jacobi_eigen_desc.  v[] receives the eigenvectors as COLUMNS; ord[] the column order of
+// descending eigenvalue.
 template <int N>
 __device__ inline void sym_eigen(double * a, double * v, int * ord)
 {
 	for (int i = 0; i < N; ++i)
 		for (int j = 0; j < N; ++j) v[i * N + j] = i == j ? 1.0 : 0.0;
-	for (int sweep = 0; sweep < 64; ++sweep)
+	for (int sweep = 0; sweep < 30; ++sweep)
 	{
-		double off = 0.0;
-		for (int i = 0; i < N; ++i)
-			for (int j = i + 1; j < N; ++j) off += a[i * N + j] * a[i * N + j];
-		if (off < 1e-300) break;
+		bool rotated = false;
 		for (int p = 0; p < N - 1; ++p)
 		{
 			for (int q = p + 1; q < N; ++q)
 			{
 				const double apq = a[p * N + q];
-				if (fabs(apq) < 1e-300) continue;
-				const double theta = (a[q * N + q] - a[p * N + p]) / (2.0 * apq);
+				const double app = a[p * N + p], aqq = a[q * N + q];
+				if (fabs(apq) <= 2.220446049250313e-16 * sqrt(fabs(app * aqq))) continue;
+				rotated = true;
+				const double theta = (aqq - app) / (2.0 * apq);
 				const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
 				const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+				a[p * N + p] = app - t * apq;
+				a[q * N + q] = aqq + t * apq;
+				a[p * N + q] = 0.0;
+				a[q * N + p] = 0.0;
 				for (int k = 0; k < N; ++k)
 				{
+					if (k == p || k == q) continue;
 					const double akp = a[k * N + p], akq = a[k * N + q];
-					a[k * N + p] = c * akp - s * akq;
-					a[k * N + q] = s * akp + c * akq;
-				}
-				for (int k = 0; k < N; ++k)
-				{
-					const double apk = a[p * N + k], aqk = a[q * N + k];
-					a[p * N + k] = c * apk - s * aqk;
-					a[q * N + k] = s * apk + c * aqk;
+					const double nkp = c * akp - s * akq, nkq = s * akp + c * akq;
+					a[k * N + p] = nkp;
+					a[p * N + k] = nkp;
+					a[k * N + q] = nkq;
+					a[q * N + k] = nkq;
 				}
 				for (int k = 0; k < N; ++k)
 				{
@@ -147,6 +151,7 @@ __device__ inline void sym_eigen(double * a, double * v, int * ord)
 				}
 			}
 		}
+		if (!rotated) break;
 	}
 	for (int i = 0; i < N; ++i) ord[i] = i;
 	for (int i = 0; i < N - 1; ++i) // selection sort, descending, stable

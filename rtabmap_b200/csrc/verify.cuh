@@ -20,7 +20,7 @@
 
 namespace lcd {
 
-constexpr int kVerifyThreads = 320; // >= Vis/Iterations hypotheses per pair, multiple of 32
+constexpr int kVerifyThreads = 128; // hypotheses evaluated per chunk = threads of the CTA
 constexpr int kMaxRansacIters = 320;
 
 struct MatchArgs
@@ -214,7 +214,7 @@ struct PnpArgs
 
 __host__ __device__ inline size_t pnp_smem_bytes(int cap)
 {
-	return static_cast<size_t>(cap) * (12 + 8 + 4 + 2 + 2 + 1) + kMaxRansacIters * (6 * 2 + 4 + 6 * 8) + (28 * 32 + 32) * 8 + 1024;
+	return static_cast<size_t>(cap) * (12 + 8 + 4 + 2 + 2 + 1) + kMaxRansacIters * (6 * 2) + kVerifyThreads * (4 + 6 * 8) + (28 * 32 + 32) * 8 + 1024;
 }
 
 __device__ inline int ransac_update_num_iters(double p, double ep, int modelPoints, int maxIters)
@@ -413,19 +413,19 @@ pnp_ransac_kernel(const PnpArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int cap = a.cap;
-	double * h_rt = reinterpret_cast<double *>(smem_raw);                    // [kMaxRansacIters][6]
-	double * s_red = h_rt + kMaxRansacIters * 6;                             // [28*32]
+	double * h_rt = reinterpret_cast<double *>(smem_raw);                    // [kVerifyThreads][6] poses of the current chunk
+	double * s_red = h_rt + kVerifyThreads * 6;                              // [28*32]
 	double * s_out = s_red + 28 * 32;                                        // [32]
 	float * X = reinterpret_cast<float *>(s_out + 32);                       // [cap][3]
 	float * uv = X + static_cast<size_t>(cap) * 3;                           // [cap][2]
 	float * errs = uv + static_cast<size_t>(cap) * 2;                        // [cap]
-	int * cnt = reinterpret_cast<int *>(errs + cap);                         // [kMaxRansacIters]
-	uint16_t * sidx = reinterpret_cast<uint16_t *>(cnt + kMaxRansacIters);   // [kMaxRansacIters][6]
+	int * cnt = reinterpret_cast<int *>(errs + cap);                         // [kVerifyThreads]
+	uint16_t * sidx = reinterpret_cast<uint16_t *>(cnt + kVerifyThreads);    // [kMaxRansacIters][6]
 	uint16_t * listA = sidx + kMaxRansacIters * 6;                           // [cap]
 	uint16_t * listB = listA + cap;                                          // [cap]
 	uint8_t * flag = reinterpret_cast<uint8_t *>(listB + cap);               // [cap]
 	__shared__ LmState lm;
-	__shared__ int s_best, s_iters_run, s_nA, s_nB, s_ctrl, s_sizes[64];
+	__shared__ int s_best, s_nA, s_nB, s_ctrl, s_sizes[64];
 	__shared__ float s_thr;
 
 	const int tid = threadIdx.x;
@@ -478,64 +478,82 @@ pnp_ransac_kernel(const PnpArgs a)
 	}
 	__syncthreads();
 
-	// ---- every hypothesis in parallel: EPnP on its sample, then its inlier count ---------------
+	// ---- hypotheses in parallel, a chunk of blockDim.x at a time: EPnP on the sample, then its inlier
+	//      count; thread 0 then replays the sequential bookkeeping of RANSACPointSetRegistrator::run
+	//      (solvepnp.cpp:358-399) over the chunk and decides whether another chunk is needed.
 	const float thr2 = static_cast<float>(static_cast<double>(a.reproj) * static_cast<double>(a.reproj));
-	for (int it = tid; it < iterations; it += blockDim.x)
-	{
-		int idx[6];
-		for (int k = 0; k < 6; ++k) idx[k] = (n == 6) ? k : sidx[it * 6 + k];
-		double rv[3], tv[3];
-		int c = -1;
-		if (solve_pnp_epnp6(X, uv, idx, cam, rv, tv))
-		{
-			double R[9];
-			rodrigues_v2m(rv, R, nullptr);
-			c = 0;
-			for (int i = 0; i < n; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
-			for (int k = 0; k < 3; ++k)
-			{
-				h_rt[it * 6 + k] = rv[k];
-				h_rt[it * 6 + 3 + k] = tv[k];
-			}
-		}
-		cnt[it] = c;
-	}
-	__syncthreads();
-
-	// ---- sequential bookkeeping of RANSACPointSetRegistrator::run (solvepnp.cpp:358-399) ---------
+	__shared__ int s_niters, s_maxgood, s_it;
 	if (tid == 0)
 	{
-		int best = -1, maxGood = 0, it = 0;
-		if (n == 6)
-		{
-			if (cnt[0] >= 0) best = 0; // count == modelPoints: single model, every point an inlier
-		}
-		else
-		{
-			int niters = iterations;
-			for (it = 0; it < niters; ++it)
-			{
-				const int c = cnt[it];
-				if (c < 0) continue;
-				if (c > max(maxGood, 5))
-				{
-					best = it;
-					maxGood = c;
-					niters = ransac_update_num_iters(0.99, static_cast<double>(n - c) / n, 6, niters);
-				}
-			}
-		}
-		s_best = best;
-		s_iters_run = it;
+		s_best = -1;
+		s_maxgood = 0;
+		s_it = 0;
+		s_niters = (n == 6) ? 1 : iterations;
 	}
 	__syncthreads();
+	for (int chunk0 = 0; chunk0 < s_niters; chunk0 += blockDim.x)
+	{
+		const int it = chunk0 + tid;
+		if (it < s_niters)
+		{
+			int idx[6];
+			for (int k = 0; k < 6; ++k) idx[k] = (n == 6) ? k : sidx[it * 6 + k];
+			double rv[3], tv[3];
+			int c = -1;
+			if (solve_pnp_epnp6(X, uv, idx, cam, rv, tv))
+			{
+				double R[9];
+				rodrigues_v2m(rv, R, nullptr);
+				c = 0;
+				for (int i = 0; i < n; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
+				for (int k = 0; k < 3; ++k)
+				{
+					h_rt[tid * 6 + k] = rv[k];
+					h_rt[tid * 6 + 3 + k] = tv[k];
+				}
+			}
+			cnt[tid] = c;
+		}
+		__syncthreads();
+		if (tid == 0)
+		{
+			int it0 = s_it, niters = s_niters, maxGood = s_maxgood;
+			const int chunk_end = chunk0 + static_cast<int>(blockDim.x);
+			if (n == 6)
+			{
+				if (cnt[0] >= 0)
+				{
+					s_best = 0;
+					for (int k = 0; k < 6; ++k) lm.param[k] = h_rt[k];
+				}
+				it0 = 0;
+			}
+			else
+			{
+				for (; it0 < niters && it0 < chunk_end; ++it0)
+				{
+					const int c = cnt[it0 - chunk0];
+					if (c < 0) continue;
+					if (c > max(maxGood, 5))
+					{
+						s_best = it0;
+						maxGood = c;
+						for (int k = 0; k < 6; ++k) lm.param[k] = h_rt[(it0 - chunk0) * 6 + k];
+						niters = ransac_update_num_iters(0.99, static_cast<double>(n - c) / n, 6, niters);
+					}
+				}
+			}
+			s_it = it0;
+			s_niters = niters;
+			s_maxgood = maxGood;
+		}
+		__syncthreads();
+	}
 	const int best = s_best;
-	if (tid == 0) a.iters_run[pair] = s_iters_run;
+	if (tid == 0) a.iters_run[pair] = s_it;
 	if (best < 0) return; // rvec/tvec keep the (identity) guess
 
 	// ---- inliers of the best minimal-sample model ----------------------------------------------
-	if (tid < 6) lm.param[tid] = h_rt[best * 6 + tid];
-	__syncthreads();
 	if (tid == 0) rodrigues_v2m(lm.param, lm.R, nullptr);
 	__syncthreads();
 	for (int i = tid; i < n; i += blockDim.x)
