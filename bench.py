@@ -7,13 +7,14 @@
 
 One "step" = one batch of B independent localisation queries (frames) through the hot path that is
 built so far (see `config.stages`): each frame = F=1000 ORB-sized binary descriptors quantised against
-the W=49 152-word dictionary (exact 2-NN + NNDR + intra-frame new words, VWDictionary::addNewWords)
-and scored by TF-IDF over the S=10 000-signature inverted index (Memory::computeLikelihood).
+the W=49 152-word dictionary (exact 2-NN + NNDR + intra-frame new words, VWDictionary::addNewWords),
+scored by TF-IDF over the S=10 000-signature inverted index (Memory::computeLikelihood), and the top
+hypothesis verified geometrically (Memory::computeTransform: descriptor matching + PnP RANSAC + refinement).
 Workload = BASELINE.json configs[1] (640x480 stream, ORB 1000 kp/frame, 49k words, 10k signatures).
 
 `value`  : frames/s with the descriptors already resident in HBM (CUDA events on the engine stream).
-`e2e`    : frames/s through the host-buffer C-ABI call lcd_localize_batch (pinned host descriptors in,
-           word ids + likelihood vectors out, H2D/D2H inside the timed region).
+`e2e`    : frames/s through the host-buffer C-ABI call lcd_process_batch (pinned host descriptors + keypoints in,
+           word ids + likelihood vectors + verified poses out, H2D/D2H inside the timed region).
 `roofline`: the dictionary-NN kernel (knn2_hamming_kernel), timed live with CUDA events on its stream.
 `cpu_baseline`: the oracle port of the reference algorithm on the host cores, bounded sample.
 """
@@ -40,10 +41,11 @@ S_SIGS = 10000
 F_FEATS = 1000
 DESC_BYTES = 32
 NNDR = 0.8
+KCAM = (525.0, 525.0, 320.0, 240.0)
 METRIC = "loop-closure queries/sec"
 UNIT = "queries/s"
-STAGES_BUILT = ["quantise(knn2+nndr+new-words)", "score(tf-idf)"]
-STAGES_MISSING = ["detect(orb)", "verify(match+pnp-ransac)"]
+STAGES_BUILT = ["quantise(knn2+nndr+new-words)", "score(tf-idf)", "verify(top-1 hypothesis: descriptor matching + pnp-ransac + refinement)"]
+STAGES_MISSING = ["detect(orb)"]
 
 
 def log(*a):
@@ -56,8 +58,9 @@ def make_workload(batch: int, n_batches: int):
     vocab = synth.make_binary_vocabulary(W_WORDS, DESC_BYTES, seed=1)
     ids = np.arange(1, W_WORDS + 1, dtype=np.int32)
     smap = synth.make_map(ids, S_SIGS, F_FEATS, seed=2)
-    q, places = synth.make_query_frames(vocab, ids, smap, batch * n_batches, F_FEATS, seed=3)
-    return vocab, ids, smap, q, places
+    store = synth.make_signature_store(vocab, ids, smap, seed=4)
+    q, uv, places, poses = synth.make_query_frames_geo(store, smap, batch * n_batches, seed=3)
+    return vocab, ids, smap, store, q, uv, places
 
 
 def peaks():
@@ -116,8 +119,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------- CPU (reference) arm
-def cpu_reference_rate(vocab, ids, smap, frames, n_frames: int, threads: int):
-    """Oracle port of addNewWords + computeLikelihood (with roll-back semantics) over `n_frames` frames."""
+def cpu_reference_rate(vocab, ids, smap, store, frames, uv, n_frames: int, threads: int):
+    """Oracle port of addNewWords + computeLikelihood (roll-back semantics) + computeTransform of the top hypothesis."""
     from oracle import oracle_py as orc
 
     o = orc.OracleDictionary(0, DESC_BYTES, True, NNDR, True)
@@ -127,7 +130,11 @@ def cpu_reference_rate(vocab, ids, smap, frames, n_frames: int, threads: int):
     o.load_csr(smap.word_ids, smap.row_ptr, smap.sig, smap.cnt)
 
     def one(b):
-        return o.localize_ro(frames[b * F_FEATS:(b + 1) * F_FEATS], smap.sig_ids, S_SIGS + 1)
+        fq = frames[b * F_FEATS:(b + 1) * F_FEATS]
+        w, l = o.localize_ro(fq, smap.sig_ids, S_SIGS + 1)
+        h = int(np.argmax(l))
+        v = orc.verify_pair(store.desc[h], store.xyz[h], fq, uv[b * F_FEATS:(b + 1) * F_FEATS], KCAM)
+        return w, l, int(smap.sig_ids[h]), v
 
     t0 = time.perf_counter()
     if threads <= 1:
@@ -145,13 +152,13 @@ def run_reference(args):
         return 0
     threads = max(1, min(os.cpu_count() or 1, args.ref_threads or (os.cpu_count() or 1)))
     per_step = threads  # one frame per thread and step: a bounded sample of the workload
-    vocab, ids, smap, q, places = make_workload(per_step, 1)
+    vocab, ids, smap, store, q, uv, places = make_workload(per_step, 1)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_rate(vocab, ids, smap, q, min(per_step, 2), threads)
+        cpu_reference_rate(vocab, ids, smap, store, q, uv, min(per_step, 2), threads)
     steps = max(1, min(args.steps, 3))
     times = []
     for _ in range(steps):
-        rate, dt, _ = cpu_reference_rate(vocab, ids, smap, q, per_step, threads)
+        rate, dt, _ = cpu_reference_rate(vocab, ids, smap, store, q, uv, per_step, threads)
         times.append(dt)
     total = float(sum(times))
     value = per_step * steps / total
@@ -161,7 +168,8 @@ def run_reference(args):
         "data": "synthetic", "config": workload_config(per_step, "cpu"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{per_step} frames/step x {steps} steps of the same workload, oracle port of VWDictionary::addNewWords + "
-                                   f"Memory::computeLikelihood (std::map structures as in the reference), frames spread over {threads} threads"},
+                                   f"Memory::computeLikelihood (std::map structures as in the reference) + Memory::computeTransform of the top hypothesis, "
+                                   f"frames spread over {threads} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -199,7 +207,7 @@ def run_b200(args):
 
     B = args.batch
     n_pool = 4
-    vocab, ids, smap, q_all, places = make_workload(B, n_pool)
+    vocab, ids, smap, store, q_all, uv_all, places = make_workload(B, n_pool)
     r0, r1 = sharding.shard_rows(W_WORDS, world, rank)
     eng = Engine(device=local, desc_dim=DESC_BYTES, max_words=W_WORDS, max_signatures=S_SIGS + 2, max_queries=F_FEATS, max_batch=B)
     eng.add_words(ids[r0:r1], vocab[r0:r1])
@@ -212,11 +220,16 @@ def run_b200(args):
         eng.set_ni(smap.sig_ids, smap.ni)
     else:
         eng.load_csr(smap.word_ids, smap.row_ptr, smap.sig, smap.cnt)
+    for s0 in range(0, S_SIGS, 1000):  # signature store (descriptors + 3-D points of every node), replicated on every rank
+        eng.sig_add_batch(smap.sig_ids[s0:s0 + 1000], store.desc[s0:s0 + 1000], store.xyz[s0:s0 + 1000])
+    vp = Engine.verify_params(KCAM)
 
     ext = torch.cuda.ExternalStream(eng.stream, device=local)
     torch.cuda.set_stream(ext)
     nq = B * F_FEATS
     d_q = [torch.from_numpy(q_all[k * nq:(k + 1) * nq]).cuda() for k in range(n_pool)]
+    d_uv = [torch.from_numpy(uv_all[k * nq:(k + 1) * nq]).cuda() for k in range(n_pool)]
+    h_uv = [torch.from_numpy(uv_all[k * nq:(k + 1) * nq]).pin_memory() for k in range(n_pool)]
     d_sig = torch.from_numpy(smap.sig_ids).cuda()
     d_words = torch.zeros(nq, dtype=torch.int32, device="cuda")
     d_like = torch.zeros(B * S_SIGS, dtype=torch.float32, device="cuda")
@@ -233,9 +246,10 @@ def run_b200(args):
 
     def step_dev(k):
         dq = d_q[k % n_pool]
+        du = d_uv[k % n_pool]
         if world == 1:
-            eng.localize_batch_dev(dq.data_ptr(), B, F_FEATS, d_sig.data_ptr(), S_SIGS, S_SIGS + 1, d_words.data_ptr(), d_like.data_ptr(),
-                                   True, NNDR, True)
+            eng.process_batch_dev(dq.data_ptr(), du.data_ptr(), B, F_FEATS, d_sig.data_ptr(), S_SIGS, S_SIGS + 1, vp, d_words.data_ptr(),
+                                  d_like.data_ptr(), True, NNDR, True)
         else:
             eng.shard_knn2_keys_dev(dq.data_ptr(), nq, d_keys.data_ptr())
             dist.all_gather_into_tensor(d_keys_all, d_keys)
@@ -243,23 +257,36 @@ def run_b200(args):
                                         d_sig.data_ptr(), S_SIGS, S_SIGS + 1, d_words.data_ptr(), d_scores.data_ptr(), True, NNDR, True)
             dist.all_reduce(d_scores, op=dist.ReduceOp.SUM)
             eng.shard_finalize_dev(d_scores.data_ptr(), B * S_SIGS, d_like.data_ptr())
+            # every rank verifies its share of the frames against the replicated signature store
+            eng.verify_top_dev(dq.data_ptr() + f0 * F_FEATS * DESC_BYTES, du.data_ptr() + f0 * F_FEATS * 8, f1 - f0, F_FEATS,
+                               d_like.data_ptr() + f0 * S_SIGS * 4, d_sig.data_ptr(), S_SIGS, vp)
 
     def step_host(k):
         hq = h_q[k % n_pool]
+        hu = h_uv[k % n_pool]
         if world == 1:
-            eng.localize_batch(hq.numpy(), B, h_sig.numpy(), S_SIGS + 1, True, NNDR, True, out_words=h_words.numpy(), out_like=h_like.numpy())
+            _, _, hyp, res = eng.process_batch(hq.numpy(), hu.numpy(), B, h_sig.numpy(), S_SIGS + 1, vp, True, NNDR, True,
+                                               out_words=h_words.numpy(), out_like=h_like.numpy())
+            return hyp, res
         else:
             dq = d_q[0]
+            du = d_uv[0]
             dq.copy_(hq, non_blocking=True)
+            du.copy_(hu, non_blocking=True)
             eng.shard_knn2_keys_dev(dq.data_ptr(), nq, d_keys.data_ptr())
             dist.all_gather_into_tensor(d_keys_all, d_keys)
             eng.shard_resolve_score_dev(dq.data_ptr(), B, F_FEATS, d_keys_all.data_ptr(), world, d_rowids.data_ptr(), W_WORDS, W_WORDS,
                                         d_sig.data_ptr(), S_SIGS, S_SIGS + 1, d_words.data_ptr(), d_scores.data_ptr(), True, NNDR, True)
             dist.all_reduce(d_scores, op=dist.ReduceOp.SUM)
             eng.shard_finalize_dev(d_scores.data_ptr(), B * S_SIGS, d_like.data_ptr())
+            eng.verify_top_dev(dq.data_ptr() + f0 * F_FEATS * DESC_BYTES, du.data_ptr() + f0 * F_FEATS * 8, f1 - f0, F_FEATS,
+                               d_like.data_ptr() + f0 * S_SIGS * 4, d_sig.data_ptr(), S_SIGS, vp)
             h_words.view(-1).copy_(d_words, non_blocking=True)
             h_like.view(-1).copy_(d_like, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            return eng.process_fetch(f1 - f0)
+
+    f0, f1 = sharding.shard_rows(B, world, rank)  # frames this rank verifies
 
     def barrier():
         if world > 1:
@@ -289,6 +316,8 @@ def run_b200(args):
     nn_ms, nn_launches = eng.profile_read(0)
     res_ms, _ = eng.profile_read(1)
     sc_ms, _ = eng.profile_read(2)
+    mt_ms, _ = eng.profile_read(3)
+    pnp_ms, _ = eng.profile_read(4)
     eng.profile_enable(False)
     if world > 1:
         t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -301,6 +330,9 @@ def run_b200(args):
     last_pool = (args.steps - 1) % n_pool
     best = d_like.view(B, S_SIGS).argmax(dim=1).cpu().numpy()
     hit = float(np.mean(smap.sig_ids[best] == places[last_pool * B:(last_pool + 1) * B]))
+    hyp_d, res_d = eng.process_fetch(f1 - f0)
+    verified = float(np.mean([r["ok"] for r in res_d]))
+    assert np.array_equal(hyp_d, places[last_pool * B + f0:last_pool * B + f1]), "verified hypothesis is not the revisited place"
 
     # ---- end-to-end timing through the host-buffer C ABI ------------------------------------
     for k in range(min(args.warmup, 3)):
@@ -311,7 +343,7 @@ def run_b200(args):
         flush.fill_(k & 0xFF)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        step_host(k)
+        hyp_h, res_h = step_host(k)
         e2e_s += time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -321,6 +353,7 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = B * args.steps / e2e_s
     e2e_hit = float(np.mean(smap.sig_ids[h_like.numpy().argmax(axis=1)] == places[last_pool * B:(last_pool + 1) * B]))
+    e2e_verified = float(np.mean([r["ok"] for r in res_h]))
 
     if rank != 0:
         if world > 1:
@@ -351,33 +384,36 @@ def run_b200(args):
         "pairs_per_s": pairs / nn_avg_s if nn_avg_s > 0 else 0.0,
         "popc_per_s": pairs * popc_per_pair / nn_avg_s if nn_avg_s > 0 else 0.0, "popc_peak_per_s": popc_peak,
         "popc_frac": (pairs * popc_per_pair / nn_avg_s) / popc_peak if nn_avg_s > 0 else 0.0,
-        "step_share": {"nn_ms": nn_ms / args.steps, "resolve_ms": res_ms / args.steps, "score_ms": sc_ms / args.steps, "step_ms": dev_ms / args.steps},
+        "step_share": {"nn_ms": nn_ms / args.steps, "resolve_ms": res_ms / args.steps, "score_ms": sc_ms / args.steps, "match_ms": mt_ms / args.steps, "pnp_ms": pnp_ms / args.steps, "step_ms": dev_ms / args.steps},
     }
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = max(1, min(os.cpu_count() or 1, 32))
         n_cpu = threads
-        rate, dt, res = cpu_reference_rate(vocab, ids, smap, q_all, n_cpu, threads)
+        rate, dt, res = cpu_reference_rate(vocab, ids, smap, store, q_all, uv_all, n_cpu, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{n_cpu} frames of the same workload ({dt:.1f} s wall), oracle port (std::map inverted index, scalar popcount NN), "
+               "sample": f"{n_cpu} frames of the same workload ({dt:.1f} s wall), oracle port (std::map inverted index, scalar popcount NN, restated EPnP/RANSAC), "
                          f"{threads} threads, one frame per thread"}
         # cross-check while we are here: first frames of pool 0 against the GPU result
-        eng.localize_batch(q_all[:F_FEATS * min(2, n_cpu)], min(2, n_cpu), smap.sig_ids, S_SIGS + 1, True, NNDR, True,
-                           out_words=h_words.numpy()[:min(2, n_cpu)], out_like=h_like.numpy()[:min(2, n_cpu)])
-        for b in range(min(2, n_cpu)):
+        nchk = min(2, n_cpu)
+        _, _, hyp_c, res_c = eng.process_batch(q_all[:F_FEATS * nchk], uv_all[:F_FEATS * nchk], nchk, smap.sig_ids, S_SIGS + 1, vp, True, NNDR, True,
+                                               out_words=h_words.numpy()[:nchk], out_like=h_like.numpy()[:nchk])
+        for b in range(nchk):
             assert np.array_equal(res[b][0], h_words.numpy()[b]), "GPU/oracle word ids differ"
             assert np.allclose(res[b][1], h_like.numpy()[b], atol=1e-4, rtol=1e-4), "GPU/oracle likelihood differ"
+            assert res[b][2] == hyp_c[b] and res[b][3]["ok"] == res_c[b]["ok"] and len(res[b][3]["inliers"]) == res_c[b]["n_inliers"]
+            assert np.allclose(res[b][3]["rvec"], res_c[b]["rvec"], atol=1e-4) and np.allclose(res[b][3]["tvec"], res_c[b]["tvec"], atol=1e-4)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": dict(workload_config(B, "gpu"), parallelism=("single GPU" if world == 1 else f"word-range shards x{world}: all-gather(top-2 keys) + all-reduce(int64 scores)")),
         "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nq * DESC_BYTES + S_SIGS * 4),
-                "d2h_bytes_per_step": int(nq * 4 + B * S_SIGS * 4), "api": "lcd_localize_batch (host buffers)" if world == 1 else "sharded *_dev calls + pinned copies",
-                "top1_place_hit_rate": e2e_hit},
-        "roofline": roofline, "cpu_baseline": cpu, "top1_place_hit_rate": hit, "wall_s_timed_region": t_wall,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nq * DESC_BYTES + nq * 8 + S_SIGS * 4),
+                "d2h_bytes_per_step": int(nq * 4 + B * S_SIGS * 4 + B * (4 + 124)), "api": "lcd_process_batch (host buffers)" if world == 1 else "sharded *_dev calls + pinned copies",
+                "top1_place_hit_rate": e2e_hit, "verified_rate": e2e_verified},
+        "roofline": roofline, "cpu_baseline": cpu, "top1_place_hit_rate": hit, "verified_rate": verified, "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -388,7 +424,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per step")

@@ -206,6 +206,40 @@ int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_fro
                      const lcd_verify_params * params, lcd_verify_result * results, int * match_ids,
                      int * inlier_ids);
 
+/* ---- signature store + fused query ----------------------------------------------------------
+ * The per-node data Memory keeps for verification (Signature::getWordsDescriptors / getWords3,
+ * corelib/include/rtabmap/core/Signature.h:155-164), resident in HBM so that the hypothesis picked
+ * from the likelihood can be verified without a host round trip.
+ * desc [n_sigs][cap][dim], xyz [n_sigs][cap][3] (NaN = no depth), n[n_sigs] valid rows. */
+int lcd_sig_add_batch(lcd_engine * e, const int * sig_ids, int n_sigs, int cap, const void * desc,
+                      const float * xyz, const int * n);
+int lcd_sig_remove(lcd_engine * e, int sig_id);
+int lcd_sig_count(const lcd_engine * e);
+
+/* One call = n_frames independent loop-closure queries through quantise -> score -> verify:
+ * lcd_localize_batch, then for every frame the signature with the highest likelihood (first maximum,
+ * > 0) is verified against the frame (Memory::computeTransform(hypothesis, frame), FROM = hypothesis
+ * with its stored 3-D points, TO = the frame's descriptors + keypoints uv[n_frames][nq][2]).
+ * hypothesis_out[n_frames] = verified signature id (0 = none).  Outputs may be NULL. */
+int lcd_process_batch(lcd_engine * e, const void * queries, const float * uv, int n_frames, int nq_per_frame,
+                      int incremental, float nndr, int new_words_compared_together,
+                      const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp,
+                      int * word_ids_out, float * likelihood_out, int * hypothesis_out,
+                      lcd_verify_result * results);
+/* Same on device-resident inputs, asynchronous on `stream`; results stay in engine buffers until
+ * lcd_process_fetch copies them back (hypothesis ids, verification results). */
+int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * d_uv, int n_frames, int nq_per_frame,
+                          int incremental, float nndr, int new_words_compared_together,
+                          const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp,
+                          int * d_word_ids_out, float * d_likelihood_out, void * stream);
+int lcd_process_fetch(lcd_engine * e, int n_frames, int * hypothesis_out, lcd_verify_result * results);
+/* The verification half alone, for likelihood rows that already exist on the device (the sharded
+ * multi-GPU path all-reduces the scores first, then every rank verifies its share of the frames):
+ * arg-max hypothesis of each of the n_frames rows of d_likelihood[n_frames][ns], then
+ * Memory::computeTransform(hypothesis, frame).  Results via lcd_process_fetch. */
+int lcd_verify_top_dev(lcd_engine * e, const void * d_queries, const float * d_uv, int n_frames, int nq_per_frame,
+                       const float * d_likelihood, const int * d_sig_ids, int ns, const lcd_verify_params * vp, void * stream);
+
 /* ---- word-range sharding across GPUs ---------------------------
  * Each rank owns the words whose row (in ascending id order) falls in its range; rows
  * are numbered globally: set the global row offset of this shard so that packed top-2

@@ -110,6 +110,13 @@ SIGNATURES = {
     "lcd_localize_batch_dev": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
     "lcd_match_pairs": (_I, [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
     "lcd_verify_batch": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lcd_sig_add_batch": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "lcd_sig_remove": (_I, [_P, _I]),
+    "lcd_sig_count": (_I, [_P]),
+    "lcd_process_batch": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "lcd_process_batch_dev": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "lcd_process_fetch": (_I, [_P, _I, _P, _P]),
+    "lcd_verify_top_dev": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "lcd_shard_set_row_offset": (_I, [_P, _I]),
     "lcd_shard_knn2_keys_dev": (_I, [_P, _P, _I, _P, _P]),
     "lcd_shard_resolve_score_dev": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
@@ -396,6 +403,66 @@ class Engine:
                         "iterations_run": r.iterations_run, "rvec": np.array(r.rvec[:]), "tvec": np.array(r.tvec[:]),
                         "transform": np.array(r.transform[:], np.float32).reshape(3, 4)})
         return out
+
+    # -- signature store + fused query -------------------------------------------------------------
+    def sig_add_batch(self, sig_ids, desc, xyz, n=None):
+        ids = _i32(sig_ids)
+        dt = np.uint8 if self.desc_type == LCD_DESC_U8 else np.float32
+        d = np.ascontiguousarray(desc, dtype=dt)
+        assert d.ndim == 3 and d.shape[0] == len(ids) and d.shape[2] == self.desc_dim
+        cap = d.shape[1]
+        x = np.ascontiguousarray(xyz, np.float32).reshape(len(ids), cap, 3)
+        nn = _i32(n if n is not None else np.full(len(ids), cap))
+        self._check(self._lib.lcd_sig_add_batch(self._h, _ptr(ids), len(ids), cap, _ptr(d), _ptr(x), _ptr(nn)))
+
+    def sig_remove(self, sig_id: int):
+        self._check(self._lib.lcd_sig_remove(self._h, int(sig_id)))
+
+    def sig_count(self) -> int:
+        return self._lib.lcd_sig_count(self._h)
+
+    @staticmethod
+    def verify_params(K4, nndr=0.8, min_inliers=20, iterations=300, reproj_error=2.0, refine_iterations=1, refine_sigma=3.0):
+        return VerifyParams(nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, *[float(k) for k in K4])
+
+    @staticmethod
+    def _results(res, n):
+        out = []
+        for i in range(n):
+            r = res[i]
+            out.append({"ok": bool(r.ok), "n_matches": r.n_matches, "n_inliers": r.n_inliers, "iterations_run": r.iterations_run,
+                        "rvec": np.array(r.rvec[:]), "tvec": np.array(r.tvec[:]), "transform": np.array(r.transform[:], np.float32).reshape(3, 4)})
+        return out
+
+    def process_batch(self, queries, uv, n_frames: int, sig_ids, n_total: int, vp: "VerifyParams", incremental: bool = True, nndr: float = 0.8,
+                      cmp_new: bool = True, out_words=None, out_like=None, want_words=True, want_likelihood=True):
+        q = self._desc(queries)
+        nq = len(q) // n_frames
+        u = np.ascontiguousarray(uv, np.float32)
+        s = _i32(sig_ids)
+        words = (out_words if out_words is not None else np.zeros((n_frames, nq), np.int32)) if want_words else None
+        like = (out_like if out_like is not None else np.zeros((n_frames, len(s)), np.float32)) if want_likelihood else None
+        hyp = np.zeros(n_frames, np.int32)
+        res = (VerifyResult * n_frames)()
+        self._check(self._lib.lcd_process_batch(self._h, _ptr(q), _ptr(u), n_frames, nq, int(incremental), float(nndr), int(cmp_new), _ptr(s), len(s),
+                                                 int(n_total), C.byref(vp), _ptr(words), _ptr(like), _ptr(hyp), res))
+        return words, like, hyp, self._results(res, n_frames)
+
+    def process_batch_dev(self, d_queries: int, d_uv: int, n_frames: int, nq: int, d_sig_ids: int, ns: int, n_total: int, vp: "VerifyParams",
+                          d_words_out: int = 0, d_like_out: int = 0, incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True, stream: int = 0):
+        self._check(self._lib.lcd_process_batch_dev(self._h, C.c_void_p(d_queries), C.c_void_p(d_uv), n_frames, nq, int(incremental), float(nndr),
+                                                     int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total), C.byref(vp),
+                                                     C.c_void_p(d_words_out or None), C.c_void_p(d_like_out or None), C.c_void_p(stream or None)))
+
+    def verify_top_dev(self, d_queries: int, d_uv: int, n_frames: int, nq: int, d_like: int, d_sig_ids: int, ns: int, vp: "VerifyParams", stream: int = 0):
+        self._check(self._lib.lcd_verify_top_dev(self._h, C.c_void_p(d_queries), C.c_void_p(d_uv), n_frames, nq, C.c_void_p(d_like),
+                                                  C.c_void_p(d_sig_ids), ns, C.byref(vp), C.c_void_p(stream or None)))
+
+    def process_fetch(self, n_frames: int):
+        hyp = np.zeros(n_frames, np.int32)
+        res = (VerifyResult * n_frames)()
+        self._check(self._lib.lcd_process_fetch(self._h, n_frames, _ptr(hyp), res))
+        return hyp, self._results(res, n_frames)
 
     # -- word-range sharding ----------------------------------------------------------------------
     def shard_set_row_offset(self, off: int):

@@ -157,6 +157,14 @@ struct lcd_engine
 	DevBuf<float> v_xyz, v_uv, v_obj, v_img, v_T;
 	DevBuf<int> v_nf, v_nt, v_mid, v_mfrom, v_mto, v_nm, v_fid, v_tid, v_inl, v_ninl, v_iters, v_ok, v_inl_ids;
 	DevBuf<double> v_rvec, v_tvec;
+	// signature store (Signature::getWordsDescriptors / getWords3 of the nodes in working memory)
+	DevBuf<uint32_t> st_desc;
+	DevBuf<float> st_xyz;
+	DevBuf<int> st_n, st_slot_of_sig;
+	std::vector<int> h_slot_of_sig, free_slots;
+	int st_cap = 0, st_slots = 0;
+	DevBuf<int> d_hyp_id, d_hyp_slot;
+	DevBuf<float> d_uv;
 
 	// measurement hooks (lcd_profile_*)
 	bool prof_on = false;
@@ -1258,7 +1266,21 @@ static int verify_upload(lcd_engine * e, int n_pairs, int cap, const void * desc
 	return LCD_OK;
 }
 
-static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool want_ids, cudaStream_t s)
+struct MatchSrc
+{
+	const uint32_t * desc_from;
+	const float * xyz_from;
+	const int * n_from;
+	const int * from_slot;
+	int cap_from;
+	const uint32_t * desc_to;
+	const float * uv_to;
+	const int * n_to;
+	int n_to_all;
+	int cap_to;
+};
+
+static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool want_ids, cudaStream_t s, const MatchSrc * src = nullptr)
 {
 	const size_t rows = static_cast<size_t>(n_pairs) * cap;
 	LCD_CUDA(e, e->v_obj.reserve(rows * 3, 0, false, s));
@@ -1273,12 +1295,32 @@ static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool w
 		LCD_CUDA(e, e->v_tid.reserve(rows, 0, false, s));
 	}
 	MatchArgs a{};
-	a.desc_from = e->v_df.p;
-	a.xyz_from = e->v_xyz.p;
-	a.n_from = e->v_nf.p;
-	a.desc_to = e->v_dt.p;
-	a.uv_to = e->v_uv.p;
-	a.n_to = e->v_nt.p;
+	if (src)
+	{
+		a.desc_from = src->desc_from;
+		a.xyz_from = src->xyz_from;
+		a.n_from = src->n_from;
+		a.from_slot = src->from_slot;
+		a.cap_from = src->cap_from;
+		a.desc_to = src->desc_to;
+		a.uv_to = src->uv_to;
+		a.n_to = src->n_to;
+		a.n_to_all = src->n_to_all;
+		a.cap_to = src->cap_to;
+	}
+	else
+	{
+		a.desc_from = e->v_df.p;
+		a.xyz_from = e->v_xyz.p;
+		a.n_from = e->v_nf.p;
+		a.from_slot = nullptr;
+		a.cap_from = cap;
+		a.desc_to = e->v_dt.p;
+		a.uv_to = e->v_uv.p;
+		a.n_to = e->v_nt.p;
+		a.n_to_all = 0;
+		a.cap_to = cap;
+	}
 	a.cap = cap;
 	a.nndr = nndr;
 	a.obj = e->v_obj.p;
@@ -1353,6 +1395,43 @@ static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_par
 	return LCD_OK;
 }
 
+// copy the per-pair verification outputs back (cap = 0: skip the id arrays)
+static int verify_download(lcd_engine * e, int n_pairs, int cap, lcd_verify_result * results, int * match_ids, int * inlier_ids, cudaStream_t s)
+{
+	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	if (cap > 0 && inlier_ids)
+	{
+		LCD_CUDA(e, e->v_inl_ids.reserve(rows, 0, false, s));
+		gather_by_index_kernel<<<dim3((cap + 255) / 256, n_pairs), 256, 0, s>>>(e->v_mid.p, e->v_inl.p, e->v_ninl.p, cap, e->v_inl_ids.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	std::vector<int> nm(n_pairs), ni(n_pairs), it(n_pairs), ok(n_pairs);
+	std::vector<double> rv(n_pairs * 3), tv(n_pairs * 3);
+	std::vector<float> T(n_pairs * 12);
+	LCD_CUDA(e, cudaMemcpyAsync(nm.data(), e->v_nm.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ni.data(), e->v_ninl.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(it.data(), e->v_iters.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ok.data(), e->v_ok.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(rv.data(), e->v_rvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(tv.data(), e->v_tvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(T.data(), e->v_T.p, n_pairs * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+	if (cap > 0 && match_ids) LCD_CUDA(e, cudaMemcpyAsync(match_ids, e->v_mid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (cap > 0 && inlier_ids) LCD_CUDA(e, cudaMemcpyAsync(inlier_ids, e->v_inl_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	for (int i = 0; i < n_pairs; ++i)
+	{
+		lcd_verify_result & r = results[i];
+		r.ok = ok[i];
+		r.n_matches = nm[i];
+		r.n_inliers = ni[i];
+		r.iterations_run = it[i];
+		memcpy(r.rvec, &rv[3 * i], 3 * sizeof(double));
+		memcpy(r.tvec, &tv[3 * i], 3 * sizeof(double));
+		memcpy(r.transform, &T[12 * i], 12 * sizeof(float));
+	}
+	return LCD_OK;
+}
+
 static int check_verify_args(lcd_engine * e, int n_pairs, int cap, const void * a, const void * b, const int * na, const int * nb)
 {
 	if (n_pairs <= 0 || cap <= 0 || !a || !b || !na || !nb) LCD_FAIL(e, LCD_ERR_INVALID, "null or empty verification input");
@@ -1389,34 +1468,195 @@ int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_fro
 	LCD_TRY(verify_upload(e, n_pairs, cap, desc_from, xyz_from, n_from, desc_to, uv_to, n_to, s));
 	LCD_TRY(launch_match(e, n_pairs, cap, params->nndr, false, s));
 	LCD_TRY(launch_pnp(e, n_pairs, cap, params, s));
-	const size_t rows = static_cast<size_t>(n_pairs) * cap;
-	LCD_CUDA(e, e->v_inl_ids.reserve(rows, 0, false, s));
-	gather_by_index_kernel<<<dim3((cap + 255) / 256, n_pairs), 256, 0, s>>>(e->v_mid.p, e->v_inl.p, e->v_ninl.p, cap, e->v_inl_ids.p);
-	LCD_CHECK_LAUNCH(e);
-	std::vector<int> nm(n_pairs), ni(n_pairs), it(n_pairs), ok(n_pairs);
-	std::vector<double> rv(n_pairs * 3), tv(n_pairs * 3);
-	std::vector<float> T(n_pairs * 12);
-	LCD_CUDA(e, cudaMemcpyAsync(nm.data(), e->v_nm.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(ni.data(), e->v_ninl.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(it.data(), e->v_iters.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(ok.data(), e->v_ok.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(rv.data(), e->v_rvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(tv.data(), e->v_tvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(T.data(), e->v_T.p, n_pairs * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
-	if (match_ids) LCD_CUDA(e, cudaMemcpyAsync(match_ids, e->v_mid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
-	if (inlier_ids) LCD_CUDA(e, cudaMemcpyAsync(inlier_ids, e->v_inl_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaStreamSynchronize(s));
-	for (int i = 0; i < n_pairs; ++i)
+	return verify_download(e, n_pairs, cap, results, match_ids, inlier_ids, s);
+}
+
+// ---- signature store + fused query -------------------------------------------------------------
+int lcd_sig_count(const lcd_engine * e) { return e ? e->st_slots - static_cast<int>(e->free_slots.size()) : 0; }
+
+int lcd_sig_add_batch(lcd_engine * e, const int * sig_ids, int n_sigs, int cap, const void * desc, const float * xyz, const int * n)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (n_sigs <= 0) return LCD_OK;
+	if (!sig_ids || !desc || !xyz || !n || cap <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null signature data");
+	if (cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "at most %d features per signature", kMaxFrameQueries);
+	LCD_TRY(set_device(e));
+	cudaStream_t s = e->stream;
+	if (e->st_cap == 0) e->st_cap = cap;
+	if (cap != e->st_cap) LCD_FAIL(e, LCD_ERR_INVALID, "signature store was created with %d rows per signature, got %d", e->st_cap, cap);
+	int max_id = 0;
+	for (int i = 0; i < n_sigs; ++i)
 	{
-		lcd_verify_result & r = results[i];
-		r.ok = ok[i];
-		r.n_matches = nm[i];
-		r.n_inliers = ni[i];
-		r.iterations_run = it[i];
-		memcpy(r.rvec, &rv[3 * i], 3 * sizeof(double));
-		memcpy(r.tvec, &tv[3 * i], 3 * sizeof(double));
-		memcpy(r.transform, &T[12 * i], 12 * sizeof(float));
+		if (sig_ids[i] <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "signature id must be positive");
+		max_id = std::max(max_id, sig_ids[i]);
 	}
+	if (static_cast<size_t>(max_id) + 1 > e->h_slot_of_sig.size())
+	{
+		const size_t old = e->h_slot_of_sig.size();
+		const size_t ncap = std::max<size_t>(max_id + 1, old + old / 2 + 1024);
+		e->h_slot_of_sig.resize(ncap, -1);
+	}
+	// slots: contiguous fresh slots when possible so that the bulk copy is one transfer
+	const size_t prev_slots = static_cast<size_t>(e->st_slots);
+	std::vector<int> slots(n_sigs);
+	bool contiguous = true;
+	for (int i = 0; i < n_sigs; ++i)
+	{
+		int slot = e->h_slot_of_sig[sig_ids[i]];
+		if (slot < 0)
+		{
+			if (!e->free_slots.empty() && !contiguous)
+			{
+				slot = e->free_slots.back();
+				e->free_slots.pop_back();
+			}
+			else slot = e->st_slots++;
+		}
+		slots[i] = slot;
+		if (i > 0 && slots[i] != slots[i - 1] + 1) contiguous = false;
+		e->h_slot_of_sig[sig_ids[i]] = slot;
+	}
+	LCD_CUDA(e, e->st_desc.reserve(static_cast<size_t>(e->st_slots) * cap * e->nw, prev_slots * cap * e->nw, false, s));
+	LCD_CUDA(e, e->st_xyz.reserve(static_cast<size_t>(e->st_slots) * cap * 3, prev_slots * cap * 3, false, s));
+	LCD_CUDA(e, e->st_n.reserve(static_cast<size_t>(e->st_slots), prev_slots, true, s));
+	const size_t drow = static_cast<size_t>(cap) * e->nw * 4, xrow = static_cast<size_t>(cap) * 3 * sizeof(float);
+	if (contiguous)
+	{
+		LCD_CUDA(e, cudaMemcpyAsync(e->st_desc.p + static_cast<size_t>(slots[0]) * cap * e->nw, desc, drow * n_sigs, cudaMemcpyHostToDevice, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->st_xyz.p + static_cast<size_t>(slots[0]) * cap * 3, xyz, xrow * n_sigs, cudaMemcpyHostToDevice, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->st_n.p + slots[0], n, n_sigs * sizeof(int), cudaMemcpyHostToDevice, s));
+	}
+	else
+	{
+		for (int i = 0; i < n_sigs; ++i)
+		{
+			LCD_CUDA(e, cudaMemcpyAsync(e->st_desc.p + static_cast<size_t>(slots[i]) * cap * e->nw, static_cast<const char *>(desc) + drow * i, drow, cudaMemcpyHostToDevice, s));
+			LCD_CUDA(e, cudaMemcpyAsync(e->st_xyz.p + static_cast<size_t>(slots[i]) * cap * 3, xyz + static_cast<size_t>(i) * cap * 3, xrow, cudaMemcpyHostToDevice, s));
+			LCD_CUDA(e, cudaMemcpyAsync(e->st_n.p + slots[i], n + i, sizeof(int), cudaMemcpyHostToDevice, s));
+		}
+	}
+	LCD_CUDA(e, e->st_slot_of_sig.reserve(e->h_slot_of_sig.size(), 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->st_slot_of_sig.p, e->h_slot_of_sig.data(), e->h_slot_of_sig.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+int lcd_sig_remove(lcd_engine * e, int sig_id)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (sig_id <= 0 || sig_id >= static_cast<int>(e->h_slot_of_sig.size()) || e->h_slot_of_sig[sig_id] < 0) return LCD_OK;
+	const int slot = e->h_slot_of_sig[sig_id];
+	e->h_slot_of_sig[sig_id] = -1;
+	e->free_slots.push_back(slot);
+	const int minus1 = -1;
+	LCD_CUDA(e, cudaMemcpyAsync(e->st_slot_of_sig.p + sig_id, &minus1, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	LCD_CUDA(e, cudaMemsetAsync(e->st_n.p + slot, 0, sizeof(int), e->stream));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	return LCD_OK;
+}
+
+static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, const float * d_like,
+                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s);
+
+static int process_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, int incremental, float nndr, int cmp_new,
+                       const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp, int * d_words, float * d_like, cudaStream_t s)
+{
+	if (!vp) LCD_FAIL(e, LCD_ERR_INVALID, "null verification parameters");
+	if (vp->iterations > kMaxRansacIters) LCD_FAIL(e, LCD_ERR_CAPACITY, "Vis/Iterations > %d", kMaxRansacIters);
+	if (e->st_cap == 0) LCD_FAIL(e, LCD_ERR_STATE, "the signature store is empty: nothing to verify against");
+	if (!d_sig_ids || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "ids list is empty");
+	if (!d_like)
+	{
+		LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
+		d_like = e->d_like.p;
+	}
+	LCD_TRY(localize_dev(e, d_q, n_frames, nq, incremental, nndr, cmp_new, d_sig_ids, ns, n_total, d_words, d_like, s));
+	return verify_top_dev(e, d_q, d_uv, n_frames, nq, d_like, d_sig_ids, ns, vp, s);
+}
+
+static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, const float * d_like,
+                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s)
+{
+	if (!vp) LCD_FAIL(e, LCD_ERR_INVALID, "null verification parameters");
+	if (vp->iterations > kMaxRansacIters) LCD_FAIL(e, LCD_ERR_CAPACITY, "Vis/Iterations > %d", kMaxRansacIters);
+	if (e->st_cap == 0) LCD_FAIL(e, LCD_ERR_STATE, "the signature store is empty: nothing to verify against");
+	LCD_CUDA(e, e->d_hyp_id.reserve(n_frames, 0, false, s));
+	LCD_CUDA(e, e->d_hyp_slot.reserve(n_frames, 0, false, s));
+	argmax_hypothesis_kernel<<<n_frames, 256, 0, s>>>(d_like, ns, d_sig_ids, e->st_slot_of_sig.p, static_cast<int>(e->h_slot_of_sig.size()),
+	                                                  e->d_hyp_id.p, e->d_hyp_slot.p);
+	LCD_CHECK_LAUNCH(e);
+	const int cap = std::max(e->st_cap, nq);
+	MatchSrc src{e->st_desc.p, e->st_xyz.p, e->st_n.p, e->d_hyp_slot.p, e->st_cap, d_q, d_uv, nullptr, nq, nq};
+	LCD_TRY(launch_match(e, n_frames, cap, vp->nndr, false, s, &src));
+	LCD_TRY(launch_pnp(e, n_frames, cap, vp, s));
+	return LCD_OK;
+}
+
+int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * d_uv, int n_frames, int nq_per_frame, int incremental, float nndr,
+                          int new_words_compared_together, const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp,
+                          int * d_word_ids_out, float * d_likelihood_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_queries || !d_uv || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	return process_dev(e, static_cast<const uint32_t *>(d_queries), d_uv, n_frames, nq_per_frame, incremental, nndr, new_words_compared_together,
+	                   d_sig_ids, ns, n_total, vp, d_word_ids_out, d_likelihood_out, s);
+}
+
+int lcd_verify_top_dev(lcd_engine * e, const void * d_queries, const float * d_uv, int n_frames, int nq_per_frame, const float * d_likelihood,
+                       const int * d_sig_ids, int ns, const lcd_verify_params * vp, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_queries || !d_uv || !d_likelihood || !d_sig_ids || n_frames <= 0 || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	return verify_top_dev(e, static_cast<const uint32_t *>(d_queries), d_uv, n_frames, nq_per_frame, d_likelihood, d_sig_ids, ns, vp, s);
+}
+
+int lcd_process_fetch(lcd_engine * e, int n_frames, int * hypothesis_out, lcd_verify_result * results)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (n_frames <= 0) return LCD_OK;
+	cudaStream_t s = e->stream;
+	LCD_CUDA(e, cudaDeviceSynchronize());
+	if (hypothesis_out) LCD_CUDA(e, cudaMemcpyAsync(hypothesis_out, e->d_hyp_id.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (results) return verify_download(e, n_frames, 0, results, nullptr, nullptr, s);
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+int lcd_process_batch(lcd_engine * e, const void * queries, const float * uv, int n_frames, int nq_per_frame, int incremental, float nndr,
+                      int new_words_compared_together, const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp,
+                      int * word_ids_out, float * likelihood_out, int * hypothesis_out, lcd_verify_result * results)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!queries || !uv || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
+	if (!sig_ids || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "ids list is empty");
+	cudaStream_t s = e->stream;
+	const size_t nq_total = static_cast<size_t>(n_frames) * nq_per_frame;
+	LCD_CUDA(e, e->d_queries.reserve(nq_total * e->nw, 0, false, s));
+	LCD_CUDA(e, e->d_uv.reserve(nq_total * 2, 0, false, s));
+	LCD_CUDA(e, e->d_sig_ids.reserve(ns, 0, false, s));
+	LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
+	if (word_ids_out) LCD_CUDA(e, e->d_word_ids.reserve(nq_total, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, nq_total * e->nw * 4, cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_uv.p, uv, nq_total * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_sig_ids.p, sig_ids, ns * sizeof(int), cudaMemcpyHostToDevice, s));
+	LCD_TRY(process_dev(e, e->d_queries.p, e->d_uv.p, n_frames, nq_per_frame, incremental, nndr, new_words_compared_together, e->d_sig_ids.p, ns,
+	                    n_total, vp, word_ids_out ? e->d_word_ids.p : nullptr, e->d_like.p, s));
+	if (word_ids_out) LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, nq_total * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (likelihood_out)
+		LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, static_cast<size_t>(n_frames) * ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+	if (hypothesis_out) LCD_CUDA(e, cudaMemcpyAsync(hypothesis_out, e->d_hyp_id.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (results) return verify_download(e, n_frames, 0, results, nullptr, nullptr, s);
+	LCD_CUDA(e, cudaStreamSynchronize(s));
 	return LCD_OK;
 }
 

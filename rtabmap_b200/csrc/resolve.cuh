@@ -9,11 +9,11 @@
 // created by descriptors 0..i-1 of the same frame (Kp/NewWordsComparedTogether,
 // VWDictionary.cpp:1139-1160) and ties in the std::multimap<float,int> keep insertion
 // order (index hits first, then new-word hits; lower row / earlier new word first).
-// Here one CTA owns one frame and solves that lower-triangular dependency by fixed-point
-// iteration: new[i] = f_i(new[0..i-1]) has a unique fixed point, which is the sequential
-// answer; after round r the first r entries are final, and in practice 2-4 rounds
-// converge because dependency chains (chains of mutually close unmatched descriptors)
-// are short.  Every round is fully parallel over the frame's descriptors.
+// Here one CTA owns one frame and walks it in chunks of 32 descriptors (resolve_rounds below):
+// words created by earlier chunks are searched by all warps in parallel, the dependencies inside
+// a chunk are settled by one warp with a ballot-mask fixed point (new[i] = f_i(new[0..i-1]) has a
+// unique fixed point = the sequential answer), so the result is exact and the cost does not depend
+// on how long the chains of mutually-near descriptors are.
 #pragma once
 #include "common.cuh"
 #include <math.h>
@@ -213,55 +213,138 @@ __device__ void score_prep(uint32_t * sbuf, int n_pad, int nq, const ResolveArgs
 	__syncthreads();
 }
 
-// Fixed-point rounds of the intra-frame new-word dependency for ONE frame held by the calling CTA.
-// On entry sa1/sa2 hold each descriptor's two best index hits, flag[i] the decision made from them
-// alone and res[i] the row of the best index hit.  On return flag[i] = 1 for descriptors that create a
-// word (rank[i] = creation order), res[i] >= 0 = matched index row, res[i] = -1-k = matched the k-th word
-// created by this frame.  Returns the number of created words.  All threads of the CTA must call it.
+// Intra-frame new-word resolution for ONE frame held by the calling CTA (exact, bounded time).
+// The reference decides descriptor i after descriptors 0..i-1 (VWDictionary.cpp:1139-1219).  Here the
+// frame is walked in chunks of 32 descriptors: (A) one warp per descriptor of the chunk scans the words
+// created by all EARLIER chunks (already final) for its two nearest, all warps in parallel; (B) one warp
+// resolves the dependencies INSIDE the chunk by fixed-point iteration over a ballot mask (at most 32
+// rounds, each descriptor of the chunk in one lane, chunk-mate distances in registers); (C) the chunk's
+// new words are appended to the list.  Cost is O(nq * n_new / 32) per warp regardless of how long the
+// chains of mutually-near descriptors are.
+// On entry sa1/sa2 hold each descriptor's two best index hits.  On return flag[i] = 1 for descriptors
+// that create a word (rank[i] = creation order, L[k] = descriptor of the k-th created word), res[i] >= 0 =
+// matched index row, res[i] = -1-k = matched the k-th word created by this frame.  Returns the number of
+// created words.  All threads of the CTA must call it.
 template <int NW>
 __device__ int resolve_rounds(const uint32_t * __restrict__ fq, int nq, const uint32_t * sa1, const uint32_t * sa2, int * res,
                               uint16_t * L, uint16_t * rank, uint8_t * flag, uint8_t * flag2, int * s_nL, float nndr, int cmp_new)
 {
+	__shared__ uint32_t s_ext[64];
 	const int tid = threadIdx.x;
-	for (int round = 0; round <= nq; ++round)
+	const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+	(void)flag2;
+	if (!cmp_new)
 	{
+		// no comparison among the frame's own new words: the index-only decision in flag[] is final
 		if (tid < 32)
 		{
 			const int n = warp0_compact(flag, nq, L, rank);
 			if (tid == 0) *s_nL = n;
 		}
 		__syncthreads();
+		return *s_nL;
+	}
+	if (tid == 0) *s_nL = 0;
+	__syncthreads();
+	for (int c0 = 0; c0 < nq; c0 += 32)
+	{
 		const int nL = *s_nL;
-		if (!cmp_new) break;
-		int changed = 0;
-		for (int i = tid; i < nq; i += blockDim.x)
+		// (A) nearest two among the words created by earlier chunks
+		for (int e = warp; e < 32; e += nwarps)
 		{
-			uint32_t n1 = kKeyNone, n2 = kKeyNone;
-			if (nL > 0 && L[0] < i)
+			const int i = c0 + e;
+			if (i >= nq) continue;
+			uint32_t k1 = kKeyNone, k2 = kKeyNone;
+			if (nL > 0)
 			{
 				uint32_t qi[NW];
 				load_desc<NW>(fq, i, qi);
-				for (int k = 0; k < nL; ++k)
+				for (int k = lane; k < nL; k += 32)
 				{
-					const int j = L[k];
-					if (j >= i) break;
 					uint32_t qj[NW];
-					load_desc<NW>(fq, j, qj);
+					load_desc<NW>(fq, L[k], qj);
 					uint32_t d = 0;
 #pragma unroll
 					for (int v = 0; v < NW; ++v) d += __popc(qi[v] ^ qj[v]);
-					top2_insert(n1, n2, (d << kKeyShift) + static_cast<uint32_t>(k));
+					top2_insert(k1, k2, (d << kKeyShift) + static_cast<uint32_t>(k));
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+				{
+					const uint32_t o1 = __shfl_down_sync(0xFFFFFFFFu, k1, o);
+					const uint32_t o2 = __shfl_down_sync(0xFFFFFFFFu, k2, o);
+					top2_insert(k1, k2, o1);
+					top2_insert(k1, k2, o2);
 				}
 			}
-			int bt;
-			const bool bad = nndr_decide(sa1[i], sa2[i], n1, n2, nndr, bt);
-			flag2[i] = bad ? 1 : 0;
-			changed |= (flag2[i] != flag[i]);
-			if (!bad) res[i] = bt >= 2 ? -1 - static_cast<int>(n1 & kKeyRowMask) : static_cast<int>(sa1[i] & kKeyRowMask);
+			if (lane == 0)
+			{
+				s_ext[2 * e] = k1;
+				s_ext[2 * e + 1] = k2;
+			}
 		}
-		changed = __syncthreads_or(changed);
-		if (!changed) break;
-		for (int i = tid; i < nq; i += blockDim.x) flag[i] = flag2[i];
+		__syncthreads();
+		// (B) dependencies inside the chunk, (C) append its new words
+		if (warp == 0)
+		{
+			const int i = c0 + lane;
+			const bool valid = i < nq;
+			uint32_t qi[NW];
+			if (valid) load_desc<NW>(fq, i, qi);
+			else
+			{
+#pragma unroll
+				for (int v = 0; v < NW; ++v) qi[v] = 0u;
+			}
+			uint32_t dl[32]; // distance to chunk-mate j (only j < lane is used)
+#pragma unroll
+			for (int jl = 0; jl < 32; ++jl)
+			{
+				uint32_t d = 0;
+#pragma unroll
+				for (int v = 0; v < NW; ++v) d += __popc(qi[v] ^ __shfl_sync(0xFFFFFFFFu, qi[v], jl));
+				dl[jl] = d;
+			}
+			const uint32_t a1 = valid ? sa1[i] : kKeyNone, a2 = valid ? sa2[i] : kKeyNone;
+			const uint32_t e1 = s_ext[2 * lane], e2 = s_ext[2 * lane + 1];
+			int bt;
+			bool bad = valid && nndr_decide(a1, a2, e1, e2, nndr, bt);
+			uint32_t n1 = e1;
+			uint32_t mask = __ballot_sync(0xFFFFFFFFu, bad);
+			for (int r = 0; r < 33; ++r)
+			{
+				n1 = e1;
+				uint32_t n2 = e2;
+#pragma unroll
+				for (int jl = 0; jl < 32; ++jl)
+				{
+					if (jl < lane && ((mask >> jl) & 1u))
+					{
+						const uint32_t kidx = static_cast<uint32_t>(nL) + __popc(mask & ((1u << jl) - 1u));
+						top2_insert(n1, n2, (dl[jl] << kKeyShift) + kidx);
+					}
+				}
+				bad = valid && nndr_decide(a1, a2, n1, n2, nndr, bt);
+				const uint32_t nm = __ballot_sync(0xFFFFFFFFu, bad);
+				if (nm == mask) break;
+				mask = nm;
+			}
+			if (valid)
+			{
+				flag[i] = bad ? 1 : 0;
+				if (bad)
+				{
+					const int k = nL + __popc(mask & ((1u << lane) - 1u));
+					rank[i] = static_cast<uint16_t>(k);
+					L[k] = static_cast<uint16_t>(i);
+				}
+				else
+				{
+					res[i] = bt >= 2 ? -1 - static_cast<int>(n1 & kKeyRowMask) : static_cast<int>(a1 & kKeyRowMask);
+				}
+			}
+			if (lane == 0) *s_nL = nL + __popc(mask);
+		}
 		__syncthreads();
 	}
 	return *s_nL;
@@ -322,7 +405,7 @@ resolve_kernel(const ResolveArgs a)
 	int n_new = 0;
 	if (a.incremental)
 	{
-		// 2. fixed-point rounds over the intra-frame dependency
+		// 2. intra-frame dependency among the words this frame creates
 		n_new = resolve_rounds<NW>(fq, nq, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, a.cmp_new);
 	}
 

@@ -25,13 +25,17 @@ constexpr int kMaxRansacIters = 320;
 
 struct MatchArgs
 {
-	const uint32_t * desc_from; // [n_pairs][cap][NW]
-	const float * xyz_from;     // [n_pairs][cap][3]   NaN = no depth
-	const int * n_from;         // [n_pairs]
-	const uint32_t * desc_to;   // [n_pairs][cap][NW]
-	const float * uv_to;        // [n_pairs][cap][2]
-	const int * n_to;           // [n_pairs]
-	int cap;
+	const uint32_t * desc_from; // [n_from_rows][cap_from][NW]
+	const float * xyz_from;     // [n_from_rows][cap_from][3]   NaN = no depth
+	const int * n_from;         // [n_from_rows]
+	const int * from_slot;      // nullptr: FROM row = pair; else row of the signature store for each pair (-1 = none)
+	int cap_from;               // row stride of the FROM arrays
+	const uint32_t * desc_to;   // [n_pairs][cap_to][NW]
+	const float * uv_to;        // [n_pairs][cap_to][2]
+	const int * n_to;           // [n_pairs] or nullptr (= n_to_all)
+	int n_to_all;
+	int cap_to;                 // row stride of the TO arrays
+	int cap;                    // stride of the outputs and size of the shared-memory arrays (>= both)
 	float nndr; // Vis/CorNNDR
 	// outputs
 	float * obj;       // [n_pairs][cap][3]
@@ -71,10 +75,14 @@ pair_match_kernel(const MatchArgs a)
 
 	const int tid = threadIdx.x;
 	const int pair = blockIdx.x;
-	const int nf = min(a.n_from[pair], cap), nt = min(a.n_to[pair], cap);
+	const int frow = a.from_slot ? a.from_slot[pair] : pair;
+	const int nf = frow >= 0 ? min(a.n_from[frow], min(cap, a.cap_from)) : 0;
+	const int nt = min(a.n_to ? a.n_to[pair] : a.n_to_all, min(cap, a.cap_to));
 	const size_t base = static_cast<size_t>(pair) * cap;
-	const uint32_t * F = a.desc_from + base * NW;
-	const uint32_t * T = a.desc_to + base * NW;
+	const size_t fbase = static_cast<size_t>(frow >= 0 ? frow : 0) * a.cap_from;
+	const size_t tbase = static_cast<size_t>(pair) * a.cap_to;
+	const uint32_t * F = a.desc_from + fbase * NW;
+	const uint32_t * T = a.desc_to + tbase * NW;
 
 	// ---- FROM side: addNewWords(descriptorsFrom, 1) on an empty dictionary -------------------
 	for (int i = tid; i < nf; i += blockDim.x)
@@ -155,7 +163,7 @@ pair_match_kernel(const MatchArgs a)
 		bool ok = cntF[k] == 1 && cntT[k] == 1;
 		if (ok)
 		{
-			const float * p = a.xyz_from + (base + idxF[k]) * 3;
+			const float * p = a.xyz_from + (fbase + idxF[k]) * 3;
 			ok = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
 		}
 		flag[k] = ok ? 1 : 0;
@@ -176,8 +184,8 @@ pair_match_kernel(const MatchArgs a)
 	{
 		const int k = L[m];
 		const int fi = idxF[k], ti = idxT[k];
-		const float * p = a.xyz_from + (base + fi) * 3;
-		const float * q = a.uv_to + (base + ti) * 2;
+		const float * p = a.xyz_from + (fbase + fi) * 3;
+		const float * q = a.uv_to + (tbase + ti) * 2;
 		a.obj[(base + m) * 3 + 0] = p[0];
 		a.obj[(base + m) * 3 + 1] = p[1];
 		a.obj[(base + m) * 3 + 2] = p[2];
@@ -698,6 +706,63 @@ pnp_ransac_kernel(const PnpArgs a)
 				T[4 * i + 3] = -(Rf[0 + i] * tf[0] + Rf[3 + i] * tf[1] + Rf[6 + i] * tf[2]);
 			}
 		}
+	}
+}
+
+// Hypothesis selection for the fused query: the signature with the highest likelihood of each frame
+// (first maximum; a zero / negative maximum selects nothing).  The reference selects through the Bayes
+// filter (Rtabmap.cpp:2133-2226, out of scope here); the raw-likelihood arg-max is what
+// the benchmark verifies.  hyp_id[frame] = signature id or 0, hyp_slot[frame] = row of the signature store or -1.
+__global__ void argmax_hypothesis_kernel(const float * __restrict__ like, int ns, const int * __restrict__ sig_ids,
+                                         const int * __restrict__ sig_slot, int slot_cap, int * __restrict__ hyp_id, int * __restrict__ hyp_slot)
+{
+	__shared__ float s_v[32];
+	__shared__ int s_i[32];
+	const int frame = blockIdx.x;
+	const float * row = like + static_cast<size_t>(frame) * ns;
+	float bv = -1.0f;
+	int bi = 0x7FFFFFFF;
+	for (int k = threadIdx.x; k < ns; k += blockDim.x)
+	{
+		const float v = row[k];
+		if (v > bv || (v == bv && k < bi))
+		{
+			bv = v;
+			bi = k;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		const float ov = __shfl_down_sync(0xFFFFFFFFu, bv, o);
+		const int oi = __shfl_down_sync(0xFFFFFFFFu, bi, o);
+		if (ov > bv || (ov == bv && oi < bi))
+		{
+			bv = ov;
+			bi = oi;
+		}
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		s_v[threadIdx.x >> 5] = bv;
+		s_i[threadIdx.x >> 5] = bi;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		for (int w = 1; w < (blockDim.x >> 5); ++w)
+			if (s_v[w] > bv || (s_v[w] == bv && s_i[w] < bi))
+			{
+				bv = s_v[w];
+				bi = s_i[w];
+			}
+		int id = 0, slot = -1;
+		if (bv > 0.0f && bi < ns)
+		{
+			id = sig_ids[bi];
+			if (id > 0 && id < slot_cap) slot = sig_slot[id];
+		}
+		hyp_id[frame] = id;
+		hyp_slot[frame] = slot;
 	}
 }
 

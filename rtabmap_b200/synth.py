@@ -97,3 +97,80 @@ def make_query_frames(vocab: np.ndarray, word_ids: np.ndarray, smap: SynthMap, n
                 d[idx[k + 1]] = flip_bits(d[idx[k]:idx[k] + 1], 0.03, rng)[0]
         out[f * feats_per_frame:(f + 1) * feats_per_frame] = d
     return out, smap.sig_ids[places]
+
+
+# ------------------------------------------------------------------------------ geometry ----------
+CAMERA_K4 = (525.0, 525.0, 320.0, 240.0)  # fx, fy, cx, cy of the 640x480 RGB-D stream
+
+
+def rodrigues(rvec: np.ndarray) -> np.ndarray:
+    theta = float(np.linalg.norm(rvec))
+    if theta < 1e-12:
+        return np.eye(3)
+    k = rvec / theta
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.cos(theta) * np.eye(3) + (1 - np.cos(theta)) * np.outer(k, k) + np.sin(theta) * Kx
+
+
+def sparse_flip_mask(shape, rng: np.random.Generator, and_terms: int = 5) -> np.ndarray:
+    """Random byte mask whose bits are set with probability 2^-and_terms (cheap bulk bit flips)."""
+    m = np.frombuffer(rng.bytes(int(np.prod(shape))), dtype=np.uint8).reshape(shape).copy()
+    for _ in range(and_terms - 1):
+        m &= np.frombuffer(rng.bytes(int(np.prod(shape))), dtype=np.uint8).reshape(shape)
+    return m
+
+
+@dataclass
+class SynthStore:
+    """Per-signature data kept for verification: descriptors and 3-D points of every feature."""
+    desc: np.ndarray  # [S, F, D] uint8
+    xyz: np.ndarray   # [S, F, 3] float32 (NaN = no depth)
+
+
+def make_signature_store(vocab: np.ndarray, word_ids: np.ndarray, smap: SynthMap, seed: int = 4, nan_frac: float = 0.02) -> SynthStore:
+    rng = np.random.default_rng(seed)
+    id2row = np.full(int(np.max(word_ids)) + 1, -1, dtype=np.int64)
+    id2row[np.asarray(word_ids)] = np.arange(len(word_ids))
+    S, F = smap.sig_words.shape
+    desc = vocab[id2row[smap.sig_words.reshape(-1)]].reshape(S, F, vocab.shape[1])
+    desc ^= sparse_flip_mask(desc.shape, rng, 5)  # ~3 % of the bits differ from the word's centre
+    xyz = np.empty((S, F, 3), np.float32)
+    z = rng.uniform(0.5, 5.0, (S, F)).astype(np.float32)
+    xyz[..., 0] = rng.uniform(-0.55, 0.55, (S, F)).astype(np.float32) * z   # inside the 640x480 frustum at f=525
+    xyz[..., 1] = rng.uniform(-0.40, 0.40, (S, F)).astype(np.float32) * z
+    xyz[..., 2] = z
+    xyz[rng.random((S, F)) < nan_frac] = np.nan
+    return SynthStore(np.ascontiguousarray(desc), xyz)
+
+
+def make_query_frames_geo(store: SynthStore, smap: SynthMap, n_frames: int, seed: int = 3, flip_terms: int = 4, pixel_noise: float = 0.5,
+                          outlier_frac: float = 0.2, K4=CAMERA_K4):
+    """Frames revisiting random places: the place's features re-observed from a nearby pose.
+    Returns desc [n_frames*F, D], uv [n_frames*F, 2], place ids [n_frames], poses (rvec, tvec) [n_frames, 6]."""
+    rng = np.random.default_rng(seed)
+    S, F, D = store.desc.shape
+    places = rng.integers(0, S, size=n_frames)
+    desc = np.empty((n_frames, F, D), np.uint8)
+    uv = np.empty((n_frames, F, 2), np.float32)
+    poses = np.zeros((n_frames, 6))
+    for f in range(n_frames):
+        p = places[f]
+        perm = rng.permutation(F)
+        d = store.desc[p][perm] ^ sparse_flip_mask((F, D), rng, flip_terms)  # ~6 % bit flips
+        X = np.nan_to_num(store.xyz[p][perm].astype(np.float64), nan=1.0)
+        rv = rng.normal(0, 0.06, 3)
+        tv = rng.normal(0, 0.1, 3)
+        Xc = X @ rodrigues(rv).T + tv
+        u = K4[0] * Xc[:, 0] / Xc[:, 2] + K4[2] + rng.normal(0, pixel_noise, F)
+        v = K4[1] * Xc[:, 1] / Xc[:, 2] + K4[3] + rng.normal(0, pixel_noise, F)
+        n_out = int(round(outlier_frac * F))
+        idx = rng.permutation(F)[:n_out]
+        d[idx] = np.frombuffer(rng.bytes(n_out * D), dtype=np.uint8).reshape(n_out, D)
+        u[idx] = rng.uniform(0, 640, n_out)
+        v[idx] = rng.uniform(0, 480, n_out)
+        desc[f] = d
+        uv[f, :, 0] = u
+        uv[f, :, 1] = v
+        poses[f, :3] = rv
+        poses[f, 3:] = tv
+    return desc.reshape(n_frames * F, D), uv.reshape(n_frames * F, 2), smap.sig_ids[places], poses

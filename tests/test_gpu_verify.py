@@ -109,3 +109,42 @@ def test_verify_rejects_unrelated_pair():
     r = eng.verify_batch(df[None], x[None], other[None], uv[None], K4)[0]
     o = orc.verify_pair(df, x, other, uv, K4)
     assert not r["ok"] and not o["ok"] and len(r["matches"]) == len(o["matches"])
+
+
+def test_process_batch_matches_oracle():
+    """Fused quantise -> score -> arg-max hypothesis -> verify against the device-resident signature store."""
+    vocab = synth.make_binary_vocabulary(6000, 32, 1)
+    ids = np.arange(1, 6001, dtype=np.int32)
+    m = synth.make_map(ids, 250, 400, seed=2)
+    st = synth.make_signature_store(vocab, ids, m)
+    B, F = 5, 400
+    q, uv, places, poses = synth.make_query_frames_geo(st, m, B)
+    eng = Engine()
+    o = orc.OracleDictionary()
+    for d in (eng, o):
+        d.add_words(ids, vocab)
+        d.last_word_id = 6000
+        d.update()
+        d.load_csr(m.word_ids, m.row_ptr, m.sig, m.cnt)
+    eng.sig_add_batch(m.sig_ids[:100], st.desc[:100], st.xyz[:100])
+    eng.sig_add_batch(m.sig_ids[100:], st.desc[100:], st.xyz[100:])
+    assert eng.sig_count() == 250
+    vp = Engine.verify_params(synth.CAMERA_K4)
+    words, like, hyp, res = eng.process_batch(q, uv, B, m.sig_ids, 251, vp)
+    for b in range(B):
+        fq, fuv = q[b * F:(b + 1) * F], uv[b * F:(b + 1) * F]
+        w_o, l_o = o.localize_ro(fq, m.sig_ids, 251)
+        assert np.array_equal(words[b], w_o)
+        assert np.allclose(like[b], l_o, atol=1e-4, rtol=1e-4)
+        h = int(m.sig_ids[np.argmax(l_o)])
+        assert hyp[b] == h == places[b]
+        v = orc.verify_pair(st.desc[h - 1], st.xyz[h - 1], fq, fuv, synth.CAMERA_K4)
+        r = res[b]
+        assert r["ok"] == v["ok"] and r["n_matches"] == len(v["matches"]) and r["n_inliers"] == len(v["inliers"])
+        assert np.allclose(r["rvec"], v["rvec"], atol=POSE_TOL) and np.allclose(r["tvec"], v["tvec"], atol=POSE_TOL)
+        assert np.allclose(r["transform"], v["transform"], atol=POSE_TOL)
+        assert r["ok"] and np.abs(r["rvec"] - poses[b, :3]).max() < 5e-3 and np.abs(r["tvec"] - poses[b, 3:]).max() < 1e-2
+    # a removed signature can no longer be verified
+    eng.sig_remove(int(places[0]))
+    _, _, hyp2, res2 = eng.process_batch(q[:F], uv[:F], 1, m.sig_ids, 251, vp)
+    assert hyp2[0] == places[0] and not res2[0]["ok"] and res2[0]["n_matches"] == 0
