@@ -69,6 +69,50 @@ const char * lcd_build_arch(void);
 /* number of kernels this engine has launched since creation (bench "gpu_launches") */
 long long lcd_launch_count(const lcd_engine * e);
 
+/* ---- detect: Feature2D (ORB) ---------------------------------------------------------------
+ * cv::KeyPoint fields the reference uses (Signature keypoints, Features2d.cpp:1657). */
+typedef struct lcd_keypoint {
+	float x, y;      /* pt, level-0 pixel coordinates */
+	float size;      /* patchSize * scale of the level */
+	float angle;     /* degrees, intensity-centroid orientation */
+	float response;  /* Harris response */
+	int octave;      /* pyramid level */
+} lcd_keypoint;
+
+typedef struct lcd_orb_params {
+	int n_features;       /* Kp/MaxFeatures: nfeatures of cv::ORB and the limit of Feature2D::limitKeypoints */
+	int n_levels;         /* ORB/NLevels (1..4) */
+	float scale_factor;   /* ORB/ScaleFactor: 2.0 (the reference default) is the only value implemented */
+	int edge_threshold;   /* ORB/EdgeThreshold (19) */
+	int fast_threshold;   /* FAST/Threshold (20) */
+	int patch_size;       /* ORB/PatchSize: 31 (the learned rBRIEF pattern) */
+	float min_depth;      /* Kp/MinDepth */
+	float max_depth;      /* Kp/MaxDepth (0 = unlimited) */
+	int depth_as_mask;    /* Mem/DepthAsMask */
+	float fx, fy, cx, cy; /* CameraModel of the frame (depth registered to the image, same size) */
+} lcd_orb_params;
+
+#define LCD_DEPTH_NONE 0
+#define LCD_DEPTH_U16_MM 1 /* CV_16UC1, millimetres */
+#define LCD_DEPTH_F32_M 2  /* CV_32FC1, metres     */
+
+/* replaces, for Kp/DetectorStrategy=2: cv::cvtColor(BGR2GRAY) (Memory.cpp:5447),
+ * Feature2D::generateKeypoints incl. the depth mask and limitKeypoints (Features2d.cpp:775-878, :356-399)
+ * -> cv::ORB::detect, Feature2D::generateDescriptors -> cv::ORB::compute (Features2d.cpp:1663-1718) and
+ * Feature2D::generateKeypoints3D -> util3d::generateKeypoints3DDepth (util3d_features.cpp:67-120), for
+ * n_frames images [n_frames][height][width][channels] (channels 1 = gray, 3 = BGR) with optional depth
+ * [n_frames][height][width].  Outputs hold `cap` rows per frame: kp_out[n_frames*cap],
+ * desc_out[n_frames*cap*32], xyz_out[n_frames*cap*3] (NaN = no depth), n_out[n_frames] valid rows. */
+int lcd_orb_detect_describe(lcd_engine * e, int n_frames, const uint8_t * images, int width, int height, int channels,
+                            const void * depth, int depth_type, const lcd_orb_params * params, int cap,
+                            lcd_keypoint * kp_out, uint8_t * desc_out, float * xyz_out, int * n_out);
+/* same with device-resident inputs and outputs (any output may be NULL), asynchronous on `stream`;
+ * d_uv_out[n_frames*cap*2] optionally receives the keypoint coordinates as a plain float2 array. */
+int lcd_orb_detect_describe_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels,
+                                const void * d_depth, int depth_type, const lcd_orb_params * params, int cap,
+                                lcd_keypoint * d_kp_out, uint8_t * d_desc_out, float * d_xyz_out, float * d_uv_out,
+                                int * d_n_out, void * stream);
+
 /* ---- dictionary: VWDictionary ------------------------------------------------ */
 /* replaces: VWDictionary::addWord (VWDictionary.cpp:1554-1580) for n words whose ids
  * the caller chose (DB load, LTM reactivation).  Words become "not indexed" until
@@ -266,7 +310,7 @@ int lcd_shard_finalize_dev(lcd_engine * e, const long long * d_scores, int n, fl
 /* ---- measurement hooks ---------------------------------------------------------------
  * Optional per-kernel timing with CUDA events recorded on the launching stream around
  * every launch of kernel class `which` (0 = dictionary NN, 1 = resolve, 2 = score, 3 = pair
- * matching, 4 = PnP RANSAC).
+ * matching, 4 = PnP RANSAC, 5 = all ORB kernels).
  * lcd_profile_read synchronises, returns the summed device time and the launch count
  * since the last reset. */
 #define LCD_PROF_NN 0
@@ -274,6 +318,7 @@ int lcd_shard_finalize_dev(lcd_engine * e, const long long * d_scores, int n, fl
 #define LCD_PROF_SCORE 2
 #define LCD_PROF_MATCH 3
 #define LCD_PROF_PNP 4
+#define LCD_PROF_ORB 5
 int lcd_profile_enable(lcd_engine * e, int on);
 int lcd_profile_read(lcd_engine * e, int which, double * total_ms, long long * launches);
 int lcd_profile_reset(lcd_engine * e);

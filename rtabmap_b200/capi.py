@@ -38,6 +38,19 @@ class _Config(C.Structure):
     ]
 
 
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float), ("response", C.c_float), ("octave", C.c_int)]
+
+
+class OrbParams(C.Structure):
+    """lcd_orb_params (Kp/*, ORB/*, FAST/*, Mem/DepthAsMask parameters of the reference)."""
+    _fields_ = [
+        ("n_features", C.c_int), ("n_levels", C.c_int), ("scale_factor", C.c_float), ("edge_threshold", C.c_int),
+        ("fast_threshold", C.c_int), ("patch_size", C.c_int), ("min_depth", C.c_float), ("max_depth", C.c_float),
+        ("depth_as_mask", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+    ]
+
+
 class VerifyParams(C.Structure):
     """lcd_verify_params (Vis/* parameters of the reference, corelib/include/rtabmap/core/Parameters.h:713-754)."""
     _fields_ = [
@@ -84,6 +97,8 @@ SIGNATURES = {
     "lcd_abi_version": (_I, []),
     "lcd_build_arch": (C.c_char_p, []),
     "lcd_launch_count": (C.c_longlong, [_P]),
+    "lcd_orb_detect_describe": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
+    "lcd_orb_detect_describe_dev": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "lcd_dict_add_words": (_I, [_P, _P, _P, _I]),
     "lcd_dict_remove_words": (_I, [_P, _P, _I]),
     "lcd_dict_update": (_I, [_P]),
@@ -223,6 +238,42 @@ class Engine:
         n = C.c_longlong(0)
         self._check(self._lib.lcd_profile_read(self._h, which, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    # -- detect (ORB) ----------------------------------------------------------------------------
+    @staticmethod
+    def orb_params(K4=(525.0, 525.0, 320.0, 240.0), n_features=1000, n_levels=3, scale_factor=2.0, edge_threshold=19, fast_threshold=20,
+                   patch_size=31, min_depth=0.0, max_depth=0.0, depth_as_mask=True):
+        return OrbParams(n_features, n_levels, scale_factor, edge_threshold, fast_threshold, patch_size, min_depth, max_depth, int(depth_as_mask),
+                         *[float(k) for k in K4])
+
+    def orb_detect_describe(self, images, depth, params: "OrbParams", cap: int = 0):
+        """images [n,h,w] (gray) or [n,h,w,3] (BGR) uint8; depth [n,h,w] uint16 (mm) / float32 (m) / None.
+        Returns per frame: (keypoints [k,6] float32 = x,y,size,angle,response,octave; desc [k,32]; xyz [k,3])."""
+        img = np.ascontiguousarray(images, np.uint8)
+        assert img.ndim in (3, 4)
+        n, h, w = img.shape[:3]
+        ch = 1 if img.ndim == 3 else img.shape[3]
+        dtype = 0
+        dptr = None
+        if depth is not None:
+            if depth.dtype == np.uint16:
+                dtype, depth = 1, np.ascontiguousarray(depth)
+            else:
+                dtype, depth = 2, np.ascontiguousarray(depth, np.float32)
+            dptr = _ptr(depth)
+        cap = cap or (params.n_features + 256)
+        kp = (Keypoint * (n * cap))()
+        desc = np.zeros((n, cap, 32), np.uint8)
+        xyz = np.zeros((n, cap, 3), np.float32)
+        cnt = np.zeros(n, np.int32)
+        self._check(self._lib.lcd_orb_detect_describe(self._h, n, _ptr(img), w, h, ch, dptr, dtype, C.byref(params), cap, kp, _ptr(desc), _ptr(xyz), _ptr(cnt)))
+        kpa = np.frombuffer(kp, dtype=np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])).reshape(n, cap)
+        out = []
+        for i in range(n):
+            k = kpa[i, :cnt[i]]
+            arr = np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"], k["octave"].astype(np.float32)], 1) if cnt[i] else np.zeros((0, 6), np.float32)
+            out.append((arr, desc[i, :cnt[i]].copy(), xyz[i, :cnt[i]].copy()))
+        return out
 
     # -- dictionary --------------------------------------------------------------------------
     def add_words(self, ids, desc):

@@ -15,6 +15,7 @@
 #include "resolve.cuh"
 #include "score.cuh"
 #include "verify.cuh"
+#include "orb.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -164,6 +165,14 @@ struct lcd_engine
 	std::vector<int> h_slot_of_sig, free_slots;
 	int st_cap = 0, st_slots = 0;
 	DevBuf<int> d_hyp_id, d_hyp_slot;
+	// ORB workspace
+	DevBuf<uint8_t> o_img, o_gray, o_mask, o_blur, o_desc;
+	DevBuf<unsigned char> o_depth;
+	DevBuf<uint32_t> o_cand;
+	DevBuf<int> o_cand_count, o_level_n, o_n, o_overflow;
+	DevBuf<OrbKeypoint> o_level_kp, o_kp;
+	DevBuf<float> o_xyz, o_uv;
+	float gauss_sigma_loaded = -1.f;
 	DevBuf<float> d_uv;
 
 	// measurement hooks (lcd_profile_*)
@@ -172,7 +181,7 @@ struct lcd_engine
 	{
 		std::vector<cudaEvent_t> ev; // start/stop pairs
 		size_t used = 0;
-	} prof[5];
+	} prof[6];
 
 	// tuning knobs (env: LCD_NN_CTAS_PER_SM, LCD_NN_TQ, LCD_NN_VARIANT, LCD_SCORE_BLOCKS)
 	int nn_ctas_per_sm = 2, nn_tq = 8, nn_variant = 2, score_blocks = 32;
@@ -689,7 +698,7 @@ int lcd_profile_reset(lcd_engine * e)
 
 int lcd_profile_read(lcd_engine * e, int which, double * total_ms, long long * launches)
 {
-	if (!e || which < 0 || which > 4) return LCD_ERR_INVALID;
+	if (!e || which < 0 || which > 5) return LCD_ERR_INVALID;
 	LCD_TRY(set_device(e));
 	LCD_CUDA(e, cudaDeviceSynchronize());
 	auto & p = e->prof[which];
@@ -1241,6 +1250,238 @@ int lcd_localize_batch(lcd_engine * e, const void * queries, int n_frames, int n
 	if (likelihood_out)
 		LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, static_cast<size_t>(n_frames) * ns * sizeof(float), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+// ---- detect (ORB) ------------------------------------------------------------------------------
+static int orb_geometry(lcd_engine * e, int width, int height, const lcd_orb_params * p, OrbGeom & g)
+{
+	if (!p) LCD_FAIL(e, LCD_ERR_INVALID, "null ORB parameters");
+	if (p->n_levels < 1 || p->n_levels > kOrbMaxLevels) LCD_FAIL(e, LCD_ERR_INVALID, "ORB/NLevels must be 1..%d", kOrbMaxLevels);
+	if (p->scale_factor != 2.0f) LCD_FAIL(e, LCD_ERR_INVALID, "only ORB/ScaleFactor=2 is implemented");
+	if (p->patch_size != 31) LCD_FAIL(e, LCD_ERR_INVALID, "only ORB/PatchSize=31 is implemented");
+	if (width <= 0 || height <= 0 || (width % (1 << (p->n_levels - 1))) || (height % (1 << (p->n_levels - 1))))
+		LCD_FAIL(e, LCD_ERR_INVALID, "image size must be a multiple of 2^(levels-1)");
+	if (static_cast<long long>(width) * height >= (1 << 24)) LCD_FAIL(e, LCD_ERR_CAPACITY, "image too large");
+	if (p->n_features <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Kp/MaxFeatures must be positive");
+	g.n_levels = p->n_levels;
+	int off = 0;
+	for (int l = 0; l < p->n_levels; ++l)
+	{
+		g.w[l] = width >> l;
+		g.h[l] = height >> l;
+		g.off[l] = off;
+		off += g.w[l] * g.h[l];
+	}
+	g.frame_stride = off;
+	g.edge = p->edge_threshold;
+	g.fast_thr = p->fast_threshold;
+	g.patch = p->patch_size;
+	// ORB computeKeyPoints: features per level (float arithmetic as in OpenCV)
+	const float factor = static_cast<float>(1.0 / static_cast<double>(p->scale_factor));
+	float nd = p->n_features * (1 - factor) / (1 - static_cast<float>(pow(static_cast<double>(factor), static_cast<double>(p->n_levels))));
+	int sum = 0;
+	for (int l = 0; l < p->n_levels - 1; ++l)
+	{
+		g.n_per_level[l] = static_cast<int>(nearbyint(nd));
+		sum += g.n_per_level[l];
+		nd *= factor;
+	}
+	g.n_per_level[p->n_levels - 1] = std::max(p->n_features - sum, 0);
+	return LCD_OK;
+}
+
+static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
+                   int depth_type, const lcd_orb_params * p, int cap, OrbKeypoint * d_kp, uint8_t * d_desc, float * d_xyz, float * d_uv,
+                   int * d_n, cudaStream_t s)
+{
+	OrbGeom g{};
+	LCD_TRY(orb_geometry(e, width, height, p, g));
+	if (channels != 1 && channels != 3) LCD_FAIL(e, LCD_ERR_INVALID, "images must be 8UC1 or 8UC3 (BGR)");
+	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap must be 1..%d", kMaxFrameQueries);
+	if (!d_depth) depth_type = LCD_DEPTH_NONE;
+	const bool use_mask = depth_type != LCD_DEPTH_NONE && p->depth_as_mask;
+	const size_t pyr = static_cast<size_t>(n_frames) * g.frame_stride;
+	LCD_CUDA(e, e->o_gray.reserve(pyr, 0, false, s));
+	LCD_CUDA(e, e->o_blur.reserve(pyr, 0, false, s));
+	if (use_mask) LCD_CUDA(e, e->o_mask.reserve(pyr, 0, false, s));
+	const int slots = n_frames * g.n_levels;
+	int level_cap = 0;
+	for (int l = 0; l < g.n_levels; ++l) level_cap = std::max(level_cap, g.n_per_level[l] + 256);
+	LCD_CUDA(e, e->o_cand.reserve(static_cast<size_t>(slots) * kOrbCandCap, 0, false, s));
+	LCD_CUDA(e, e->o_cand_count.reserve(slots, 0, false, s));
+	LCD_CUDA(e, e->o_level_n.reserve(slots, 0, false, s));
+	LCD_CUDA(e, e->o_level_kp.reserve(static_cast<size_t>(slots) * level_cap, 0, false, s));
+	LCD_CUDA(e, e->o_overflow.reserve(1, 0, true, s));
+	if (!d_kp)
+	{
+		LCD_CUDA(e, e->o_kp.reserve(static_cast<size_t>(n_frames) * cap, 0, false, s));
+		d_kp = e->o_kp.p;
+	}
+	if (!d_n)
+	{
+		LCD_CUDA(e, e->o_n.reserve(n_frames, 0, false, s));
+		d_n = e->o_n.p;
+	}
+	if (e->gauss_sigma_loaded != 2.0f)
+	{
+		// cv::getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, stored as float
+		double t[7], sum = 0;
+		for (int i = 0; i < 7; ++i)
+		{
+			t[i] = exp(-0.5 * (i - 3) * (i - 3) / 4.0);
+			sum += t[i];
+		}
+		float kf[7];
+		for (int i = 0; i < 7; ++i) kf[i] = static_cast<float>(t[i] / sum);
+		LCD_CUDA(e, cudaMemcpyToSymbolAsync(kOrbGauss7, kf, sizeof(kf), 0, cudaMemcpyHostToDevice, s));
+		LCD_CUDA(e, cudaStreamSynchronize(s));
+		e->gauss_sigma_loaded = 2.0f;
+	}
+	prof_mark(e, LCD_PROF_ORB, s);
+	LCD_CUDA(e, cudaMemsetAsync(e->o_cand_count.p, 0, slots * sizeof(int), s));
+	{
+		OrbPrepArgs a{};
+		a.images = d_images;
+		a.channels = channels;
+		a.depth = use_mask ? d_depth : nullptr;
+		a.depth_type = depth_type;
+		a.min_depth = p->min_depth;
+		a.max_depth = p->max_depth;
+		a.gray = e->o_gray.p;
+		a.mask = use_mask ? e->o_mask.p : nullptr;
+		a.g = g;
+		dim3 blk(32, 8), grd(((width + 1) / 2 + 31) / 32, ((height + 1) / 2 + 7) / 8, n_frames);
+		orb_prepare_kernel<<<grd, blk, 0, s>>>(a);
+		LCD_CHECK_LAUNCH(e);
+	}
+	for (int l = 2; l < g.n_levels; ++l)
+	{
+		dim3 blk(32, 8), grd((g.w[l] + 31) / 32, (g.h[l] + 7) / 8, n_frames);
+		orb_down_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, use_mask ? e->o_mask.p : nullptr, g, l);
+		LCD_CHECK_LAUNCH(e);
+	}
+	for (int l = 0; l < g.n_levels; ++l)
+	{
+		dim3 blk(kFastTile, kFastTile), grd((g.w[l] + kFastTile - 1) / kFastTile, (g.h[l] + kFastTile - 1) / kFastTile, n_frames);
+		orb_fast_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, use_mask ? e->o_mask.p : nullptr, g, l, e->o_cand.p, e->o_cand_count.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	{
+		OrbSelectArgs a{};
+		a.gray = e->o_gray.p;
+		a.g = g;
+		a.cand = e->o_cand.p;
+		a.cand_count = e->o_cand_count.p;
+		a.level_kp = e->o_level_kp.p;
+		a.level_n = e->o_level_n.p;
+		a.level_cap = level_cap;
+		a.overflow = e->o_overflow.p;
+		const size_t smem = static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2);
+		LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+		orb_select_kernel<<<slots, kOrbSelectThreads, smem, s>>>(a);
+		LCD_CHECK_LAUNCH(e);
+	}
+	{
+		int pad = 1;
+		while (pad < g.n_levels * level_cap) pad <<= 1;
+		orb_merge_kernel<<<n_frames, 1024, pad * sizeof(unsigned long long), s>>>(e->o_level_kp.p, e->o_level_n.p, g.n_levels, level_cap, p->n_features,
+		                                                                          d_kp, d_n, cap);
+		LCD_CHECK_LAUNCH(e);
+	}
+	if (d_desc)
+	{
+		for (int l = 0; l < g.n_levels; ++l)
+		{
+			dim3 blk(16, 16), grd((g.w[l] + 15) / 16, (g.h[l] + 15) / 16, n_frames);
+			orb_blur_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, e->o_blur.p, g, l);
+			LCD_CHECK_LAUNCH(e);
+		}
+		dim3 grd((cap * 32 + 255) / 256, n_frames);
+		orb_describe_kernel<<<grd, 256, 0, s>>>(e->o_gray.p, e->o_blur.p, g, d_kp, d_n, cap, d_desc);
+		LCD_CHECK_LAUNCH(e);
+	}
+	if (d_xyz || d_uv)
+	{
+		if (d_xyz)
+		{
+			OrbXyzArgs a{};
+			a.depth = depth_type != LCD_DEPTH_NONE ? d_depth : nullptr;
+			a.depth_type = depth_type;
+			a.w = width;
+			a.h = height;
+			a.fx = p->fx;
+			a.fy = p->fy;
+			a.cx = p->cx;
+			a.cy = p->cy;
+			a.min_depth = p->min_depth;
+			a.max_depth = p->max_depth;
+			a.kps = d_kp;
+			a.n_kp = d_n;
+			a.cap = cap;
+			a.xyz = d_xyz;
+			dim3 grd((cap + 255) / 256, n_frames);
+			orb_xyz_kernel<<<grd, 256, 0, s>>>(a);
+			LCD_CHECK_LAUNCH(e);
+		}
+		if (d_uv)
+		{
+			dim3 grd((cap + 255) / 256, n_frames);
+			orb_uv_kernel<<<grd, 256, 0, s>>>(d_kp, d_n, cap, d_uv);
+			LCD_CHECK_LAUNCH(e);
+		}
+	}
+	prof_mark(e, LCD_PROF_ORB, s);
+	return LCD_OK;
+}
+
+int lcd_orb_detect_describe_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
+                                int depth_type, const lcd_orb_params * params, int cap, lcd_keypoint * d_kp_out, uint8_t * d_desc_out,
+                                float * d_xyz_out, float * d_uv_out, int * d_n_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_images || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null image");
+	static_assert(sizeof(lcd_keypoint) == sizeof(OrbKeypoint), "keypoint layout");
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	return orb_run(e, n_frames, d_images, width, height, channels, d_depth, depth_type, params, cap, reinterpret_cast<OrbKeypoint *>(d_kp_out),
+	               d_desc_out, d_xyz_out, d_uv_out, d_n_out, s);
+}
+
+int lcd_orb_detect_describe(lcd_engine * e, int n_frames, const uint8_t * images, int width, int height, int channels, const void * depth,
+                            int depth_type, const lcd_orb_params * params, int cap, lcd_keypoint * kp_out, uint8_t * desc_out, float * xyz_out,
+                            int * n_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!images || n_frames <= 0 || width <= 0 || height <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null image");
+	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap must be 1..%d", kMaxFrameQueries);
+	cudaStream_t s = e->stream;
+	const size_t px = static_cast<size_t>(n_frames) * width * height;
+	LCD_CUDA(e, e->o_img.reserve(px * channels, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->o_img.p, images, px * channels, cudaMemcpyHostToDevice, s));
+	if (!depth) depth_type = LCD_DEPTH_NONE;
+	const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+	if (depth_type != LCD_DEPTH_NONE)
+	{
+		LCD_CUDA(e, e->o_depth.reserve(px * dbytes, 0, false, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->o_depth.p, depth, px * dbytes, cudaMemcpyHostToDevice, s));
+	}
+	const size_t rows = static_cast<size_t>(n_frames) * cap;
+	LCD_CUDA(e, e->o_kp.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->o_desc.reserve(rows * 32, 0, false, s));
+	LCD_CUDA(e, e->o_xyz.reserve(rows * 3, 0, false, s));
+	LCD_CUDA(e, e->o_n.reserve(n_frames, 0, false, s));
+	LCD_TRY(orb_run(e, n_frames, e->o_img.p, width, height, channels, depth_type != LCD_DEPTH_NONE ? e->o_depth.p : nullptr, depth_type, params, cap,
+	                e->o_kp.p, desc_out ? e->o_desc.p : nullptr, xyz_out ? e->o_xyz.p : nullptr, nullptr, e->o_n.p, s));
+	if (kp_out) LCD_CUDA(e, cudaMemcpyAsync(kp_out, e->o_kp.p, rows * sizeof(OrbKeypoint), cudaMemcpyDeviceToHost, s));
+	if (desc_out) LCD_CUDA(e, cudaMemcpyAsync(desc_out, e->o_desc.p, rows * 32, cudaMemcpyDeviceToHost, s));
+	if (xyz_out) LCD_CUDA(e, cudaMemcpyAsync(xyz_out, e->o_xyz.p, rows * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+	if (n_out) LCD_CUDA(e, cudaMemcpyAsync(n_out, e->o_n.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	int overflow = 0;
+	LCD_CUDA(e, cudaMemcpyAsync(&overflow, e->o_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	if (overflow) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d FAST corners in one pyramid level (or too many ties): raise FAST/Threshold", kOrbCandCap);
 	return LCD_OK;
 }
 

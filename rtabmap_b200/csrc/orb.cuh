@@ -1,0 +1,764 @@
+// orb.cuh — ORB keypoint detection and description on the incoming frame (the DETECT stage).
+//
+// Replaces: Feature2D::generateKeypoints / generateDescriptors / generateKeypoints3D for
+// Kp/DetectorStrategy=2 (corelib/src/Features2d.cpp:775-878, :1621-1718, :905-1116), i.e. OpenCV's
+// cv::ORB::detect + compute [third-party; algorithm restated in-tree at corelib/src/opencv/Orb.cpp:61-134
+// (Harris, IC angle), :138-258 (steered BRIEF), :737-852 (pyramid + FAST + retainBest)], the depth mask
+// (Features2d.cpp:783-808), Feature2D::limitKeypoints (:356-399), cv::cvtColor(BGR2GRAY) (Memory.cpp:5447)
+// and util3d::generateKeypoints3DDepth (util3d_features.cpp:67-120; util2d::getDepth, util2d.cpp:947-1108).
+//
+// Bit-exactness notes (each pinned against opencv-python 4.13, tests/test_gpu_orb.py):
+//   * gray = (B*3735 + G*19235 + R*9798 + 2^14) >> 15;
+//   * pyramid (ORB/ScaleFactor = 2 only): INTER_LINEAR_EXACT by exactly 2 = (a+b+c+d+2) >> 2, level l from
+//     level l-1; mask levels = 2x2 AND (resize + THRESH_TOZERO 254);
+//   * FAST-9/16 score = max over the 16 arcs of the min |difference| - 1, 3x3 strict non-max suppression,
+//     keypoints in raster order; border (ORB/EdgeThreshold) and mask filters after suppression;
+//   * KeyPointsFilter::retainBest keeps ties and leaves the keypoints in the order libstdc++'s
+//     std::nth_element (introselect, median-of-3, unguarded Hoare partition) and std::partition produce;
+//     that order is the order of the frame's descriptors and therefore of its words, so the two
+//     algorithms are replayed literally (sequentially, one thread per frame and level);
+//   * Harris response and IC angle use float arithmetic in OpenCV's operation order, without FMA;
+//     fastAtan2's polynomial coefficients are float products (c * 57.29578f);
+//   * the 7x7 sigma=2 blur runs on a sub-matrix of the pyramid buffer, which sends OpenCV down the float
+//     sepFilter2D path (not the fixed-point one): row pass in plain order, column pass symmetric, both with
+//     fused multiply-add (AVX2 dispatch), round-to-nearest-even to uint8; descriptor taps that fall outside
+//     the level read the UNBLURRED reflected border.
+#pragma once
+#include "common.cuh"
+#include "orb_pattern.h"
+#include <math.h>
+
+namespace lcd {
+
+constexpr int kOrbMaxLevels = 4;
+constexpr int kOrbCandCap = 16384; // FAST corners kept per frame and level before retainBest
+constexpr int kOrbSelectThreads = 512;
+
+struct OrbKeypoint // cv::KeyPoint fields used by the reference
+{
+	float x, y, size, angle, response;
+	int octave;
+};
+
+struct OrbGeom
+{
+	int n_levels;
+	int w[kOrbMaxLevels], h[kOrbMaxLevels];
+	int off[kOrbMaxLevels]; // plane offset of each level inside one frame's pyramid
+	int frame_stride;       // bytes of one frame's pyramid
+	int n_per_level[kOrbMaxLevels];
+	int edge, fast_thr, patch;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+	if (i < 0) i = -i;
+	if (i >= n) i = 2 * n - 2 - i;
+	return i;
+}
+
+// ---- K1: gray + depth mask (level 0) and level 1 -------------------------------------------------
+// One thread per level-1 pixel (a 2x2 block of the input).
+struct OrbPrepArgs
+{
+	const uint8_t * images; // [n_frames][h][w][channels]
+	int channels;
+	const void * depth;     // [n_frames][h][w] u16 (mm) or f32 (m), or nullptr
+	int depth_type;         // 0 none, 1 u16, 2 f32
+	float min_depth, max_depth;
+	uint8_t * gray;         // pyramids
+	uint8_t * mask;         // pyramids or nullptr
+	OrbGeom g;
+};
+
+__device__ __forceinline__ uint8_t depth_to_mask(const void * depth, int type, size_t idx, float min_depth, float max_depth)
+{
+	float value = 0.0f;
+	if (type == 1)
+	{
+		const unsigned short d = static_cast<const unsigned short *>(depth)[idx];
+		if (d > 0 && d < 65535) value = static_cast<float>(d) * 0.001f;
+	}
+	else
+	{
+		value = static_cast<const float *>(depth)[idx];
+	}
+	return (value > min_depth && (max_depth == 0.0f || value <= max_depth) && isfinite(value)) ? 255 : 0;
+}
+
+__global__ void orb_prepare_kernel(const OrbPrepArgs a)
+{
+	const int x1 = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y1 = blockIdx.y * blockDim.y + threadIdx.y;
+	const int frame = blockIdx.z;
+	const int w = a.g.w[0], h = a.g.h[0];
+	if (x1 * 2 >= w || y1 * 2 >= h) return;
+	uint8_t * gray = a.gray + static_cast<size_t>(frame) * a.g.frame_stride;
+	uint8_t * mask = a.mask ? a.mask + static_cast<size_t>(frame) * a.g.frame_stride : nullptr;
+	const uint8_t * img = a.images + static_cast<size_t>(frame) * w * h * a.channels;
+	int sum = 0;
+	int mall = 255;
+#pragma unroll
+	for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+		for (int dx = 0; dx < 2; ++dx)
+		{
+			const int x = 2 * x1 + dx, y = 2 * y1 + dy;
+			int gv;
+			if (a.channels == 1) gv = img[static_cast<size_t>(y) * w + x];
+			else
+			{
+				const uint8_t * p = img + (static_cast<size_t>(y) * w + x) * a.channels;
+				gv = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15;
+			}
+			gray[static_cast<size_t>(y) * w + x] = static_cast<uint8_t>(gv);
+			sum += gv;
+			if (mask)
+			{
+				const uint8_t m = depth_to_mask(a.depth, a.depth_type, static_cast<size_t>(frame) * w * h + static_cast<size_t>(y) * w + x, a.min_depth, a.max_depth);
+				mask[static_cast<size_t>(y) * w + x] = m;
+				mall &= m;
+			}
+		}
+	if (a.g.n_levels > 1)
+	{
+		gray[a.g.off[1] + static_cast<size_t>(y1) * a.g.w[1] + x1] = static_cast<uint8_t>((sum + 2) >> 2);
+		if (mask) mask[a.g.off[1] + static_cast<size_t>(y1) * a.g.w[1] + x1] = static_cast<uint8_t>(mall);
+	}
+}
+
+// level l (>= 2) from level l-1
+__global__ void orb_down_kernel(uint8_t * gray_all, uint8_t * mask_all, const OrbGeom g, int level)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y;
+	const int frame = blockIdx.z;
+	if (x >= g.w[level] || y >= g.h[level]) return;
+	uint8_t * gray = gray_all + static_cast<size_t>(frame) * g.frame_stride;
+	const uint8_t * src = gray + g.off[level - 1];
+	const int sw = g.w[level - 1];
+	const int s = src[static_cast<size_t>(2 * y) * sw + 2 * x] + src[static_cast<size_t>(2 * y) * sw + 2 * x + 1] +
+	              src[static_cast<size_t>(2 * y + 1) * sw + 2 * x] + src[static_cast<size_t>(2 * y + 1) * sw + 2 * x + 1];
+	gray[g.off[level] + static_cast<size_t>(y) * g.w[level] + x] = static_cast<uint8_t>((s + 2) >> 2);
+	if (mask_all)
+	{
+		uint8_t * mask = mask_all + static_cast<size_t>(frame) * g.frame_stride;
+		const uint8_t * ms = mask + g.off[level - 1];
+		const int m = ms[static_cast<size_t>(2 * y) * sw + 2 * x] & ms[static_cast<size_t>(2 * y) * sw + 2 * x + 1] &
+		              ms[static_cast<size_t>(2 * y + 1) * sw + 2 * x] & ms[static_cast<size_t>(2 * y + 1) * sw + 2 * x + 1];
+		mask[g.off[level] + static_cast<size_t>(y) * g.w[level] + x] = static_cast<uint8_t>(m);
+	}
+}
+
+// ---- K2: FAST-9/16 score + 3x3 non-max suppression + border/mask filters -> candidate list --------
+constexpr int kFastTile = 16;
+
+__device__ __forceinline__ int fast_score(const uint8_t * t, int stride, int thr)
+{
+	// t points at the pixel inside a shared tile; ring offsets of the 16-pixel Bresenham circle
+	const int v = t[0];
+	int d[16];
+	d[0] = v - t[3 * stride];
+	d[8] = v - t[-3 * stride];
+	d[4] = v - t[3];
+	d[12] = v - t[-3];
+	// every 9-arc contains pixel 0 or 8, and pixel 4 or 12
+	if ((abs(d[0]) <= thr && abs(d[8]) <= thr) || (abs(d[4]) <= thr && abs(d[12]) <= thr)) return 0;
+	d[1] = v - t[3 * stride + 1];
+	d[2] = v - t[2 * stride + 2];
+	d[3] = v - t[1 * stride + 3];
+	d[5] = v - t[-1 * stride + 3];
+	d[6] = v - t[-2 * stride + 2];
+	d[7] = v - t[-3 * stride + 1];
+	d[9] = v - t[-3 * stride - 1];
+	d[10] = v - t[-2 * stride - 2];
+	d[11] = v - t[-1 * stride - 3];
+	d[13] = v - t[1 * stride - 3];
+	d[14] = v - t[2 * stride - 2];
+	d[15] = v - t[3 * stride - 1];
+	int best = -1000;
+#pragma unroll
+	for (int s = 0; s < 16; ++s)
+	{
+		int mb = d[s], md = -d[s];
+#pragma unroll
+		for (int k = 1; k < 9; ++k)
+		{
+			mb = min(mb, d[(s + k) & 15]);
+			md = min(md, -d[(s + k) & 15]);
+		}
+		best = max(best, max(mb, md));
+	}
+	return best > thr ? best - 1 : 0;
+}
+
+__global__ void __launch_bounds__(kFastTile * kFastTile)
+orb_fast_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restrict__ mask_all, const OrbGeom g, int level,
+                uint32_t * __restrict__ cand, int * __restrict__ cand_count)
+{
+	constexpr int T = kFastTile, R = T + 2 + 6; // tile + nms halo + ring halo
+	__shared__ uint8_t tile[R][R + 4];
+	__shared__ uint8_t sc[T + 2][T + 2];
+	const int frame = blockIdx.z;
+	const int w = g.w[level], h = g.h[level];
+	const uint8_t * gray = gray_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
+	const int tid = threadIdx.y * T + threadIdx.x;
+	for (int i = tid; i < R * R; i += T * T)
+	{
+		const int ty = i / R, tx = i % R;
+		const int x = x0 + tx - 4, y = y0 + ty - 4;
+		tile[ty][tx] = (x >= 0 && x < w && y >= 0 && y < h) ? gray[static_cast<size_t>(y) * w + x] : 0;
+	}
+	__syncthreads();
+	for (int i = tid; i < (T + 2) * (T + 2); i += T * T)
+	{
+		const int sy = i / (T + 2), sx = i % (T + 2);
+		const int x = x0 + sx - 1, y = y0 + sy - 1;
+		int s = 0;
+		if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) s = fast_score(&tile[sy + 3][sx + 3], R + 4, g.fast_thr);
+		sc[sy][sx] = static_cast<uint8_t>(s);
+	}
+	__syncthreads();
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	if (x >= w || y >= h) return;
+	const int s = sc[threadIdx.y + 1][threadIdx.x + 1];
+	if (s == 0) return;
+	const int sx = threadIdx.x + 1, sy = threadIdx.y + 1;
+	const bool is_max = s > sc[sy - 1][sx - 1] && s > sc[sy - 1][sx] && s > sc[sy - 1][sx + 1] && s > sc[sy][sx - 1] && s > sc[sy][sx + 1] &&
+	                    s > sc[sy + 1][sx - 1] && s > sc[sy + 1][sx] && s > sc[sy + 1][sx + 1];
+	if (!is_max) return;
+	// KeyPointsFilter::runByPixelsMask, then runByImageBorder(edgeThreshold)
+	if (mask_all && mask_all[static_cast<size_t>(frame) * g.frame_stride + g.off[level] + static_cast<size_t>(y) * w + x] == 0) return;
+	if (x < g.edge || x >= w - g.edge || y < g.edge || y >= h - g.edge) return;
+	const int slot = frame * g.n_levels + level;
+	const int k = atomicAdd(&cand_count[slot], 1);
+	if (k < kOrbCandCap) cand[static_cast<size_t>(slot) * kOrbCandCap + k] = (static_cast<uint32_t>(y * w + x) << 8) | static_cast<uint32_t>(s);
+}
+
+// ---- K3: per (frame, level) selection: raster order, retainBest(2N) on FAST score, Harris, retainBest(N),
+//          IC angle.  One CTA; the two retainBest replays are sequential (thread 0). -----------------------
+struct RespGreater
+{
+	const float * resp;
+	const uint16_t * perm;
+	__device__ __forceinline__ bool operator()(int a, int b) const { return resp[perm[a]] > resp[perm[b]]; }
+};
+
+// libstdc++ std::nth_element(first, nth, last, comp) on perm[first..last)
+__device__ inline void nth_element_replay(uint16_t * perm, const float * resp, int first, int nth, int last)
+{
+	if (first == last || nth == last) return;
+	auto comp = [&](int a, int b) { return resp[perm[a]] > resp[perm[b]]; };
+	auto swp = [&](int a, int b) {
+		const uint16_t t = perm[a];
+		perm[a] = perm[b];
+		perm[b] = t;
+	};
+	int depth = 2 * (31 - __clz(last - first));
+	while (last - first > 3)
+	{
+		if (depth == 0)
+		{
+			// __heap_select fallback of introselect: cannot occur before 2*log2(n) unbalanced partitions;
+			// a plain selection keeps the SET right even then (order parity is lost, flagged by the tests)
+			for (int i = first; i <= nth; ++i)
+			{
+				int b = i;
+				for (int j = i + 1; j < last; ++j)
+					if (comp(j, b)) b = j;
+				swp(i, b);
+			}
+			return;
+		}
+		--depth;
+		const int mid = first + (last - first) / 2;
+		// __move_median_to_first(first, first+1, mid, last-1)
+		{
+			const int r = first, a = first + 1, b = mid, c = last - 1;
+			if (comp(a, b))
+			{
+				if (comp(b, c)) swp(r, b);
+				else if (comp(a, c)) swp(r, c);
+				else swp(r, a);
+			}
+			else if (comp(a, c)) swp(r, a);
+			else if (comp(b, c)) swp(r, c);
+			else swp(r, b);
+		}
+		// __unguarded_partition(first+1, last, pivot = first)
+		int lo = first + 1, hi = last;
+		const float pv = resp[perm[first]];
+		for (;;)
+		{
+			while (resp[perm[lo]] > pv) ++lo;
+			--hi;
+			while (pv > resp[perm[hi]]) --hi;
+			if (!(lo < hi)) break;
+			swp(lo, hi);
+			++lo;
+		}
+		const int cut = lo;
+		if (cut <= nth) first = cut;
+		else last = cut;
+	}
+	// __insertion_sort(first, last)
+	for (int i = first + 1; i < last; ++i)
+	{
+		const uint16_t val = perm[i];
+		const float rv = resp[val];
+		if (rv > resp[perm[first]])
+		{
+			for (int j = i; j > first; --j) perm[j] = perm[j - 1];
+			perm[first] = val;
+		}
+		else
+		{
+			int j = i;
+			while (rv > resp[perm[j - 1]])
+			{
+				perm[j] = perm[j - 1];
+				--j;
+			}
+			perm[j] = val;
+		}
+	}
+}
+
+// KeyPointsFilter::retainBest(keypoints, n_points): returns the new size
+__device__ inline int retain_best_replay(uint16_t * perm, const float * resp, int n, int n_points)
+{
+	if (n_points < 0 || n <= n_points) return n;
+	if (n_points == 0) return 0;
+	nth_element_replay(perm, resp, 0, n_points - 1, n);
+	const float amb = resp[perm[n_points - 1]];
+	// std::partition(perm + n_points, perm + n, response >= amb)  (bidirectional version)
+	int first = n_points, last = n;
+	for (;;)
+	{
+		for (;;)
+		{
+			if (first == last) return first;
+			if (resp[perm[first]] >= amb) ++first;
+			else break;
+		}
+		--last;
+		for (;;)
+		{
+			if (first == last) return first;
+			if (!(resp[perm[last]] >= amb)) --last;
+			else break;
+		}
+		const uint16_t t = perm[first];
+		perm[first] = perm[last];
+		perm[last] = t;
+		++first;
+	}
+}
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+	const float K = static_cast<float>(180.0 / 3.141592653589793238462643383279502884197169399375);
+	const float p1 = __fmul_rn(0.9997878412794807f, K), p3 = __fmul_rn(-0.3258083974640975f, K), p5 = __fmul_rn(0.1555786518463281f, K),
+	            p7 = __fmul_rn(-0.04432655554792128f, K);
+	const float ax = fabsf(x), ay = fabsf(y);
+	const float eps = static_cast<float>(2.220446049250313e-16);
+	float a, c, c2;
+	if (ax >= ay)
+	{
+		c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+		c2 = __fmul_rn(c, c);
+		a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+	}
+	else
+	{
+		c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+		c2 = __fmul_rn(c, c);
+		a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+	}
+	if (x < 0) a = __fsub_rn(180.f, a);
+	if (y < 0) a = __fsub_rn(360.f, a);
+	return a;
+}
+
+struct OrbSelectArgs
+{
+	const uint8_t * gray;
+	OrbGeom g;
+	const uint32_t * cand;
+	const int * cand_count;
+	OrbKeypoint * level_kp; // [n_frames][n_levels][level_cap]
+	int * level_n;          // [n_frames][n_levels]
+	int level_cap;
+	int * overflow;         // set when a candidate list had to be truncated
+};
+
+__global__ void __launch_bounds__(kOrbSelectThreads)
+orb_select_kernel(const OrbSelectArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint32_t * keys = reinterpret_cast<uint32_t *>(smem_raw);          // [kOrbCandCap]
+	float * resp = reinterpret_cast<float *>(keys + kOrbCandCap);        // [kOrbCandCap]
+	uint16_t * perm = reinterpret_cast<uint16_t *>(resp + kOrbCandCap);  // [kOrbCandCap]
+	__shared__ int s_n;
+	__shared__ int s_umax[20];
+
+	const int tid = threadIdx.x;
+	const int frame = blockIdx.x / a.g.n_levels, level = blockIdx.x % a.g.n_levels;
+	const int slot = blockIdx.x;
+	const int w = a.g.w[level], h = a.g.h[level];
+	const uint8_t * img = a.gray + static_cast<size_t>(frame) * a.g.frame_stride + a.g.off[level];
+	int n = a.cand_count[slot];
+	if (n > kOrbCandCap)
+	{
+		n = kOrbCandCap;
+		if (tid == 0) atomicExch(a.overflow, 1);
+	}
+	int n_pad = 1;
+	while (n_pad < n) n_pad <<= 1;
+	for (int i = tid; i < n_pad; i += blockDim.x) keys[i] = i < n ? a.cand[static_cast<size_t>(slot) * kOrbCandCap + i] : 0xFFFFFFFFu;
+	if (tid == 0)
+	{
+		// umax table of the circular patch (ORB computeKeyPoints)
+		const int half = a.g.patch / 2;
+		const int vmax = static_cast<int>(floorf(half * sqrtf(2.f) / 2 + 1));
+		const int vmin = static_cast<int>(ceilf(half * sqrtf(2.f) / 2));
+		for (int v = 0; v <= vmax; ++v) s_umax[v] = static_cast<int>(rint(sqrt(static_cast<double>(half) * half - static_cast<double>(v) * v)));
+		for (int v = half, v0 = 0; v >= vmin; --v)
+		{
+			while (s_umax[v0] == s_umax[v0 + 1]) ++v0;
+			s_umax[v] = v0;
+			++v0;
+		}
+	}
+	__syncthreads();
+	// raster order (FAST emits keypoints row by row)
+	for (int k = 2; k <= n_pad; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1)
+		{
+			for (int idx = tid; idx < n_pad; idx += blockDim.x)
+			{
+				const int ixj = idx ^ j;
+				if (ixj > idx)
+				{
+					const uint32_t x = keys[idx], y = keys[ixj];
+					if ((x > y) == ((idx & k) == 0))
+					{
+						keys[idx] = y;
+						keys[ixj] = x;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	for (int i = tid; i < n; i += blockDim.x)
+	{
+		resp[i] = static_cast<float>(keys[i] & 0xFFu);
+		perm[i] = static_cast<uint16_t>(i);
+	}
+	__syncthreads();
+	const int n_level = a.g.n_per_level[level];
+	if (tid == 0) s_n = retain_best_replay(perm, resp, n, 2 * n_level);
+	__syncthreads();
+	int m = s_n;
+	// Harris responses of the kept candidates (HarrisResponses, blockSize 7, k 0.04)
+	for (int i = tid; i < m; i += blockDim.x)
+	{
+		const int pos = static_cast<int>(keys[perm[i]] >> 8);
+		const int x0 = pos % w, y0 = pos / w;
+		int A = 0, B = 0, Cc = 0;
+		for (int dy = -3; dy <= 3; ++dy)
+			for (int dx = -3; dx <= 3; ++dx)
+			{
+				const int x = x0 + dx, y = y0 + dy;
+				const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w), ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+				const int xc = reflect101(x, w), yc = reflect101(y, h);
+				const int p00 = img[ym * w + xm], p01 = img[ym * w + xc], p02 = img[ym * w + xp];
+				const int p10 = img[yc * w + xm], p12 = img[yc * w + xp];
+				const int p20 = img[yp * w + xm], p21 = img[yp * w + xc], p22 = img[yp * w + xp];
+				const int Ix = (p12 - p10) * 2 + (p02 - p00) + (p22 - p20);
+				const int Iy = (p21 - p01) * 2 + (p20 - p00) + (p22 - p02);
+				A += Ix * Ix;
+				B += Iy * Iy;
+				Cc += Ix * Iy;
+			}
+		const float scale = __fdiv_rn(1.f, __fmul_rn(static_cast<float>(4 * 7), 255.f));
+		const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+		const float fa = static_cast<float>(A), fb = static_cast<float>(B), fc = static_cast<float>(Cc);
+		const float t3 = __fadd_rn(fa, fb);
+		resp[perm[i]] = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, t3), t3)), s4);
+	}
+	__syncthreads();
+	if (tid == 0) s_n = retain_best_replay(perm, resp, m, n_level);
+	__syncthreads();
+	m = min(s_n, a.level_cap);
+	if (tid == 0)
+	{
+		a.level_n[slot] = m;
+		if (s_n > a.level_cap) atomicExch(a.overflow, 1);
+	}
+	// IC angle + output
+	const int half = a.g.patch / 2;
+	const float sf = static_cast<float>(1 << level);
+	for (int i = tid; i < m; i += blockDim.x)
+	{
+		const int pos = static_cast<int>(keys[perm[i]] >> 8);
+		const int x0 = pos % w, y0 = pos / w;
+		int m01 = 0, m10 = 0;
+		for (int u = -half; u <= half; ++u) m10 += u * img[reflect101(y0, h) * w + reflect101(x0 + u, w)];
+		for (int v = 1; v <= half; ++v)
+		{
+			int vsum = 0;
+			const int d = s_umax[v];
+			const int yp = reflect101(y0 + v, h), ym = reflect101(y0 - v, h);
+			for (int u = -d; u <= d; ++u)
+			{
+				const int xx = reflect101(x0 + u, w);
+				const int vp = img[yp * w + xx], vm = img[ym * w + xx];
+				vsum += vp - vm;
+				m10 += u * (vp + vm);
+			}
+			m01 += v * vsum;
+		}
+		OrbKeypoint kp;
+		kp.x = __fmul_rn(static_cast<float>(x0), sf);
+		kp.y = __fmul_rn(static_cast<float>(y0), sf);
+		kp.size = __fmul_rn(static_cast<float>(a.g.patch), sf);
+		kp.angle = fast_atan2_deg(static_cast<float>(m01), static_cast<float>(m10));
+		kp.response = resp[perm[i]];
+		kp.octave = level;
+		a.level_kp[static_cast<size_t>(slot) * a.level_cap + i] = kp;
+	}
+}
+
+// ---- K4: concatenate the levels of a frame and apply Feature2D::limitKeypoints -----------------------
+__global__ void __launch_bounds__(1024)
+orb_merge_kernel(const OrbKeypoint * __restrict__ level_kp, const int * __restrict__ level_n, int n_levels, int level_cap, int max_features,
+                 OrbKeypoint * __restrict__ out, int * __restrict__ out_n, int out_cap)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	unsigned long long * skey = reinterpret_cast<unsigned long long *>(smem_raw); // [pad]
+	__shared__ int s_off[kOrbMaxLevels + 1];
+	const int frame = blockIdx.x, tid = threadIdx.x;
+	if (tid == 0)
+	{
+		s_off[0] = 0;
+		for (int l = 0; l < n_levels; ++l) s_off[l + 1] = s_off[l] + level_n[frame * n_levels + l];
+	}
+	__syncthreads();
+	const int total = s_off[n_levels];
+	auto src = [&](int i) -> const OrbKeypoint & {
+		int l = 0;
+		while (i >= s_off[l + 1]) ++l;
+		return level_kp[(static_cast<size_t>(frame) * n_levels + l) * level_cap + (i - s_off[l])];
+	};
+	if (max_features <= 0 || total <= max_features)
+	{
+		const int n = min(total, out_cap);
+		for (int i = tid; i < n; i += blockDim.x) out[static_cast<size_t>(frame) * out_cap + i] = src(i);
+		if (tid == 0) out_n[frame] = n;
+		return;
+	}
+	// multimap<fabs(response), index> walked in reverse: strongest first, later index first among equals
+	int pad = 1;
+	while (pad < total) pad <<= 1;
+	for (int i = tid; i < pad; i += blockDim.x)
+	{
+		unsigned long long k = 0ull; // sorts last in descending order
+		if (i < total)
+		{
+			const float r = fabsf(src(i).response);
+			k = (static_cast<unsigned long long>(__float_as_uint(r)) << 32) | static_cast<unsigned>(i + 1);
+		}
+		skey[i] = k;
+	}
+	__syncthreads();
+	for (int k = 2; k <= pad; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1)
+		{
+			for (int idx = tid; idx < pad; idx += blockDim.x)
+			{
+				const int ixj = idx ^ j;
+				if (ixj > idx)
+				{
+					const unsigned long long x = skey[idx], y = skey[ixj];
+					if ((x < y) == ((idx & k) == 0)) // descending
+					{
+						skey[idx] = y;
+						skey[ixj] = x;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	const int n = min(max_features, out_cap);
+	for (int i = tid; i < n; i += blockDim.x) out[static_cast<size_t>(frame) * out_cap + i] = src(static_cast<int>(skey[i] & 0xFFFFFFFFull) - 1);
+	if (tid == 0) out_n[frame] = n;
+}
+
+// ---- K5: 7x7 sigma=2 blur of every level (float sepFilter2D semantics) -------------------------------
+__constant__ float kOrbGauss7[7];
+
+__global__ void __launch_bounds__(256)
+orb_blur_kernel(const uint8_t * __restrict__ gray_all, uint8_t * __restrict__ blur_all, const OrbGeom g, int level)
+{
+	constexpr int T = 16;
+	__shared__ float rowf[T + 6][T];
+	const int frame = blockIdx.z;
+	const int w = g.w[level], h = g.h[level];
+	const uint8_t * img = gray_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	uint8_t * out = blur_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
+	const int tid = threadIdx.y * T + threadIdx.x;
+	// row pass (plain order, fused multiply-add) for the T+6 rows the column pass needs
+	for (int i = tid; i < (T + 6) * T; i += T * T)
+	{
+		const int ry = i / T, rx = i % T;
+		const int y = reflect101(y0 + ry - 3, h);
+		const int x = x0 + rx;
+		float s = 0.f;
+		if (x < w)
+		{
+			const uint8_t * row = img + static_cast<size_t>(y) * w;
+			s = __fmul_rn(static_cast<float>(row[reflect101(x - 3, w)]), kOrbGauss7[0]);
+#pragma unroll
+			for (int k = 1; k < 7; ++k) s = __fmaf_rn(static_cast<float>(row[reflect101(x - 3 + k, w)]), kOrbGauss7[k], s);
+		}
+		rowf[ry][rx] = s;
+	}
+	__syncthreads();
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	if (x >= w || y >= h) return;
+	// column pass (symmetric, fused multiply-add), then saturate_cast<uchar> (round half to even)
+	const int c = threadIdx.y + 3;
+	float s = __fmul_rn(rowf[c][threadIdx.x], kOrbGauss7[3]);
+#pragma unroll
+	for (int k = 1; k <= 3; ++k) s = __fmaf_rn(__fadd_rn(rowf[c + k][threadIdx.x], rowf[c - k][threadIdx.x]), kOrbGauss7[3 + k], s);
+	int v = __float2int_rn(s);
+	v = v < 0 ? 0 : (v > 255 ? 255 : v);
+	out[static_cast<size_t>(y) * w + x] = static_cast<uint8_t>(v);
+}
+
+// ---- K6: steered BRIEF (computeOrbDescriptors, WTA_K = 2) --------------------------------------------
+__global__ void orb_describe_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restrict__ blur_all, const OrbGeom g,
+                                    const OrbKeypoint * __restrict__ kps, const int * __restrict__ n_kp, int cap, uint8_t * __restrict__ desc)
+{
+	const int frame = blockIdx.y;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int ki = t >> 5, byte = t & 31;
+	if (ki >= n_kp[frame]) return;
+	const OrbKeypoint kp = kps[static_cast<size_t>(frame) * cap + ki];
+	const int level = kp.octave;
+	const int w = g.w[level], h = g.h[level];
+	const uint8_t * raw = gray_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	const uint8_t * blr = blur_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	const float scale = __fdiv_rn(1.f, static_cast<float>(1 << level));
+	const float angle = __fmul_rn(kp.angle, static_cast<float>(3.141592653589793238462643383279502884197169399375 / 180.0));
+	const float ca = static_cast<float>(cos(static_cast<double>(angle))), sa = static_cast<float>(sin(static_cast<double>(angle)));
+	const int cx = __float2int_rn(__fmul_rn(kp.x, scale)), cy = __float2int_rn(__fmul_rn(kp.y, scale));
+	auto tap = [&](int px, int py) -> int {
+		const float fx = __fsub_rn(__fmul_rn(static_cast<float>(px), ca), __fmul_rn(static_cast<float>(py), sa));
+		const float fy = __fadd_rn(__fmul_rn(static_cast<float>(px), sa), __fmul_rn(static_cast<float>(py), ca));
+		const int x = cx + __float2int_rn(fx), y = cy + __float2int_rn(fy);
+		if (x >= 0 && x < w && y >= 0 && y < h) return blr[static_cast<size_t>(y) * w + x];
+		return raw[static_cast<size_t>(reflect101(y, h)) * w + reflect101(x, w)]; // unblurred reflected border
+	};
+	int val = 0;
+#pragma unroll
+	for (int b = 0; b < 8; ++b)
+	{
+		const signed char * p = kOrbPattern31 + (byte * 8 + b) * 4;
+		const int t0 = tap(p[0], p[1]), t1 = tap(p[2], p[3]);
+		val |= (t0 < t1) << b;
+	}
+	desc[(static_cast<size_t>(frame) * cap + ki) * 32 + byte] = static_cast<uint8_t>(val);
+}
+
+// ---- K7: generateKeypoints3DDepth (depth the size of the image, one camera, identity local transform) ---
+struct OrbXyzArgs
+{
+	const void * depth;
+	int depth_type, w, h;
+	float fx, fy, cx, cy, min_depth, max_depth;
+	const OrbKeypoint * kps;
+	const int * n_kp;
+	int cap;
+	float * xyz;
+};
+
+__device__ __forceinline__ float depth_at(const void * depth, int type, size_t base, int w, int v, int u)
+{
+	if (type == 1)
+	{
+		const unsigned short d = static_cast<const unsigned short *>(depth)[base + static_cast<size_t>(v) * w + u];
+		return (d > 0 && d < 65535) ? __fmul_rn(static_cast<float>(d), 0.001f) : 0.0f;
+	}
+	return static_cast<const float *>(depth)[base + static_cast<size_t>(v) * w + u];
+}
+
+__global__ void orb_xyz_kernel(const OrbXyzArgs a)
+{
+	const int frame = blockIdx.y;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n_kp[frame]) return;
+	const OrbKeypoint kp = a.kps[static_cast<size_t>(frame) * a.cap + i];
+	float * out = a.xyz + (static_cast<size_t>(frame) * a.cap + i) * 3;
+	const float nan = __int_as_float(0x7FC00000);
+	out[0] = out[1] = out[2] = nan;
+	if (!a.depth) return;
+	const size_t base = static_cast<size_t>(frame) * a.w * a.h;
+	const float x = kp.x, y = kp.y;
+	int u = static_cast<int>(__fadd_rn(x, 0.5f)), v = static_cast<int>(__fadd_rn(y, 0.5f));
+	if (u == a.w && x < static_cast<float>(a.w)) u = a.w - 1;
+	if (v == a.h && y < static_cast<float>(a.h)) v = a.h - 1;
+	if (!(u >= 0 && u < a.w && v >= 0 && v < a.h)) return;
+	float depth = depth_at(a.depth, a.depth_type, base, a.w, v, u);
+	if (depth == 0.0f || !isfinite(depth)) return;
+	// util2d::getDepth smoothing: 3x3 window, neighbours within 2 % of the centre, weights 4/2/1
+	float sumWeights = 0.f, sumDepths = 0.f;
+	const float depthError = __fmul_rn(0.02f, depth);
+	for (int uu = max(u - 1, 0); uu <= min(u + 1, a.w - 1); ++uu)
+		for (int vv = max(v - 1, 0); vv <= min(v + 1, a.h - 1); ++vv)
+		{
+			if (uu == u && vv == v) continue;
+			float d = depth_at(a.depth, a.depth_type, base, a.w, vv, uu);
+			if (d != 0.0f && isfinite(d) && fabsf(__fsub_rn(d, depth)) < depthError)
+			{
+				if (uu == u || vv == v)
+				{
+					sumWeights = __fadd_rn(sumWeights, 2.0f);
+					d = __fmul_rn(d, 2.0f);
+				}
+				else sumWeights = __fadd_rn(sumWeights, 1.0f);
+				sumDepths = __fadd_rn(sumDepths, d);
+			}
+		}
+	depth = __fmul_rn(depth, 4.0f);
+	sumWeights = __fadd_rn(sumWeights, 4.0f);
+	depth = __fdiv_rn(__fadd_rn(depth, sumDepths), sumWeights);
+	if (!(depth > 0.0f)) return;
+	const float cx = a.cx > 0.0f ? a.cx : __fsub_rn(static_cast<float>(a.w / 2), 0.5f);
+	const float cy = a.cy > 0.0f ? a.cy : __fsub_rn(static_cast<float>(a.h / 2), 0.5f);
+	const float px = __fdiv_rn(__fmul_rn(__fsub_rn(x, cx), depth), a.fx);
+	const float py = __fdiv_rn(__fmul_rn(__fsub_rn(y, cy), depth), a.fy);
+	if ((a.min_depth < 0.0f || depth > a.min_depth) && (a.max_depth <= 0.0f || depth <= a.max_depth))
+	{
+		out[0] = px;
+		out[1] = py;
+		out[2] = depth;
+	}
+}
+
+// keypoint coordinates as a plain float2 array (the TO side of the verification kernels)
+__global__ void orb_uv_kernel(const OrbKeypoint * __restrict__ kps, const int * __restrict__ n_kp, int cap, float * __restrict__ uv)
+{
+	const int frame = blockIdx.y;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cap) return;
+	const size_t o = static_cast<size_t>(frame) * cap + i;
+	const bool ok = i < n_kp[frame];
+	uv[2 * o] = ok ? kps[o].x : 0.f;
+	uv[2 * o + 1] = ok ? kps[o].y : 0.f;
+}
+
+} // namespace lcd

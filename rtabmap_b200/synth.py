@@ -174,3 +174,48 @@ def make_query_frames_geo(store: SynthStore, smap: SynthMap, n_frames: int, seed
         poses[f, :3] = rv
         poses[f, 3:] = tv
     return desc.reshape(n_frames * F, D), uv.reshape(n_frames * F, 2), smap.sig_ids[places], poses
+
+
+# ------------------------------------------------------------------------------ images ------------
+def make_image(height: int = 480, width: int = 640, seed: int = 5, n_rects: int = 1500, bgr: bool = False) -> np.ndarray:
+    """Textured synthetic frame: three octaves of smooth value noise plus random
+    high-contrast rectangles so that FAST fires a few thousand times."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((height, width), np.float32)
+    for octv, amp in ((8, 60.0), (16, 40.0), (32, 30.0)):
+        small = rng.random((height // octv + 2, width // octv + 2)).astype(np.float32)
+        up = np.kron(small, np.ones((octv, octv), np.float32))[:height + octv, :width + octv]
+        # cheap smoothing of the blocky upsampling
+        k = octv // 2
+        up = (up[:-octv, :-octv] + up[k:k - octv, :-octv] + up[:-octv, k:k - octv] + up[k:k - octv, k:k - octv]) * 0.25
+        img += amp * up[:height, :width]
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    xs = rng.integers(0, width - 30, n_rects)
+    ys = rng.integers(0, height - 30, n_rects)
+    ws = rng.integers(4, 30, n_rects)
+    hs = rng.integers(4, 30, n_rects)
+    vals = rng.integers(0, 256, n_rects)
+    for x, y, w_, h_, v in zip(xs, ys, ws, hs, vals):
+        img[y:y + h_, x:x + w_] = v
+    if not bgr:
+        return img
+    out = np.stack([img, np.roll(img, 3, axis=1), np.roll(img, 5, axis=0)], axis=2)
+    out ^= (rng.integers(0, 8, out.shape, dtype=np.uint8))
+    return np.ascontiguousarray(out)
+
+
+def make_depth(height: int = 480, width: int = 640, seed: int = 6, zero_frac: float = 0.02, as_float: bool = False) -> np.ndarray:
+    """Depth of a slanted plane at 1-4 m with 5 mm noise and a few invalid pixels / blocks (CV_16UC1 mm or CV_32FC1 m)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    z = 1.0 + 3.0 * (0.6 * xx / width + 0.4 * yy / height) + rng.normal(0, 0.005, (height, width)).astype(np.float32)
+    mm = np.clip(z * 1000.0, 1, 65000).astype(np.uint16)
+    mm[rng.random((height, width)) < zero_frac] = 0
+    for _ in range(6):
+        x, y = rng.integers(0, width - 80), rng.integers(0, height - 60)
+        mm[y:y + rng.integers(20, 60), x:x + rng.integers(20, 80)] = 0
+    if as_float:
+        f = mm.astype(np.float32) * np.float32(0.001)
+        f[mm == 0] = np.nan if seed % 2 else 0.0
+        return f
+    return mm
