@@ -323,6 +323,11 @@ int lcd_profile_enable(lcd_engine * e, int on);
 int lcd_profile_read(lcd_engine * e, int which, double * total_ms, long long * launches);
 int lcd_profile_reset(lcd_engine * e);
 
+/* copy an internal ORB buffer of the last lcd_orb_* call back to the host (diagnostics / tests):
+ * which = 0 gray pyramid, 1 mask pyramid, 2 blurred pyramid, 3 FAST candidate keys, 4 candidate counts,
+ * 5 keypoints per level counts, 6 FAST score pyramid.  Returns the number of bytes copied (<= cap_bytes) or <0. */
+long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long cap_bytes);
+
 /* engine stream (cudaStream_t as void*) and a full device sync, for harnesses */
 void * lcd_stream(lcd_engine * e);
 int lcd_synchronize(lcd_engine * e);

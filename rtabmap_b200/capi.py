@@ -139,6 +139,7 @@ SIGNATURES = {
     "lcd_profile_enable": (_I, [_P, _I]),
     "lcd_profile_read": (_I, [_P, _I, _P, _P]),
     "lcd_profile_reset": (_I, [_P]),
+    "lcd_debug_orb_buffer": (C.c_longlong, [_P, _I, _P, C.c_longlong]),
     "lcd_stream": (_P, [_P]),
     "lcd_synchronize": (_I, [_P]),
 }
@@ -274,6 +275,13 @@ class Engine:
             arr = np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"], k["octave"].astype(np.float32)], 1) if cnt[i] else np.zeros((0, 6), np.float32)
             out.append((arr, desc[i, :cnt[i]].copy(), xyz[i, :cnt[i]].copy()))
         return out
+
+    def debug_orb_buffer(self, which: int, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        buf = np.zeros(nbytes, np.uint8)
+        n = self._lib.lcd_debug_orb_buffer(self._h, which, _ptr(buf), nbytes)
+        if n < 0:
+            self._check(int(n))
+        return buf[:n].view(dtype)
 
     # -- dictionary --------------------------------------------------------------------------
     def add_words(self, ids, desc):

@@ -166,7 +166,7 @@ struct lcd_engine
 	int st_cap = 0, st_slots = 0;
 	DevBuf<int> d_hyp_id, d_hyp_slot;
 	// ORB workspace
-	DevBuf<uint8_t> o_img, o_gray, o_mask, o_blur, o_desc;
+	DevBuf<uint8_t> o_img, o_gray, o_mask, o_blur, o_desc, o_score;
 	DevBuf<unsigned char> o_depth;
 	DevBuf<uint32_t> o_cand;
 	DevBuf<int> o_cand_count, o_level_n, o_n, o_overflow;
@@ -1361,10 +1361,13 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		orb_down_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, use_mask ? e->o_mask.p : nullptr, g, l);
 		LCD_CHECK_LAUNCH(e);
 	}
+	LCD_CUDA(e, e->o_score.reserve(pyr, 0, false, s));
 	for (int l = 0; l < g.n_levels; ++l)
 	{
-		dim3 blk(kFastTile, kFastTile), grd((g.w[l] + kFastTile - 1) / kFastTile, (g.h[l] + kFastTile - 1) / kFastTile, n_frames);
-		orb_fast_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, use_mask ? e->o_mask.p : nullptr, g, l, e->o_cand.p, e->o_cand_count.p);
+		dim3 blk(32, 8), grd((g.w[l] + 31) / 32, (g.h[l] + 7) / 8, n_frames);
+		orb_fast_score_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, g, l, e->o_score.p);
+		LCD_CHECK_LAUNCH(e);
+		orb_fast_nms_kernel<<<grd, blk, 0, s>>>(e->o_score.p, use_mask ? e->o_mask.p : nullptr, g, l, e->o_cand.p, e->o_cand_count.p);
 		LCD_CHECK_LAUNCH(e);
 	}
 	{
@@ -1483,6 +1486,29 @@ int lcd_orb_detect_describe(lcd_engine * e, int n_frames, const uint8_t * images
 	LCD_CUDA(e, cudaStreamSynchronize(s));
 	if (overflow) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d FAST corners in one pyramid level (or too many ties): raise FAST/Threshold", kOrbCandCap);
 	return LCD_OK;
+}
+
+long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long cap_bytes)
+{
+	if (!e || !out) return LCD_ERR_INVALID;
+	if (set_device(e) != LCD_OK) return LCD_ERR_CUDA;
+	const void * src = nullptr;
+	size_t bytes = 0;
+	switch (which)
+	{
+	case 0: src = e->o_gray.p; bytes = e->o_gray.cap; break;
+	case 1: src = e->o_mask.p; bytes = e->o_mask.cap; break;
+	case 6: src = e->o_score.p; bytes = e->o_score.cap; break;
+	case 2: src = e->o_blur.p; bytes = e->o_blur.cap; break;
+	case 3: src = e->o_cand.p; bytes = e->o_cand.cap * sizeof(uint32_t); break;
+	case 4: src = e->o_cand_count.p; bytes = e->o_cand_count.cap * sizeof(int); break;
+	case 5: src = e->o_level_n.p; bytes = e->o_level_n.cap * sizeof(int); break;
+	default: return LCD_ERR_INVALID;
+	}
+	if (!src) return 0;
+	bytes = std::min<size_t>(bytes, static_cast<size_t>(cap_bytes));
+	if (cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return LCD_ERR_CUDA;
+	return static_cast<long long>(bytes);
 }
 
 // ---- geometric verification ------------------------------------------------------------------

@@ -155,82 +155,88 @@ constexpr int kFastTile = 16;
 
 __device__ __forceinline__ int fast_score(const uint8_t * t, int stride, int thr)
 {
-	// t points at the pixel inside a shared tile; ring offsets of the 16-pixel Bresenham circle
+	// t points at the pixel inside a shared tile; d[k] = centre - k-th pixel of the 16-pixel Bresenham circle
+	// (OpenCV order: (0,3) (1,3) (2,2) (3,1) (3,0) (3,-1) (2,-2) (1,-3) (0,-3) (-1,-3) (-2,-2) (-3,-1) (-3,0) (-3,1) (-2,2) (-1,3))
 	const int v = t[0];
 	int d[16];
-	d[0] = v - t[3 * stride];
-	d[8] = v - t[-3 * stride];
-	d[4] = v - t[3];
-	d[12] = v - t[-3];
-	// every 9-arc contains pixel 0 or 8, and pixel 4 or 12
-	if ((abs(d[0]) <= thr && abs(d[8]) <= thr) || (abs(d[4]) <= thr && abs(d[12]) <= thr)) return 0;
-	d[1] = v - t[3 * stride + 1];
-	d[2] = v - t[2 * stride + 2];
-	d[3] = v - t[1 * stride + 3];
-	d[5] = v - t[-1 * stride + 3];
-	d[6] = v - t[-2 * stride + 2];
-	d[7] = v - t[-3 * stride + 1];
-	d[9] = v - t[-3 * stride - 1];
-	d[10] = v - t[-2 * stride - 2];
-	d[11] = v - t[-1 * stride - 3];
-	d[13] = v - t[1 * stride - 3];
-	d[14] = v - t[2 * stride - 2];
-	d[15] = v - t[3 * stride - 1];
-	int best = -1000;
-#pragma unroll
-	for (int s = 0; s < 16; ++s)
+	d[0] = v - static_cast<int>(t[3 * stride]);
+	d[1] = v - static_cast<int>(t[3 * stride + 1]);
+	d[2] = v - static_cast<int>(t[2 * stride + 2]);
+	d[3] = v - static_cast<int>(t[stride + 3]);
+	d[4] = v - static_cast<int>(t[3]);
+	d[5] = v - static_cast<int>(t[3 - stride]);
+	d[6] = v - static_cast<int>(t[2 - 2 * stride]);
+	d[7] = v - static_cast<int>(t[1 - 3 * stride]);
+	d[8] = v - static_cast<int>(t[-3 * stride]);
+	d[9] = v - static_cast<int>(t[-3 * stride - 1]);
+	d[10] = v - static_cast<int>(t[-2 * stride - 2]);
+	d[11] = v - static_cast<int>(t[-stride - 3]);
+	d[12] = v - static_cast<int>(t[-3]);
+	d[13] = v - static_cast<int>(t[stride - 3]);
+	d[14] = v - static_cast<int>(t[2 * stride - 2]);
+	d[15] = v - static_cast<int>(t[3 * stride - 1]);
+	// every 9-arc contains pixel 0 or 8, and pixel 4 or 12: cheap rejection of flat neighbourhoods
+	const bool reject = (abs(d[0]) <= thr && abs(d[8]) <= thr) || (abs(d[4]) <= thr && abs(d[12]) <= thr);
+	int best = 0;
+	if (!reject)
 	{
-		int mb = d[s], md = -d[s];
+		// The arc minima are taken on biased, strictly positive values (d + 256 and 256 - d): nvcc 12.9 packs
+		// this min/max chain into VIMNMX.U16x2, whose unsigned lanes mis-order negative differences.
+		unsigned bb = 0u, bd = 0u;
 #pragma unroll
-		for (int k = 1; k < 9; ++k)
+		for (int s = 0; s < 16; ++s)
 		{
-			mb = min(mb, d[(s + k) & 15]);
-			md = min(md, -d[(s + k) & 15]);
+			unsigned mb = static_cast<unsigned>(d[s] + 256), md = static_cast<unsigned>(256 - d[s]);
+#pragma unroll
+			for (int k = 1; k < 9; ++k)
+			{
+				const int e = d[(s + k) & 15];
+				mb = min(mb, static_cast<unsigned>(e + 256));
+				md = min(md, static_cast<unsigned>(256 - e));
+			}
+			bb = max(bb, mb);
+			bd = max(bd, md);
 		}
-		best = max(best, max(mb, md));
+		best = static_cast<int>(max(bb, bd)) - 256;
 	}
 	return best > thr ? best - 1 : 0;
 }
 
-__global__ void __launch_bounds__(kFastTile * kFastTile)
-orb_fast_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restrict__ mask_all, const OrbGeom g, int level,
-                uint32_t * __restrict__ cand, int * __restrict__ cand_count)
+// FAST score of every pixel of one level -> score plane (0 = not a corner).  Reads straight from the gray
+// plane (L1/L2 resident); the 4-pixel rejection test leaves few pixels that need the whole ring.
+__global__ void __launch_bounds__(256)
+orb_fast_score_kernel(const uint8_t * __restrict__ gray_all, const OrbGeom g, int level, uint8_t * __restrict__ score_all)
 {
-	constexpr int T = kFastTile, R = T + 2 + 6; // tile + nms halo + ring halo
-	__shared__ uint8_t tile[R][R + 4];
-	__shared__ uint8_t sc[T + 2][T + 2];
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y;
 	const int frame = blockIdx.z;
 	const int w = g.w[level], h = g.h[level];
-	const uint8_t * gray = gray_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
-	const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
-	const int tid = threadIdx.y * T + threadIdx.x;
-	for (int i = tid; i < R * R; i += T * T)
-	{
-		const int ty = i / R, tx = i % R;
-		const int x = x0 + tx - 4, y = y0 + ty - 4;
-		tile[ty][tx] = (x >= 0 && x < w && y >= 0 && y < h) ? gray[static_cast<size_t>(y) * w + x] : 0;
-	}
-	__syncthreads();
-	for (int i = tid; i < (T + 2) * (T + 2); i += T * T)
-	{
-		const int sy = i / (T + 2), sx = i % (T + 2);
-		const int x = x0 + sx - 1, y = y0 + sy - 1;
-		int s = 0;
-		if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) s = fast_score(&tile[sy + 3][sx + 3], R + 4, g.fast_thr);
-		sc[sy][sx] = static_cast<uint8_t>(s);
-	}
-	__syncthreads();
-	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
 	if (x >= w || y >= h) return;
-	const int s = sc[threadIdx.y + 1][threadIdx.x + 1];
-	if (s == 0) return;
-	const int sx = threadIdx.x + 1, sy = threadIdx.y + 1;
-	const bool is_max = s > sc[sy - 1][sx - 1] && s > sc[sy - 1][sx] && s > sc[sy - 1][sx + 1] && s > sc[sy][sx - 1] && s > sc[sy][sx + 1] &&
-	                    s > sc[sy + 1][sx - 1] && s > sc[sy + 1][sx] && s > sc[sy + 1][sx + 1];
-	if (!is_max) return;
-	// KeyPointsFilter::runByPixelsMask, then runByImageBorder(edgeThreshold)
-	if (mask_all && mask_all[static_cast<size_t>(frame) * g.frame_stride + g.off[level] + static_cast<size_t>(y) * w + x] == 0) return;
+	const size_t plane = static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	int s = 0;
+	if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) s = fast_score(gray_all + plane + static_cast<size_t>(y) * w + x, w, g.fast_thr);
+	score_all[plane + static_cast<size_t>(y) * w + x] = static_cast<uint8_t>(s);
+}
+
+// 3x3 strict non-max suppression, then KeyPointsFilter::runByPixelsMask and runByImageBorder -> candidate list
+__global__ void __launch_bounds__(256)
+orb_fast_nms_kernel(const uint8_t * __restrict__ score_all, const uint8_t * __restrict__ mask_all, const OrbGeom g, int level,
+                    uint32_t * __restrict__ cand, int * __restrict__ cand_count)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y;
+	const int frame = blockIdx.z;
+	const int w = g.w[level], h = g.h[level];
+	// corners exist only in [3, w-3) x [3, h-3); the border filter below is at least as strict
+	if (x < 3 || x >= w - 3 || y < 3 || y >= h - 3) return;
 	if (x < g.edge || x >= w - g.edge || y < g.edge || y >= h - g.edge) return;
+	const size_t plane = static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	const uint8_t * sc = score_all + plane + static_cast<size_t>(y) * w + x;
+	const int s = sc[0];
+	if (s == 0) return;
+	const bool is_max = s > sc[-w - 1] && s > sc[-w] && s > sc[-w + 1] && s > sc[-1] && s > sc[1] && s > sc[w - 1] && s > sc[w] && s > sc[w + 1];
+	if (!is_max) return;
+	if (mask_all && mask_all[plane + static_cast<size_t>(y) * w + x] == 0) return;
 	const int slot = frame * g.n_levels + level;
 	const int k = atomicAdd(&cand_count[slot], 1);
 	if (k < kOrbCandCap) cand[static_cast<size_t>(slot) * kOrbCandCap + k] = (static_cast<uint32_t>(y * w + x) << 8) | static_cast<uint32_t>(s);
