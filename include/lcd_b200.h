@@ -277,6 +277,23 @@ int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * 
                           const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp,
                           int * d_word_ids_out, float * d_likelihood_out, void * stream);
 int lcd_process_fetch(lcd_engine * e, int n_frames, int * hypothesis_out, lcd_verify_result * results);
+/* The whole hot path for n_frames frames: Memory::update (detect + quantise, Rtabmap.cpp:1470) ->
+ * Memory::computeLikelihood (:2117) -> Memory::computeTransform of the top hypothesis (:3143), as
+ * independent localisation queries (no mutation).  Host buffers in, host results out: n_kp_out[n_frames]
+ * keypoints found, word_ids_out[n_frames * params->n_features] (0 in the padding rows of short frames),
+ * likelihood_out[n_frames*ns], hypothesis_out / results as lcd_process_batch (vp may be NULL: no verify). */
+int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int width, int height, int channels,
+                       const void * depth, int depth_type, const lcd_orb_params * params,
+                       int incremental, float nndr, int new_words_compared_together,
+                       const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp,
+                       int * n_kp_out, int * word_ids_out, float * likelihood_out, int * hypothesis_out,
+                       lcd_verify_result * results);
+int lcd_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels,
+                           const void * d_depth, int depth_type, const lcd_orb_params * params,
+                           int incremental, float nndr, int new_words_compared_together,
+                           const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp,
+                           int * d_word_ids_out, float * d_likelihood_out, void * stream);
+
 /* The verification half alone, for likelihood rows that already exist on the device (the sharded
  * multi-GPU path all-reduces the scores first, then every rank verifies its share of the frames):
  * arg-max hypothesis of each of the n_frames rows of d_likelihood[n_frames][ns], then

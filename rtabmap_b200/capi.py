@@ -131,6 +131,8 @@ SIGNATURES = {
     "lcd_process_batch": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "lcd_process_batch_dev": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
     "lcd_process_fetch": (_I, [_P, _I, _P, _P]),
+    "lcd_process_frames": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "lcd_process_frames_dev": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
     "lcd_verify_top_dev": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "lcd_shard_set_row_offset": (_I, [_P, _I]),
     "lcd_shard_knn2_keys_dev": (_I, [_P, _P, _I, _P, _P]),
@@ -512,6 +514,39 @@ class Engine:
         self._check(self._lib.lcd_process_batch_dev(self._h, C.c_void_p(d_queries), C.c_void_p(d_uv), n_frames, nq, int(incremental), float(nndr),
                                                      int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total), C.byref(vp),
                                                      C.c_void_p(d_words_out or None), C.c_void_p(d_like_out or None), C.c_void_p(stream or None)))
+
+    def process_frames(self, images, depth, op: "OrbParams", sig_ids, n_total: int, vp: "VerifyParams" = None, incremental: bool = True,
+                       nndr: float = 0.8, cmp_new: bool = True, out_words=None, out_like=None):
+        """The whole hot path from host images: returns (n_kp, words, likelihood, hypothesis, results)."""
+        img = np.ascontiguousarray(images, np.uint8)
+        n, h, w = img.shape[:3]
+        ch = 1 if img.ndim == 3 else img.shape[3]
+        dtype, dptr = 0, None
+        if depth is not None:
+            if depth.dtype == np.uint16:
+                dtype, depth = 1, np.ascontiguousarray(depth)
+            else:
+                dtype, depth = 2, np.ascontiguousarray(depth, np.float32)
+            dptr = _ptr(depth)
+        s = _i32(sig_ids)
+        cap = op.n_features
+        words = out_words if out_words is not None else np.zeros((n, cap), np.int32)
+        like = out_like if out_like is not None else np.zeros((n, len(s)), np.float32)
+        nkp = np.zeros(n, np.int32)
+        hyp = np.zeros(n, np.int32)
+        res = (VerifyResult * n)()
+        self._check(self._lib.lcd_process_frames(self._h, n, _ptr(img), w, h, ch, dptr, dtype, C.byref(op), int(incremental), float(nndr), int(cmp_new),
+                                                  _ptr(s), len(s), int(n_total), C.byref(vp) if vp is not None else None, _ptr(nkp), _ptr(words),
+                                                  _ptr(like), _ptr(hyp), res))
+        return nkp, words, like, hyp, (self._results(res, n) if vp is not None else None)
+
+    def process_frames_dev(self, d_images: int, n_frames: int, w: int, h: int, ch: int, d_depth: int, depth_type: int, op: "OrbParams", d_sig_ids: int,
+                           ns: int, n_total: int, vp: "VerifyParams", d_words_out: int = 0, d_like_out: int = 0, incremental: bool = True,
+                           nndr: float = 0.8, cmp_new: bool = True, stream: int = 0):
+        self._check(self._lib.lcd_process_frames_dev(self._h, n_frames, C.c_void_p(d_images), w, h, ch, C.c_void_p(d_depth or None), depth_type,
+                                                      C.byref(op), int(incremental), float(nndr), int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total),
+                                                      C.byref(vp) if vp is not None else None, C.c_void_p(d_words_out or None),
+                                                      C.c_void_p(d_like_out or None), C.c_void_p(stream or None)))
 
     def verify_top_dev(self, d_queries: int, d_uv: int, n_frames: int, nq: int, d_like: int, d_sig_ids: int, ns: int, vp: "VerifyParams", stream: int = 0):
         self._check(self._lib.lcd_verify_top_dev(self._h, C.c_void_p(d_queries), C.c_void_p(d_uv), n_frames, nq, C.c_void_p(d_like),

@@ -565,7 +565,8 @@ int check_queries(lcd_engine * e, const void * q, int nq)
 
 // quantise + score of n_frames independent frames on device buffers, no mutation
 int localize_dev(lcd_engine * e, const uint32_t * d_q, int n_frames, int nq, int incremental, float nndr, int cmp_new,
-                 const int * d_sig_ids, int ns, int n_total, int * d_word_ids_out, float * d_like_out, cudaStream_t s)
+                 const int * d_sig_ids, int ns, int n_total, int * d_word_ids_out, float * d_like_out, cudaStream_t s,
+                 const int * d_nq_frame = nullptr)
 {
 	if (e->n_indexed == 0 && !incremental) LCD_FAIL(e, LCD_ERR_STATE, "Dictionary mode is set to fixed but no words are in it!");
 	const int nq_total = n_frames * nq;
@@ -575,6 +576,7 @@ int localize_dev(lcd_engine * e, const uint32_t * d_q, int n_frames, int nq, int
 	ResolveArgs a{};
 	a.queries = d_q;
 	a.nq = nq;
+	a.nq_frame = d_nq_frame;
 	a.nq_total = nq_total;
 	a.partial = e->d_partial.p;
 	a.n_chunks = n_chunks;
@@ -1824,7 +1826,7 @@ int lcd_sig_remove(lcd_engine * e, int sig_id)
 }
 
 static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, const float * d_like,
-                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s);
+                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s, const int * d_nq_frame = nullptr);
 
 static int process_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, int incremental, float nndr, int cmp_new,
                        const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp, int * d_words, float * d_like, cudaStream_t s)
@@ -1843,7 +1845,7 @@ static int process_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv,
 }
 
 static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, const float * d_like,
-                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s)
+                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s, const int * d_nq_frame)
 {
 	if (!vp) LCD_FAIL(e, LCD_ERR_INVALID, "null verification parameters");
 	if (vp->iterations > kMaxRansacIters) LCD_FAIL(e, LCD_ERR_CAPACITY, "Vis/Iterations > %d", kMaxRansacIters);
@@ -1854,7 +1856,7 @@ static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_
 	                                                  e->d_hyp_id.p, e->d_hyp_slot.p);
 	LCD_CHECK_LAUNCH(e);
 	const int cap = std::max(e->st_cap, nq);
-	MatchSrc src{e->st_desc.p, e->st_xyz.p, e->st_n.p, e->d_hyp_slot.p, e->st_cap, d_q, d_uv, nullptr, nq, nq};
+	MatchSrc src{e->st_desc.p, e->st_xyz.p, e->st_n.p, e->d_hyp_slot.p, e->st_cap, d_q, d_uv, d_nq_frame, nq, nq};
 	LCD_TRY(launch_match(e, n_frames, cap, vp->nndr, false, s, &src));
 	LCD_TRY(launch_pnp(e, n_frames, cap, vp, s));
 	return LCD_OK;
@@ -1871,6 +1873,89 @@ int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * 
 	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
 	return process_dev(e, static_cast<const uint32_t *>(d_queries), d_uv, n_frames, nq_per_frame, incremental, nndr, new_words_compared_together,
 	                   d_sig_ids, ns, n_total, vp, d_word_ids_out, d_likelihood_out, s);
+}
+
+// images -> detect -> quantise -> score -> verify, all on device buffers
+static int process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
+                              int depth_type, const lcd_orb_params * op, int incremental, float nndr, int cmp_new, const int * d_sig_ids, int ns,
+                              int n_total, const lcd_verify_params * vp, int * d_words, float * d_like, cudaStream_t s)
+{
+	if (!op) LCD_FAIL(e, LCD_ERR_INVALID, "null ORB parameters");
+	if (e->cfg.desc_type != LCD_DESC_U8 || e->cfg.desc_dim != 32) LCD_FAIL(e, LCD_ERR_INVALID, "ORB descriptors need an engine with 32-byte binary descriptors");
+	const int cap = op->n_features;
+	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "Kp/MaxFeatures must be 1..%d", kMaxFrameQueries);
+	const size_t rows = static_cast<size_t>(n_frames) * cap;
+	LCD_CUDA(e, e->o_kp.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->o_desc.reserve(rows * 32, 0, false, s));
+	LCD_CUDA(e, e->o_xyz.reserve(rows * 3, 0, false, s));
+	LCD_CUDA(e, e->o_uv.reserve(rows * 2, 0, false, s));
+	LCD_CUDA(e, e->o_n.reserve(n_frames, 0, false, s));
+	// padding rows of short frames must hold defined bytes for the NN kernel
+	LCD_CUDA(e, cudaMemsetAsync(e->o_desc.p, 0, rows * 32, s));
+	LCD_TRY(orb_run(e, n_frames, d_images, width, height, channels, d_depth, depth_type, op, cap, e->o_kp.p, e->o_desc.p, e->o_xyz.p, e->o_uv.p,
+	                e->o_n.p, s));
+	if (!d_like)
+	{
+		LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
+		d_like = e->d_like.p;
+	}
+	const uint32_t * d_q = reinterpret_cast<const uint32_t *>(e->o_desc.p);
+	LCD_TRY(localize_dev(e, d_q, n_frames, cap, incremental, nndr, cmp_new, d_sig_ids, ns, n_total, d_words, d_like, s, e->o_n.p));
+	if (vp) LCD_TRY(verify_top_dev(e, d_q, e->o_uv.p, n_frames, cap, d_like, d_sig_ids, ns, vp, s, e->o_n.p));
+	return LCD_OK;
+}
+
+int lcd_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
+                           int depth_type, const lcd_orb_params * op, int incremental, float nndr, int new_words_compared_together,
+                           const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp, int * d_word_ids_out,
+                           float * d_likelihood_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_images || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null image");
+	if (!d_sig_ids || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "ids list is empty");
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	return process_frames_dev(e, n_frames, d_images, width, height, channels, d_depth, depth_type, op, incremental, nndr, new_words_compared_together,
+	                          d_sig_ids, ns, n_total, vp, d_word_ids_out, d_likelihood_out, s);
+}
+
+int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int width, int height, int channels, const void * depth, int depth_type,
+                       const lcd_orb_params * op, int incremental, float nndr, int new_words_compared_together, const int * sig_ids, int ns,
+                       int n_total, const lcd_verify_params * vp, int * n_kp_out, int * word_ids_out, float * likelihood_out, int * hypothesis_out,
+                       lcd_verify_result * results)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!images || n_frames <= 0 || width <= 0 || height <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null image");
+	if (!sig_ids || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "ids list is empty");
+	if (!op) LCD_FAIL(e, LCD_ERR_INVALID, "null ORB parameters");
+	cudaStream_t s = e->stream;
+	const size_t px = static_cast<size_t>(n_frames) * width * height;
+	LCD_CUDA(e, e->o_img.reserve(px * channels, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->o_img.p, images, px * channels, cudaMemcpyHostToDevice, s));
+	if (!depth) depth_type = LCD_DEPTH_NONE;
+	if (depth_type != LCD_DEPTH_NONE)
+	{
+		const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+		LCD_CUDA(e, e->o_depth.reserve(px * dbytes, 0, false, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->o_depth.p, depth, px * dbytes, cudaMemcpyHostToDevice, s));
+	}
+	const int cap = op->n_features;
+	const size_t rows = static_cast<size_t>(n_frames) * std::max(cap, 1);
+	LCD_CUDA(e, e->d_sig_ids.reserve(ns, 0, false, s));
+	LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
+	LCD_CUDA(e, e->d_word_ids.reserve(rows, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_sig_ids.p, sig_ids, ns * sizeof(int), cudaMemcpyHostToDevice, s));
+	LCD_TRY(process_frames_dev(e, n_frames, e->o_img.p, width, height, channels, depth_type != LCD_DEPTH_NONE ? e->o_depth.p : nullptr, depth_type, op,
+	                           incremental, nndr, new_words_compared_together, e->d_sig_ids.p, ns, n_total, vp, e->d_word_ids.p, e->d_like.p, s));
+	if (n_kp_out) LCD_CUDA(e, cudaMemcpyAsync(n_kp_out, e->o_n.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (word_ids_out) LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (likelihood_out)
+		LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, static_cast<size_t>(n_frames) * ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+	if (vp && hypothesis_out) LCD_CUDA(e, cudaMemcpyAsync(hypothesis_out, e->d_hyp_id.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (vp && results) return verify_download(e, n_frames, 0, results, nullptr, nullptr, s);
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
 }
 
 int lcd_verify_top_dev(lcd_engine * e, const void * d_queries, const float * d_uv, int n_frames, int nq_per_frame, const float * d_likelihood,

@@ -28,7 +28,8 @@ constexpr uint32_t kSortNone = 0x7FFFFFFFu;
 struct ResolveArgs
 {
 	const uint32_t * queries; // [n_frames*nq][NW]
-	int nq;                   // descriptors per frame
+	int nq;                   // descriptor rows per frame (stride of every per-frame array)
+	const int * nq_frame;     // valid descriptors of each frame (<= nq), or nullptr (= nq for all)
 	int nq_total;             // n_frames*nq (stride of `partial`)
 	const uint2 * partial;    // [n_chunks][nq_total] top-2 keys per vocabulary chunk / per rank
 	int n_chunks;
@@ -356,23 +357,24 @@ __global__ void __launch_bounds__(kResolveThreads)
 resolve_kernel(const ResolveArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	const int nq = a.nq;
+	const int cap = a.nq; // rows per frame
 	int nq_pad = 32;
-	while (nq_pad < nq) nq_pad <<= 1;
+	while (nq_pad < cap) nq_pad <<= 1;
 	uint32_t * sa1 = reinterpret_cast<uint32_t *>(smem_raw);
-	uint32_t * sa2 = sa1 + nq;
-	int * res = reinterpret_cast<int *>(sa2 + nq);              // >=0 row, -1-k new word k, INT_MIN none
-	uint32_t * sbuf = reinterpret_cast<uint32_t *>(res + nq);    // [nq_pad]
-	uint16_t * L = reinterpret_cast<uint16_t *>(sbuf + nq_pad);  // [nq]
-	uint16_t * rank = L + nq;                                    // [nq]
-	uint8_t * flag = reinterpret_cast<uint8_t *>(rank + nq);     // [nq]
-	uint8_t * flag2 = flag + nq;                                 // [nq]
+	uint32_t * sa2 = sa1 + cap;
+	int * res = reinterpret_cast<int *>(sa2 + cap);              // >=0 row, -1-k new word k, INT_MIN none
+	uint32_t * sbuf = reinterpret_cast<uint32_t *>(res + cap);   // [nq_pad]
+	uint16_t * L = reinterpret_cast<uint16_t *>(sbuf + nq_pad);  // [cap]
+	uint16_t * rank = L + cap;                                   // [cap]
+	uint8_t * flag = reinterpret_cast<uint8_t *>(rank + cap);    // [cap]
+	uint8_t * flag2 = flag + cap;                                // [cap]
 	__shared__ int s_nL;
 
 	const int tid = threadIdx.x;
 	const int frame = blockIdx.x;
-	const uint32_t * fq = a.queries + static_cast<size_t>(frame) * nq * NW;
-	const size_t pbase = static_cast<size_t>(frame) * nq;
+	const int nq = a.nq_frame ? min(max(a.nq_frame[frame], 0), cap) : cap; // valid descriptors of this frame
+	const uint32_t * fq = a.queries + static_cast<size_t>(frame) * cap * NW;
+	const size_t pbase = static_cast<size_t>(frame) * cap;
 
 	// 1. merge the per-chunk top-2 keys (FlannIndex::knnSearch result of this descriptor)
 	for (int i = tid; i < nq; i += blockDim.x)
@@ -442,12 +444,16 @@ resolve_kernel(const ResolveArgs a)
 		if (a.word_ids_out) a.word_ids_out[pbase + i] = wid;
 		sbuf[i] = sv;
 	}
-	for (int i = nq + tid; i < nq_pad; i += blockDim.x) sbuf[i] = kSortNone;
+	for (int i = nq + tid; i < nq_pad; i += blockDim.x)
+	{
+		sbuf[i] = kSortNone;
+		if (i < cap && a.word_ids_out) a.word_ids_out[pbase + i] = 0; // padding rows of a short frame
+	}
 	if (tid == 0 && a.n_new_out) a.n_new_out[frame] = n_new;
 	__syncthreads();
 
 	// 4. unique matched words -> idf + posting extents for the scoring kernel
-	if (a.do_prep) score_prep(sbuf, nq_pad, nq, a, frame);
+	if (a.do_prep) score_prep(sbuf, nq_pad, cap, a, frame);
 }
 
 // TF-IDF preparation from host-provided word ids (lcd_index_score): applies uUniqueKeys and

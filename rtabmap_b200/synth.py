@@ -219,3 +219,93 @@ def make_depth(height: int = 480, width: int = 640, seed: int = 6, zero_frac: fl
         f[mm == 0] = np.nan if seed % 2 else 0.0
         return f
     return mm
+
+
+# ------------------------------------------------------------------------------ image-level world --
+def render_view(image: np.ndarray, depth: np.ndarray, dx: int, dy: int, noise_sigma: float, rng: np.random.Generator):
+    """A revisit of a place: the frame shifted by (dx, dy) pixels (edge-replicated) with sensor noise."""
+    h, w = depth.shape
+    ys = np.clip(np.arange(h) - dy, 0, h - 1)
+    xs = np.clip(np.arange(w) - dx, 0, w - 1)
+    img = image[ys][:, xs]
+    dep = depth[ys][:, xs]
+    if noise_sigma > 0:
+        noise = rng.normal(0, noise_sigma, img.shape)
+        img = np.clip(img.astype(np.float32) + noise, 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(img), np.ascontiguousarray(dep)
+
+
+@dataclass
+class PlaceWorld:
+    """A map built from P textured places seen S times (BASELINE configs[1] at image level):
+    the vocabulary is made of the places' own ORB descriptors, every signature is a view of a place."""
+    images: np.ndarray        # [P, H, W, 3] uint8 BGR
+    depths: np.ndarray        # [P, H, W] uint16 mm
+    vocab: np.ndarray         # [W, 32] uint8
+    word_ids: np.ndarray      # [W] int32 (1..W)
+    smap: SynthMap            # inverted index of the S signatures
+    store: SynthStore         # per-signature descriptors and 3-D points
+    sig_place: np.ndarray     # [S] place of every signature
+
+
+def make_place_world(orb_fn, n_places: int = 50, n_words: int = 49152, n_signatures: int = 10000, feats: int = 1000,
+                     height: int = 480, width: int = 640, seed: int = 7) -> PlaceWorld:
+    """orb_fn(image_bgr, depth) -> (keypoints [n,6], descriptors [n,32], xyz [n,3]) is supplied by the caller
+    (the benchmark uses the OpenCV-based checker for this untimed set-up)."""
+    rng = np.random.default_rng(seed)
+    images = np.stack([make_image(height, width, 100 + p, bgr=True) for p in range(n_places)])
+    depths = np.stack([make_depth(height, width, 200 + p, zero_frac=0.01) for p in range(n_places)])
+    desc = np.zeros((n_places, feats, 32), np.uint8)
+    xyz = np.full((n_places, feats, 3), np.nan, np.float32)
+    cnt = np.zeros(n_places, np.int64)
+    for p in range(n_places):
+        kp, d, x = orb_fn(images[p], depths[p])
+        n = min(len(d), feats)
+        desc[p, :n], xyz[p, :n], cnt[p] = d[:n], x[:n], n
+    # vocabulary: the places' descriptors, in place order
+    flat_place = np.repeat(np.arange(n_places), feats)
+    flat_idx = np.tile(np.arange(feats), n_places)
+    valid = flat_idx < cnt[flat_place]
+    all_desc = desc.reshape(-1, 32)[valid]
+    W = min(n_words, len(all_desc))
+    vocab = np.ascontiguousarray(all_desc[:W])
+    word_ids = np.arange(1, W + 1, dtype=np.int32)
+    word_of = np.zeros((n_places, feats), np.int32)  # 0 = the descriptor is not a vocabulary word
+    word_of.reshape(-1)[np.nonzero(valid)[0][:W]] = word_ids
+    # signatures: S views of the places, round-robin
+    sig_place = (np.arange(n_signatures) % n_places).astype(np.int64)
+    sig_ids = np.arange(1, n_signatures + 1, dtype=np.int32)
+    sig_words = word_of[sig_place]                                  # [S, feats]
+    sdesc = desc[sig_place] ^ sparse_flip_mask((n_signatures, feats, 32), rng, 6)   # ~1.6 % bit noise per view
+    sxyz = xyz[sig_place] + rng.normal(0, 0.002, (n_signatures, feats, 3)).astype(np.float32)
+    ni = cnt[sig_place].astype(np.int32)
+    # inverted index (word -> signatures), every occurrence counts once per feature
+    fw = sig_words.reshape(-1).astype(np.int64)
+    fs = np.repeat(sig_ids.astype(np.int64), feats)
+    keep = fw > 0
+    key = fw[keep] * (int(n_signatures) + 2) + fs[keep]
+    uk, c = np.unique(key, return_counts=True)
+    pw = (uk // (int(n_signatures) + 2)).astype(np.int32)
+    ps = (uk % (int(n_signatures) + 2)).astype(np.int32)
+    uw, start = np.unique(pw, return_index=True)
+    row_ptr = np.concatenate([start, [len(pw)]]).astype(np.int64)
+    smap = SynthMap(uw.astype(np.int32), row_ptr, ps, c.astype(np.int32), sig_ids, ni, sig_words)
+    # rows beyond a place's keypoint count carry no data
+    for p in range(n_places):
+        if cnt[p] < feats:
+            sel = sig_place == p
+            sxyz[sel, cnt[p]:] = np.nan
+    return PlaceWorld(images, depths, vocab, word_ids, smap, SynthStore(np.ascontiguousarray(sdesc), sxyz.astype(np.float32)), sig_place)
+
+
+def make_view_frames(world: PlaceWorld, n_frames: int, seed: int = 3, max_shift: int = 6, noise_sigma: float = 2.0):
+    """Query frames: noisy, slightly shifted views of random places. Returns images [n,H,W,3], depths [n,H,W], places [n]."""
+    rng = np.random.default_rng(seed)
+    P = len(world.images)
+    places = rng.integers(0, P, n_frames)
+    imgs = np.empty((n_frames,) + world.images.shape[1:], np.uint8)
+    deps = np.empty((n_frames,) + world.depths.shape[1:], np.uint16)
+    for f in range(n_frames):
+        dx, dy = rng.integers(-max_shift, max_shift + 1, 2)
+        imgs[f], deps[f] = render_view(world.images[places[f]], world.depths[places[f]], int(dx), int(dy), noise_sigma, rng)
+    return imgs, deps, places

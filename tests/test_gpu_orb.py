@@ -77,3 +77,44 @@ def test_orb_rejects_unsupported_parameters():
         eng.orb_detect_describe(img, None, Engine.orb_params(K4, scale_factor=1.2))
     with pytest.raises(LcdError):
         eng.orb_detect_describe(np.zeros((1, 481, 641), np.uint8), None, Engine.orb_params(K4))
+
+
+def test_process_frames_full_path_matches_oracle():
+    """images -> detect -> quantise -> score -> verify through lcd_process_frames against cv2.ORB + the oracle."""
+    from oracle import oracle_py as orc
+
+    p = f2d.OrbParams(n_features=600)
+    orb_fn = lambda img, dep: f2d.detect_describe(img, dep, K4, p)
+    world = synth.make_place_world(orb_fn, n_places=5, n_words=2800, n_signatures=120, feats=600, height=240, width=320, seed=9)
+    imgs, deps, places = synth.make_view_frames(world, 4, seed=5, max_shift=4)
+    imgs[3] = 7            # a textureless frame: no keypoints at all
+    eng = Engine()
+    o = orc.OracleDictionary()
+    for d in (eng, o):
+        d.add_words(world.word_ids, world.vocab)
+        d.last_word_id = int(world.word_ids.max())
+        d.update()
+        d.load_csr(world.smap.word_ids, world.smap.row_ptr, world.smap.sig, world.smap.cnt)
+        d.set_ni(world.smap.sig_ids, world.smap.ni)
+    eng.sig_add_batch(world.smap.sig_ids, world.store.desc, world.store.xyz, world.smap.ni)
+    K4s = (262.5, 262.5, 160.0, 120.0)
+    op = Engine.orb_params(K4s, n_features=600)
+    vp = Engine.verify_params(K4s)
+    nkp, words, like, hyp, res = eng.process_frames(imgs, deps, op, world.smap.sig_ids, 121, vp)
+    p2 = f2d.OrbParams(n_features=600)
+    for b in range(4):
+        kp, d, x = f2d.detect_describe(imgs[b], deps[b], K4s, p2)
+        assert nkp[b] == len(kp)
+        if len(kp) == 0:
+            assert not res[b]["ok"] and (words[b] == 0).all()
+            continue
+        w_o, l_o = o.localize_ro(d, world.smap.sig_ids, 121)
+        assert np.array_equal(words[b][:len(w_o)], w_o) and (words[b][len(w_o):] == 0).all()
+        assert np.allclose(like[b], l_o, atol=1e-4, rtol=1e-4)
+        h = int(np.argmax(l_o))
+        assert hyp[b] == world.smap.sig_ids[h] and world.sig_place[h] == places[b]
+        n = int(world.smap.ni[h])
+        v = orc.verify_pair(world.store.desc[h][:n], world.store.xyz[h][:n], d, kp[:, :2], K4s)
+        assert res[b]["ok"] == v["ok"] and res[b]["n_matches"] == len(v["matches"]) and res[b]["n_inliers"] == len(v["inliers"])
+        assert np.allclose(res[b]["rvec"], v["rvec"], atol=1e-4) and np.allclose(res[b]["tvec"], v["tvec"], atol=1e-4)
+        assert res[b]["ok"]
