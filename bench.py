@@ -226,6 +226,7 @@ def run_b200(args):
         raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     if world_size > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     if B % world_size:
