@@ -156,6 +156,7 @@ struct lcd_engine
 	// verification scratch
 	DevBuf<uint32_t> v_df, v_dt;
 	DevBuf<float> v_xyz, v_uv, v_obj, v_img, v_T;
+	DevBuf<long long> v_clk;
 	DevBuf<int> v_nf, v_nt, v_mid, v_mfrom, v_mto, v_nm, v_fid, v_tid, v_inl, v_ninl, v_iters, v_ok, v_inl_ids;
 	DevBuf<double> v_rvec, v_tvec;
 	// signature store (Signature::getWordsDescriptors / getWords3 of the nodes in working memory)
@@ -1382,7 +1383,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		a.level_n = e->o_level_n.p;
 		a.level_cap = level_cap;
 		a.overflow = e->o_overflow.p;
-		const size_t smem = static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2);
+		const size_t smem = static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2);
 		LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 		orb_select_kernel<<<slots, kOrbSelectThreads, smem, s>>>(a);
 		LCD_CHECK_LAUNCH(e);
@@ -1505,6 +1506,7 @@ long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long 
 	case 3: src = e->o_cand.p; bytes = e->o_cand.cap * sizeof(uint32_t); break;
 	case 4: src = e->o_cand_count.p; bytes = e->o_cand_count.cap * sizeof(int); break;
 	case 5: src = e->o_level_n.p; bytes = e->o_level_n.cap * sizeof(int); break;
+	case 7: src = e->v_clk.p; bytes = e->v_clk.cap * sizeof(long long); break;
 	default: return LCD_ERR_INVALID;
 	}
 	if (!src) return 0;
@@ -1635,6 +1637,7 @@ static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_par
 	LCD_CUDA(e, e->v_iters.reserve(n_pairs, 0, false, s));
 	LCD_CUDA(e, e->v_ok.reserve(n_pairs, 0, false, s));
 	LCD_CUDA(e, e->v_T.reserve(n_pairs * 12, 0, false, s));
+	LCD_CUDA(e, e->v_clk.reserve(n_pairs * 16, 0, false, s));
 	PnpArgs a{};
 	a.obj = e->v_obj.p;
 	a.img = e->v_img.p;
@@ -1653,6 +1656,7 @@ static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_par
 	a.iters_run = e->v_iters.p;
 	a.ok = e->v_ok.p;
 	a.transform = e->v_T.p;
+	a.phase_clk = e->v_clk.p;
 	const size_t smem = pnp_smem_bytes(cap);
 	if (smem > static_cast<size_t>(e->smem_optin)) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap %d needs %zu B of shared memory", cap, smem);
 	if (smem > 48 * 1024)

@@ -33,6 +33,7 @@ namespace lcd {
 constexpr int kOrbMaxLevels = 4;
 constexpr int kOrbCandCap = 16384; // FAST corners kept per frame and level before retainBest
 constexpr int kOrbSelectThreads = 512;
+static_assert(kOrbCandCap <= 32 * kOrbSelectThreads, "partition_replay keeps one 32-bit stop mask per thread");
 
 struct OrbKeypoint // cv::KeyPoint fields used by the reference
 {
@@ -244,15 +245,97 @@ orb_fast_nms_kernel(const uint8_t * __restrict__ score_all, const uint8_t * __re
 
 // ---- K3: per (frame, level) selection: raster order, retainBest(2N) on FAST score, Harris, retainBest(N),
 //          IC angle.  One CTA; the two retainBest replays are sequential (thread 0). -----------------------
-struct RespGreater
+// Scratch of the block-cooperative replays below.
+struct SelectScratch
 {
-	const float * resp;
-	const uint16_t * perm;
-	__device__ __forceinline__ bool operator()(int a, int b) const { return resp[perm[a]] > resp[perm[b]]; }
+	uint16_t * rpos; // [kOrbCandCap] positions of the right-hand scan's stops, by rank from the right
+	int * warp_tot;  // [32]
+	int * cut;       // [1]
 };
 
-// libstdc++ std::nth_element(first, nth, last, comp) on perm[first..last)
-__device__ inline void nth_element_replay(uint16_t * perm, const float * resp, int first, int nth, int last)
+// One Hoare-style partition pass over perm[lo..hi), replayed by the whole CTA.
+//
+// Both libstdc++ loops this file replays (std::__unguarded_partition and the bidirectional std::__partition)
+// have the same shape: a left cursor that walks up and STOPS at elements with stop_l(x), a right cursor that walks
+// down and stops at elements with stop_r(x), the two stopped elements are swapped and both cursors move on; the
+// loop ends when the cursors meet.  Because each cursor only ever visits positions the other has not touched
+// yet, the k-th stop of either cursor is the k-th element (from its side) of the ORIGINAL array that satisfies its
+// predicate, and pair k is swapped iff L_k < R_k (monotone in k).  So the sequential result is: swap (L_k, R_k) for
+// all k with L_k < R_k, and the left cursor ends at min(first unswapped L, last swapped R).  Ranks come from one
+// block-wide prefix sum; every thread owns a contiguous segment of <= 32 positions (kOrbCandCap / kOrbSelectThreads).
+// Returns the final left cursor (INT_MAX if neither exists).  All threads must call; result is uniform.
+template <class StopL, class StopR>
+__device__ inline int partition_replay(uint16_t * perm, const float * resp, int lo, int hi, const SelectScratch & sc, StopL stop_l, StopR stop_r)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+	const int len = hi - lo;
+	const int seg = (len + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
+	const int b = lo + tid * seg, e = min(b + seg, hi);
+	uint32_t ml = 0, mr = 0;
+	for (int i = b; i < e; ++i)
+	{
+		const float x = resp[perm[i]];
+		ml |= (stop_l(x) ? 1u : 0u) << (i - b);
+		mr |= (stop_r(x) ? 1u : 0u) << (i - b);
+	}
+	// block exclusive scan of (count_l | count_r << 16)
+	const int mine = __popc(ml) | (__popc(mr) << 16);
+	int incl = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	if (lane == 31) sc.warp_tot[warp] = incl;
+	if (tid == 0) *sc.cut = 0x7FFFFFFF;
+	__syncthreads();
+	int pre = 0, total = 0;
+	for (int w = 0; w < nwarps; ++w)
+	{
+		const int t = sc.warp_tot[w];
+		if (w < warp) pre += t;
+		total += t;
+	}
+	const int ex = pre + incl - mine;
+	const int ex_l = ex & 0xFFFF, ex_r = ex >> 16, tot_r = total >> 16;
+	{
+		int r = tot_r - 1 - ex_r; // rank from the right of this segment's first right-stop
+		for (uint32_t m = mr; m; m &= m - 1)
+		{
+			sc.rpos[r] = static_cast<uint16_t>(b + __ffs(m) - 1);
+			--r;
+		}
+	}
+	__syncthreads();
+	{
+		int k = ex_l;
+		int best = 0x7FFFFFFF;
+		for (uint32_t m = ml; m; m &= m - 1, ++k)
+		{
+			const int i = b + __ffs(m) - 1;
+			const int j = k < tot_r ? static_cast<int>(sc.rpos[k]) : -1;
+			if (i < j)
+			{
+				const uint16_t t = perm[i];
+				perm[i] = perm[j];
+				perm[j] = t;
+				best = min(best, j);
+			}
+			else best = min(best, i);
+		}
+		if (best != 0x7FFFFFFF) atomicMin(sc.cut, best);
+	}
+	__syncthreads();
+	const int cut = *sc.cut;
+	__syncthreads(); // *sc.cut is re-armed by the next call
+	return cut;
+}
+
+// libstdc++ std::nth_element(first, nth, last, greater-by-response) on perm[first..last): introselect with the
+// median-of-three pivot moved to `first`, __unguarded_partition on [first+1, last), insertion sort of the last <= 3.
+// Called by all threads of the CTA; thread 0 does the O(1) steps.
+__device__ inline void nth_element_replay(uint16_t * perm, const float * resp, int first, int nth, int last, const SelectScratch & sc)
 {
 	if (first == last || nth == last) return;
 	auto comp = [&](int a, int b) { return resp[perm[a]] > resp[perm[b]]; };
@@ -268,20 +351,22 @@ __device__ inline void nth_element_replay(uint16_t * perm, const float * resp, i
 		{
 			// __heap_select fallback of introselect: cannot occur before 2*log2(n) unbalanced partitions;
 			// a plain selection keeps the SET right even then (order parity is lost, flagged by the tests)
-			for (int i = first; i <= nth; ++i)
-			{
-				int b = i;
-				for (int j = i + 1; j < last; ++j)
-					if (comp(j, b)) b = j;
-				swp(i, b);
-			}
+			if (threadIdx.x == 0)
+				for (int i = first; i <= nth; ++i)
+				{
+					int b = i;
+					for (int j = i + 1; j < last; ++j)
+						if (comp(j, b)) b = j;
+					swp(i, b);
+				}
+			__syncthreads();
 			return;
 		}
 		--depth;
-		const int mid = first + (last - first) / 2;
-		// __move_median_to_first(first, first+1, mid, last-1)
+		if (threadIdx.x == 0)
 		{
-			const int r = first, a = first + 1, b = mid, c = last - 1;
+			// __move_median_to_first(first, first+1, mid, last-1)
+			const int r = first, a = first + 1, b = first + (last - first) / 2, c = last - 1;
 			if (comp(a, b))
 			{
 				if (comp(b, c)) swp(r, b);
@@ -292,74 +377,64 @@ __device__ inline void nth_element_replay(uint16_t * perm, const float * resp, i
 			else if (comp(b, c)) swp(r, c);
 			else swp(r, b);
 		}
-		// __unguarded_partition(first+1, last, pivot = first)
-		int lo = first + 1, hi = last;
+		__syncthreads();
 		const float pv = resp[perm[first]];
-		for (;;)
-		{
-			while (resp[perm[lo]] > pv) ++lo;
-			--hi;
-			while (pv > resp[perm[hi]]) --hi;
-			if (!(lo < hi)) break;
-			swp(lo, hi);
-			++lo;
-		}
-		const int cut = lo;
+		// __unguarded_partition(first+1, last, pivot): left stops at !(x > pv), right at !(pv > x)
+		const int cut = partition_replay(perm, resp, first + 1, last, sc, [pv](float x) { return !(x > pv); }, [pv](float x) { return !(pv > x); });
 		if (cut <= nth) first = cut;
 		else last = cut;
 	}
-	// __insertion_sort(first, last)
-	for (int i = first + 1; i < last; ++i)
+	if (threadIdx.x == 0)
 	{
-		const uint16_t val = perm[i];
-		const float rv = resp[val];
-		if (rv > resp[perm[first]])
+		// __insertion_sort(first, last)
+		for (int i = first + 1; i < last; ++i)
 		{
-			for (int j = i; j > first; --j) perm[j] = perm[j - 1];
-			perm[first] = val;
-		}
-		else
-		{
-			int j = i;
-			while (rv > resp[perm[j - 1]])
+			const uint16_t val = perm[i];
+			const float rv = resp[val];
+			if (rv > resp[perm[first]])
 			{
-				perm[j] = perm[j - 1];
-				--j;
+				for (int j = i; j > first; --j) perm[j] = perm[j - 1];
+				perm[first] = val;
 			}
-			perm[j] = val;
+			else
+			{
+				int j = i;
+				while (rv > resp[perm[j - 1]])
+				{
+					perm[j] = perm[j - 1];
+					--j;
+				}
+				perm[j] = val;
+			}
 		}
 	}
+	__syncthreads();
 }
 
-// KeyPointsFilter::retainBest(keypoints, n_points): returns the new size
-__device__ inline int retain_best_replay(uint16_t * perm, const float * resp, int n, int n_points)
+// KeyPointsFilter::retainBest(keypoints, n_points): returns the new size.  Called by all threads of the CTA.
+__device__ inline int retain_best_replay(uint16_t * perm, const float * resp, int n, int n_points, const SelectScratch & sc)
 {
 	if (n_points < 0 || n <= n_points) return n;
 	if (n_points == 0) return 0;
-	nth_element_replay(perm, resp, 0, n_points - 1, n);
+	nth_element_replay(perm, resp, 0, n_points - 1, n, sc);
 	const float amb = resp[perm[n_points - 1]];
-	// std::partition(perm + n_points, perm + n, response >= amb)  (bidirectional version)
-	int first = n_points, last = n;
-	for (;;)
+	// std::partition(perm + n_points, perm + n, response >= amb) (bidirectional version): left stops at
+	// !(x >= amb), right stops at x >= amb; the result is n_points + #{x >= amb}
+	int keep = 0;
 	{
-		for (;;)
-		{
-			if (first == last) return first;
-			if (resp[perm[first]] >= amb) ++first;
-			else break;
-		}
-		--last;
-		for (;;)
-		{
-			if (first == last) return first;
-			if (!(resp[perm[last]] >= amb)) --last;
-			else break;
-		}
-		const uint16_t t = perm[first];
-		perm[first] = perm[last];
-		perm[last] = t;
-		++first;
+		// count first (the partition below permutes positions, not values, so the count is order-free)
+		__shared__ int s_keep;
+		if (threadIdx.x == 0) s_keep = 0;
+		__syncthreads();
+		int c = 0;
+		for (int i = n_points + threadIdx.x; i < n; i += blockDim.x) c += resp[perm[i]] >= amb ? 1 : 0;
+		if (c) atomicAdd(&s_keep, c);
+		__syncthreads();
+		keep = s_keep;
+		__syncthreads();
 	}
+	partition_replay(perm, resp, n_points, n, sc, [amb](float x) { return !(x >= amb); }, [amb](float x) { return x >= amb; });
+	return n_points + keep;
 }
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
@@ -406,12 +481,15 @@ orb_select_kernel(const OrbSelectArgs a)
 	uint32_t * keys = reinterpret_cast<uint32_t *>(smem_raw);          // [kOrbCandCap]
 	float * resp = reinterpret_cast<float *>(keys + kOrbCandCap);        // [kOrbCandCap]
 	uint16_t * perm = reinterpret_cast<uint16_t *>(resp + kOrbCandCap);  // [kOrbCandCap]
-	__shared__ int s_n;
+	__shared__ int s_warp_tot[32], s_cut;
+	const SelectScratch sc{perm + kOrbCandCap, s_warp_tot, &s_cut};
 	__shared__ int s_umax[20];
 
 	const int tid = threadIdx.x;
-	const int frame = blockIdx.x / a.g.n_levels, level = blockIdx.x % a.g.n_levels;
-	const int slot = blockIdx.x;
+	// level-major block order: the level-0 CTAs (most candidates) are scheduled first
+	const int n_frames = gridDim.x / a.g.n_levels;
+	const int level = blockIdx.x / n_frames, frame = blockIdx.x % n_frames;
+	const int slot = frame * a.g.n_levels + level;
 	const int w = a.g.w[level], h = a.g.h[level];
 	const uint8_t * img = a.gray + static_cast<size_t>(frame) * a.g.frame_stride + a.g.off[level];
 	int n = a.cand_count[slot];
@@ -464,9 +542,7 @@ orb_select_kernel(const OrbSelectArgs a)
 	}
 	__syncthreads();
 	const int n_level = a.g.n_per_level[level];
-	if (tid == 0) s_n = retain_best_replay(perm, resp, n, 2 * n_level);
-	__syncthreads();
-	int m = s_n;
+	int m = retain_best_replay(perm, resp, n, 2 * n_level, sc);
 	// Harris responses of the kept candidates (HarrisResponses, blockSize 7, k 0.04)
 	for (int i = tid; i < m; i += blockDim.x)
 	{
@@ -495,13 +571,12 @@ orb_select_kernel(const OrbSelectArgs a)
 		resp[perm[i]] = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, t3), t3)), s4);
 	}
 	__syncthreads();
-	if (tid == 0) s_n = retain_best_replay(perm, resp, m, n_level);
-	__syncthreads();
-	m = min(s_n, a.level_cap);
+	const int kept = retain_best_replay(perm, resp, m, n_level, sc);
+	m = min(kept, a.level_cap);
 	if (tid == 0)
 	{
 		a.level_n[slot] = m;
-		if (s_n > a.level_cap) atomicExch(a.overflow, 1);
+		if (kept > a.level_cap) atomicExch(a.overflow, 1);
 	}
 	// IC angle + output
 	const int half = a.g.patch / 2;

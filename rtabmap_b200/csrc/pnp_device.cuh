@@ -468,8 +468,10 @@ struct Epnp6
 	}
 
 	// returns false when the pose is not finite
+	long long * clk = nullptr; // diagnostics: clock64() after each stage
 	__device__ bool compute_pose(double * R, double * t)
 	{
+		if (clk) clk[0] = clock64();
 		choose_control_points();
 		compute_barycentric_coordinates();
 		double mtm[144], vecs[144];
@@ -491,7 +493,9 @@ struct Epnp6
 			for (int a = 0; a < 12; ++a)
 				for (int b = 0; b < 12; ++b) mtm[a * 12 + b] += m1[a] * m1[b] + m2[a] * m2[b];
 		}
+		if (clk) clk[1] = clock64();
 		sym_eigen<12>(mtm, vecs, ord);
+		if (clk) clk[2] = clock64();
 		// L_6x10 and rho
 		double l[60], rho[6];
 		{
@@ -631,10 +635,12 @@ struct Epnp6
 
 // cv::solvePnP(SOLVEPNP_EPNP) on six correspondences (object float xyz, image float pixels, no distortion):
 // undistortPoints stores the normalised coordinates as float before EPnP multiplies them back.
-__device__ inline bool solve_pnp_epnp6(const float * X, const float * uv, const int * idx, const CamK & cam, double * rvec, double * tvec)
+__device__ inline bool solve_pnp_epnp6(const float * X, const float * uv, const int * idx, const CamK & cam, double * rvec, double * tvec,
+                                       long long * clk = nullptr)
 {
 	Epnp6 e;
 	e.cam = cam;
+	e.clk = clk;
 	for (int i = 0; i < 6; ++i)
 	{
 		const float * p = X + 3 * idx[i];
@@ -649,6 +655,7 @@ __device__ inline bool solve_pnp_epnp6(const float * X, const float * uv, const 
 	}
 	double R[9], t[3];
 	if (!e.compute_pose(R, t)) return false;
+	if (clk) clk[3] = clock64();
 	rodrigues_m2v(R, rvec);
 	tvec[0] = t[0];
 	tvec[1] = t[1];

@@ -218,6 +218,7 @@ struct PnpArgs
 	int * iters_run;    // [n_pairs]
 	int * ok;           // [n_pairs] 1 = accepted (inliers >= min_inliers)
 	float * transform;  // [n_pairs][12] (localTransform * pnp)^-1, localTransform = identity
+	long long * phase_clk; // [n_pairs][16] clock64() at the phase boundaries (diagnostics; may be null)
 };
 
 __host__ __device__ inline size_t pnp_smem_bytes(int cap)
@@ -443,6 +444,8 @@ pnp_ransac_kernel(const PnpArgs a)
 	const CamK cam = a.cam;
 	const int iterations = min(max(a.iterations, 1), kMaxRansacIters);
 	const int min_inliers = max(a.min_inliers, 4);
+#define PNP_PHASE(k) do { if (a.phase_clk && tid == 0) a.phase_clk[pair * 16 + (k)] = clock64(); } while (0)
+	PNP_PHASE(0);
 
 	if (tid < 3)
 	{
@@ -485,6 +488,7 @@ pnp_ransac_kernel(const PnpArgs a)
 		}
 	}
 	__syncthreads();
+	PNP_PHASE(1);
 
 	// ---- hypotheses in parallel, a chunk of blockDim.x at a time: EPnP on the sample, then its inlier
 	//      count; thread 0 then replays the sequential bookkeeping of RANSACPointSetRegistrator::run
@@ -508,8 +512,10 @@ pnp_ransac_kernel(const PnpArgs a)
 			for (int k = 0; k < 6; ++k) idx[k] = (n == 6) ? k : sidx[it * 6 + k];
 			double rv[3], tv[3];
 			int c = -1;
-			if (solve_pnp_epnp6(X, uv, idx, cam, rv, tv))
+			long long * clk = (a.phase_clk && tid == 0 && chunk0 == 0) ? a.phase_clk + pair * 16 + 8 : nullptr;
+			if (solve_pnp_epnp6(X, uv, idx, cam, rv, tv, clk))
 			{
+				if (clk) clk[4] = clock64();
 				double R[9];
 				rodrigues_v2m(rv, R, nullptr);
 				c = 0;
@@ -519,10 +525,12 @@ pnp_ransac_kernel(const PnpArgs a)
 					h_rt[tid * 6 + k] = rv[k];
 					h_rt[tid * 6 + 3 + k] = tv[k];
 				}
+				if (clk) clk[5] = clock64();
 			}
 			cnt[tid] = c;
 		}
 		__syncthreads();
+		if (chunk0 == 0) PNP_PHASE(2);
 		if (tid == 0)
 		{
 			int it0 = s_it, niters = s_niters, maxGood = s_maxgood;
@@ -558,6 +566,7 @@ pnp_ransac_kernel(const PnpArgs a)
 		__syncthreads();
 	}
 	const int best = s_best;
+	PNP_PHASE(3);
 	if (tid == 0) a.iters_run[pair] = s_it;
 	if (best < 0) return; // rvec/tvec keep the (identity) guess
 
@@ -680,6 +689,7 @@ pnp_ransac_kernel(const PnpArgs a)
 		n_fin = n_new;
 	}
 	__syncthreads();
+	PNP_PHASE(4);
 
 	if (tid < 3)
 	{

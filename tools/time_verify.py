@@ -31,3 +31,9 @@ dt = (time.perf_counter() - t0) / n
 m = eng.profile_read(3); p = eng.profile_read(4)
 print(json.dumps({"pairs": B, "wall_ms": dt * 1e3, "pairs_per_s": B / dt, "match_ms": m[0] / m[1], "pnp_ms": p[0] / p[1],
                   "ok": sum(o["ok"] for o in out), "inliers": [len(o["inliers"]) for o in out[:4]], "iters": [o["iterations_run"] for o in out[:8]]}))
+clk = eng.debug_orb_buffer(7, B * 16 * 8, np.int64).reshape(B, 16)
+d = np.diff(clk[:, :5], axis=1).astype(np.float64)
+print(json.dumps({"pnp_phase_kcycles_mean": {k: round(float(v) / 1e3, 1) for k, v in zip(("sample", "chunk0", "more_chunks", "refine"), d.mean(0))},
+                  "pnp_phase_kcycles_max": {k: round(float(v) / 1e3, 1) for k, v in zip(("sample", "chunk0", "more_chunks", "refine"), d.max(0))}}))
+e = np.diff(clk[:, 8:14], axis=1).astype(np.float64)
+print(json.dumps({"epnp_thread0_kcycles_mean": {k: round(float(v) / 1e3, 1) for k, v in zip(("ctrl+MtM", "eigen12", "betas+GN+Rt", "m2v", "count"), e.mean(0))}}))
