@@ -271,6 +271,7 @@ def _vlib():
         L.orcv_solve_pnp_iterative.argtypes = [_P, _P, _I, _P, _P, _P]
         L.orcv_project.argtypes = [_P, _I, _P, _P, _P, _P]
         L.orcv_rodrigues.argtypes = [_P, _P]
+        L.orcv_sym_eigen.argtypes = [_P, _I, _I, _P, _P]
         L.orcv_rodrigues_inv.argtypes = [_P, _P]
         L.orcv_rng_draws.argtypes = [_I, _I, _P]
         L.orcv_pnp_ransac.argtypes = [_P, _P, _I, _P, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P]
@@ -280,6 +281,16 @@ def _vlib():
         L.orcv_verify_pair.restype = _I
         L._verify_ready = True
     return L
+
+
+def sym_eigen(a, method=0):
+    """Eigenvalues (descending) and eigenvectors (rows) of a symmetric matrix; method 0 = Householder+QL, 1 = Jacobi."""
+    a = np.ascontiguousarray(a, np.float64)
+    n = a.shape[0]
+    w = np.zeros(n)
+    vt = np.zeros((n, n))
+    _vlib().orcv_sym_eigen(_p(a), n, method, _p(w), _p(vt))
+    return w, vt
 
 
 def solve_pnp_epnp(X, uv, K4):

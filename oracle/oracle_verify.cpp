@@ -353,7 +353,7 @@ struct Epnp
 				for (int r = 0; r < 2 * n; ++r) s += M[r * 12 + a] * M[r * 12 + b];
 				mtm[a * 12 + b] = s;
 			}
-		jacobi_eigen_desc(mtm, 12, d, ut);
+		sym_eigen_desc(mtm, 12, d, ut);
 		double l[60], rho[6];
 		compute_L_6x10(ut, l);
 		compute_rho(rho);
@@ -462,7 +462,7 @@ void solve_pnp_iterative_guess(const float * opts, const float * ipts, int n, co
 		double A[36], w[6], vt[36], dx[6] = {0, 0, 0, 0, 0, 0};
 		memcpy(A, JtJ, sizeof(A));
 		for (int i = 0; i < 6; ++i) A[i * 6 + i] *= 1.0 + lambda;
-		jacobi_eigen_desc(A, 6, w, vt);
+		sym_eigen_desc(A, 6, w, vt);
 		for (int k = 0; k < 6; ++k)
 		{
 			if (w[k] <= DBL_EPSILON * 6 * w[0]) continue;
@@ -757,6 +757,13 @@ int orc_add_new_words(void * h, const void * desc, int n, int sig_id, int * out_
 extern "C" {
 
 void orcv_set_sign_mask(int m) { g_epnp_sign_mask = m; }
+
+// symmetric eigen-decomposition (method 0: Householder + QL, the one the restatement uses; 1: cyclic Jacobi cross-check)
+void orcv_sym_eigen(const double * a, int n, int method, double * w, double * vt)
+{
+	if (method == 0) sym_eigen_desc(a, n, w, vt);
+	else jacobi_eigen_desc(a, n, w, vt);
+}
 
 // RegistrationVis global matching (RegistrationVis.cpp:1482-1546) with Vis/CorNNType in {0,3}: a temporary
 // incremental VWDictionary quantises the FROM descriptors (signature 1), is updated, then quantises the TO

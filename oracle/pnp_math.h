@@ -8,6 +8,127 @@
 
 namespace orc_pnp {
 
+// Eigen-decomposition of a symmetric n x n matrix (row-major, n <= 12): Householder reduction to tridiagonal
+// form followed by the implicit-shift QL iteration (Wilkinson), every sum taken in ascending index order and
+// the plane rotations normalised with sqrt(f*f + g*g) so that the CUDA kernels (rtabmap_b200/csrc/pnp_device.cuh,
+// sym_eigen) can follow the same operation sequence.  This is what the PnP restatement uses wherever OpenCV takes
+// the SVD of a small symmetric Gram matrix (MtM of EPnP, JtJ of the LM step, A^T A of the least-squares solves);
+// jacobi_eigen_desc below is kept as an independent cross-check (tests/test_oracle_verify.py).
+// On return: w[k] eigenvalues in DESCENDING order, vt row k = the matching unit eigenvector.
+inline void sym_eigen_desc(const double * a_in, int n, double * w, double * vt)
+{
+	double a[144], z[144], d[12], e[12], v[12], p[12], wv[12];
+	memcpy(a, a_in, sizeof(double) * n * n);
+	for (int i = 0; i < n; ++i)
+		for (int j = 0; j < n; ++j) z[i * n + j] = i == j ? 1.0 : 0.0;
+	// ---- A = Q T Q^T, Q = H_0 H_1 ... accumulated in z
+	for (int k = 0; k + 2 < n; ++k)
+	{
+		double sigma = 0;
+		for (int i = k + 2; i < n; ++i) sigma += a[i * n + k] * a[i * n + k];
+		if (sigma == 0.0) continue; // column already tridiagonal
+		const double x0 = a[(k + 1) * n + k];
+		const double nrm = std::sqrt(x0 * x0 + sigma);
+		const double alpha = x0 > 0 ? -nrm : nrm;
+		v[k + 1] = x0 - alpha;
+		for (int i = k + 2; i < n; ++i) v[i] = a[i * n + k];
+		const double beta = 2.0 / (v[k + 1] * v[k + 1] + sigma);
+		for (int i = k + 1; i < n; ++i)
+		{
+			double s = 0;
+			for (int j = k + 1; j < n; ++j) s += a[i * n + j] * v[j];
+			p[i] = beta * s;
+		}
+		double vp = 0;
+		for (int i = k + 1; i < n; ++i) vp += v[i] * p[i];
+		const double K = 0.5 * beta * vp;
+		for (int i = k + 1; i < n; ++i) wv[i] = p[i] - K * v[i];
+		for (int i = k + 1; i < n; ++i)
+			for (int j = k + 1; j < n; ++j) a[i * n + j] -= v[i] * wv[j] + wv[i] * v[j];
+		a[(k + 1) * n + k] = alpha;
+		a[k * n + k + 1] = alpha;
+		for (int i = k + 2; i < n; ++i)
+		{
+			a[i * n + k] = 0.0;
+			a[k * n + i] = 0.0;
+		}
+		for (int r = 0; r < n; ++r)
+		{
+			double s = 0;
+			for (int j = k + 1; j < n; ++j) s += z[r * n + j] * v[j];
+			s *= beta;
+			for (int j = k + 1; j < n; ++j) z[r * n + j] -= s * v[j];
+		}
+	}
+	for (int i = 0; i < n; ++i)
+	{
+		d[i] = a[i * n + i];
+		e[i] = i + 1 < n ? a[(i + 1) * n + i] : 0.0;
+	}
+	// ---- implicit-shift QL on (d, e), rotations accumulated in the columns of z
+	for (int l = 0; l < n; ++l)
+	{
+		for (int iter = 0; iter < 60; ++iter)
+		{
+			int m = l;
+			for (; m + 1 < n; ++m)
+				if (std::fabs(e[m]) <= 2.220446049250313e-16 * (std::fabs(d[m]) + std::fabs(d[m + 1]))) break;
+			if (m == l) break;
+			double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+			double r = std::sqrt(g * g + 1.0);
+			g = d[m] - d[l] + e[l] / (g + (g >= 0 ? r : -r));
+			double sn = 1.0, cs = 1.0, pp = 0.0;
+			int i = m - 1;
+			for (; i >= l; --i)
+			{
+				double f = sn * e[i];
+				const double b = cs * e[i];
+				r = std::sqrt(f * f + g * g);
+				e[i + 1] = r;
+				if (r == 0.0)
+				{
+					d[i + 1] -= pp;
+					e[m] = 0.0;
+					break;
+				}
+				sn = f / r;
+				cs = g / r;
+				g = d[i + 1] - pp;
+				r = (d[i] - g) * sn + 2.0 * cs * b;
+				pp = sn * r;
+				d[i + 1] = g + pp;
+				g = cs * r - b;
+				for (int k = 0; k < n; ++k)
+				{
+					f = z[k * n + i + 1];
+					z[k * n + i + 1] = sn * z[k * n + i] + cs * f;
+					z[k * n + i] = cs * z[k * n + i] - sn * f;
+				}
+			}
+			if (r == 0.0 && i >= l) continue;
+			d[l] -= pp;
+			e[l] = g;
+			e[m] = 0.0;
+		}
+	}
+	int order[12];
+	for (int i = 0; i < n; ++i) order[i] = i;
+	for (int i = 0; i < n - 1; ++i) // selection sort, descending, stable
+	{
+		int j = i;
+		for (int k = i + 1; k < n; ++k)
+			if (d[order[k]] > d[order[j]]) j = k;
+		const int t = order[j];
+		for (int k = j; k > i; --k) order[k] = order[k - 1];
+		order[i] = t;
+	}
+	for (int k = 0; k < n; ++k)
+	{
+		w[k] = d[order[k]];
+		for (int i = 0; i < n; ++i) vt[k * n + i] = z[i * n + order[k]];
+	}
+}
+
 // Cyclic two-sided Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, n <= 12).
 // Rotations annihilate a_pq exactly; a pair is skipped once |a_pq| <= eps*sqrt(|a_pp a_qq|) and the
 // iteration stops after a sweep without rotations (at most 30 sweeps).  The CUDA kernels use the same
@@ -195,7 +316,7 @@ inline void solve_ls(const double * A, const double * b, int m, int n, double * 
 		for (int k = 0; k < m; ++k) s += A[k * n + i] * b[k];
 		atb[i] = s;
 	}
-	jacobi_eigen_desc(ata, n, w, vt);
+	sym_eigen_desc(ata, n, w, vt);
 	for (int i = 0; i < n; ++i) x[i] = 0;
 	const double tol = w[0] * 1e-14 * n;
 	for (int k = 0; k < n; ++k)
@@ -219,7 +340,7 @@ inline void svd3(const double * M, double * U, double * w, double * V)
 			for (int k = 0; k < 3; ++k) s += M[k * 3 + i] * M[k * 3 + j];
 			mtm[i * 3 + j] = s;
 		}
-	jacobi_eigen_desc(mtm, 3, ew, vt);
+	sym_eigen_desc(mtm, 3, ew, vt);
 	for (int k = 0; k < 3; ++k)
 	{
 		w[k] = std::sqrt(std::max(ew[k], 0.0));

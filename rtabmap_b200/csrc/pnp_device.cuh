@@ -105,60 +105,122 @@ __device__ inline void svd_rows_jacobi3(double * At, double * W)
 	}
 }
 
-// Cyclic two-sided Jacobi eigen-decomposition of a symmetric N x N matrix held in a[] (destroyed).
-// Rotations annihilate a_pq exactly; a pair is skipped once |a_pq| <= eps*sqrt(|a_pp a_qq|) and the
-// iteration stops after a sweep without rotations (<= 30 sweeps) — the same operation sequence as the
-// CPU oracle's jacobi_eigen_desc.  v[] receives the eigenvectors as COLUMNS; ord[] the column order of
-// descending eigenvalue.
+// Eigen-decomposition of a symmetric N x N matrix held in a[] (destroyed; the eigenvalues are left on its
+// diagonal): Householder reduction to tridiagonal form, then the implicit-shift QL iteration — the same operation
+// sequence as the CPU oracle's sym_eigen_desc (oracle/pnp_math.h), every sum in ascending index order.  v[] receives
+// the eigenvectors as COLUMNS; ord[] the column order of descending eigenvalue.  About 15x fewer dependent
+// operations than the cyclic Jacobi sweeps this replaces (one thread per RANSAC hypothesis is latency-bound).
 template <int N>
-__device__ inline void sym_eigen(double * a, double * v, int * ord)
+__device__ inline void sym_eigen(double * a, double * z, int * ord)
 {
+	double d[N], e[N], hv[N], hp[N], hw[N];
+#pragma unroll
 	for (int i = 0; i < N; ++i)
-		for (int j = 0; j < N; ++j) v[i * N + j] = i == j ? 1.0 : 0.0;
-	for (int sweep = 0; sweep < 30; ++sweep)
+#pragma unroll
+		for (int j = 0; j < N; ++j) z[i * N + j] = i == j ? 1.0 : 0.0;
+	for (int k = 0; k + 2 < N; ++k)
 	{
-		bool rotated = false;
-		for (int p = 0; p < N - 1; ++p)
+		double sigma = 0;
+		for (int i = k + 2; i < N; ++i) sigma += a[i * N + k] * a[i * N + k];
+		if (sigma == 0.0) continue;
+		const double x0 = a[(k + 1) * N + k];
+		const double nrm = sqrt(x0 * x0 + sigma);
+		const double alpha = x0 > 0 ? -nrm : nrm;
+		hv[k + 1] = x0 - alpha;
+		for (int i = k + 2; i < N; ++i) hv[i] = a[i * N + k];
+		const double beta = 2.0 / (hv[k + 1] * hv[k + 1] + sigma);
+		for (int i = k + 1; i < N; ++i)
 		{
-			for (int q = p + 1; q < N; ++q)
+			double s = 0;
+			for (int j = k + 1; j < N; ++j) s += a[i * N + j] * hv[j];
+			hp[i] = beta * s;
+		}
+		double vp = 0;
+		for (int i = k + 1; i < N; ++i) vp += hv[i] * hp[i];
+		const double K = 0.5 * beta * vp;
+		for (int i = k + 1; i < N; ++i) hw[i] = hp[i] - K * hv[i];
+		for (int i = k + 1; i < N; ++i)
+			for (int j = k + 1; j < N; ++j) a[i * N + j] -= hv[i] * hw[j] + hw[i] * hv[j];
+		a[(k + 1) * N + k] = alpha;
+		a[k * N + k + 1] = alpha;
+		for (int i = k + 2; i < N; ++i)
+		{
+			a[i * N + k] = 0.0;
+			a[k * N + i] = 0.0;
+		}
+		for (int r = 0; r < N; ++r)
+		{
+			double s = 0;
+			for (int j = k + 1; j < N; ++j) s += z[r * N + j] * hv[j];
+			s *= beta;
+			for (int j = k + 1; j < N; ++j) z[r * N + j] -= s * hv[j];
+		}
+	}
+	for (int i = 0; i < N; ++i)
+	{
+		d[i] = a[i * N + i];
+		e[i] = i + 1 < N ? a[(i + 1) * N + i] : 0.0;
+	}
+	for (int l = 0; l < N; ++l)
+	{
+		for (int iter = 0; iter < 60; ++iter)
+		{
+			int m = l;
+			for (; m + 1 < N; ++m)
+				if (fabs(e[m]) <= 2.220446049250313e-16 * (fabs(d[m]) + fabs(d[m + 1]))) break;
+			if (m == l) break;
+			double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+			double r = sqrt(g * g + 1.0);
+			g = d[m] - d[l] + e[l] / (g + (g >= 0 ? r : -r));
+			double sn = 1.0, cs = 1.0, pp = 0.0;
+			int i = m - 1;
+			for (; i >= l; --i)
 			{
-				const double apq = a[p * N + q];
-				const double app = a[p * N + p], aqq = a[q * N + q];
-				if (fabs(apq) <= 2.220446049250313e-16 * sqrt(fabs(app * aqq))) continue;
-				rotated = true;
-				const double theta = (aqq - app) / (2.0 * apq);
-				const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-				const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-				a[p * N + p] = app - t * apq;
-				a[q * N + q] = aqq + t * apq;
-				a[p * N + q] = 0.0;
-				a[q * N + p] = 0.0;
-				for (int k = 0; k < N; ++k)
+				double f = sn * e[i];
+				const double b = cs * e[i];
+				r = sqrt(f * f + g * g);
+				e[i + 1] = r;
+				if (r == 0.0)
 				{
-					if (k == p || k == q) continue;
-					const double akp = a[k * N + p], akq = a[k * N + q];
-					const double nkp = c * akp - s * akq, nkq = s * akp + c * akq;
-					a[k * N + p] = nkp;
-					a[p * N + k] = nkp;
-					a[k * N + q] = nkq;
-					a[q * N + k] = nkq;
+					d[i + 1] -= pp;
+					e[m] = 0.0;
+					break;
 				}
+				sn = f / r;
+				cs = g / r;
+				g = d[i + 1] - pp;
+				r = (d[i] - g) * sn + 2.0 * cs * b;
+				pp = sn * r;
+				d[i + 1] = g + pp;
+				g = cs * r - b;
+				// columns i, i+1 of z: loads first, then arithmetic and stores (off the critical chain)
+				double zi[N], zj[N];
+#pragma unroll
 				for (int k = 0; k < N; ++k)
 				{
-					const double vkp = v[k * N + p], vkq = v[k * N + q];
-					v[k * N + p] = c * vkp - s * vkq;
-					v[k * N + q] = s * vkp + c * vkq;
+					zi[k] = z[k * N + i];
+					zj[k] = z[k * N + i + 1];
+				}
+#pragma unroll
+				for (int k = 0; k < N; ++k)
+				{
+					z[k * N + i + 1] = sn * zi[k] + cs * zj[k];
+					z[k * N + i] = cs * zi[k] - sn * zj[k];
 				}
 			}
+			if (r == 0.0 && i >= l) continue;
+			d[l] -= pp;
+			e[l] = g;
+			e[m] = 0.0;
 		}
-		if (!rotated) break;
 	}
+	for (int i = 0; i < N; ++i) a[i * N + i] = d[i];
 	for (int i = 0; i < N; ++i) ord[i] = i;
 	for (int i = 0; i < N - 1; ++i) // selection sort, descending, stable
 	{
 		int j = i;
 		for (int k = i + 1; k < N; ++k)
-			if (a[ord[k] * N + ord[k]] > a[ord[j] * N + ord[j]]) j = k;
+			if (d[ord[k]] > d[ord[j]]) j = k;
 		const int t = ord[j];
 		for (int k = j; k > i; --k) ord[k] = ord[k - 1];
 		ord[i] = t;

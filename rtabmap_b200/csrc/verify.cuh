@@ -464,29 +464,6 @@ pnp_ransac_kernel(const PnpArgs a)
 
 	for (int i = tid; i < n * 3; i += blockDim.x) X[i] = a.obj[base * 3 + i];
 	for (int i = tid; i < n * 2; i += blockDim.x) uv[i] = a.img[base * 2 + i];
-	if (tid == 0)
-	{
-		// RANSACPointSetRegistrator::getSubset with cv::RNG((uint64)-1): draws depend only on n
-		unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
-		for (int it = 0; it < iterations; ++it)
-		{
-			for (int i = 0; i < 6;)
-			{
-				int idx_i;
-				for (;;)
-				{
-					state = static_cast<unsigned long long>(static_cast<unsigned>(state)) * 4164903690ull + static_cast<unsigned>(state >> 32);
-					idx_i = static_cast<int>(static_cast<unsigned>(state) % static_cast<unsigned>(n));
-					int j;
-					for (j = 0; j < i; ++j)
-						if (idx_i == sidx[it * 6 + j]) break;
-					if (j == i) break;
-				}
-				sidx[it * 6 + i] = static_cast<uint16_t>(idx_i);
-				++i;
-			}
-		}
-	}
 	__syncthreads();
 	PNP_PHASE(1);
 
@@ -503,8 +480,38 @@ pnp_ransac_kernel(const PnpArgs a)
 		s_niters = (n == 6) ? 1 : iterations;
 	}
 	__syncthreads();
+	__shared__ unsigned long long s_rng;
+	if (tid == 0) s_rng = 0xFFFFFFFFFFFFFFFFull;
+	__syncthreads();
 	for (int chunk0 = 0; chunk0 < s_niters; chunk0 += blockDim.x)
 	{
+		if (tid == 0 && n != 6)
+		{
+			// RANSACPointSetRegistrator::getSubset with cv::RNG((uint64)-1): the draws depend only on n and are
+			// consumed in iteration order, so the samples of a chunk are generated when the chunk is reached
+			unsigned long long state = s_rng;
+			const int it_end = min(chunk0 + static_cast<int>(blockDim.x), s_niters);
+			for (int it = chunk0; it < it_end; ++it)
+			{
+				for (int i = 0; i < 6;)
+				{
+					int idx_i;
+					for (;;)
+					{
+						state = static_cast<unsigned long long>(static_cast<unsigned>(state)) * 4164903690ull + static_cast<unsigned>(state >> 32);
+						idx_i = static_cast<int>(static_cast<unsigned>(state) % static_cast<unsigned>(n));
+						int j;
+						for (j = 0; j < i; ++j)
+							if (idx_i == sidx[it * 6 + j]) break;
+						if (j == i) break;
+					}
+					sidx[it * 6 + i] = static_cast<uint16_t>(idx_i);
+					++i;
+				}
+			}
+			s_rng = state;
+		}
+		__syncthreads();
 		const int it = chunk0 + tid;
 		if (it < s_niters)
 		{
@@ -519,6 +526,7 @@ pnp_ransac_kernel(const PnpArgs a)
 				double R[9];
 				rodrigues_v2m(rv, R, nullptr);
 				c = 0;
+#pragma unroll 4
 				for (int i = 0; i < n; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
 				for (int k = 0; k < 3; ++k)
 				{
