@@ -12,6 +12,7 @@
 #include "../../include/lcd_b200.h"
 #include "common.cuh"
 #include "nn_hamming.cuh"
+#include "nn_tensor.cuh"
 #include "resolve.cuh"
 #include "score.cuh"
 #include "verify.cuh"
@@ -140,6 +141,7 @@ struct lcd_engine
 	// --- scratch
 	DevBuf<uint32_t> d_queries;
 	DevBuf<uint2> d_partial;
+	DevBuf<uint4> tc_words, tc_queries; // int8 operand images of the tensor-core 2-NN
 	DevBuf<uint32_t> d_keys;
 	DevBuf<int> d_word_ids, d_n_new, d_in_ids;
 	DevBuf<int> uq_count, uq_word, uq_prefix;
@@ -186,6 +188,8 @@ struct lcd_engine
 
 	// tuning knobs (env: LCD_NN_CTAS_PER_SM, LCD_NN_TQ, LCD_NN_VARIANT, LCD_SCORE_BLOCKS)
 	int nn_ctas_per_sm = 2, nn_tq = 8, nn_variant = 2, score_blocks = 32;
+	int nn_tensor = 1;   // 256-bit descriptors: tcgen05 int8 path (nn_tensor.cuh); 0 = POPC kernel (nn_hamming.cuh)
+	int nn_last_tensor = 0; // which kernel the last run_knn used (bench / diagnostics)
 };
 
 #define LCD_FAIL(e, code, ...)                          \
@@ -345,6 +349,46 @@ int launch_knn_nw(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows
 int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int * n_chunks_out, cudaStream_t s)
 {
 	if (e->row_offset + n_rows > kMaxRowsPacked) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d indexed words", kMaxRowsPacked);
+	e->nn_last_tensor = 0;
+	if (e->nn_tensor && e->nw == 8 && n_rows > 0 && nq_total > 0 && kTcSmemBytes <= static_cast<size_t>(e->smem_optin))
+	{
+		// tensor-core path: expand both operands to the int8 images, then one CTA per (query tile, word split)
+		const int n_wtiles = (n_rows + kTcBN - 1) / kTcBN, n_qtiles = (nq_total + kTcBM - 1) / kTcBM;
+		int best_split = 1;
+		long best_cost = -1;
+		for (int sp = 1; sp <= std::min(n_wtiles, 16); ++sp)
+		{
+			const int tps = (n_wtiles + sp - 1) / sp;
+			const int real_sp = (n_wtiles + tps - 1) / tps;
+			if (real_sp != sp) continue;
+			const long waves = (static_cast<long>(n_qtiles) * sp + e->sm_count - 1) / e->sm_count;
+			const long cost = waves * (tps + 3); // +3: prologue (TMEM alloc, first loads) and drain, in tile times
+			if (best_cost < 0 || cost < best_cost)
+			{
+				best_cost = cost;
+				best_split = sp;
+			}
+		}
+		const int tps = (n_wtiles + best_split - 1) / best_split;
+		LCD_CUDA(e, e->tc_words.reserve(static_cast<size_t>(n_wtiles) * kTcBN * 16, 0, false, s));
+		LCD_CUDA(e, e->tc_queries.reserve(static_cast<size_t>(n_qtiles) * kTcBM * 16, 0, false, s));
+		LCD_CUDA(e, e->d_partial.reserve(static_cast<size_t>(best_split) * nq_total, 0, false, s));
+		{
+			const size_t tw = static_cast<size_t>(n_wtiles) * kTcBN * 16, tq = static_cast<size_t>(n_qtiles) * kTcBM * 16;
+			tc_expand_kernel<<<static_cast<unsigned>((tw + 255) / 256), 256, 0, s>>>(e->vocab.p, n_rows, kTcBN, n_wtiles, e->tc_words.p);
+			tc_expand_kernel<<<static_cast<unsigned>((tq + 255) / 256), 256, 0, s>>>(d_q, nq_total, kTcBM, n_qtiles, e->tc_queries.p);
+		}
+		LCD_CUDA(e, cudaFuncSetAttribute(knn2_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
+		prof_mark(e, LCD_PROF_NN, s);
+		knn2_tensor_kernel<<<dim3(n_qtiles, best_split), kTcThreads, kTcSmemBytes, s>>>(e->tc_words.p, n_rows, e->row_offset, e->tc_queries.p, nq_total,
+		                                                                               e->d_partial.p, tps);
+		prof_mark(e, LCD_PROF_NN, s);
+		LCD_CHECK_LAUNCH(e);
+		e->launches += 2; // the two expand kernels (LCD_CHECK_LAUNCH counted the 2-NN kernel)
+		e->nn_last_tensor = 1;
+		*n_chunks_out = best_split;
+		return LCD_OK;
+	}
 	const int max_rows_smem = static_cast<int>((static_cast<size_t>(e->smem_optin) - 16 - 1024) / (e->nw * 4));
 	int n_chunks = e->sm_count * e->nn_ctas_per_sm;
 	n_chunks = std::min(n_chunks, std::max(1, (n_rows + 31) / 32));
@@ -658,6 +702,7 @@ lcd_engine * lcd_create(const lcd_config * cfg)
 	e->nn_ctas_per_sm = std::max(1, env_int("LCD_NN_CTAS_PER_SM", e->nn_ctas_per_sm));
 	e->nn_tq = env_int("LCD_NN_TQ", e->nn_tq);
 	e->nn_variant = env_int("LCD_NN_VARIANT", e->nn_variant);
+	e->nn_tensor = env_int("LCD_NN_TENSOR", e->nn_tensor);
 	e->score_blocks = std::max(1, env_int("LCD_SCORE_BLOCKS", e->score_blocks));
 	if (ensure_rows(e, std::max(cfg->max_words, 1024)) != LCD_OK || ensure_ids(e, std::max(cfg->max_words, 1024)) != LCD_OK ||
 	    ensure_sigs(e, std::max(cfg->max_signatures, 1024)) != LCD_OK)
