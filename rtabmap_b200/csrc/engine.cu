@@ -372,7 +372,7 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 		const int tps = (n_wtiles + best_split - 1) / best_split;
 		LCD_CUDA(e, e->tc_words.reserve(static_cast<size_t>(n_wtiles) * kTcBN * 16, 0, false, s));
 		LCD_CUDA(e, e->tc_queries.reserve(static_cast<size_t>(n_qtiles) * kTcBM * 16, 0, false, s));
-		LCD_CUDA(e, e->d_partial.reserve(static_cast<size_t>(best_split) * nq_total, 0, false, s));
+		LCD_CUDA(e, e->d_partial.reserve(static_cast<size_t>(best_split) * kTcEpiGroups * nq_total, 0, false, s));
 		{
 			const size_t tw = static_cast<size_t>(n_wtiles) * kTcBN * 16, tq = static_cast<size_t>(n_qtiles) * kTcBM * 16;
 			tc_expand_kernel<<<static_cast<unsigned>((tw + 255) / 256), 256, 0, s>>>(e->vocab.p, n_rows, kTcBN, n_wtiles, e->tc_words.p);
@@ -386,7 +386,7 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 		LCD_CHECK_LAUNCH(e);
 		e->launches += 2; // the two expand kernels (LCD_CHECK_LAUNCH counted the 2-NN kernel)
 		e->nn_last_tensor = 1;
-		*n_chunks_out = best_split;
+		*n_chunks_out = best_split * kTcEpiGroups;
 		return LCD_OK;
 	}
 	const int max_rows_smem = static_cast<int>((static_cast<size_t>(e->smem_optin) - 16 - 1024) / (e->nw * 4));

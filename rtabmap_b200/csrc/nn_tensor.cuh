@@ -15,8 +15,9 @@
 //   warp 1  MMA       : one thread issues 8 x tcgen05.mma (M128 N256 K32) per word tile into one of two TMEM
 //                       accumulator stages, then tcgen05.commit to the smem-empty and accumulator-full barriers
 //   warp 2  TMEM alloc/dealloc (512 columns)
-//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time; a 32-value max against the running second-best
-//                       filters almost every group, only improving candidates reach the packed-key insert
+//   warps 4-19 epilogue: warp w reads TMEM lanes 32*(w%4).. (its queries) and the 64 columns of column group
+//                       (w-4)/4: two tcgen05.ld.x32 in flight, a max over the 64 values against the running
+//                       second-best filters almost every group, only improving candidates reach the key insert
 //
 // Operand images (written by the expand kernels below): K-major, 128-byte swizzle (the canonical UMMA/TMA layout:
 // 16-byte chunk c of row r of every 8-row x 128-byte block sits at chunk c ^ (r & 7)), split in K/128 "atoms":
@@ -33,7 +34,9 @@ constexpr int kTcBN = 256;       // words per tile (UMMA N)
 constexpr int kTcK = 256;        // descriptor bits = int8 K extent
 constexpr int kTcAtoms = kTcK / 128;
 constexpr int kTcStages = 3;     // word-tile smem stages
-constexpr int kTcThreads = 256;
+constexpr int kTcEpiGroups = 4;  // column groups of a tile, one set of 4 epilogue warps each
+constexpr int kTcEpiCols = kTcBN / kTcEpiGroups;
+constexpr int kTcThreads = 128 + 128 * kTcEpiGroups;
 constexpr uint32_t kTcABytes = kTcBM * kTcK;
 constexpr uint32_t kTcBBytes = kTcBN * kTcK;
 constexpr size_t kTcSmemBytes = 1024 /* alignment slack */ + kTcABytes + kTcStages * kTcBBytes + 256 /* barriers */;
@@ -136,7 +139,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32])
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-// grid = (query tiles, word splits).  partial[split * nq_pad + query] = (best key, second key) over the split's rows.
+// grid = (query tiles, word splits).  partial[(split * kTcEpiGroups + column group) * nq + query] = (best key, second key)
+// over the rows of that split that fall in that column group of their tile.
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offset, const uint4 * __restrict__ query_img, int nq,
                    uint2 * __restrict__ partial, int tiles_per_split)
@@ -170,7 +174,7 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 		for (int s = 0; s < 2; ++s)
 		{
 			mbar_init(&tfull[s], 1);
-			mbar_init(&tempty[s], 4); // one arrival per epilogue warp
+			mbar_init(&tempty[s], 4 * kTcEpiGroups); // one arrival per epilogue warp
 		}
 		mbar_init(afull, 1);
 		mbar_fence_init();
@@ -228,7 +232,8 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 	}
 	else if (warp >= 4)
 	{
-		const int quarter = warp - 4;                 // TMEM lanes [32*quarter, 32*quarter+32)
+		const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp id % 4)
+		const int cg = (warp - 4) >> 2;               // column group
 		const int qi = qtile * kTcBM + quarter * 32 + lane;
 		uint32_t k1 = kKeyNone, k2 = kKeyNone;
 		int thr = -100000;                            // accumulator value a candidate has to exceed to enter the top-2
@@ -237,37 +242,66 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 			const int acc = t & 1;
 			mbar_wait(&tfull[acc], (t >> 1) & 1);
 			tc_fence_after();
-			const int row0 = (tile_begin + t) * kTcBN;
-			const int valid = min(kTcBN, n_rows - row0); // columns of this tile that are real words
-			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTcBN);
-#pragma unroll 1
-			for (int c0 = 0; c0 < kTcBN; c0 += 32)
-			{
-				int v[32];
-				tc_ld32(taddr + c0, v);
-				tc_wait_ld();
-				int m = v[0];
+			const int row0 = (tile_begin + t) * kTcBN + cg * kTcEpiCols;
+			const int valid = n_rows - row0;              // columns of this group that are real words (may be <= 0)
+			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTcBN + cg * kTcEpiCols);
+			int v[kTcEpiCols];
 #pragma unroll
-				for (int j = 1; j < 32; ++j) m = max(m, v[j]);
-				if (m > thr)
-				{
-#pragma unroll
-					for (int j = 0; j < 32; ++j)
-					{
-						if (v[j] > thr && c0 + j < valid)
-						{
-							const uint32_t key = (static_cast<uint32_t>(kTcK - v[j]) << (kKeyShift - 1)) + static_cast<uint32_t>(row_offset + row0 + c0 + j);
-							top2_insert(k1, k2, key);
-							thr = k2 == kKeyNone ? -100000 : kTcK - 2 * static_cast<int>(k2 >> kKeyShift);
-						}
-					}
-				}
-			}
+			for (int c0 = 0; c0 < kTcEpiCols; c0 += 32) tc_ld32(taddr + c0, *reinterpret_cast<int(*)[32]>(&v[c0]));
+			tc_wait_ld();
+			// the accumulator stage is free as soon as the values are in registers
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&tempty[acc]);
+			if (valid >= kTcEpiCols)
+			{
+				// Branch-free top-2 over the 64 columns with 16-bit keys, two columns per register:
+				//   key16 = distance * 64 + j = acc * (-32) + (8192 + j)   (distance = (256 - acc) / 2 <= 256, j < 32)
+				// The low half-word carries column j, the high half-word column j + 32; S = acc_hi * 65536 + acc_lo and
+				// K = S * (-32) + (8192 + j) * 65537 is that pair of keys exactly (every field stays in [0, 65536), so no
+				// carry crosses the halves).  Two IMADs (FMA pipe) and three VIMNMX.U16x2 (ALU pipe) per column pair.
+				uint32_t p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
+#pragma unroll
+				for (int j = 0; j < 32; ++j)
+				{
+					const uint32_t sp = static_cast<uint32_t>(v[j + 32]) * 65536u + static_cast<uint32_t>(v[j]);
+					const uint32_t kp = sp * static_cast<uint32_t>(-32) + static_cast<uint32_t>(8192 + j) * 65537u;
+					const uint32_t mx = __vmaxu2(p1, kp);
+					p1 = __vminu2(p1, kp);
+					p2 = __vminu2(p2, mx);
+				}
+				// the four survivors (two per half) go into the running packed keys only if they can improve them
+				const uint32_t best16 = min(p1 & 0xFFFFu, p1 >> 16);
+				if (static_cast<int>(best16 >> 6) * 2 < kTcK - thr)
+				{
+					const uint32_t base = static_cast<uint32_t>(row_offset + row0);
+					const uint32_t c[4] = {p1 & 0xFFFFu, p2 & 0xFFFFu, p1 >> 16, p2 >> 16};
+#pragma unroll
+					for (int u = 0; u < 4; ++u)
+					{
+						const uint32_t key = ((c[u] >> 6) << kKeyShift) + base + (c[u] & 63u) + (u >= 2 ? 32u : 0u);
+						top2_insert(k1, k2, key);
+					}
+					thr = k2 == kKeyNone ? -100000 : kTcK - 2 * static_cast<int>(k2 >> kKeyShift);
+				}
+			}
+			else if (valid > 0)
+			{
+				// last, partly filled tile: plain insertion of the real columns
+#pragma unroll
+				for (int j = 0; j < kTcEpiCols; ++j)
+				{
+					if (j < valid)
+					{
+						const uint32_t key = (static_cast<uint32_t>(kTcK - v[j]) << (kKeyShift - 1)) + static_cast<uint32_t>(row_offset + row0 + j);
+						top2_insert(k1, k2, key);
+					}
+				}
+				thr = k2 == kKeyNone ? -100000 : kTcK - 2 * static_cast<int>(k2 >> kKeyShift);
+			}
+			__syncwarp();
 		}
-		if (qi < nq) partial[static_cast<size_t>(blockIdx.y) * nq + qi] = make_uint2(k1, k2);
+		if (qi < nq) partial[(static_cast<size_t>(blockIdx.y) * kTcEpiGroups + cg) * nq + qi] = make_uint2(k1, k2);
 	}
 
 	tc_fence_before();
