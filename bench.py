@@ -19,7 +19,7 @@ likelihood arg-max is a true loop closure and its verification succeeds.
 `value`   frames/s with images + depth already resident in HBM (CUDA events on the engine stream).
 `e2e`     frames/s through the host-buffer C-ABI call lcd_process_frames (pinned host images + depth in,
           word ids + likelihood + verified poses out; H2D/D2H inside the timed region).
-`roofline` the dictionary-NN kernel (knn2_hamming_kernel), timed live with CUDA events on its stream.
+`roofline` the dictionary-NN kernel (knn2_tensor_kernel; knn2_hamming_kernel with LCD_NN_TENSOR=0), timed live with CUDA events on its stream.
 `cpu_baseline` / --impl reference: cv2.ORB + the oracle port of the reference algorithm on the host cores.
 """
 from __future__ import annotations
@@ -64,6 +64,17 @@ def peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def tensor_peak_tops():
+    """Dense s8 tensor peak in Tera-op/s: MEASURED_PEAKS.json holds the measured bf16 figure (burst: the kernel is timed
+    alone); tcgen05 kind::i8 runs at twice the bf16 rate (K=32 per instruction against K=16), so the s8 roof is 2x it."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if "bf16_tflops" in d:
+            return 2.0 * float(d["bf16_tflops"]), "2 x measured bf16 dense (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 2.0 * 2250.0, "2 x nominal bf16 dense (B200_PROFILING.md fallback)"
 
 
 class ClockSampler:
@@ -414,16 +425,38 @@ def run_b200(args):
             traffic = json.loads(tp.read_text()).get("knn2_hamming_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {
-        "kernel": "knn2_hamming_kernel<8,8,2>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-        "avg_launch_ms": nn_avg_s * 1e3, "launches_timed": int(nn_launches),
-        "binding_resource": "integer pipes (POPC 16 lanes/clk/SM on XU + LOP3 on ALU): the vocabulary is SMEM/L2 resident, see DESIGN.md §4",
-        "pairs_per_s": pairs / nn_avg_s if nn_avg_s > 0 else 0.0,
-        "popc_per_s": pairs * popc_per_pair / nn_avg_s if nn_avg_s > 0 else 0.0, "popc_peak_per_s": popc_peak,
-        "popc_frac": (pairs * popc_per_pair / nn_avg_s) / popc_peak if nn_avg_s > 0 else 0.0,
-        "step_share_ms": dict({k + "_ms": v[0] / args.steps for k, v in prof.items()}, step_ms=dev_ms / args.steps),
-    }
+    share = dict({k + "_ms": v[0] / args.steps for k, v in prof.items()}, step_ms=dev_ms / args.steps)
+    if os.environ.get("LCD_NN_TENSOR", "1") != "0":
+        # dominant kernel: knn2_tensor_kernel (tcgen05 kind::i8).  Algorithmic work per launch = one s8 multiply-add per
+        # (query, word, descriptor bit): 2 * Q * W * 256 operations.
+        ops = 2.0 * pairs * DESC_BYTES * 8
+        tpeak, tsrc = tensor_peak_tops()
+        ach = ops / nn_avg_s / 1e12 if nn_avg_s > 0 else 0.0
+        traffic_t = None
+        if tp.exists():
+            try:
+                traffic_t = json.loads(tp.read_text()).get("knn2_tensor_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic_t = None
+        roofline = {
+            "kernel": "knn2_tensor_kernel (tcgen05.mma kind::i8, M128 N256 K32)", "bound": "tensor", "achieved": ach, "peak": tpeak,
+            "unit": "TFLOP/s", "frac": ach / tpeak, "peak_source": tsrc, "traffic": traffic_t,
+            "algorithmic_ops_per_launch": ops, "algorithmic_bytes_per_launch": alg_bytes,
+            "avg_launch_ms": nn_avg_s * 1e3, "launches_timed": int(nn_launches),
+            "note": "s8 operations counted as FLOPs of the +-1 encoded Hamming GEMM; results are exact integers (parity tests)",
+            "pairs_per_s": pairs / nn_avg_s if nn_avg_s > 0 else 0.0, "step_share_ms": share,
+        }
+    else:
+        roofline = {
+            "kernel": "knn2_hamming_kernel<8,8,2>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "peak_source": peak_src, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+            "avg_launch_ms": nn_avg_s * 1e3, "launches_timed": int(nn_launches),
+            "binding_resource": "integer pipes (POPC 16 lanes/clk/SM on XU + LOP3 on ALU): the vocabulary is SMEM/L2 resident, see DESIGN.md §4",
+            "pairs_per_s": pairs / nn_avg_s if nn_avg_s > 0 else 0.0,
+            "popc_per_s": pairs * popc_per_pair / nn_avg_s if nn_avg_s > 0 else 0.0, "popc_peak_per_s": popc_peak,
+            "popc_frac": (pairs * popc_per_pair / nn_avg_s) / popc_peak if nn_avg_s > 0 else 0.0,
+            "step_share_ms": share,
+        }
 
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:

@@ -381,7 +381,7 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 		LCD_CUDA(e, cudaFuncSetAttribute(knn2_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
 		prof_mark(e, LCD_PROF_NN, s);
 		knn2_tensor_kernel<<<dim3(n_qtiles, best_split), kTcThreads, kTcSmemBytes, s>>>(e->tc_words.p, n_rows, e->row_offset, e->tc_queries.p, nq_total,
-		                                                                               e->d_partial.p, tps);
+		                                                                               e->d_partial.p, tps, static_cast<uint32_t>(-32));
 		prof_mark(e, LCD_PROF_NN, s);
 		LCD_CHECK_LAUNCH(e);
 		e->launches += 2; // the two expand kernels (LCD_CHECK_LAUNCH counted the 2-NN kernel)

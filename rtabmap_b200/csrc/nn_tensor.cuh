@@ -139,11 +139,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32])
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- the kernel ------------------------------------------------------------------------------------
+// neg32 = (uint32_t)-32, passed as an argument so that the key arithmetic stays an IMAD on the FMA pipe instead of being
+// strength-reduced to a shift-add on the ALU pipe, which the min/max network needs.
 // grid = (query tiles, word splits).  partial[(split * kTcEpiGroups + column group) * nq + query] = (best key, second key)
 // over the rows of that split that fall in that column group of their tile.
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offset, const uint4 * __restrict__ query_img, int nq,
-                   uint2 * __restrict__ partial, int tiles_per_split)
+                   uint2 * __restrict__ partial, int tiles_per_split, uint32_t neg32)
 {
 	extern __shared__ unsigned char smem_dyn[];
 	unsigned char * smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -265,7 +267,7 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 				for (int j = 0; j < 32; ++j)
 				{
 					const uint32_t sp = static_cast<uint32_t>(v[j + 32]) * 65536u + static_cast<uint32_t>(v[j]);
-					const uint32_t kp = sp * static_cast<uint32_t>(-32) + static_cast<uint32_t>(8192 + j) * 65537u;
+					const uint32_t kp = sp * neg32 + static_cast<uint32_t>(8192 + j) * 65537u;
 					const uint32_t mx = __vmaxu2(p1, kp);
 					p1 = __vminu2(p1, kp);
 					p2 = __vminu2(p2, mx);
