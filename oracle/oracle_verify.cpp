@@ -319,7 +319,7 @@ struct Epnp
 				                 rl[6] * betas[0] * betas[3] + rl[7] * betas[1] * betas[3] + rl[8] * betas[2] * betas[3] +
 				                 rl[9] * betas[3] * betas[3]);
 			}
-			solve_ls(A, b, 6, 4, x);
+			if (!qr_solve_ls(A, b, 6, 4, x)) return;
 			for (int i = 0; i < 4; ++i) betas[i] += x[i];
 		}
 	}

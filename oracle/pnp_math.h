@@ -329,6 +329,45 @@ inline void solve_ls(const double * A, const double * b, int m, int n, double * 
 	}
 }
 
+// Least squares of A x = b (A is m x n row-major, m >= n <= 6, full column rank) by Householder QR — what EPnP's
+// Gauss-Newton refinement of the betas uses (OpenCV epnp.cpp, epnp::qr_solve on the 6x4 Jacobian).  A and b are
+// destroyed.  Returns false (x untouched) when a column is exactly zero.  Same operation sequence as qr_solve in
+// rtabmap_b200/csrc/pnp_device.cuh.
+inline bool qr_solve_ls(double * A, double * b, int m, int n, double * x)
+{
+	double rdiag[6], v[12];
+	for (int k = 0; k < n; ++k)
+	{
+		double sigma = 0;
+		for (int i = k; i < m; ++i) sigma += A[i * n + k] * A[i * n + k];
+		if (sigma == 0.0) return false;
+		const double akk = A[k * n + k];
+		const double alpha = akk > 0 ? -std::sqrt(sigma) : std::sqrt(sigma);
+		const double beta = 1.0 / (sigma - akk * alpha);
+		v[k] = akk - alpha;
+		for (int i = k + 1; i < m; ++i) v[i] = A[i * n + k];
+		for (int j = k + 1; j < n; ++j)
+		{
+			double s = 0;
+			for (int i = k; i < m; ++i) s += v[i] * A[i * n + j];
+			s *= beta;
+			for (int i = k; i < m; ++i) A[i * n + j] -= s * v[i];
+		}
+		double s = 0;
+		for (int i = k; i < m; ++i) s += v[i] * b[i];
+		s *= beta;
+		for (int i = k; i < m; ++i) b[i] -= s * v[i];
+		rdiag[k] = alpha;
+	}
+	for (int k = n - 1; k >= 0; --k)
+	{
+		double s = b[k];
+		for (int j = k + 1; j < n; ++j) s -= A[k * n + j] * x[j];
+		x[k] = s / rdiag[k];
+	}
+	return true;
+}
+
 // SVD of a 3x3 matrix M = U diag(w) V^T (row-major U and V, columns are singular vectors).
 inline void svd3(const double * M, double * U, double * w, double * V)
 {

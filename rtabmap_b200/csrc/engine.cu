@@ -1552,6 +1552,14 @@ long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long 
 	case 4: src = e->o_cand_count.p; bytes = e->o_cand_count.cap * sizeof(int); break;
 	case 5: src = e->o_level_n.p; bytes = e->o_level_n.cap * sizeof(int); break;
 	case 7: src = e->v_clk.p; bytes = e->v_clk.cap * sizeof(long long); break;
+	case 8:
+	{
+		void * sym = nullptr;
+		if (cudaGetSymbolAddress(&sym, g_pnp_dbg) != cudaSuccess) return LCD_ERR_CUDA;
+		src = sym;
+		bytes = sizeof(long long) * 8;
+		break;
+	}
 	default: return LCD_ERR_INVALID;
 	}
 	if (!src) return 0;

@@ -110,57 +110,81 @@ __device__ inline void svd_rows_jacobi3(double * At, double * W)
 // sequence as the CPU oracle's sym_eigen_desc (oracle/pnp_math.h), every sum in ascending index order.  v[] receives
 // the eigenvectors as COLUMNS; ord[] the column order of descending eigenvalue.  About 15x fewer dependent
 // operations than the cyclic Jacobi sweeps this replaces (one thread per RANSAC hypothesis is latency-bound).
+__device__ long long g_pnp_dbg[8];
+
 template <int N>
-__device__ inline void sym_eigen(double * a, double * z, int * ord)
+__device__ inline void sym_eigen(double * a, double * z, int * ord, long long * dbg = nullptr)
 {
+	const long long t_start = dbg ? clock64() : 0;
+	const unsigned mask = __activemask();
 	double d[N], e[N], hv[N], hp[N], hw[N];
 #pragma unroll
 	for (int i = 0; i < N; ++i)
 #pragma unroll
 		for (int j = 0; j < N; ++j) z[i * N + j] = i == j ? 1.0 : 0.0;
+	// fully unrolled: every index below is a compile-time constant, so the compiler is free to keep the matrix in
+	// registers / schedule its spills instead of chasing dynamically indexed local memory one load at a time
+#pragma unroll
 	for (int k = 0; k + 2 < N; ++k)
 	{
 		double sigma = 0;
+#pragma unroll
 		for (int i = k + 2; i < N; ++i) sigma += a[i * N + k] * a[i * N + k];
 		if (sigma == 0.0) continue;
 		const double x0 = a[(k + 1) * N + k];
 		const double nrm = sqrt(x0 * x0 + sigma);
 		const double alpha = x0 > 0 ? -nrm : nrm;
 		hv[k + 1] = x0 - alpha;
+#pragma unroll
 		for (int i = k + 2; i < N; ++i) hv[i] = a[i * N + k];
 		const double beta = 2.0 / (hv[k + 1] * hv[k + 1] + sigma);
+#pragma unroll
 		for (int i = k + 1; i < N; ++i)
 		{
 			double s = 0;
+#pragma unroll
 			for (int j = k + 1; j < N; ++j) s += a[i * N + j] * hv[j];
 			hp[i] = beta * s;
 		}
 		double vp = 0;
+#pragma unroll
 		for (int i = k + 1; i < N; ++i) vp += hv[i] * hp[i];
 		const double K = 0.5 * beta * vp;
+#pragma unroll
 		for (int i = k + 1; i < N; ++i) hw[i] = hp[i] - K * hv[i];
+#pragma unroll
 		for (int i = k + 1; i < N; ++i)
+#pragma unroll
 			for (int j = k + 1; j < N; ++j) a[i * N + j] -= hv[i] * hw[j] + hw[i] * hv[j];
 		a[(k + 1) * N + k] = alpha;
 		a[k * N + k + 1] = alpha;
+#pragma unroll
 		for (int i = k + 2; i < N; ++i)
 		{
 			a[i * N + k] = 0.0;
 			a[k * N + i] = 0.0;
 		}
+#pragma unroll
 		for (int r = 0; r < N; ++r)
 		{
 			double s = 0;
+#pragma unroll
 			for (int j = k + 1; j < N; ++j) s += z[r * N + j] * hv[j];
 			s *= beta;
+#pragma unroll
 			for (int j = k + 1; j < N; ++j) z[r * N + j] -= s * hv[j];
 		}
 	}
+#pragma unroll
 	for (int i = 0; i < N; ++i)
 	{
 		d[i] = a[i * N + i];
 		e[i] = i + 1 < N ? a[(i + 1) * N + i] : 0.0;
 	}
+	if (dbg) dbg[0] = clock64() - t_start;
+	// The QL sweeps are data dependent (iterations per eigenvalue, deflation point m).  Lanes of a warp that drift apart
+	// here would serialise, so every iteration starts from a warp vote: lanes that have converged on this l idle through
+	// the iteration instead of running ahead.  The arithmetic of each lane is untouched.
 	for (int l = 0; l < N; ++l)
 	{
 		for (int iter = 0; iter < 60; ++iter)
@@ -168,50 +192,57 @@ __device__ inline void sym_eigen(double * a, double * z, int * ord)
 			int m = l;
 			for (; m + 1 < N; ++m)
 				if (fabs(e[m]) <= 2.220446049250313e-16 * (fabs(d[m]) + fabs(d[m + 1]))) break;
-			if (m == l) break;
-			double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
-			double r = sqrt(g * g + 1.0);
-			g = d[m] - d[l] + e[l] / (g + (g >= 0 ? r : -r));
-			double sn = 1.0, cs = 1.0, pp = 0.0;
-			int i = m - 1;
-			for (; i >= l; --i)
+			const bool done = m == l;
+			if (__all_sync(mask, done)) break;
+			if (!done)
 			{
-				double f = sn * e[i];
-				const double b = cs * e[i];
-				r = sqrt(f * f + g * g);
-				e[i + 1] = r;
-				if (r == 0.0)
+				double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+				double r = sqrt(g * g + 1.0);
+				g = d[m] - d[l] + e[l] / (g + (g >= 0 ? r : -r));
+				double sn = 1.0, cs = 1.0, pp = 0.0;
+				bool underflow = false;
+				for (int i = m - 1; i >= l; --i)
 				{
-					d[i + 1] -= pp;
+					double f = sn * e[i];
+					const double b = cs * e[i];
+					r = sqrt(f * f + g * g);
+					e[i + 1] = r;
+					if (r == 0.0)
+					{
+						d[i + 1] -= pp;
+						e[m] = 0.0;
+						underflow = true;
+						break;
+					}
+					sn = f / r;
+					cs = g / r;
+					g = d[i + 1] - pp;
+					r = (d[i] - g) * sn + 2.0 * cs * b;
+					pp = sn * r;
+					d[i + 1] = g + pp;
+					g = cs * r - b;
+					// columns i, i+1 of z: loads first, then arithmetic and stores (off the critical chain)
+					double zi[N], zj[N];
+#pragma unroll
+					for (int k = 0; k < N; ++k)
+					{
+						zi[k] = z[k * N + i];
+						zj[k] = z[k * N + i + 1];
+					}
+#pragma unroll
+					for (int k = 0; k < N; ++k)
+					{
+						z[k * N + i + 1] = sn * zi[k] + cs * zj[k];
+						z[k * N + i] = cs * zi[k] - sn * zj[k];
+					}
+				}
+				if (!underflow)
+				{
+					d[l] -= pp;
+					e[l] = g;
 					e[m] = 0.0;
-					break;
-				}
-				sn = f / r;
-				cs = g / r;
-				g = d[i + 1] - pp;
-				r = (d[i] - g) * sn + 2.0 * cs * b;
-				pp = sn * r;
-				d[i + 1] = g + pp;
-				g = cs * r - b;
-				// columns i, i+1 of z: loads first, then arithmetic and stores (off the critical chain)
-				double zi[N], zj[N];
-#pragma unroll
-				for (int k = 0; k < N; ++k)
-				{
-					zi[k] = z[k * N + i];
-					zj[k] = z[k * N + i + 1];
-				}
-#pragma unroll
-				for (int k = 0; k < N; ++k)
-				{
-					z[k * N + i + 1] = sn * zi[k] + cs * zj[k];
-					z[k * N + i] = cs * zi[k] - sn * zj[k];
 				}
 			}
-			if (r == 0.0 && i >= l) continue;
-			d[l] -= pp;
-			e[l] = g;
-			e[m] = 0.0;
 		}
 	}
 	for (int i = 0; i < N; ++i) a[i * N + i] = d[i];
@@ -259,6 +290,55 @@ __device__ inline void solve_ls(const double * A, const double * b, double * x)
 		c /= w;
 		for (int i = 0; i < N; ++i) x[i] += c * v[i * N + k];
 	}
+}
+
+// Least squares of A x = b (A is M x N row-major, full column rank) by Householder QR — EPnP's Gauss-Newton step
+// (OpenCV epnp.cpp, epnp::qr_solve).  Same operation sequence as the oracle's qr_solve_ls (oracle/pnp_math.h); every
+// index is a compile-time constant, so it runs out of registers with uniform control flow.
+template <int M, int N>
+__device__ inline bool qr_solve(double * A, double * b, double * x)
+{
+	double rdiag[N], v[M];
+#pragma unroll
+	for (int k = 0; k < N; ++k)
+	{
+		double sigma = 0;
+#pragma unroll
+		for (int i = k; i < M; ++i) sigma += A[i * N + k] * A[i * N + k];
+		if (sigma == 0.0) return false;
+		const double akk = A[k * N + k];
+		const double alpha = akk > 0 ? -sqrt(sigma) : sqrt(sigma);
+		const double beta = 1.0 / (sigma - akk * alpha);
+		v[k] = akk - alpha;
+#pragma unroll
+		for (int i = k + 1; i < M; ++i) v[i] = A[i * N + k];
+#pragma unroll
+		for (int j = k + 1; j < N; ++j)
+		{
+			double s = 0;
+#pragma unroll
+			for (int i = k; i < M; ++i) s += v[i] * A[i * N + j];
+			s *= beta;
+#pragma unroll
+			for (int i = k; i < M; ++i) A[i * N + j] -= s * v[i];
+		}
+		double s = 0;
+#pragma unroll
+		for (int i = k; i < M; ++i) s += v[i] * b[i];
+		s *= beta;
+#pragma unroll
+		for (int i = k; i < M; ++i) b[i] -= s * v[i];
+		rdiag[k] = alpha;
+	}
+#pragma unroll
+	for (int k = N - 1; k >= 0; --k)
+	{
+		double s = b[k];
+#pragma unroll
+		for (int j = k + 1; j < N; ++j) s -= A[k * N + j] * x[j];
+		x[k] = s / rdiag[k];
+	}
+	return true;
 }
 
 // SVD of a 3x3 matrix M = U diag(w) V^T; U, V row-major with singular vectors as columns
@@ -524,7 +604,7 @@ struct Epnp6
 				                 rl[6] * betas[0] * betas[3] + rl[7] * betas[1] * betas[3] + rl[8] * betas[2] * betas[3] +
 				                 rl[9] * betas[3] * betas[3]);
 			}
-			solve_ls<6, 4>(A, b, x);
+			if (!qr_solve<6, 4>(A, b, x)) return;
 			for (int i = 0; i < 4; ++i) betas[i] += x[i];
 		}
 	}
@@ -556,7 +636,7 @@ struct Epnp6
 				for (int b = 0; b < 12; ++b) mtm[a * 12 + b] += m1[a] * m1[b] + m2[a] * m2[b];
 		}
 		if (clk) clk[1] = clock64();
-		sym_eigen<12>(mtm, vecs, ord);
+		sym_eigen<12>(mtm, vecs, ord, clk ? g_pnp_dbg : nullptr);
 		if (clk) clk[2] = clock64();
 		// L_6x10 and rho
 		double l[60], rho[6];
@@ -679,9 +759,16 @@ struct Epnp6
 				betas[2] = b5[3] / betas[0];
 				betas[3] = 0.0;
 			}
+			const long long t_a = clk ? clock64() : 0;
 			gauss_newton(l, rho, betas);
+			const long long t_b = clk ? clock64() : 0;
 			double Rc[9], tc[3];
 			const double rep = compute_R_and_t(vecs, ord, betas, Rc, tc);
+			if (clk)
+			{
+				g_pnp_dbg[1 + approx] = t_b - t_a;
+				g_pnp_dbg[4 + approx] = clock64() - t_b;
+			}
 			// N = 1; if (rep[2] < rep[1]) N = 2; if (rep[3] < rep[N]) N = 3;
 			if (!have || rep < best_rep)
 			{

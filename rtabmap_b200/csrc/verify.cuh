@@ -20,7 +20,8 @@
 
 namespace lcd {
 
-constexpr int kVerifyThreads = 128; // hypotheses evaluated per chunk = threads of the CTA
+constexpr int kPnpChunk = 128;      // RANSAC hypotheses evaluated per chunk (one thread each for EPnP)
+constexpr int kVerifyThreads = 256; // threads of the CTA: the second half helps with the inlier counts, LM sums and error passes
 constexpr int kMaxRansacIters = 320;
 
 struct MatchArgs
@@ -223,7 +224,7 @@ struct PnpArgs
 
 __host__ __device__ inline size_t pnp_smem_bytes(int cap)
 {
-	return static_cast<size_t>(cap) * (12 + 8 + 4 + 2 + 2 + 1) + kMaxRansacIters * (6 * 2) + kVerifyThreads * (4 + 6 * 8) + (28 * 32 + 32) * 8 + 1024;
+	return static_cast<size_t>(cap) * (12 + 8 + 4 + 2 + 2 + 1) + kMaxRansacIters * (6 * 2) + kPnpChunk * (4 + 6 * 8) + (28 * 32 + 32) * 8 + 1024;
 }
 
 __device__ inline int ransac_update_num_iters(double p, double ep, int modelPoints, int maxIters)
@@ -422,14 +423,14 @@ pnp_ransac_kernel(const PnpArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int cap = a.cap;
-	double * h_rt = reinterpret_cast<double *>(smem_raw);                    // [kVerifyThreads][6] poses of the current chunk
-	double * s_red = h_rt + kVerifyThreads * 6;                              // [28*32]
+	double * h_rt = reinterpret_cast<double *>(smem_raw);                    // [kPnpChunk][6] poses of the current chunk
+	double * s_red = h_rt + kPnpChunk * 6;                              // [28*32]
 	double * s_out = s_red + 28 * 32;                                        // [32]
 	float * X = reinterpret_cast<float *>(s_out + 32);                       // [cap][3]
 	float * uv = X + static_cast<size_t>(cap) * 3;                           // [cap][2]
 	float * errs = uv + static_cast<size_t>(cap) * 2;                        // [cap]
-	int * cnt = reinterpret_cast<int *>(errs + cap);                         // [kVerifyThreads]
-	uint16_t * sidx = reinterpret_cast<uint16_t *>(cnt + kVerifyThreads);    // [kMaxRansacIters][6]
+	int * cnt = reinterpret_cast<int *>(errs + cap);                         // [kPnpChunk]
+	uint16_t * sidx = reinterpret_cast<uint16_t *>(cnt + kPnpChunk);    // [kMaxRansacIters][6]
 	uint16_t * listA = sidx + kMaxRansacIters * 6;                           // [cap]
 	uint16_t * listB = listA + cap;                                          // [cap]
 	uint8_t * flag = reinterpret_cast<uint8_t *>(listB + cap);               // [cap]
@@ -483,14 +484,14 @@ pnp_ransac_kernel(const PnpArgs a)
 	__shared__ unsigned long long s_rng;
 	if (tid == 0) s_rng = 0xFFFFFFFFFFFFFFFFull;
 	__syncthreads();
-	for (int chunk0 = 0; chunk0 < s_niters; chunk0 += blockDim.x)
+	for (int chunk0 = 0; chunk0 < s_niters; chunk0 += kPnpChunk)
 	{
 		if (tid == 0 && n != 6)
 		{
 			// RANSACPointSetRegistrator::getSubset with cv::RNG((uint64)-1): the draws depend only on n and are
 			// consumed in iteration order, so the samples of a chunk are generated when the chunk is reached
 			unsigned long long state = s_rng;
-			const int it_end = min(chunk0 + static_cast<int>(blockDim.x), s_niters);
+			const int it_end = min(chunk0 + kPnpChunk, s_niters);
 			for (int it = chunk0; it < it_end; ++it)
 			{
 				for (int i = 0; i < 6;)
@@ -512,37 +513,52 @@ pnp_ransac_kernel(const PnpArgs a)
 			s_rng = state;
 		}
 		__syncthreads();
-		const int it = chunk0 + tid;
-		if (it < s_niters)
+		// EPnP: one thread per hypothesis (threads [0, kPnpChunk))
+		if (tid < kPnpChunk)
 		{
-			int idx[6];
-			for (int k = 0; k < 6; ++k) idx[k] = (n == 6) ? k : sidx[it * 6 + k];
-			double rv[3], tv[3];
+			const int it = chunk0 + tid;
 			int c = -1;
-			long long * clk = (a.phase_clk && tid == 0 && chunk0 == 0) ? a.phase_clk + pair * 16 + 8 : nullptr;
-			if (solve_pnp_epnp6(X, uv, idx, cam, rv, tv, clk))
+			if (it < s_niters)
 			{
-				if (clk) clk[4] = clock64();
-				double R[9];
-				rodrigues_v2m(rv, R, nullptr);
-				c = 0;
-#pragma unroll 4
-				for (int i = 0; i < n; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
-				for (int k = 0; k < 3; ++k)
+				int idx[6];
+				for (int k = 0; k < 6; ++k) idx[k] = (n == 6) ? k : sidx[it * 6 + k];
+				double rv[3], tv[3];
+				long long * clk = (a.phase_clk && tid == 0 && chunk0 == 0) ? a.phase_clk + pair * 16 + 8 : nullptr;
+				if (solve_pnp_epnp6(X, uv, idx, cam, rv, tv, clk))
 				{
-					h_rt[tid * 6 + k] = rv[k];
-					h_rt[tid * 6 + 3 + k] = tv[k];
+					if (clk) clk[4] = clock64();
+					c = 0;
+					for (int k = 0; k < 3; ++k)
+					{
+						h_rt[tid * 6 + k] = rv[k];
+						h_rt[tid * 6 + 3 + k] = tv[k];
+					}
 				}
-				if (clk) clk[5] = clock64();
 			}
 			cnt[tid] = c;
+		}
+		__syncthreads();
+		// inlier counts: every hypothesis is counted by blockDim.x / kPnpChunk threads, each over a slice of the points
+		{
+			const int h = tid % kPnpChunk, part = tid / kPnpChunk, parts = blockDim.x / kPnpChunk;
+			if (cnt[h] >= 0)
+			{
+				double R[9];
+				rodrigues_v2m(h_rt + h * 6, R, nullptr);
+				const double tv[3] = {h_rt[h * 6 + 3], h_rt[h * 6 + 4], h_rt[h * 6 + 5]};
+				const int i0 = static_cast<int>(static_cast<long long>(n) * part / parts), i1 = static_cast<int>(static_cast<long long>(n) * (part + 1) / parts);
+				int c = 0;
+				for (int i = i0; i < i1; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
+				if (c) atomicAdd(&cnt[h], c);
+			}
+			if (a.phase_clk && tid == 0 && chunk0 == 0) a.phase_clk[pair * 16 + 8 + 5] = clock64();
 		}
 		__syncthreads();
 		if (chunk0 == 0) PNP_PHASE(2);
 		if (tid == 0)
 		{
 			int it0 = s_it, niters = s_niters, maxGood = s_maxgood;
-			const int chunk_end = chunk0 + static_cast<int>(blockDim.x);
+			const int chunk_end = chunk0 + kPnpChunk;
 			if (n == 6)
 			{
 				if (cnt[0] >= 0)
