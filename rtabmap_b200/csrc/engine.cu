@@ -1448,7 +1448,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 			orb_blur_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, e->o_blur.p, g, l);
 			LCD_CHECK_LAUNCH(e);
 		}
-		dim3 grd((cap * 32 + 255) / 256, n_frames);
+		dim3 grd((cap + kOrbDescribeKp - 1) / kOrbDescribeKp, n_frames);
 		orb_describe_kernel<<<grd, 256, 0, s>>>(e->o_gray.p, e->o_blur.p, g, d_kp, d_n, cap, d_desc);
 		LCD_CHECK_LAUNCH(e);
 	}
@@ -1552,6 +1552,14 @@ long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long 
 	case 4: src = e->o_cand_count.p; bytes = e->o_cand_count.cap * sizeof(int); break;
 	case 5: src = e->o_level_n.p; bytes = e->o_level_n.cap * sizeof(int); break;
 	case 7: src = e->v_clk.p; bytes = e->v_clk.cap * sizeof(long long); break;
+	case 9:
+	{
+		void * sym = nullptr;
+		if (cudaGetSymbolAddress(&sym, g_match_dbg) != cudaSuccess) return LCD_ERR_CUDA;
+		src = sym;
+		bytes = sizeof(long long) * 8;
+		break;
+	}
 	case 8:
 	{
 		void * sym = nullptr;

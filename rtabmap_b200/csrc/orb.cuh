@@ -721,38 +721,58 @@ orb_blur_kernel(const uint8_t * __restrict__ gray_all, uint8_t * __restrict__ bl
 }
 
 // ---- K6: steered BRIEF (computeOrbDescriptors, WTA_K = 2) --------------------------------------------
-__global__ void orb_describe_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restrict__ blur_all, const OrbGeom g,
-                                    const OrbKeypoint * __restrict__ kps, const int * __restrict__ n_kp, int cap, uint8_t * __restrict__ desc)
+constexpr int kOrbDescribeKp = 32;  // keypoints per CTA of the describe kernel
+
+__global__ void __launch_bounds__(256)
+orb_describe_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restrict__ blur_all, const OrbGeom g,
+                    const OrbKeypoint * __restrict__ kps, const int * __restrict__ n_kp, int cap, uint8_t * __restrict__ desc)
 {
+	// phase 1: the rotation of each keypoint once per keypoint (double-precision cos / sin rounded to float, as
+	// computeOrbDescriptors does), phase 2: one thread per (keypoint, descriptor byte)
+	__shared__ float s_ca[kOrbDescribeKp], s_sa[kOrbDescribeKp];
+	__shared__ int s_cx[kOrbDescribeKp], s_cy[kOrbDescribeKp], s_level[kOrbDescribeKp];
 	const int frame = blockIdx.y;
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	const int ki = t >> 5, byte = t & 31;
-	if (ki >= n_kp[frame]) return;
-	const OrbKeypoint kp = kps[static_cast<size_t>(frame) * cap + ki];
-	const int level = kp.octave;
-	const int w = g.w[level], h = g.h[level];
-	const uint8_t * raw = gray_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
-	const uint8_t * blr = blur_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
-	const float scale = __fdiv_rn(1.f, static_cast<float>(1 << level));
-	const float angle = __fmul_rn(kp.angle, static_cast<float>(3.141592653589793238462643383279502884197169399375 / 180.0));
-	const float ca = static_cast<float>(cos(static_cast<double>(angle))), sa = static_cast<float>(sin(static_cast<double>(angle)));
-	const int cx = __float2int_rn(__fmul_rn(kp.x, scale)), cy = __float2int_rn(__fmul_rn(kp.y, scale));
-	auto tap = [&](int px, int py) -> int {
-		const float fx = __fsub_rn(__fmul_rn(static_cast<float>(px), ca), __fmul_rn(static_cast<float>(py), sa));
-		const float fy = __fadd_rn(__fmul_rn(static_cast<float>(px), sa), __fmul_rn(static_cast<float>(py), ca));
-		const int x = cx + __float2int_rn(fx), y = cy + __float2int_rn(fy);
-		if (x >= 0 && x < w && y >= 0 && y < h) return blr[static_cast<size_t>(y) * w + x];
-		return raw[static_cast<size_t>(reflect101(y, h)) * w + reflect101(x, w)]; // unblurred reflected border
-	};
-	int val = 0;
-#pragma unroll
-	for (int b = 0; b < 8; ++b)
+	const int kp0 = blockIdx.x * kOrbDescribeKp;
+	const int n = min(n_kp[frame] - kp0, kOrbDescribeKp);
+	if (n <= 0) return;
+	for (int i = threadIdx.x; i < n; i += blockDim.x)
 	{
-		const signed char * p = kOrbPattern31 + (byte * 8 + b) * 4;
-		const int t0 = tap(p[0], p[1]), t1 = tap(p[2], p[3]);
-		val |= (t0 < t1) << b;
+		const OrbKeypoint kp = kps[static_cast<size_t>(frame) * cap + kp0 + i];
+		const float scale = __fdiv_rn(1.f, static_cast<float>(1 << kp.octave));
+		const float angle = __fmul_rn(kp.angle, static_cast<float>(3.141592653589793238462643383279502884197169399375 / 180.0));
+		s_ca[i] = static_cast<float>(cos(static_cast<double>(angle)));
+		s_sa[i] = static_cast<float>(sin(static_cast<double>(angle)));
+		s_cx[i] = __float2int_rn(__fmul_rn(kp.x, scale));
+		s_cy[i] = __float2int_rn(__fmul_rn(kp.y, scale));
+		s_level[i] = kp.octave;
 	}
-	desc[(static_cast<size_t>(frame) * cap + ki) * 32 + byte] = static_cast<uint8_t>(val);
+	__syncthreads();
+	for (int t = threadIdx.x; t < n * 32; t += blockDim.x)
+	{
+		const int ki = t >> 5, byte = t & 31;
+		const int level = s_level[ki];
+		const int w = g.w[level], h = g.h[level];
+		const uint8_t * raw = gray_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+		const uint8_t * blr = blur_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+		const float ca = s_ca[ki], sa = s_sa[ki];
+		const int cx = s_cx[ki], cy = s_cy[ki];
+		auto tap = [&](int px, int py) -> int {
+			const float fx = __fsub_rn(__fmul_rn(static_cast<float>(px), ca), __fmul_rn(static_cast<float>(py), sa));
+			const float fy = __fadd_rn(__fmul_rn(static_cast<float>(px), sa), __fmul_rn(static_cast<float>(py), ca));
+			const int x = cx + __float2int_rn(fx), y = cy + __float2int_rn(fy);
+			if (x >= 0 && x < w && y >= 0 && y < h) return blr[static_cast<size_t>(y) * w + x];
+			return raw[static_cast<size_t>(reflect101(y, h)) * w + reflect101(x, w)]; // unblurred reflected border
+		};
+		int val = 0;
+#pragma unroll
+		for (int b = 0; b < 8; ++b)
+		{
+			const signed char * p = kOrbPattern31 + (byte * 8 + b) * 4;
+			const int t0 = tap(p[0], p[1]), t1 = tap(p[2], p[3]);
+			val |= (t0 < t1) << b;
+		}
+		desc[(static_cast<size_t>(frame) * cap + kp0 + ki) * 32 + byte] = static_cast<uint8_t>(val);
+	}
 }
 
 // ---- K7: generateKeypoints3DDepth (depth the size of the image, one camera, identity local transform) ---

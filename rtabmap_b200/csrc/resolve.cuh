@@ -16,6 +16,7 @@
 // on how long the chains of mutually-near descriptors are.
 #pragma once
 #include "common.cuh"
+#include "nn_hamming.cuh"
 #include <math.h>
 #include <limits.h>
 
@@ -264,9 +265,7 @@ __device__ int resolve_rounds(const uint32_t * __restrict__ fq, int nq, const ui
 				{
 					uint32_t qj[NW];
 					load_desc<NW>(fq, L[k], qj);
-					uint32_t d = 0;
-#pragma unroll
-					for (int v = 0; v < NW; ++v) d += __popc(qi[v] ^ qj[v]);
+					const uint32_t d = hamming<NW, 2>(qi, qj);
 					top2_insert(k1, k2, (d << kKeyShift) + static_cast<uint32_t>(k));
 				}
 #pragma unroll

@@ -54,10 +54,14 @@ __host__ __device__ inline size_t match_smem_bytes(int cap, int nw)
 	return static_cast<size_t>(cap) * (4 + 4 + 4 + 2 + 2 + 1 + 1 + 4 + 4 + 2 + 2) + static_cast<size_t>(cap) * nw * 4 + 128;
 }
 
+__device__ long long g_match_dbg[8];
+#define MATCH_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_match_dbg[k] = clock64(); } while (0)
+
 template <int NW>
 __global__ void __launch_bounds__(kResolveThreads)
 pair_match_kernel(const MatchArgs a)
 {
+	MATCH_PHASE(0);
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int cap = a.cap;
 	uint32_t * dict = reinterpret_cast<uint32_t *>(smem_raw);             // [cap][NW]
@@ -97,6 +101,7 @@ pair_match_kernel(const MatchArgs a)
 	int n_dict = 0;
 	if (nf > 0) n_dict = resolve_rounds<NW>(F, nf, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
 	__syncthreads();
+	MATCH_PHASE(1);
 	for (int k = tid; k < n_dict; k += blockDim.x)
 	{
 		cntF[k] = 0;
@@ -116,6 +121,7 @@ pair_match_kernel(const MatchArgs a)
 	}
 	__syncthreads();
 
+	MATCH_PHASE(2);
 	// ---- TO side: update(); addNewWords(descriptorsTo, 2) --------------------------------------
 	for (int j = tid; j < nt; j += blockDim.x)
 	{
@@ -125,13 +131,17 @@ pair_match_kernel(const MatchArgs a)
 		for (int k = 0; k < n_dict; ++k)
 		{
 			const uint4 * row = reinterpret_cast<const uint4 *>(dict + static_cast<size_t>(k) * NW);
-			uint32_t d = 0;
+			uint32_t w[NW];
 #pragma unroll
 			for (int v = 0; v < NW / 4; ++v)
 			{
 				const uint4 x = row[v];
-				d += __popc(q[4 * v] ^ x.x) + __popc(q[4 * v + 1] ^ x.y) + __popc(q[4 * v + 2] ^ x.z) + __popc(q[4 * v + 3] ^ x.w);
+				w[4 * v] = x.x;
+				w[4 * v + 1] = x.y;
+				w[4 * v + 2] = x.z;
+				w[4 * v + 3] = x.w;
 			}
+			const uint32_t d = hamming<NW, 2>(q, w); // carry-save tree: 5 POPC instead of 8 for 256-bit descriptors
 			top2_insert(k1, k2, (d << kKeyShift) + static_cast<uint32_t>(k));
 		}
 		sa1[j] = k1;
@@ -141,8 +151,10 @@ pair_match_kernel(const MatchArgs a)
 		res[j] = static_cast<int>(k1 & kKeyRowMask);
 	}
 	__syncthreads();
+	MATCH_PHASE(3);
 	if (nt > 0) resolve_rounds<NW>(T, nt, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
 	__syncthreads();
+	MATCH_PHASE(4);
 	for (int j = tid; j < nt; j += blockDim.x)
 	{
 		int id;
@@ -196,6 +208,7 @@ pair_match_kernel(const MatchArgs a)
 		a.match_from[base + m] = fi;
 		a.match_to[base + m] = ti;
 	}
+	MATCH_PHASE(5);
 }
 
 // ------------------------------------------------------------------------------------ PnP RANSAC

@@ -39,3 +39,5 @@ e = np.diff(clk[:, 8:14], axis=1).astype(np.float64)
 print(json.dumps({"epnp_thread0_kcycles_mean": {k: round(float(v) / 1e3, 1) for k, v in zip(("ctrl+MtM", "eigen12", "betas+GN+Rt", "m2v", "count"), e.mean(0))}}))
 g = eng.debug_orb_buffer(8, 64, np.int64)
 print(json.dumps({"last_writer_kcycles": {"tred2": g[0] / 1e3, "gn": [g[2] / 1e3, g[3] / 1e3, g[4] / 1e3], "Rt": [g[5] / 1e3, g[6] / 1e3, g[7] / 1e3]}}))
+g = eng.debug_orb_buffer(9, 64, np.int64)
+print(json.dumps({"match_block0_kcycles": dict(zip(("from_resolve", "dict_build", "to_knn", "to_resolve", "correspondences"), (np.diff(g[:6]) / 1e3).round(1).tolist()))}))
