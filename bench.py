@@ -387,12 +387,57 @@ def run_b200(args):
         step_host(k)
     barrier()
     e2e_s = 0.0
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
+    if world_size == 1:
+        # the call a relocalisation service makes: lcd_process_frames_submit / _wait, two batches in flight, so the PCIe upload
+        # of batch k+1 runs under the kernels of batch k.  Every step's images + depth come from pinned host memory and every
+        # step's word ids, likelihood rows, hypotheses and verification results are copied back; all of it inside the timed
+        # region, and so is the L2 flush between steps (queued on the engine stream).
+        from rtabmap_b200.capi import VerifyResult
+        sets = []
+        for _ in range(2):
+            sets.append(dict(nkp=torch.zeros(B, dtype=torch.int32).pin_memory(), words=torch.zeros((B, F_FEATS), dtype=torch.int32).pin_memory(),
+                             like=torch.zeros((B, S_SIGS), dtype=torch.float32).pin_memory(), hyp=torch.zeros(B, dtype=torch.int32).pin_memory(),
+                             res=(VerifyResult * B)()))
+        sig_np = h_sig.numpy()
+
+        def submit(k):
+            o = sets[k & 1]
+            eng.process_frames_submit(h_img[k % n_pool].numpy(), h_dep[k % n_pool].numpy().view(np.uint16), op, sig_np, S_SIGS + 1, vp,
+                                      o["nkp"].numpy(), o["words"].numpy(), o["like"].numpy(), o["hyp"].numpy(), o["res"], True, NNDR, True)
+
+        def collect(k):
+            eng.process_frames_wait()
+            o = sets[k & 1]
+            return o["hyp"].numpy().copy(), [{"ok": int(r.ok)} for r in o["res"]]
+
+        for k in range(2):  # warm-up of the pipelined path (allocates the two staging slots)
+            submit(k)
+        collect(0)
+        collect(1)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        hyp_h, res_h = step_host(k)
-        e2e_s += time.perf_counter() - t0
+        with torch.cuda.stream(ext):
+            t0 = time.perf_counter()
+            trace = [] if os.environ.get("LCD_BENCH_TRACE") else None
+            submit(0)
+            for k in range(1, args.steps):
+                flush.fill_(k & 0xFF)
+                ta = time.perf_counter()
+                submit(k)
+                tb = time.perf_counter()
+                hyp_h, res_h = collect(k - 1)
+                if trace is not None:
+                    trace.append((round((ta - t0) * 1e3, 2), round((tb - ta) * 1e3, 2), round((time.perf_counter() - tb) * 1e3, 2)))
+            hyp_h, res_h = collect(args.steps - 1)
+            e2e_s = time.perf_counter() - t0
+            if trace:
+                print("e2e trace (t_submit_ms, submit_call_ms, collect_call_ms):", trace[:10], file=sys.stderr)
+    else:
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hyp_h, res_h = step_host(k)
+            e2e_s += time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
     if world_size > 1:
@@ -485,7 +530,7 @@ def run_b200(args):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (img_bytes + dep_bytes) + S_SIGS * 4),
                 "d2h_bytes_per_step": int(nq * 4 + B * S_SIGS * 4 + B * (4 + 4 + 124)),
-                "api": "lcd_process_frames (host buffers)" if world_size == 1 else "sharded *_dev calls + pinned copies",
+                "api": "lcd_process_frames_submit/_wait (pinned host buffers, 2 batches in flight, L2 flush between steps inside the timed region)" if world_size == 1 else "sharded *_dev calls + pinned copies",
                 "top1_place_hit_rate": e2e_hit, "verified_rate": e2e_verified},
         "roofline": roofline, "cpu_baseline": cpu, "top1_place_hit_rate": hit, "verified_rate": verified, "wall_s_timed_region": t_wall,
     }

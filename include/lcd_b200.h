@@ -288,6 +288,17 @@ int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int
                        const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp,
                        int * n_kp_out, int * word_ids_out, float * likelihood_out, int * hypothesis_out,
                        lcd_verify_result * results);
+/* Pipelined form of lcd_process_frames for a stream of batches (a relocalisation service): _submit queues the upload
+ * and the kernels of a batch and returns; _wait blocks until the OLDEST submitted batch is complete and its output
+ * arrays are filled.  Two batches may be in flight, so the PCIe upload of batch k+1 runs under the kernels of batch k.
+ * Input and output host arrays must stay valid (and should be pinned) until the matching _wait returns. */
+int lcd_process_frames_submit(lcd_engine * e, int n_frames, const uint8_t * images, int width, int height, int channels,
+                              const void * depth, int depth_type, const lcd_orb_params * params,
+                              int incremental, float nndr, int new_words_compared_together,
+                              const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp,
+                              int * n_kp_out, int * word_ids_out, float * likelihood_out, int * hypothesis_out,
+                              lcd_verify_result * results);
+int lcd_process_frames_wait(lcd_engine * e);
 int lcd_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels,
                            const void * d_depth, int depth_type, const lcd_orb_params * params,
                            int incremental, float nndr, int new_words_compared_together,

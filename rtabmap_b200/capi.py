@@ -132,6 +132,8 @@ SIGNATURES = {
     "lcd_process_batch_dev": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
     "lcd_process_fetch": (_I, [_P, _I, _P, _P]),
     "lcd_process_frames": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "lcd_process_frames_submit": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "lcd_process_frames_wait": (_I, [_P]),
     "lcd_process_frames_dev": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
     "lcd_verify_top_dev": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "lcd_shard_set_row_offset": (_I, [_P, _I]),
@@ -539,6 +541,24 @@ class Engine:
                                                   _ptr(s), len(s), int(n_total), C.byref(vp) if vp is not None else None, _ptr(nkp), _ptr(words),
                                                   _ptr(like), _ptr(hyp), res))
         return nkp, words, like, hyp, (self._results(res, n) if vp is not None else None)
+
+    def process_frames_submit(self, images, depth, op: "OrbParams", sig_ids, n_total: int, vp: "VerifyParams", out_nkp, out_words, out_like,
+                              out_hyp, out_res, incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True):
+        """Pipelined lcd_process_frames: queue one batch (all arrays must stay alive, ideally pinned, until process_frames_wait).
+        images uint8 [n,h,w,(ch)], depth uint16/float32 [n,h,w] or None; out_* numpy arrays; out_res a (VerifyResult * n)() array."""
+        n, h, w = images.shape[:3]
+        ch = 1 if images.ndim == 3 else images.shape[3]
+        dtype, dptr = 0, None
+        if depth is not None:
+            dtype = 1 if depth.dtype == np.uint16 else 2
+            dptr = _ptr(depth)
+        self._check(self._lib.lcd_process_frames_submit(self._h, n, _ptr(images), w, h, ch, dptr, dtype, C.byref(op), int(incremental), float(nndr),
+                                                         int(cmp_new), _ptr(sig_ids), len(sig_ids), int(n_total),
+                                                         C.byref(vp) if vp is not None else None, _ptr(out_nkp), _ptr(out_words), _ptr(out_like),
+                                                         _ptr(out_hyp), out_res))
+
+    def process_frames_wait(self):
+        self._check(self._lib.lcd_process_frames_wait(self._h))
 
     def process_frames_dev(self, d_images: int, n_frames: int, w: int, h: int, ch: int, d_depth: int, depth_type: int, op: "OrbParams", d_sig_ids: int,
                            ns: int, n_total: int, vp: "VerifyParams", d_words_out: int = 0, d_like_out: int = 0, incremental: bool = True,

@@ -97,6 +97,24 @@ struct PinBuf
 	}
 };
 
+// Zero-fill on the SMs.  cudaMemsetAsync may be scheduled on a copy engine, where it queues behind the (much longer) host ->
+// device upload of the NEXT batch and stalls the kernels of the current one (measured: 1.8 ms per step in the pipelined path).
+__global__ void zero_fill_kernel(uint4 * __restrict__ p16, size_t n16, unsigned char * __restrict__ tail, size_t n_tail)
+{
+	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < n16) p16[i] = make_uint4(0, 0, 0, 0);
+	if (i < n_tail) tail[i] = 0;
+}
+static cudaError_t zero_fill_async(void * p, size_t bytes, cudaStream_t s)
+{
+	if (!bytes) return cudaSuccess;
+	if (reinterpret_cast<uintptr_t>(p) & 15) return cudaMemsetAsync(p, 0, bytes, s);
+	const size_t n16 = bytes / 16, n_tail = bytes % 16;
+	const size_t n = std::max(n16, n_tail);
+	zero_fill_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<uint4 *>(p), n16, static_cast<unsigned char *>(p) + n16 * 16, n_tail);
+	return cudaGetLastError();
+}
+
 int env_int(const char * name, int def)
 {
 	const char * v = getenv(name);
@@ -111,6 +129,26 @@ struct lcd_engine
 	int nw = 0; // 32-bit words per descriptor
 	mutable std::string err;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;       // host -> device image chunks of lcd_process_frames
+	std::vector<cudaEvent_t> copy_events;     // one per chunk
+	cudaEvent_t copy_fence = nullptr;
+	// lcd_process_frames_submit / _wait: two batches in flight
+	struct Flight
+	{
+		DevBuf<uint8_t> img;
+		DevBuf<unsigned char> depth;
+		DevBuf<int> sig_ids;
+		PinBuf<PackedVerifyResult> res;
+		cudaEvent_t uploaded = nullptr, done = nullptr;
+		lcd_verify_result * user_results = nullptr;
+		int n_frames = 0;
+		cudaEvent_t t_h0 = nullptr, t_h1 = nullptr, t_c0 = nullptr, t_c1 = nullptr; // LCD_DEBUG_TIMELINE
+	};
+	cudaEvent_t t_base = nullptr;
+	Flight flights[2];
+	int flight_head = 0, flights_busy = 0;
+	DevBuf<PackedVerifyResult> v_packed;
+	PinBuf<PackedVerifyResult> h_packed;
 	long long launches = 0;
 	int sm_count = 148;
 	int smem_optin = 0;
@@ -638,7 +676,7 @@ int localize_dev(lcd_engine * e, const uint32_t * d_q, int n_frames, int nq, int
 	{
 		LCD_TRY(ensure_uq(e, n_frames, nq, s));
 		LCD_TRY(ensure_acc(e, n_frames));
-		LCD_CUDA(e, cudaMemsetAsync(e->acc.p, 0, static_cast<size_t>(e->acc_stride) * n_frames * sizeof(long long), s));
+		LCD_CUDA(e, zero_fill_async(e->acc.p, static_cast<size_t>(e->acc_stride) * n_frames * sizeof(long long), s));
 		fill_prep(e, a, static_cast<float>(n_total), 1);
 	}
 	LCD_TRY(launch_resolve(e, a, n_frames, s));
@@ -721,6 +759,14 @@ void lcd_destroy(lcd_engine * e)
 	if (e->stream)
 	{
 		cudaStreamSynchronize(e->stream);
+		if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+		for (cudaEvent_t ev : e->copy_events) cudaEventDestroy(ev);
+		if (e->copy_fence) cudaEventDestroy(e->copy_fence);
+		for (auto & f : e->flights)
+		{
+			if (f.uploaded) cudaEventDestroy(f.uploaded);
+			if (f.done) cudaEventDestroy(f.done);
+		}
 		cudaStreamDestroy(e->stream);
 	}
 	for (auto & p : e->prof)
@@ -1339,38 +1385,60 @@ static int orb_geometry(lcd_engine * e, int width, int height, const lcd_orb_par
 	return LCD_OK;
 }
 
+// Detect + describe frames [frame0, frame0 + n_frames) of a batch of total_frames (total_frames = 0: the range is the whole
+// batch).  Every input, workspace and output pointer addresses frame 0 of the batch; ranges are independent, so the host
+// path runs them chunk by chunk while the next chunk's images are still on their way over PCIe.
 static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
                    int depth_type, const lcd_orb_params * p, int cap, OrbKeypoint * d_kp, uint8_t * d_desc, float * d_xyz, float * d_uv,
-                   int * d_n, cudaStream_t s)
+                   int * d_n, cudaStream_t s, int frame0 = 0, int total_frames = 0)
 {
+	if (total_frames <= 0) total_frames = frame0 + n_frames;
 	OrbGeom g{};
 	LCD_TRY(orb_geometry(e, width, height, p, g));
 	if (channels != 1 && channels != 3) LCD_FAIL(e, LCD_ERR_INVALID, "images must be 8UC1 or 8UC3 (BGR)");
 	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap must be 1..%d", kMaxFrameQueries);
 	if (!d_depth) depth_type = LCD_DEPTH_NONE;
 	const bool use_mask = depth_type != LCD_DEPTH_NONE && p->depth_as_mask;
-	const size_t pyr = static_cast<size_t>(n_frames) * g.frame_stride;
+	const size_t pyr = static_cast<size_t>(total_frames) * g.frame_stride;
 	LCD_CUDA(e, e->o_gray.reserve(pyr, 0, false, s));
 	LCD_CUDA(e, e->o_blur.reserve(pyr, 0, false, s));
 	if (use_mask) LCD_CUDA(e, e->o_mask.reserve(pyr, 0, false, s));
-	const int slots = n_frames * g.n_levels;
+	const int slots = n_frames * g.n_levels, total_slots = total_frames * g.n_levels, slot0 = frame0 * g.n_levels;
 	int level_cap = 0;
 	for (int l = 0; l < g.n_levels; ++l) level_cap = std::max(level_cap, g.n_per_level[l] + 256);
-	LCD_CUDA(e, e->o_cand.reserve(static_cast<size_t>(slots) * kOrbCandCap, 0, false, s));
-	LCD_CUDA(e, e->o_cand_count.reserve(slots, 0, false, s));
-	LCD_CUDA(e, e->o_level_n.reserve(slots, 0, false, s));
-	LCD_CUDA(e, e->o_level_kp.reserve(static_cast<size_t>(slots) * level_cap, 0, false, s));
-	LCD_CUDA(e, e->o_overflow.reserve(1, 0, true, s));
+	LCD_CUDA(e, e->o_cand.reserve(static_cast<size_t>(total_slots) * kOrbCandCap, 0, false, s));
+	LCD_CUDA(e, e->o_cand_count.reserve(total_slots, 0, false, s));
+	LCD_CUDA(e, e->o_level_n.reserve(total_slots, 0, false, s));
+	LCD_CUDA(e, e->o_level_kp.reserve(static_cast<size_t>(total_slots) * level_cap, 0, false, s));
+	if (frame0 == 0) LCD_CUDA(e, e->o_overflow.reserve(1, 0, true, s));
+	LCD_CUDA(e, e->o_score.reserve(pyr, 0, false, s));
 	if (!d_kp)
 	{
-		LCD_CUDA(e, e->o_kp.reserve(static_cast<size_t>(n_frames) * cap, 0, false, s));
+		LCD_CUDA(e, e->o_kp.reserve(static_cast<size_t>(total_frames) * cap, 0, false, s));
 		d_kp = e->o_kp.p;
 	}
 	if (!d_n)
 	{
-		LCD_CUDA(e, e->o_n.reserve(n_frames, 0, false, s));
+		LCD_CUDA(e, e->o_n.reserve(total_frames, 0, false, s));
 		d_n = e->o_n.p;
 	}
+	// pointers of the range
+	const size_t px = static_cast<size_t>(width) * height;
+	d_images += static_cast<size_t>(frame0) * px * channels;
+	if (d_depth) d_depth = static_cast<const unsigned char *>(d_depth) + static_cast<size_t>(frame0) * px * (depth_type == LCD_DEPTH_U16_MM ? 2 : 4);
+	uint8_t * const w_gray = e->o_gray.p + static_cast<size_t>(frame0) * g.frame_stride;
+	uint8_t * const w_blur = e->o_blur.p + static_cast<size_t>(frame0) * g.frame_stride;
+	uint8_t * const w_mask = use_mask ? e->o_mask.p + static_cast<size_t>(frame0) * g.frame_stride : nullptr;
+	uint8_t * const w_score = e->o_score.p + static_cast<size_t>(frame0) * g.frame_stride;
+	uint32_t * const w_cand = e->o_cand.p + static_cast<size_t>(slot0) * kOrbCandCap;
+	int * const w_cand_count = e->o_cand_count.p + slot0;
+	int * const w_level_n = e->o_level_n.p + slot0;
+	OrbKeypoint * const w_level_kp = e->o_level_kp.p + static_cast<size_t>(slot0) * level_cap;
+	d_kp += static_cast<size_t>(frame0) * cap;
+	d_n += frame0;
+	if (d_desc) d_desc += static_cast<size_t>(frame0) * cap * 32;
+	if (d_xyz) d_xyz += static_cast<size_t>(frame0) * cap * 3;
+	if (d_uv) d_uv += static_cast<size_t>(frame0) * cap * 2;
 	if (e->gauss_sigma_loaded != 2.0f)
 	{
 		// cv::getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, stored as float
@@ -1387,7 +1455,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		e->gauss_sigma_loaded = 2.0f;
 	}
 	prof_mark(e, LCD_PROF_ORB, s);
-	LCD_CUDA(e, cudaMemsetAsync(e->o_cand_count.p, 0, slots * sizeof(int), s));
+	LCD_CUDA(e, zero_fill_async(w_cand_count, slots * sizeof(int), s));
 	{
 		OrbPrepArgs a{};
 		a.images = d_images;
@@ -1396,8 +1464,8 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		a.depth_type = depth_type;
 		a.min_depth = p->min_depth;
 		a.max_depth = p->max_depth;
-		a.gray = e->o_gray.p;
-		a.mask = use_mask ? e->o_mask.p : nullptr;
+		a.gray = w_gray;
+		a.mask = w_mask;
 		a.g = g;
 		dim3 blk(32, 8), grd(((width + 1) / 2 + 31) / 32, ((height + 1) / 2 + 7) / 8, n_frames);
 		orb_prepare_kernel<<<grd, blk, 0, s>>>(a);
@@ -1406,26 +1474,25 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	for (int l = 2; l < g.n_levels; ++l)
 	{
 		dim3 blk(32, 8), grd((g.w[l] + 31) / 32, (g.h[l] + 7) / 8, n_frames);
-		orb_down_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, use_mask ? e->o_mask.p : nullptr, g, l);
+		orb_down_kernel<<<grd, blk, 0, s>>>(w_gray, w_mask, g, l);
 		LCD_CHECK_LAUNCH(e);
 	}
-	LCD_CUDA(e, e->o_score.reserve(pyr, 0, false, s));
 	for (int l = 0; l < g.n_levels; ++l)
 	{
 		dim3 blk(32, 8), grd((g.w[l] + 31) / 32, (g.h[l] + 7) / 8, n_frames);
-		orb_fast_score_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, g, l, e->o_score.p);
+		orb_fast_score_kernel<<<grd, blk, 0, s>>>(w_gray, g, l, w_score);
 		LCD_CHECK_LAUNCH(e);
-		orb_fast_nms_kernel<<<grd, blk, 0, s>>>(e->o_score.p, use_mask ? e->o_mask.p : nullptr, g, l, e->o_cand.p, e->o_cand_count.p);
+		orb_fast_nms_kernel<<<grd, blk, 0, s>>>(w_score, w_mask, g, l, w_cand, w_cand_count);
 		LCD_CHECK_LAUNCH(e);
 	}
 	{
 		OrbSelectArgs a{};
-		a.gray = e->o_gray.p;
+		a.gray = w_gray;
 		a.g = g;
-		a.cand = e->o_cand.p;
-		a.cand_count = e->o_cand_count.p;
-		a.level_kp = e->o_level_kp.p;
-		a.level_n = e->o_level_n.p;
+		a.cand = w_cand;
+		a.cand_count = w_cand_count;
+		a.level_kp = w_level_kp;
+		a.level_n = w_level_n;
 		a.level_cap = level_cap;
 		a.overflow = e->o_overflow.p;
 		const size_t smem = static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2);
@@ -1436,7 +1503,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	{
 		int pad = 1;
 		while (pad < g.n_levels * level_cap) pad <<= 1;
-		orb_merge_kernel<<<n_frames, 1024, pad * sizeof(unsigned long long), s>>>(e->o_level_kp.p, e->o_level_n.p, g.n_levels, level_cap, p->n_features,
+		orb_merge_kernel<<<n_frames, 1024, pad * sizeof(unsigned long long), s>>>(w_level_kp, w_level_n, g.n_levels, level_cap, p->n_features,
 		                                                                          d_kp, d_n, cap);
 		LCD_CHECK_LAUNCH(e);
 	}
@@ -1445,11 +1512,11 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		for (int l = 0; l < g.n_levels; ++l)
 		{
 			dim3 blk(16, 16), grd((g.w[l] + 15) / 16, (g.h[l] + 15) / 16, n_frames);
-			orb_blur_kernel<<<grd, blk, 0, s>>>(e->o_gray.p, e->o_blur.p, g, l);
+			orb_blur_kernel<<<grd, blk, 0, s>>>(w_gray, w_blur, g, l);
 			LCD_CHECK_LAUNCH(e);
 		}
 		dim3 grd((cap + kOrbDescribeKp - 1) / kOrbDescribeKp, n_frames);
-		orb_describe_kernel<<<grd, 256, 0, s>>>(e->o_gray.p, e->o_blur.p, g, d_kp, d_n, cap, d_desc);
+		orb_describe_kernel<<<grd, 256, 0, s>>>(w_gray, w_blur, g, d_kp, d_n, cap, d_desc);
 		LCD_CHECK_LAUNCH(e);
 	}
 	if (d_xyz || d_uv)
@@ -1739,30 +1806,17 @@ static int verify_download(lcd_engine * e, int n_pairs, int cap, lcd_verify_resu
 		gather_by_index_kernel<<<dim3((cap + 255) / 256, n_pairs), 256, 0, s>>>(e->v_mid.p, e->v_inl.p, e->v_ninl.p, cap, e->v_inl_ids.p);
 		LCD_CHECK_LAUNCH(e);
 	}
-	std::vector<int> nm(n_pairs), ni(n_pairs), it(n_pairs), ok(n_pairs);
-	std::vector<double> rv(n_pairs * 3), tv(n_pairs * 3);
-	std::vector<float> T(n_pairs * 12);
-	LCD_CUDA(e, cudaMemcpyAsync(nm.data(), e->v_nm.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(ni.data(), e->v_ninl.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(it.data(), e->v_iters.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(ok.data(), e->v_ok.p, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(rv.data(), e->v_rvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(tv.data(), e->v_tvec.p, n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-	LCD_CUDA(e, cudaMemcpyAsync(T.data(), e->v_T.p, n_pairs * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, e->v_packed.reserve(n_pairs, 0, false, s));
+	LCD_CUDA(e, e->h_packed.reserve(n_pairs));
+	pack_verify_results_kernel<<<(n_pairs + 127) / 128, 128, 0, s>>>(n_pairs, e->v_ok.p, e->v_nm.p, e->v_ninl.p, e->v_iters.p, e->v_rvec.p, e->v_tvec.p,
+	                                                                e->v_T.p, e->v_packed.p);
+	LCD_CHECK_LAUNCH(e);
+	LCD_CUDA(e, cudaMemcpyAsync(e->h_packed.p, e->v_packed.p, n_pairs * sizeof(PackedVerifyResult), cudaMemcpyDeviceToHost, s));
 	if (cap > 0 && match_ids) LCD_CUDA(e, cudaMemcpyAsync(match_ids, e->v_mid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
 	if (cap > 0 && inlier_ids) LCD_CUDA(e, cudaMemcpyAsync(inlier_ids, e->v_inl_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaStreamSynchronize(s));
-	for (int i = 0; i < n_pairs; ++i)
-	{
-		lcd_verify_result & r = results[i];
-		r.ok = ok[i];
-		r.n_matches = nm[i];
-		r.n_inliers = ni[i];
-		r.iterations_run = it[i];
-		memcpy(r.rvec, &rv[3 * i], 3 * sizeof(double));
-		memcpy(r.tvec, &tv[3 * i], 3 * sizeof(double));
-		memcpy(r.transform, &T[12 * i], 12 * sizeof(float));
-	}
+	static_assert(sizeof(PackedVerifyResult) == sizeof(lcd_verify_result), "PackedVerifyResult must mirror lcd_verify_result");
+	memcpy(results, e->h_packed.p, n_pairs * sizeof(lcd_verify_result));
 	return LCD_OK;
 }
 
@@ -1943,7 +1997,8 @@ int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * 
 // images -> detect -> quantise -> score -> verify, all on device buffers
 static int process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
                               int depth_type, const lcd_orb_params * op, int incremental, float nndr, int cmp_new, const int * d_sig_ids, int ns,
-                              int n_total, const lcd_verify_params * vp, int * d_words, float * d_like, cudaStream_t s)
+                              int n_total, const lcd_verify_params * vp, int * d_words, float * d_like, cudaStream_t s,
+                              const uint8_t * h_images = nullptr, const void * h_depth = nullptr)
 {
 	if (!op) LCD_FAIL(e, LCD_ERR_INVALID, "null ORB parameters");
 	if (e->cfg.desc_type != LCD_DESC_U8 || e->cfg.desc_dim != 32) LCD_FAIL(e, LCD_ERR_INVALID, "ORB descriptors need an engine with 32-byte binary descriptors");
@@ -1956,9 +2011,54 @@ static int process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_im
 	LCD_CUDA(e, e->o_uv.reserve(rows * 2, 0, false, s));
 	LCD_CUDA(e, e->o_n.reserve(n_frames, 0, false, s));
 	// padding rows of short frames must hold defined bytes for the NN kernel
-	LCD_CUDA(e, cudaMemsetAsync(e->o_desc.p, 0, rows * 32, s));
-	LCD_TRY(orb_run(e, n_frames, d_images, width, height, channels, d_depth, depth_type, op, cap, e->o_kp.p, e->o_desc.p, e->o_xyz.p, e->o_uv.p,
-	                e->o_n.p, s));
+	LCD_CUDA(e, zero_fill_async(e->o_desc.p, rows * 32, s));
+	if (!h_images)
+	{
+		LCD_TRY(orb_run(e, n_frames, d_images, width, height, channels, d_depth, depth_type, op, cap, e->o_kp.p, e->o_desc.p, e->o_xyz.p, e->o_uv.p,
+		                e->o_n.p, s));
+	}
+	else
+	{
+		// host frames: upload in chunks on the copy stream and run detect + describe on each chunk as soon as it has
+		// landed, so that the PCIe transfer of chunk c+1 hides behind the ORB kernels of chunk c
+		if (!e->copy_stream)
+		{
+			LCD_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+			LCD_CUDA(e, cudaEventCreateWithFlags(&e->copy_fence, cudaEventDisableTiming));
+		}
+		const int chunk_env = env_int("LCD_UPLOAD_CHUNK", 0); // 0: one chunk (per-chunk ORB launches are latency-bound, measured: chunking only pays for very large batches)
+		const int chunk = chunk_env > 0 ? chunk_env : n_frames;
+		const int n_chunks = (n_frames + chunk - 1) / chunk;
+		while (static_cast<int>(e->copy_events.size()) < n_chunks)
+		{
+			cudaEvent_t ev;
+			LCD_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+			e->copy_events.push_back(ev);
+		}
+		const size_t px = static_cast<size_t>(width) * height;
+		const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+		// the device staging buffers may still be read by work queued on s (a previous call): order the copies after it
+		LCD_CUDA(e, cudaEventRecord(e->copy_fence, s));
+		LCD_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->copy_fence, 0));
+		for (int c = 0; c < n_chunks; ++c)
+		{
+			const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+			LCD_CUDA(e, cudaMemcpyAsync(const_cast<uint8_t *>(d_images) + f0 * px * channels, h_images + f0 * px * channels, nf * px * channels,
+			                            cudaMemcpyHostToDevice, e->copy_stream));
+			if (h_depth && d_depth)
+				LCD_CUDA(e, cudaMemcpyAsync(static_cast<unsigned char *>(const_cast<void *>(d_depth)) + f0 * px * dbytes,
+				                            static_cast<const unsigned char *>(h_depth) + f0 * px * dbytes, nf * px * dbytes, cudaMemcpyHostToDevice,
+				                            e->copy_stream));
+			LCD_CUDA(e, cudaEventRecord(e->copy_events[c], e->copy_stream));
+		}
+		for (int c = 0; c < n_chunks; ++c)
+		{
+			const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+			LCD_CUDA(e, cudaStreamWaitEvent(s, e->copy_events[c], 0));
+			LCD_TRY(orb_run(e, nf, d_images, width, height, channels, d_depth, depth_type, op, cap, e->o_kp.p, e->o_desc.p, e->o_xyz.p, e->o_uv.p,
+			                e->o_n.p, s, f0, n_frames));
+		}
+	}
 	if (!d_like)
 	{
 		LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
@@ -1997,14 +2097,13 @@ int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int
 	cudaStream_t s = e->stream;
 	const size_t px = static_cast<size_t>(n_frames) * width * height;
 	LCD_CUDA(e, e->o_img.reserve(px * channels, 0, false, s));
-	LCD_CUDA(e, cudaMemcpyAsync(e->o_img.p, images, px * channels, cudaMemcpyHostToDevice, s));
 	if (!depth) depth_type = LCD_DEPTH_NONE;
 	if (depth_type != LCD_DEPTH_NONE)
 	{
 		const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
 		LCD_CUDA(e, e->o_depth.reserve(px * dbytes, 0, false, s));
-		LCD_CUDA(e, cudaMemcpyAsync(e->o_depth.p, depth, px * dbytes, cudaMemcpyHostToDevice, s));
 	}
+	// the frames themselves are uploaded chunk by chunk inside process_frames_dev, overlapped with detect + describe
 	const int cap = op->n_features;
 	const size_t rows = static_cast<size_t>(n_frames) * std::max(cap, 1);
 	LCD_CUDA(e, e->d_sig_ids.reserve(ns, 0, false, s));
@@ -2012,7 +2111,8 @@ int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int
 	LCD_CUDA(e, e->d_word_ids.reserve(rows, 0, false, s));
 	LCD_CUDA(e, cudaMemcpyAsync(e->d_sig_ids.p, sig_ids, ns * sizeof(int), cudaMemcpyHostToDevice, s));
 	LCD_TRY(process_frames_dev(e, n_frames, e->o_img.p, width, height, channels, depth_type != LCD_DEPTH_NONE ? e->o_depth.p : nullptr, depth_type, op,
-	                           incremental, nndr, new_words_compared_together, e->d_sig_ids.p, ns, n_total, vp, e->d_word_ids.p, e->d_like.p, s));
+	                           incremental, nndr, new_words_compared_together, e->d_sig_ids.p, ns, n_total, vp, e->d_word_ids.p, e->d_like.p, s, images,
+	                           depth_type != LCD_DEPTH_NONE ? depth : nullptr));
 	if (n_kp_out) LCD_CUDA(e, cudaMemcpyAsync(n_kp_out, e->o_n.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
 	if (word_ids_out) LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
 	if (likelihood_out)
@@ -2020,6 +2120,119 @@ int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int
 	if (vp && hypothesis_out) LCD_CUDA(e, cudaMemcpyAsync(hypothesis_out, e->d_hyp_id.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
 	if (vp && results) return verify_download(e, n_frames, 0, results, nullptr, nullptr, s);
 	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+// ---- pipelined host path: two batches in flight ------------------------------------------------------------
+int lcd_process_frames_submit(lcd_engine * e, int n_frames, const uint8_t * images, int width, int height, int channels, const void * depth,
+                              int depth_type, const lcd_orb_params * op, int incremental, float nndr, int new_words_compared_together,
+                              const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp, int * n_kp_out, int * word_ids_out,
+                              float * likelihood_out, int * hypothesis_out, lcd_verify_result * results)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!images || n_frames <= 0 || width <= 0 || height <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null image");
+	if (!sig_ids || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "ids list is empty");
+	if (!op) LCD_FAIL(e, LCD_ERR_INVALID, "null ORB parameters");
+	if (e->flights_busy >= 2) LCD_FAIL(e, LCD_ERR_INVALID, "two batches are already in flight: call lcd_process_frames_wait first");
+	cudaStream_t s = e->stream;
+	const int slot = (e->flight_head + e->flights_busy) & 1;
+	lcd_engine::Flight & f = e->flights[slot];
+	if (!e->copy_stream)
+	{
+		LCD_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+		LCD_CUDA(e, cudaEventCreateWithFlags(&e->copy_fence, cudaEventDisableTiming));
+	}
+	if (!f.uploaded)
+	{
+		LCD_CUDA(e, cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
+		LCD_CUDA(e, cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+	}
+	const size_t px = static_cast<size_t>(n_frames) * width * height;
+	if (!depth) depth_type = LCD_DEPTH_NONE;
+	const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+	// upload on the copy stream: the slot's previous batch was waited for, so its staging buffers are free
+	static const int dbg_tl = env_int("LCD_DEBUG_TIMELINE", 0);
+	if (dbg_tl && !f.t_h0)
+	{
+		cudaEventCreate(&f.t_h0);
+		cudaEventCreate(&f.t_h1);
+		cudaEventCreate(&f.t_c0);
+		cudaEventCreate(&f.t_c1);
+		if (!e->t_base)
+		{
+			cudaEventCreate(&e->t_base);
+			cudaEventRecord(e->t_base, e->copy_stream);
+		}
+	}
+	if (dbg_tl) cudaEventRecord(f.t_h0, e->copy_stream);
+	static const int dbg_skip = env_int("LCD_DEBUG_SKIP_UPLOAD", 0); // diagnostics: 1 = reuse the slot's previous upload
+	const bool skip = dbg_skip && f.img.cap >= px * channels;
+	LCD_CUDA(e, f.img.reserve(px * channels, 0, false, e->copy_stream));
+	if (!skip) LCD_CUDA(e, cudaMemcpyAsync(f.img.p, images, px * channels, cudaMemcpyHostToDevice, e->copy_stream));
+	if (depth_type != LCD_DEPTH_NONE)
+	{
+		LCD_CUDA(e, f.depth.reserve(px * dbytes, 0, false, e->copy_stream));
+		if (!skip) LCD_CUDA(e, cudaMemcpyAsync(f.depth.p, depth, px * dbytes, cudaMemcpyHostToDevice, e->copy_stream));
+	}
+	// the signature id list rides on the copy stream too: a host -> device copy queued on the compute stream would sit in the
+	// same copy-engine queue as the next batch's images and serialise the two batches (measured)
+	LCD_CUDA(e, f.sig_ids.reserve(ns, 0, false, e->copy_stream));
+	LCD_CUDA(e, cudaMemcpyAsync(f.sig_ids.p, sig_ids, ns * sizeof(int), cudaMemcpyHostToDevice, e->copy_stream));
+	if (dbg_tl) cudaEventRecord(f.t_h1, e->copy_stream);
+	LCD_CUDA(e, cudaEventRecord(f.uploaded, e->copy_stream));
+	// compute on the engine stream, behind the previous batch
+	const int cap = op->n_features;
+	const size_t rows = static_cast<size_t>(n_frames) * std::max(cap, 1);
+	LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
+	LCD_CUDA(e, e->d_word_ids.reserve(rows, 0, false, s));
+	LCD_CUDA(e, cudaStreamWaitEvent(s, f.uploaded, 0));
+	if (dbg_tl) cudaEventRecord(f.t_c0, s);
+	LCD_TRY(process_frames_dev(e, n_frames, f.img.p, width, height, channels, depth_type != LCD_DEPTH_NONE ? f.depth.p : nullptr, depth_type, op,
+	                           incremental, nndr, new_words_compared_together, f.sig_ids.p, ns, n_total, vp, e->d_word_ids.p, e->d_like.p, s));
+	if (n_kp_out) LCD_CUDA(e, cudaMemcpyAsync(n_kp_out, e->o_n.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (word_ids_out) LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (likelihood_out)
+		LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, static_cast<size_t>(n_frames) * ns * sizeof(float), cudaMemcpyDeviceToHost, s));
+	if (vp && hypothesis_out) LCD_CUDA(e, cudaMemcpyAsync(hypothesis_out, e->d_hyp_id.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	f.user_results = nullptr;
+	if (vp && results)
+	{
+		LCD_CUDA(e, e->v_packed.reserve(n_frames, 0, false, s));
+		LCD_CUDA(e, f.res.reserve(n_frames));
+		pack_verify_results_kernel<<<(n_frames + 127) / 128, 128, 0, s>>>(n_frames, e->v_ok.p, e->v_nm.p, e->v_ninl.p, e->v_iters.p, e->v_rvec.p,
+		                                                                 e->v_tvec.p, e->v_T.p, e->v_packed.p);
+		LCD_CHECK_LAUNCH(e);
+		LCD_CUDA(e, cudaMemcpyAsync(f.res.p, e->v_packed.p, n_frames * sizeof(PackedVerifyResult), cudaMemcpyDeviceToHost, s));
+		f.user_results = results;
+	}
+	f.n_frames = n_frames;
+	if (dbg_tl) cudaEventRecord(f.t_c1, s);
+	LCD_CUDA(e, cudaEventRecord(f.done, s));
+	++e->flights_busy;
+	return LCD_OK;
+}
+
+int lcd_process_frames_wait(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (e->flights_busy <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "no batch in flight");
+	lcd_engine::Flight & f = e->flights[e->flight_head];
+	LCD_CUDA(e, cudaEventSynchronize(f.done));
+	if (f.t_h0 && e->t_base)
+	{
+		float a = 0, b = 0, c = 0, d = 0;
+		cudaEventElapsedTime(&a, e->t_base, f.t_h0);
+		cudaEventElapsedTime(&b, e->t_base, f.t_h1);
+		cudaEventElapsedTime(&c, e->t_base, f.t_c0);
+		cudaEventElapsedTime(&d, e->t_base, f.t_c1);
+		fprintf(stderr, "[lcd timeline] upload %.2f..%.2f  compute %.2f..%.2f ms\n", a, b, c, d);
+	}
+	if (f.user_results) memcpy(f.user_results, f.res.p, f.n_frames * sizeof(lcd_verify_result));
+	f.user_results = nullptr;
+	e->flight_head ^= 1;
+	--e->flights_busy;
 	return LCD_OK;
 }
 
@@ -2126,7 +2339,7 @@ int lcd_shard_resolve_score_dev(lcd_engine * e, const void * d_queries, int n_fr
 	{
 		LCD_TRY(ensure_uq(e, n_frames, nq_per_frame, s));
 		LCD_TRY(ensure_acc(e, n_frames));
-		LCD_CUDA(e, cudaMemsetAsync(e->acc.p, 0, static_cast<size_t>(e->acc_stride) * n_frames * sizeof(long long), s));
+		LCD_CUDA(e, zero_fill_async(e->acc.p, static_cast<size_t>(e->acc_stride) * n_frames * sizeof(long long), s));
 		fill_prep(e, a, static_cast<float>(n_total), 1);
 	}
 	LCD_TRY(launch_resolve(e, a, n_frames, s));

@@ -756,6 +756,33 @@ pnp_ransac_kernel(const PnpArgs a)
 	}
 }
 
+// Pack the per-pair verification outputs into lcd_verify_result records (one device->host copy instead of seven).
+struct PackedVerifyResult // layout of lcd_verify_result (include/lcd_b200.h)
+{
+	int ok, n_matches, n_inliers, iterations_run;
+	double rvec[3], tvec[3];
+	float transform[12];
+};
+__global__ void pack_verify_results_kernel(int n_pairs, const int * __restrict__ ok, const int * __restrict__ n_match, const int * __restrict__ n_inl,
+                                           const int * __restrict__ iters, const double * __restrict__ rvec, const double * __restrict__ tvec,
+                                           const float * __restrict__ T, PackedVerifyResult * __restrict__ out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pairs) return;
+	PackedVerifyResult r;
+	r.ok = ok[i];
+	r.n_matches = n_match[i];
+	r.n_inliers = n_inl[i];
+	r.iterations_run = iters[i];
+	for (int k = 0; k < 3; ++k)
+	{
+		r.rvec[k] = rvec[3 * i + k];
+		r.tvec[k] = tvec[3 * i + k];
+	}
+	for (int k = 0; k < 12; ++k) r.transform[k] = T[12 * i + k];
+	out[i] = r;
+}
+
 // Hypothesis selection for the fused query: the signature with the highest likelihood of each frame
 // (first maximum; a zero / negative maximum selects nothing).  The reference selects through the Bayes
 // filter (Rtabmap.cpp:2133-2226, out of scope here); the raw-likelihood arg-max is what
