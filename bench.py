@@ -503,6 +503,26 @@ def run_b200(args):
             "step_share_ms": share,
         }
 
+    # the XOR/POPC kernel on the same resident data (three untimed-region steps), for comparison with the tensor kernel
+    if world_size == 1 and os.environ.get("LCD_NN_TENSOR", "1") != "0":
+        eng.nn_select(0)
+        eng.profile_enable(True)
+        eng.profile_reset()
+        for k in range(3):
+            step_dev(k)
+        torch.cuda.synchronize()
+        p_ms, p_n = eng.profile_read(0)
+        eng.profile_enable(False)
+        eng.nn_select(1)
+        p_s = (p_ms / max(p_n, 1)) * 1e-3
+        roofline["popcount_kernel"] = {
+            "kernel": "knn2_hamming_kernel<8,8,2> (lcd_nn_select(e, 0))", "avg_launch_ms": p_s * 1e3, "launches_timed": int(p_n),
+            "bound": "integer pipes (POPC 16 lanes/clk/SM)", "popc_per_s": pairs * popc_per_pair / p_s if p_s > 0 else 0.0,
+            "popc_peak_per_s": popc_peak, "popc_frac": (pairs * popc_per_pair / p_s) / popc_peak if p_s > 0 else 0.0,
+            "hbm_GBps": alg_bytes / p_s / 1e9 if p_s > 0 else 0.0, "hbm_frac": (alg_bytes / p_s / 1e9) / hbm_peak if p_s > 0 else 0.0,
+            "traffic": traffic,
+        }
+
     cpu = None
     if world_size == 1 and not args.no_cpu_baseline:
         threads = max(1, min(os.cpu_count() or 1, 32))

@@ -139,6 +139,13 @@ int lcd_dict_has_word(const lcd_engine * e, int word_id);
  * Mirrors what _dataTree/_mapIndexId hold (VWDictionary.cpp:650-676). */
 int lcd_dict_get_indexed(lcd_engine * e, int * ids, void * desc, int cap_rows);
 
+/* The 2-NN of 32-byte binary descriptors has two bit-identical implementations: kernel 1 (default) computes the Hamming
+ * distances as an exact s8 GEMM on the tensor cores (nn_tensor.cuh), kernel 0 with XOR + POPC on the integer pipes
+ * (nn_hamming.cuh; the only one for other descriptor sizes).  Mirrors choosing Kp/NNStrategy in the reference
+ * (VWDictionary::setNNStrategy, VWDictionary.cpp:316-338).  lcd_nn_last_kernel: which one the last search used. */
+int lcd_nn_select(lcd_engine * e, int kernel);
+int lcd_nn_last_kernel(const lcd_engine * e);
+
 /* replaces: FlannIndex::knnSearch(k=2) on a LinearIndex (FlannIndex.cpp:701-745 ->
  * rtflann linear_index.h:129-146 + result_set.h:151-172): exact 2-NN of every query
  * row over the INDEXED words; ties -> lowest row.  id = 0 and dist = -1 where fewer

@@ -110,6 +110,8 @@ SIGNATURES = {
     "lcd_dict_set_last_word_id": (_I, [_P, _I]),
     "lcd_dict_has_word": (_I, [_P, _I]),
     "lcd_dict_get_indexed": (_I, [_P, _P, _P, _I]),
+    "lcd_nn_select": (_I, [_P, _I]),
+    "lcd_nn_last_kernel": (_I, [_P]),
     "lcd_dict_knn2": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "lcd_dict_quantize": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
     "lcd_dict_find_nn": (_I, [_P, _P, _I, _I, _F, _P]),
@@ -334,6 +336,14 @@ class Engine:
             if r < 0:
                 self._check(r)
         return ids, desc
+
+    def nn_select(self, kernel: int):
+        """0 = XOR/POPC kernel, 1 = tensor-core kernel (default for 32-byte descriptors)."""
+        self._check(self._lib.lcd_nn_select(self._h, int(kernel)))
+
+    @property
+    def nn_last_kernel(self) -> int:
+        return int(self._lib.lcd_nn_last_kernel(self._h))
 
     def knn2(self, queries):
         q = self._desc(queries)

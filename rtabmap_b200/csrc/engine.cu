@@ -700,6 +700,16 @@ const char * lcd_build_arch(void) { return "sm_100a"; }
 
 const char * lcd_last_error(const lcd_engine * e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 long long lcd_launch_count(const lcd_engine * e) { return e ? e->launches : 0; }
+
+int lcd_nn_select(lcd_engine * e, int kernel)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (kernel != 0 && kernel != 1) LCD_FAIL(e, LCD_ERR_INVALID, "kernel must be 0 (popcount) or 1 (tensor)");
+	e->nn_tensor = kernel;
+	return LCD_OK;
+}
+
+int lcd_nn_last_kernel(const lcd_engine * e) { return e ? e->nn_last_tensor : LCD_ERR_INVALID; }
 void * lcd_stream(lcd_engine * e) { return e ? static_cast<void *>(e->stream) : nullptr; }
 
 lcd_engine * lcd_create(const lcd_config * cfg)

@@ -68,6 +68,27 @@ def test_knn2_ties_resolve_to_lowest_row():
     assert (id1[0], d1[0], id2[0], d2[0]) == (4, 0.0, 101, 0.0)
 
 
+@pytest.mark.parametrize("n_words,nq", [(1, 1), (255, 129), (256, 128), (257, 300), (4097, 1000), (20000, 2500)])
+def test_nn_kernels_agree(n_words, nq):
+    """The tensor-core kernel (s8 GEMM of the +-1 encoded bits) and the XOR/POPC kernel return the same two neighbours and
+    distances for every query, including ties (lowest row wins), partly filled word / query tiles and duplicate words."""
+    eng, o, vocab, ids = make_pair(n_words, id_stride=2, seed=n_words)
+    rng = np.random.default_rng(n_words + nq)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    k = min(nq, n_words)
+    q[:k] = synth.flip_bits(vocab[rng.integers(0, n_words, k)], 0.04, rng)
+    q[0] = vocab[0]
+    eng.nn_select(1)
+    t = eng.knn2(q)
+    assert eng.nn_last_kernel == 1
+    eng.nn_select(0)
+    p = eng.knn2(q)
+    assert eng.nn_last_kernel == 0
+    w = o.knn2(q)
+    for a, b, c in zip(t, p, w):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
 @pytest.mark.parametrize("dim", [16, 64])
 def test_knn2_other_descriptor_sizes(dim):
     eng, o, vocab, ids = make_pair(700, dim=dim, seed=9)
