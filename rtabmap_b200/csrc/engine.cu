@@ -1489,10 +1489,8 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	}
 	for (int l = 0; l < g.n_levels; ++l)
 	{
-		dim3 blk(32, 8), grd((g.w[l] + 31) / 32, (g.h[l] + 7) / 8, n_frames);
-		orb_fast_score_kernel<<<grd, blk, 0, s>>>(w_gray, g, l, w_score);
-		LCD_CHECK_LAUNCH(e);
-		orb_fast_nms_kernel<<<grd, blk, 0, s>>>(w_score, w_mask, g, l, w_cand, w_cand_count);
+		dim3 grd((g.w[l] + kFastTW - 1) / kFastTW, (g.h[l] + kFastTH - 1) / kFastTH, n_frames);
+		orb_fast_kernel<<<grd, 256, 0, s>>>(w_gray, w_mask, g, l, w_cand, w_cand_count);
 		LCD_CHECK_LAUNCH(e);
 	}
 	{
@@ -1505,9 +1503,18 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		a.level_n = w_level_n;
 		a.level_cap = level_cap;
 		a.overflow = e->o_overflow.p;
-		const size_t smem = static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2);
-		LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-		orb_select_kernel<<<slots, kOrbSelectThreads, smem, s>>>(a);
+		// one launch per level: level l holds at most kOrbCandCap >> l candidates in shared memory (192 KB, 96 KB, 48 KB, ...), so
+		// the coarse levels run several CTAs per SM and level 0 (n_frames CTAs) is a single wave for up to 148 frames
+		for (int l = 0; l < g.n_levels; ++l)
+		{
+			a.level = l;
+			a.cand_cap = std::max(2048, kOrbCandCap >> l);
+			const size_t smem = static_cast<size_t>(a.cand_cap) * (4 + 4 + 2 + 2);
+			LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                 static_cast<int>(static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2))));
+			orb_select_kernel<<<n_frames, kOrbSelectThreads, smem, s>>>(a);
+			if (l + 1 < g.n_levels) LCD_CHECK_LAUNCH(e);
+		}
 		LCD_CHECK_LAUNCH(e);
 	}
 	{
@@ -1521,8 +1528,8 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	{
 		for (int l = 0; l < g.n_levels; ++l)
 		{
-			dim3 blk(16, 16), grd((g.w[l] + 15) / 16, (g.h[l] + 15) / 16, n_frames);
-			orb_blur_kernel<<<grd, blk, 0, s>>>(w_gray, w_blur, g, l);
+			dim3 grd((g.w[l] + kBlurTW - 1) / kBlurTW, (g.h[l] + kBlurTH - 1) / kBlurTH, n_frames);
+			orb_blur_kernel<<<grd, 256, 0, s>>>(w_gray, w_blur, g, l);
 			LCD_CHECK_LAUNCH(e);
 		}
 		dim3 grd((cap + kOrbDescribeKp - 1) / kOrbDescribeKp, n_frames);
@@ -1609,7 +1616,7 @@ int lcd_orb_detect_describe(lcd_engine * e, int n_frames, const uint8_t * images
 	int overflow = 0;
 	LCD_CUDA(e, cudaMemcpyAsync(&overflow, e->o_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaStreamSynchronize(s));
-	if (overflow) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d FAST corners in one pyramid level (or too many ties): raise FAST/Threshold", kOrbCandCap);
+	if (overflow) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d FAST corners in pyramid level 0 (half as many per further level): raise FAST/Threshold", kOrbCandCap);
 	return LCD_OK;
 }
 

@@ -243,6 +243,102 @@ orb_fast_nms_kernel(const uint8_t * __restrict__ score_all, const uint8_t * __re
 	if (k < kOrbCandCap) cand[static_cast<size_t>(slot) * kOrbCandCap + k] = (static_cast<uint32_t>(y * w + x) << 8) | static_cast<uint32_t>(s);
 }
 
+// Fused FAST stage: score + 3x3 non-max suppression + border / mask filters -> candidate list, one 32x16 tile per CTA.
+// The gray tile (4-pixel halo) is staged in shared memory; a cheap compass test (every 9-arc contains pixel 0 or 8 and
+// pixel 4 or 12) compacts the few pixels that can be corners into a shared list, so the expensive arc minima run on
+// dense warps instead of being dragged through every warp that holds one corner; the scores never leave shared memory.
+constexpr int kFastTW = 32, kFastTH = 16;
+__global__ void __launch_bounds__(256)
+orb_fast_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restrict__ mask_all, const OrbGeom g, int level,
+                uint32_t * __restrict__ cand, int * __restrict__ cand_count)
+{
+	constexpr int GW = kFastTW + 8, GH = kFastTH + 8, SW = kFastTW + 2, SH = kFastTH + 2;
+	__shared__ uint8_t s_gray[GH * GW];
+	__shared__ uint8_t s_score[SH * SW];
+	__shared__ uint16_t s_list[SH * SW];
+	__shared__ int s_n;
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int frame = blockIdx.z;
+	const int w = g.w[level], h = g.h[level];
+	const int x0 = blockIdx.x * kFastTW, y0 = blockIdx.y * kFastTH;
+	const size_t plane = static_cast<size_t>(frame) * g.frame_stride + g.off[level];
+	const uint8_t * img = gray_all + plane;
+	for (int i = tid; i < GH * GW; i += 256)
+	{
+		const int gy = y0 - 4 + i / GW, gx = x0 - 4 + i % GW;
+		s_gray[i] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? img[gy * w + gx] : 0;
+	}
+	for (int i = tid; i < SH * SW; i += 256) s_score[i] = 0;
+	if (tid == 0) s_n = 0;
+	__syncthreads();
+	const int thr = g.fast_thr;
+	// compass test over the tile + 1-pixel ring (the ring's scores feed the non-max suppression of the tile's edge)
+	for (int i0 = 0; i0 < SH * SW; i0 += 256)
+	{
+		const int i = i0 + tid;
+		bool maybe = false;
+		if (i < SH * SW)
+		{
+			const int sy = i / SW - 1, sx = i % SW - 1;
+			const int x = x0 + sx, y = y0 + sy;
+			if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3)
+			{
+				const uint8_t * t = s_gray + (sy + 4) * GW + sx + 4;
+				const int v = t[0];
+				const int d0 = abs(v - t[3 * GW]), d8 = abs(v - t[-3 * GW]), d4 = abs(v - t[3]), d12 = abs(v - t[-3]);
+				maybe = !((d0 <= thr && d8 <= thr) || (d4 <= thr && d12 <= thr));
+			}
+		}
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, maybe);
+		if (m)
+		{
+			int base = 0;
+			if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (maybe) s_list[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(i);
+		}
+	}
+	__syncthreads();
+	const int n_list = s_n;
+	for (int k = tid; k < n_list; k += 256)
+	{
+		const int i = s_list[k];
+		const int sy = i / SW - 1, sx = i % SW - 1;
+		s_score[i] = static_cast<uint8_t>(fast_score(s_gray + (sy + 4) * GW + sx + 4, GW, thr));
+	}
+	__syncthreads();
+	// 3x3 strict non-max suppression, KeyPointsFilter::runByPixelsMask and runByImageBorder
+	const int slot = frame * g.n_levels + level;
+	for (int i0 = 0; i0 < kFastTW * kFastTH; i0 += 256)
+	{
+		const int i = i0 + tid;
+		const int ty = i / kFastTW, tx = i % kFastTW;
+		const int x = x0 + tx, y = y0 + ty;
+		bool keep = false;
+		int sc0 = 0;
+		if (x >= g.edge && x < w - g.edge && y >= g.edge && y < h - g.edge && x >= 3 && x < w - 3 && y >= 3 && y < h - 3)
+		{
+			const uint8_t * sc = s_score + (ty + 1) * SW + tx + 1;
+			sc0 = sc[0];
+			keep = sc0 > 0 && sc0 > sc[-SW - 1] && sc0 > sc[-SW] && sc0 > sc[-SW + 1] && sc0 > sc[-1] && sc0 > sc[1] && sc0 > sc[SW - 1] && sc0 > sc[SW] &&
+			       sc0 > sc[SW + 1];
+			if (keep && mask_all && mask_all[plane + static_cast<size_t>(y) * w + x] == 0) keep = false;
+		}
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+		if (m)
+		{
+			int base = 0;
+			if (lane == 0) base = atomicAdd(&cand_count[slot], __popc(m));
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (keep)
+			{
+				const int k = base + __popc(m & ((1u << lane) - 1u));
+				if (k < kOrbCandCap) cand[static_cast<size_t>(slot) * kOrbCandCap + k] = (static_cast<uint32_t>(y * w + x) << 8) | static_cast<uint32_t>(sc0);
+			}
+		}
+	}
+}
+
 // ---- K3: per (frame, level) selection: raster order, retainBest(2N) on FAST score, Harris, retainBest(N),
 //          IC angle.  One CTA; the two retainBest replays are sequential (thread 0). -----------------------
 // Scratch of the block-cooperative replays below.
@@ -472,30 +568,31 @@ struct OrbSelectArgs
 	int * level_n;          // [n_frames][n_levels]
 	int level_cap;
 	int * overflow;         // set when a candidate list had to be truncated
+	int level;              // pyramid level this launch handles (one launch per level: shared memory is sized per level)
+	int cand_cap;           // candidates of this level kept in shared memory (<= kOrbCandCap)
 };
 
 __global__ void __launch_bounds__(kOrbSelectThreads)
 orb_select_kernel(const OrbSelectArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	uint32_t * keys = reinterpret_cast<uint32_t *>(smem_raw);          // [kOrbCandCap]
-	float * resp = reinterpret_cast<float *>(keys + kOrbCandCap);        // [kOrbCandCap]
-	uint16_t * perm = reinterpret_cast<uint16_t *>(resp + kOrbCandCap);  // [kOrbCandCap]
+	const int ccap = a.cand_cap;
+	uint32_t * keys = reinterpret_cast<uint32_t *>(smem_raw);   // [ccap]
+	float * resp = reinterpret_cast<float *>(keys + ccap);        // [ccap]
+	uint16_t * perm = reinterpret_cast<uint16_t *>(resp + ccap);  // [ccap]
 	__shared__ int s_warp_tot[32], s_cut;
-	const SelectScratch sc{perm + kOrbCandCap, s_warp_tot, &s_cut};
+	const SelectScratch sc{perm + ccap, s_warp_tot, &s_cut};
 	__shared__ int s_umax[20];
 
 	const int tid = threadIdx.x;
-	// level-major block order: the level-0 CTAs (most candidates) are scheduled first
-	const int n_frames = gridDim.x / a.g.n_levels;
-	const int level = blockIdx.x / n_frames, frame = blockIdx.x % n_frames;
+	const int level = a.level, frame = blockIdx.x;
 	const int slot = frame * a.g.n_levels + level;
 	const int w = a.g.w[level], h = a.g.h[level];
 	const uint8_t * img = a.gray + static_cast<size_t>(frame) * a.g.frame_stride + a.g.off[level];
 	int n = a.cand_count[slot];
-	if (n > kOrbCandCap)
+	if (n > ccap)
 	{
-		n = kOrbCandCap;
+		n = ccap;
 		if (tid == 0) atomicExch(a.overflow, 1);
 	}
 	int n_pad = 1;
@@ -680,44 +777,52 @@ orb_merge_kernel(const OrbKeypoint * __restrict__ level_kp, const int * __restri
 // ---- K5: 7x7 sigma=2 blur of every level (float sepFilter2D semantics) -------------------------------
 __constant__ float kOrbGauss7[7];
 
+constexpr int kBlurTW = 32, kBlurTH = 16;
+
 __global__ void __launch_bounds__(256)
 orb_blur_kernel(const uint8_t * __restrict__ gray_all, uint8_t * __restrict__ blur_all, const OrbGeom g, int level)
 {
-	constexpr int T = 16;
-	__shared__ float rowf[T + 6][T];
+	// gray tile with a 3-pixel reflect-101 halo -> shared memory, row pass into floats, column pass; every pixel of the
+	// level is read from global memory ~1.6 times instead of once per tap
+	__shared__ uint8_t s_g[kBlurTH + 6][kBlurTW + 8];
+	__shared__ float rowf[kBlurTH + 6][kBlurTW];
 	const int frame = blockIdx.z;
 	const int w = g.w[level], h = g.h[level];
 	const uint8_t * img = gray_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
 	uint8_t * out = blur_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
-	const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
-	const int tid = threadIdx.y * T + threadIdx.x;
-	// row pass (plain order, fused multiply-add) for the T+6 rows the column pass needs
-	for (int i = tid; i < (T + 6) * T; i += T * T)
+	const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
+	const int tid = threadIdx.x;
+	for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256)
 	{
-		const int ry = i / T, rx = i % T;
-		const int y = reflect101(y0 + ry - 3, h);
-		const int x = x0 + rx;
-		float s = 0.f;
-		if (x < w)
-		{
-			const uint8_t * row = img + static_cast<size_t>(y) * w;
-			s = __fmul_rn(static_cast<float>(row[reflect101(x - 3, w)]), kOrbGauss7[0]);
+		const int ry = i / (kBlurTW + 6), rx = i % (kBlurTW + 6);
+		const int y = reflect101(min(y0 + ry - 3, h + 2), h), x = reflect101(min(x0 + rx - 3, w + 2), w);
+		s_g[ry][rx] = img[y * w + x];
+	}
+	__syncthreads();
+	// row pass (plain order, fused multiply-add) for the TH+6 rows the column pass needs
+	for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256)
+	{
+		const int ry = i / kBlurTW, rx = i % kBlurTW;
+		float s = __fmul_rn(static_cast<float>(s_g[ry][rx]), kOrbGauss7[0]);
 #pragma unroll
-			for (int k = 1; k < 7; ++k) s = __fmaf_rn(static_cast<float>(row[reflect101(x - 3 + k, w)]), kOrbGauss7[k], s);
-		}
+		for (int k = 1; k < 7; ++k) s = __fmaf_rn(static_cast<float>(s_g[ry][rx + k]), kOrbGauss7[k], s);
 		rowf[ry][rx] = s;
 	}
 	__syncthreads();
-	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-	if (x >= w || y >= h) return;
 	// column pass (symmetric, fused multiply-add), then saturate_cast<uchar> (round half to even)
-	const int c = threadIdx.y + 3;
-	float s = __fmul_rn(rowf[c][threadIdx.x], kOrbGauss7[3]);
+	const int tx = tid % kBlurTW;
+	for (int ty = tid / kBlurTW; ty < kBlurTH; ty += 256 / kBlurTW)
+	{
+		const int x = x0 + tx, y = y0 + ty;
+		if (x >= w || y >= h) continue;
+		const int c = ty + 3;
+		float s = __fmul_rn(rowf[c][tx], kOrbGauss7[3]);
 #pragma unroll
-	for (int k = 1; k <= 3; ++k) s = __fmaf_rn(__fadd_rn(rowf[c + k][threadIdx.x], rowf[c - k][threadIdx.x]), kOrbGauss7[3 + k], s);
-	int v = __float2int_rn(s);
-	v = v < 0 ? 0 : (v > 255 ? 255 : v);
-	out[static_cast<size_t>(y) * w + x] = static_cast<uint8_t>(v);
+		for (int k = 1; k <= 3; ++k) s = __fmaf_rn(__fadd_rn(rowf[c + k][tx], rowf[c - k][tx]), kOrbGauss7[3 + k], s);
+		int v = __float2int_rn(s);
+		v = v < 0 ? 0 : (v > 255 ? 255 : v);
+		out[static_cast<size_t>(y) * w + x] = static_cast<uint8_t>(v);
+	}
 }
 
 // ---- K6: steered BRIEF (computeOrbDescriptors, WTA_K = 2) --------------------------------------------
@@ -729,12 +834,18 @@ orb_describe_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __res
 {
 	// phase 1: the rotation of each keypoint once per keypoint (double-precision cos / sin rounded to float, as
 	// computeOrbDescriptors does), phase 2: one thread per (keypoint, descriptor byte)
+	// the 256 test locations as floats in shared memory: lanes of a warp read DIFFERENT tests (byte = lane), which the
+	// constant cache would serialise 32 ways
+	__shared__ float4 s_pat[256];
 	__shared__ float s_ca[kOrbDescribeKp], s_sa[kOrbDescribeKp];
 	__shared__ int s_cx[kOrbDescribeKp], s_cy[kOrbDescribeKp], s_level[kOrbDescribeKp];
 	const int frame = blockIdx.y;
 	const int kp0 = blockIdx.x * kOrbDescribeKp;
 	const int n = min(n_kp[frame] - kp0, kOrbDescribeKp);
 	if (n <= 0) return;
+	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+		s_pat[i] = make_float4(static_cast<float>(kOrbPattern31[4 * i]), static_cast<float>(kOrbPattern31[4 * i + 1]),
+		                       static_cast<float>(kOrbPattern31[4 * i + 2]), static_cast<float>(kOrbPattern31[4 * i + 3]));
 	for (int i = threadIdx.x; i < n; i += blockDim.x)
 	{
 		const OrbKeypoint kp = kps[static_cast<size_t>(frame) * cap + kp0 + i];
@@ -756,19 +867,22 @@ orb_describe_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __res
 		const uint8_t * blr = blur_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
 		const float ca = s_ca[ki], sa = s_sa[ki];
 		const int cx = s_cx[ki], cy = s_cy[ki];
-		auto tap = [&](int px, int py) -> int {
-			const float fx = __fsub_rn(__fmul_rn(static_cast<float>(px), ca), __fmul_rn(static_cast<float>(py), sa));
-			const float fy = __fadd_rn(__fmul_rn(static_cast<float>(px), sa), __fmul_rn(static_cast<float>(py), ca));
+		// rotated taps reach at most ceil(13 * sqrt(2)) = 19 pixels from the centre: keypoints further than that from every
+		// border (almost all of them) skip the bounds test
+		const bool inside = cx >= 19 && cy >= 19 && cx < w - 19 && cy < h - 19;
+		auto tap = [&](float px, float py) -> int {
+			const float fx = __fsub_rn(__fmul_rn(px, ca), __fmul_rn(py, sa));
+			const float fy = __fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca));
 			const int x = cx + __float2int_rn(fx), y = cy + __float2int_rn(fy);
-			if (x >= 0 && x < w && y >= 0 && y < h) return blr[static_cast<size_t>(y) * w + x];
-			return raw[static_cast<size_t>(reflect101(y, h)) * w + reflect101(x, w)]; // unblurred reflected border
+			if (inside || (x >= 0 && x < w && y >= 0 && y < h)) return blr[y * w + x];
+			return raw[reflect101(y, h) * w + reflect101(x, w)]; // unblurred reflected border
 		};
 		int val = 0;
 #pragma unroll
 		for (int b = 0; b < 8; ++b)
 		{
-			const signed char * p = kOrbPattern31 + (byte * 8 + b) * 4;
-			const int t0 = tap(p[0], p[1]), t1 = tap(p[2], p[3]);
+			const float4 p = s_pat[byte * 8 + b];
+			const int t0 = tap(p.x, p.y), t1 = tap(p.z, p.w);
 			val |= (t0 < t1) << b;
 		}
 		desc[(static_cast<size_t>(frame) * cap + kp0 + ki) * 32 + byte] = static_cast<uint8_t>(val);
