@@ -132,6 +132,8 @@ struct lcd_engine
 	cudaStream_t copy_stream = nullptr;       // host -> device image chunks of lcd_process_frames
 	std::vector<cudaEvent_t> copy_events;     // one per chunk
 	cudaEvent_t copy_fence = nullptr;
+	cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr}; // fork/join side streams (coarse pyramid levels of the ORB selection)
+	cudaEvent_t aux_fork = nullptr, aux_join[4] = {nullptr, nullptr, nullptr, nullptr};
 	// lcd_process_frames_submit / _wait: two batches in flight
 	struct Flight
 	{
@@ -772,6 +774,12 @@ void lcd_destroy(lcd_engine * e)
 		if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
 		for (cudaEvent_t ev : e->copy_events) cudaEventDestroy(ev);
 		if (e->copy_fence) cudaEventDestroy(e->copy_fence);
+		for (int i = 0; i < 4; ++i)
+		{
+			if (e->aux_stream[i]) cudaStreamDestroy(e->aux_stream[i]);
+			if (e->aux_join[i]) cudaEventDestroy(e->aux_join[i]);
+		}
+		if (e->aux_fork) cudaEventDestroy(e->aux_fork);
 		for (auto & f : e->flights)
 		{
 			if (f.uploaded) cudaEventDestroy(f.uploaded);
@@ -1505,17 +1513,36 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		a.overflow = e->o_overflow.p;
 		// one launch per level: level l holds at most kOrbCandCap >> l candidates in shared memory (192 KB, 96 KB, 48 KB, ...), so
 		// the coarse levels run several CTAs per SM and level 0 (n_frames CTAs) is a single wave for up to 148 frames
-		for (int l = 0; l < g.n_levels; ++l)
+		// The levels are independent and latency-bound: level 0 stays on the caller's stream, the coarser ones fork onto side
+		// streams and join before the merge.
+		LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                                 static_cast<int>(static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2))));
+		if (!e->aux_fork)
+		{
+			LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_fork, cudaEventDisableTiming));
+			for (int i = 0; i < 4; ++i)
+			{
+				LCD_CUDA(e, cudaStreamCreateWithFlags(&e->aux_stream[i], cudaStreamNonBlocking));
+				LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_join[i], cudaEventDisableTiming));
+			}
+		}
+		LCD_CUDA(e, cudaEventRecord(e->aux_fork, s));
+		for (int l = g.n_levels - 1; l >= 0; --l)
 		{
 			a.level = l;
 			a.cand_cap = std::max(2048, kOrbCandCap >> l);
 			const size_t smem = static_cast<size_t>(a.cand_cap) * (4 + 4 + 2 + 2);
-			LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                 static_cast<int>(static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2))));
-			orb_select_kernel<<<n_frames, kOrbSelectThreads, smem, s>>>(a);
-			if (l + 1 < g.n_levels) LCD_CHECK_LAUNCH(e);
+			cudaStream_t ls = s;
+			if (l > 0)
+			{
+				ls = e->aux_stream[(l - 1) & 3];
+				LCD_CUDA(e, cudaStreamWaitEvent(ls, e->aux_fork, 0));
+			}
+			orb_select_kernel<<<n_frames, kOrbSelectThreads, smem, ls>>>(a);
+			LCD_CHECK_LAUNCH(e);
+			if (l > 0 && (l <= 4 || l == g.n_levels - 1)) LCD_CUDA(e, cudaEventRecord(e->aux_join[(l - 1) & 3], ls));
 		}
-		LCD_CHECK_LAUNCH(e);
+		for (int l = 1; l < g.n_levels && l <= 4; ++l) LCD_CUDA(e, cudaStreamWaitEvent(s, e->aux_join[l - 1], 0));
 	}
 	{
 		int pad = 1;

@@ -181,24 +181,24 @@ __device__ __forceinline__ int fast_score(const uint8_t * t, int stride, int thr
 	int best = 0;
 	if (!reject)
 	{
-		// The arc minima are taken on biased, strictly positive values (d + 256 and 256 - d): nvcc 12.9 packs
-		// this min/max chain into VIMNMX.U16x2, whose unsigned lanes mis-order negative differences.
-		unsigned bb = 0u, bd = 0u;
+		// cornerScore: max over the 16 arcs of 9 consecutive ring pixels of min(centre - pixel) (darker arcs) and of
+		// min(pixel - centre) (brighter arcs).  Both polarities ride in one register as biased, strictly positive 16-bit
+		// lanes, low = 256 + d, high = 256 - d (packed = d * (1 - 65536) + 0x01000100), and the minimum over each window of 9
+		// comes from a doubling table (windows of 2, 4, 8, then one more element): 4 x 16 VIMNMX.U16x2 instead of 2 x 8 x 16.
+		uint32_t p[16], q[16];
 #pragma unroll
-		for (int s = 0; s < 16; ++s)
-		{
-			unsigned mb = static_cast<unsigned>(d[s] + 256), md = static_cast<unsigned>(256 - d[s]);
+		for (int i = 0; i < 16; ++i) p[i] = static_cast<uint32_t>(d[i]) * 0xFFFF0001u + 0x01000100u;
 #pragma unroll
-			for (int k = 1; k < 9; ++k)
-			{
-				const int e = d[(s + k) & 15];
-				mb = min(mb, static_cast<unsigned>(e + 256));
-				md = min(md, static_cast<unsigned>(256 - e));
-			}
-			bb = max(bb, mb);
-			bd = max(bd, md);
-		}
-		best = static_cast<int>(max(bb, bd)) - 256;
+		for (int i = 0; i < 16; ++i) q[i] = __vminu2(p[i], p[(i + 1) & 15]);          // windows of 2
+		uint32_t r[16];
+#pragma unroll
+		for (int i = 0; i < 16; ++i) r[i] = __vminu2(q[i], q[(i + 2) & 15]);          // windows of 4
+#pragma unroll
+		for (int i = 0; i < 16; ++i) q[i] = __vminu2(r[i], r[(i + 4) & 15]);          // windows of 8
+		uint32_t m = 0u;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) m = __vmaxu2(m, __vminu2(q[i], p[(i + 8) & 15])); // windows of 9, maximum over the arcs
+		best = static_cast<int>(max(m & 0xFFFFu, m >> 16)) - 256;
 	}
 	return best > thr ? best - 1 : 0;
 }
@@ -646,6 +646,27 @@ orb_select_kernel(const OrbSelectArgs a)
 		const int pos = static_cast<int>(keys[perm[i]] >> 8);
 		const int x0 = pos % w, y0 = pos / w;
 		int A = 0, B = 0, Cc = 0;
+		if (x0 >= 4 && x0 < w - 4 && y0 >= 4 && y0 < h - 4)
+		{
+			// the 9x9 neighbourhood once into registers (81 loads instead of 8 per position of the 7x7 block)
+			int pt[9][9];
+#pragma unroll
+			for (int r = 0; r < 9; ++r)
+#pragma unroll
+				for (int c = 0; c < 9; ++c) pt[r][c] = img[(y0 - 4 + r) * w + x0 - 4 + c];
+#pragma unroll
+			for (int r = 1; r <= 7; ++r)
+#pragma unroll
+				for (int c = 1; c <= 7; ++c)
+				{
+					const int Ix = (pt[r][c + 1] - pt[r][c - 1]) * 2 + (pt[r - 1][c + 1] - pt[r - 1][c - 1]) + (pt[r + 1][c + 1] - pt[r + 1][c - 1]);
+					const int Iy = (pt[r + 1][c] - pt[r - 1][c]) * 2 + (pt[r + 1][c - 1] - pt[r - 1][c - 1]) + (pt[r + 1][c + 1] - pt[r - 1][c + 1]);
+					A += Ix * Ix;
+					B += Iy * Iy;
+					Cc += Ix * Iy;
+				}
+		}
+		else
 		for (int dy = -3; dy <= 3; ++dy)
 			for (int dx = -3; dx <= 3; ++dx)
 			{
@@ -683,20 +704,41 @@ orb_select_kernel(const OrbSelectArgs a)
 		const int pos = static_cast<int>(keys[perm[i]] >> 8);
 		const int x0 = pos % w, y0 = pos / w;
 		int m01 = 0, m10 = 0;
-		for (int u = -half; u <= half; ++u) m10 += u * img[reflect101(y0, h) * w + reflect101(x0 + u, w)];
-		for (int v = 1; v <= half; ++v)
+		if (x0 >= half && x0 < w - half && y0 >= half && y0 < h - half)
 		{
-			int vsum = 0;
-			const int d = s_umax[v];
-			const int yp = reflect101(y0 + v, h), ym = reflect101(y0 - v, h);
-			for (int u = -d; u <= d; ++u)
+			const uint8_t * c = img + y0 * w + x0;
+			for (int u = -half; u <= half; ++u) m10 += u * c[u];
+			for (int v = 1; v <= half; ++v)
 			{
-				const int xx = reflect101(x0 + u, w);
-				const int vp = img[yp * w + xx], vm = img[ym * w + xx];
-				vsum += vp - vm;
-				m10 += u * (vp + vm);
+				int vsum = 0;
+				const int d = s_umax[v];
+				const uint8_t * rp = c + v * w, * rm = c - v * w;
+				for (int u = -d; u <= d; ++u)
+				{
+					const int vp = rp[u], vm = rm[u];
+					vsum += vp - vm;
+					m10 += u * (vp + vm);
+				}
+				m01 += v * vsum;
 			}
-			m01 += v * vsum;
+		}
+		else
+		{
+			for (int u = -half; u <= half; ++u) m10 += u * img[reflect101(y0, h) * w + reflect101(x0 + u, w)];
+			for (int v = 1; v <= half; ++v)
+			{
+				int vsum = 0;
+				const int d = s_umax[v];
+				const int yp = reflect101(y0 + v, h), ym = reflect101(y0 - v, h);
+				for (int u = -d; u <= d; ++u)
+				{
+					const int xx = reflect101(x0 + u, w);
+					const int vp = img[yp * w + xx], vm = img[ym * w + xx];
+					vsum += vp - vm;
+					m10 += u * (vp + vm);
+				}
+				m01 += v * vsum;
+			}
 		}
 		OrbKeypoint kp;
 		kp.x = __fmul_rn(static_cast<float>(x0), sf);
