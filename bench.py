@@ -208,7 +208,7 @@ def run_reference(args):
     hit = float(np.mean([world.sig_place[r[4] - 1] == places[b] for b, r in enumerate(res)]))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": workload_config(per_step, "cpu"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{per_step} frames/step x {steps} steps of the same workload: cv2.ORB (OpenCV 4.13, 1 thread per frame) + oracle port of "
