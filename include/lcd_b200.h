@@ -329,6 +329,18 @@ int lcd_shard_set_row_offset(lcd_engine * e, int global_row_offset);
  * (0xFFFFFFFF = none).  All-gather these across ranks, then call stage 2 on every rank. */
 int lcd_shard_knn2_keys_dev(lcd_engine * e, const void * d_queries, int nq, uint32_t * d_keys_out,
                             void * stream);
+/* stage 2, sharded by FRAME (what scales): every rank resolves only its own frames [frame0, frame0+n_frames) of the job's
+ * n_frames_total — merge of the G gathered key sets [G][2 * n_frames_total * nq] + NNDR / new-word pass — and writes their
+ * word ids (d_word_ids_out[n_frames*nq], 0 in padding rows; d_n_per_frame[n_frames_total] valid descriptors per frame or NULL).
+ * All-gather the word ids, then lcd_shard_score_ids_dev on every rank accumulates this rank's share (its word range) of the
+ * TF-IDF scores of ALL frames from the ids (uUniqueKeys + "id > 0" filter of Memory::computeLikelihood, Memory.cpp:2238-2256)
+ * into d_scores_out[n_frames*ns]; all-reduce(sum), then lcd_shard_finalize_dev. */
+int lcd_shard_resolve_frames_dev(lcd_engine * e, const void * d_queries_all, int frame0, int n_frames, int n_frames_total,
+                                 int nq_per_frame, const uint32_t * d_keys_gathered, int n_ranks, const int * d_row_ids,
+                                 int last_word_id, int incremental, float nndr, int new_words_compared_together,
+                                 const int * d_n_per_frame, int * d_word_ids_out, void * stream);
+int lcd_shard_score_ids_dev(lcd_engine * e, const int * d_word_ids_all, int n_frames, int nq_per_frame,
+                            const int * d_sig_ids, int ns, int n_total, long long * d_scores_out, void * stream);
 /* stage 2: merge G gathered key sets [G][2*nq], run the replicated NNDR / new-word pass,
  * and accumulate this rank's share of the TF-IDF scores into d_scores_out[n_frames*ns]
  * (fixed-point int64, exact and order-independent; all-reduce(sum) them, then call

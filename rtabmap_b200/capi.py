@@ -141,6 +141,8 @@ SIGNATURES = {
     "lcd_shard_set_row_offset": (_I, [_P, _I]),
     "lcd_shard_knn2_keys_dev": (_I, [_P, _P, _I, _P, _P]),
     "lcd_shard_resolve_score_dev": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
+    "lcd_shard_resolve_frames_dev": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _F, _I, _P, _P, _P]),
+    "lcd_shard_score_ids_dev": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P]),
     "lcd_shard_finalize_dev": (_I, [_P, _P, _I, _P, _P]),
     "lcd_profile_enable": (_I, [_P, _I]),
     "lcd_profile_read": (_I, [_P, _I, _P, _P]),
@@ -602,6 +604,19 @@ class Engine:
             self._h, C.c_void_p(d_queries), n_frames, nq, C.c_void_p(d_keys_gathered), n_ranks, C.c_void_p(d_row_ids), total_rows,
             last_word_id, int(incremental), float(nndr), int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total),
             C.c_void_p(d_words_out or None), C.c_void_p(d_scores_out or None), C.c_void_p(stream or None)))
+
+    def shard_resolve_frames_dev(self, d_queries_all: int, frame0: int, n_frames: int, n_frames_total: int, nq: int, d_keys_gathered: int,
+                                 n_ranks: int, d_row_ids: int, last_word_id: int, d_n_per_frame: int, d_words_out: int, incremental: bool = True,
+                                 nndr: float = 0.8, cmp_new: bool = True, stream: int = 0):
+        self._check(self._lib.lcd_shard_resolve_frames_dev(
+            self._h, C.c_void_p(d_queries_all), frame0, n_frames, n_frames_total, nq, C.c_void_p(d_keys_gathered), n_ranks, C.c_void_p(d_row_ids),
+            last_word_id, int(incremental), float(nndr), int(cmp_new), C.c_void_p(d_n_per_frame or None), C.c_void_p(d_words_out),
+            C.c_void_p(stream or None)))
+
+    def shard_score_ids_dev(self, d_word_ids_all: int, n_frames: int, nq: int, d_sig_ids: int, ns: int, n_total: int, d_scores_out: int,
+                            stream: int = 0):
+        self._check(self._lib.lcd_shard_score_ids_dev(self._h, C.c_void_p(d_word_ids_all), n_frames, nq, C.c_void_p(d_sig_ids), ns, int(n_total),
+                                                       C.c_void_p(d_scores_out), C.c_void_p(stream or None)))
 
     def shard_finalize_dev(self, d_scores: int, n: int, d_like_out: int, stream: int = 0):
         self._check(self._lib.lcd_shard_finalize_dev(self._h, C.c_void_p(d_scores), n, C.c_void_p(d_like_out), C.c_void_p(stream or None)))

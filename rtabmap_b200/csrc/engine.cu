@@ -2397,6 +2397,60 @@ int lcd_shard_resolve_score_dev(lcd_engine * e, const void * d_queries, int n_fr
 	return LCD_OK;
 }
 
+int lcd_shard_resolve_frames_dev(lcd_engine * e, const void * d_queries_all, int frame0, int n_frames, int n_frames_total, int nq_per_frame,
+                                 const uint32_t * d_keys_gathered, int n_ranks, const int * d_row_ids, int last_word_id, int incremental,
+                                 float nndr, int new_words_compared_together, const int * d_n_per_frame, int * d_word_ids_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_queries_all || !d_keys_gathered || !d_row_ids || !d_word_ids_out || n_frames <= 0 || n_ranks <= 0 || frame0 < 0 ||
+	    frame0 + n_frames > n_frames_total)
+		LCD_FAIL(e, LCD_ERR_INVALID, "null argument or frame range outside the job");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	ResolveArgs a{};
+	a.queries = static_cast<const uint32_t *>(d_queries_all) + static_cast<size_t>(frame0) * nq_per_frame * e->nw;
+	a.nq = nq_per_frame;
+	a.nq_total = n_frames_total * nq_per_frame;                                     // stride between the gathered key sets
+	a.partial = reinterpret_cast<const uint2 *>(d_keys_gathered) + static_cast<size_t>(frame0) * nq_per_frame;
+	a.n_chunks = n_ranks;
+	a.row_ids = d_row_ids;
+	a.incremental = incremental;
+	a.nndr = nndr;
+	a.cmp_new = new_words_compared_together;
+	a.last_word_id = last_word_id;
+	a.word_ids_out = d_word_ids_out;
+	a.nq_frame = d_n_per_frame ? d_n_per_frame + frame0 : nullptr;
+	return launch_resolve(e, a, n_frames, s);
+}
+
+int lcd_shard_score_ids_dev(lcd_engine * e, const int * d_word_ids_all, int n_frames, int nq_per_frame, const int * d_sig_ids, int ns, int n_total,
+                            long long * d_scores_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_word_ids_all || !d_sig_ids || !d_scores_out || n_frames <= 0 || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d words per signature", kMaxFrameQueries);
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	LCD_TRY(ensure_uq(e, n_frames, nq_per_frame, s));
+	LCD_TRY(ensure_acc(e, n_frames));
+	LCD_CUDA(e, zero_fill_async(e->acc.p, static_cast<size_t>(e->acc_stride) * n_frames * sizeof(long long), s));
+	ResolveArgs a{};
+	a.nq = nq_per_frame;
+	fill_prep(e, a, static_cast<float>(n_total), 1);
+	int nq_pad = 32;
+	while (nq_pad < nq_per_frame) nq_pad <<= 1;
+	prof_mark(e, LCD_PROF_RESOLVE, s);
+	prep_from_ids_kernel<<<n_frames, kResolveThreads, nq_pad * sizeof(uint32_t), s>>>(d_word_ids_all, a);
+	prof_mark(e, LCD_PROF_RESOLVE, s);
+	LCD_CHECK_LAUNCH(e);
+	LCD_TRY(launch_score(e, n_frames, nq_per_frame, s));
+	dim3 grid((ns + 255) / 256, n_frames);
+	gather_fixed_kernel<<<grid, 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), d_sig_ids, ns, d_scores_out);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
 int lcd_shard_finalize_dev(lcd_engine * e, const long long * d_scores, int n, float * d_likelihood_out, void * stream)
 {
 	if (!e) return LCD_ERR_INVALID;
