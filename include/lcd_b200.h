@@ -277,6 +277,15 @@ int lcd_process_batch(lcd_engine * e, const void * queries, const float * uv, in
                       const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp,
                       int * word_ids_out, float * likelihood_out, int * hypothesis_out,
                       lcd_verify_result * results);
+/* replaces: Rtabmap::adjustLikelihood (Rtabmap.cpp:5691-5760; uMean / uVariance of the values > 0, UMath.h:419-431, :512-526),
+ * the step between Memory::computeLikelihood and the Bayes filter.  likelihood[n_frames*ns] are rows in ascending signature id
+ * order (as lcd_index_score / lcd_localize_batch return them); adjusted_out[n_frames*(ns+1)]: element 0 of every row is the virtual
+ * place, then the ns adjusted values.  virtual_place_ratio = Rtabmap/VirtualPlaceLikelihoodRatio (0 or 1).  Bit-identical to the
+ * reference's float arithmetic (the sums run in list order). */
+int lcd_adjust_likelihood(lcd_engine * e, const float * likelihood, int n_frames, int ns, int virtual_place_ratio,
+                          float * adjusted_out);
+int lcd_adjust_likelihood_dev(lcd_engine * e, const float * d_likelihood, int n_frames, int ns, int virtual_place_ratio,
+                              float * d_adjusted_out, void * stream);
 /* Same on device-resident inputs, asynchronous on `stream`; results stay in engine buffers until
  * lcd_process_fetch copies them back (hypothesis ids, verification results). */
 int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * d_uv, int n_frames, int nq_per_frame,

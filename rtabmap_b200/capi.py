@@ -123,6 +123,8 @@ SIGNATURES = {
     "lcd_index_total_refs": (C.c_longlong, [_P]),
     "lcd_index_get_refs": (_I, [_P, _I, _P, _P, _I]),
     "lcd_index_score": (_I, [_P, _P, _I, _P, _I, _I, _P]),
+    "lcd_adjust_likelihood": (_I, [_P, _P, _I, _I, _I, _P]),
+    "lcd_adjust_likelihood_dev": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "lcd_localize_batch": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P]),
     "lcd_localize_batch_dev": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
     "lcd_match_pairs": (_I, [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
@@ -415,6 +417,15 @@ class Engine:
         return out
 
     # -- batched localisation ------------------------------------------------------------------
+    def adjust_likelihood(self, likelihood, virtual_place_ratio: int = 0) -> np.ndarray:
+        """Rtabmap::adjustLikelihood of rows [n_frames, ns] (or one row): returns [n_frames, ns + 1], column 0 = virtual place."""
+        l = np.ascontiguousarray(likelihood, np.float32)
+        one = l.ndim == 1
+        l2 = l.reshape(1, -1) if one else l
+        out = np.zeros((l2.shape[0], l2.shape[1] + 1), np.float32)
+        self._check(self._lib.lcd_adjust_likelihood(self._h, _ptr(l2), l2.shape[0], l2.shape[1], int(virtual_place_ratio), _ptr(out)))
+        return out[0] if one else out
+
     def localize_batch(self, queries, n_frames: int, sig_ids, n_total: int, incremental: bool = True, nndr: float = 0.8,
                        cmp_new: bool = True, want_words: bool = True, want_likelihood: bool = True,
                        out_words=None, out_like=None):

@@ -1321,6 +1321,34 @@ int lcd_index_score(lcd_engine * e, const int * query_word_ids, int nq, const in
 	return LCD_OK;
 }
 
+int lcd_adjust_likelihood_dev(lcd_engine * e, const float * d_likelihood, int n_frames, int ns, int virtual_place_ratio, float * d_adjusted_out,
+                              void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!d_likelihood || !d_adjusted_out || n_frames <= 0 || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "likelihood is empty");
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	adjust_likelihood_kernel<<<n_frames, kAdjustThreads, 0, s>>>(d_likelihood, ns, virtual_place_ratio, d_adjusted_out);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+int lcd_adjust_likelihood(lcd_engine * e, const float * likelihood, int n_frames, int ns, int virtual_place_ratio, float * adjusted_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!likelihood || !adjusted_out || n_frames <= 0 || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "likelihood is empty");
+	cudaStream_t s = e->stream;
+	const size_t n_in = static_cast<size_t>(n_frames) * ns, n_out = static_cast<size_t>(n_frames) * (ns + 1);
+	LCD_CUDA(e, e->d_f1.reserve(n_in, 0, false, s));
+	LCD_CUDA(e, e->d_f2.reserve(n_out, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_f1.p, likelihood, n_in * sizeof(float), cudaMemcpyHostToDevice, s));
+	LCD_TRY(lcd_adjust_likelihood_dev(e, e->d_f1.p, n_frames, ns, virtual_place_ratio, e->d_f2.p, s));
+	LCD_CUDA(e, cudaMemcpyAsync(adjusted_out, e->d_f2.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
 // ---- batched localisation ------------------------------------------------------------------
 int lcd_localize_batch_dev(lcd_engine * e, const void * d_queries, int n_frames, int nq_per_frame, int incremental, float nndr,
                            int new_words_compared_together, const int * d_sig_ids, int ns, int n_total,

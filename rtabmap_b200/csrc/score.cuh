@@ -214,4 +214,131 @@ __global__ void gather_rows_kernel(const uint32_t * __restrict__ src, const int 
 	dst[i] = src[static_cast<size_t>(src_row[r]) * nw + c];
 }
 
+// ---- Rtabmap::adjustLikelihood (Rtabmap.cpp:5691-5760), one CTA per frame ------------------------------------
+// in: like[frame][ns] raw likelihood of the ids the caller listed (ascending id order, as the std::map iterates);
+// out: adj[frame][ns + 1], element 0 = the virtual place.  uMean / uVariance (UMath.h:419-431, :512-526) are float sums in
+// list order over the values > 0: the positive values are compacted chunk by chunk (order preserved) and thread 0 adds each
+// chunk sequentially, so mean, standard deviation and every adjusted value are bit-identical to the reference arithmetic.
+constexpr int kAdjustThreads = 256;
+constexpr int kAdjustChunk = 2048;
+
+__device__ inline int adjust_compact_chunk(const float * __restrict__ row, int c0, int n, float * s_val, int * s_cnt)
+{
+	// stable compaction of row[c0 .. c0+n) > 0 into s_val; returns the count (valid in all threads)
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	__shared__ int s_warp[kAdjustThreads / 32];
+	int base = 0;
+	for (int i0 = 0; i0 < n; i0 += kAdjustThreads)
+	{
+		const int i = i0 + tid;
+		const float v = i < n ? row[c0 + i] : 0.f;
+		const bool keep = i < n && v > 0.f;
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+		if (lane == 0) s_warp[warp] = __popc(m);
+		__syncthreads();
+		int off = base;
+		for (int w = 0; w < warp; ++w) off += s_warp[w];
+		int tot = 0;
+		for (int w = 0; w < kAdjustThreads / 32; ++w) tot += s_warp[w];
+		if (keep) s_val[off + __popc(m & ((1u << lane) - 1u))] = v;
+		base += tot;
+		__syncthreads();
+	}
+	if (tid == 0) *s_cnt = base;
+	__syncthreads();
+	return *s_cnt;
+}
+
+__global__ void __launch_bounds__(kAdjustThreads)
+adjust_likelihood_kernel(const float * __restrict__ like, int ns, int virtual_place_ratio, float * __restrict__ adj)
+{
+	__shared__ float s_val[kAdjustChunk];
+	__shared__ int s_cnt;
+	__shared__ float s_acc, s_mean, s_std, s_max[kAdjustThreads / 32];
+	__shared__ long long s_n;
+	const int tid = threadIdx.x;
+	const float * row = like + static_cast<size_t>(blockIdx.x) * ns;
+	float * out = adj + static_cast<size_t>(blockIdx.x) * (ns + 1);
+	if (tid == 0)
+	{
+		s_acc = 0.f;
+		s_n = 0;
+	}
+	__syncthreads();
+	// pass 1: mean of the values > 0
+	for (int c0 = 0; c0 < ns; c0 += kAdjustChunk)
+	{
+		const int cnt = adjust_compact_chunk(row, c0, min(kAdjustChunk, ns - c0), s_val, &s_cnt);
+		if (tid == 0)
+		{
+			float m = s_acc;
+			for (int i = 0; i < cnt; ++i) m = __fadd_rn(m, s_val[i]);
+			s_acc = m;
+			s_n += cnt;
+		}
+		__syncthreads();
+	}
+	if (tid == 0)
+	{
+		s_mean = s_n ? __fdiv_rn(s_acc, static_cast<float>(static_cast<unsigned long long>(s_n))) : 0.f;
+		s_acc = 0.f;
+	}
+	__syncthreads();
+	const float mean = s_mean;
+	const long long n_pos = s_n;
+	// pass 2: variance (n - 1 in the denominator)
+	if (n_pos > 1)
+	{
+		for (int c0 = 0; c0 < ns; c0 += kAdjustChunk)
+		{
+			const int cnt = adjust_compact_chunk(row, c0, min(kAdjustChunk, ns - c0), s_val, &s_cnt);
+			if (tid == 0)
+			{
+				float sum = s_acc;
+				for (int i = 0; i < cnt; ++i)
+				{
+					const float d = __fsub_rn(s_val[i], mean);
+					sum = __fadd_rn(sum, __fmul_rn(d, d));
+				}
+				s_acc = sum;
+			}
+			__syncthreads();
+		}
+	}
+	if (tid == 0)
+	{
+		const float var = n_pos > 1 ? __fdiv_rn(s_acc, static_cast<float>(static_cast<unsigned long long>(n_pos - 1))) : 0.f;
+		s_std = sqrtf(var);
+	}
+	__syncthreads();
+	const float sd = s_std;
+	const float epsilon = 0.0001f;
+	const float thr = __fadd_rn(mean, sd);
+	float mx = 0.f;
+	for (int i = tid; i < ns; i += kAdjustThreads)
+	{
+		const float value = row[i];
+		float r = 1.0f;
+		if (value > thr)
+		{
+			if (virtual_place_ratio == 0 && mean != 0.f) r = __fdiv_rn(__fsub_rn(value, __fsub_rn(sd, epsilon)), mean);
+			else if (virtual_place_ratio != 0 && sd != 0.f) r = __fdiv_rn(__fsub_rn(value, mean), sd);
+		}
+		out[1 + i] = r;
+		mx = fmaxf(mx, value);
+	}
+	for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o));
+	if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+	__syncthreads();
+	if (tid == 0)
+	{
+		float m = 0.f;
+		for (int w = 0; w < kAdjustThreads / 32; ++w) m = fmaxf(m, s_max[w]);
+		float vp = 2.0f;
+		if (virtual_place_ratio == 0 && sd > epsilon && m != 0.f) vp = __fadd_rn(__fdiv_rn(mean, sd), 1.0f);
+		else if (virtual_place_ratio != 0 && m > mean) vp = __fadd_rn(__fdiv_rn(sd, __fsub_rn(m, mean)), 1.0f);
+		out[0] = vp;
+	}
+}
+
 } // namespace lcd

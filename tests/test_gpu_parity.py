@@ -263,3 +263,30 @@ def test_vwdictionary_mirror_interface():
     d.update()
     lik = d.computeLikelihood([some, some, 0, -1], [1, 2, 3, 4, 9], 5)
     assert set(lik) == {1, 2, 3, 4, 9} and lik[9] > 0
+
+
+# ---------------------------------------------------------------- adjustLikelihood ---------------
+@pytest.mark.parametrize("ratio", [0, 1])
+def test_adjust_likelihood_bit_exact(ratio):
+    """Rtabmap::adjustLikelihood: mean / standard deviation of the values > 0 summed in list order, so the CUDA result has to
+    equal the restated float arithmetic bit for bit; rows with no / one / equal positive values take the reference's branches."""
+    rng = np.random.default_rng(40 + ratio)
+    eng = Engine()
+    rows = []
+    for n in (1, 2, 7, 300, 2048, 2049, 10000):
+        r = np.abs(rng.standard_normal(n)).astype(np.float32) * 0.01
+        r[rng.random(n) < 0.6] = 0.0          # most signatures share no word with the frame
+        if n >= 7:
+            r[rng.integers(0, n, 3)] = rng.random(3).astype(np.float32)   # a few loop-closure candidates
+        rows.append(r)
+    rows.append(np.zeros(50, np.float32))                       # nothing in common with any signature
+    one = np.zeros(50, np.float32); one[17] = 0.25; rows.append(one)   # a single positive value: variance 0
+    rows.append(np.full(64, 0.125, np.float32))                 # all equal: stdDev 0
+    for r in rows:
+        got = eng.adjust_likelihood(r, ratio)
+        want = orc.adjust_likelihood(np.concatenate([[0.0], r]).astype(np.float32), ratio)
+        assert got.shape == want.shape and np.array_equal(got, want), (len(r), ratio)
+    batch = np.stack([rows[3], rows[3][::-1].copy(), np.zeros(300, np.float32)])
+    got = eng.adjust_likelihood(batch, ratio)
+    for b in range(3):
+        assert np.array_equal(got[b], orc.adjust_likelihood(np.concatenate([[0.0], batch[b]]).astype(np.float32), ratio))
