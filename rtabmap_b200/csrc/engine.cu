@@ -133,7 +133,7 @@ struct lcd_engine
 	std::vector<cudaEvent_t> copy_events;     // one per chunk
 	cudaEvent_t copy_fence = nullptr;
 	cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr}; // fork/join side streams (coarse pyramid levels of the ORB selection)
-	cudaEvent_t aux_fork = nullptr, aux_join[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t aux_fork = nullptr, aux_blur_done = nullptr, aux_join[4] = {nullptr, nullptr, nullptr, nullptr};
 	// lcd_process_frames_submit / _wait: two batches in flight
 	struct Flight
 	{
@@ -780,6 +780,7 @@ void lcd_destroy(lcd_engine * e)
 			if (e->aux_join[i]) cudaEventDestroy(e->aux_join[i]);
 		}
 		if (e->aux_fork) cudaEventDestroy(e->aux_fork);
+		if (e->aux_blur_done) cudaEventDestroy(e->aux_blur_done);
 		for (auto & f : e->flights)
 		{
 			if (f.uploaded) cudaEventDestroy(f.uploaded);
@@ -1523,6 +1524,30 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		orb_down_kernel<<<grd, blk, 0, s>>>(w_gray, w_mask, g, l);
 		LCD_CHECK_LAUNCH(e);
 	}
+	if (!e->aux_fork)
+	{
+		LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_fork, cudaEventDisableTiming));
+		LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_blur_done, cudaEventDisableTiming));
+		for (int i = 0; i < 4; ++i)
+		{
+			LCD_CUDA(e, cudaStreamCreateWithFlags(&e->aux_stream[i], cudaStreamNonBlocking));
+			LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_join[i], cudaEventDisableTiming));
+		}
+	}
+	if (d_desc)
+	{
+		// the blurred pyramid only feeds the descriptors: it runs on a side stream under FAST and the (latency-bound) selection
+		LCD_CUDA(e, cudaEventRecord(e->aux_fork, s));
+		cudaStream_t bs = e->aux_stream[3];
+		LCD_CUDA(e, cudaStreamWaitEvent(bs, e->aux_fork, 0));
+		for (int l = 0; l < g.n_levels; ++l)
+		{
+			dim3 grd((g.w[l] + kBlurTW - 1) / kBlurTW, (g.h[l] + kBlurTH - 1) / kBlurTH, n_frames);
+			orb_blur_kernel<<<grd, 256, 0, bs>>>(w_gray, w_blur, g, l);
+			LCD_CHECK_LAUNCH(e);
+		}
+		LCD_CUDA(e, cudaEventRecord(e->aux_blur_done, bs));
+	}
 	for (int l = 0; l < g.n_levels; ++l)
 	{
 		dim3 grd((g.w[l] + kFastTW - 1) / kFastTW, (g.h[l] + kFastTH - 1) / kFastTH, n_frames);
@@ -1545,15 +1570,6 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		// streams and join before the merge.
 		LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                 static_cast<int>(static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2))));
-		if (!e->aux_fork)
-		{
-			LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_fork, cudaEventDisableTiming));
-			for (int i = 0; i < 4; ++i)
-			{
-				LCD_CUDA(e, cudaStreamCreateWithFlags(&e->aux_stream[i], cudaStreamNonBlocking));
-				LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_join[i], cudaEventDisableTiming));
-			}
-		}
 		LCD_CUDA(e, cudaEventRecord(e->aux_fork, s));
 		for (int l = g.n_levels - 1; l >= 0; --l)
 		{
@@ -1563,14 +1579,14 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 			cudaStream_t ls = s;
 			if (l > 0)
 			{
-				ls = e->aux_stream[(l - 1) & 3];
+				ls = e->aux_stream[(l - 1) % 3];
 				LCD_CUDA(e, cudaStreamWaitEvent(ls, e->aux_fork, 0));
 			}
 			orb_select_kernel<<<n_frames, kOrbSelectThreads, smem, ls>>>(a);
 			LCD_CHECK_LAUNCH(e);
-			if (l > 0 && (l <= 4 || l == g.n_levels - 1)) LCD_CUDA(e, cudaEventRecord(e->aux_join[(l - 1) & 3], ls));
+			if (l > 0 && l <= 3) LCD_CUDA(e, cudaEventRecord(e->aux_join[l - 1], ls));
 		}
-		for (int l = 1; l < g.n_levels && l <= 4; ++l) LCD_CUDA(e, cudaStreamWaitEvent(s, e->aux_join[l - 1], 0));
+		for (int l = 1; l < g.n_levels && l <= 3; ++l) LCD_CUDA(e, cudaStreamWaitEvent(s, e->aux_join[l - 1], 0));
 	}
 	{
 		int pad = 1;
@@ -1581,12 +1597,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	}
 	if (d_desc)
 	{
-		for (int l = 0; l < g.n_levels; ++l)
-		{
-			dim3 grd((g.w[l] + kBlurTW - 1) / kBlurTW, (g.h[l] + kBlurTH - 1) / kBlurTH, n_frames);
-			orb_blur_kernel<<<grd, 256, 0, s>>>(w_gray, w_blur, g, l);
-			LCD_CHECK_LAUNCH(e);
-		}
+		LCD_CUDA(e, cudaStreamWaitEvent(s, e->aux_blur_done, 0));
 		dim3 grd((cap + kOrbDescribeKp - 1) / kOrbDescribeKp, n_frames);
 		orb_describe_kernel<<<grd, 256, 0, s>>>(w_gray, w_blur, g, d_kp, d_n, cap, d_desc);
 		LCD_CHECK_LAUNCH(e);
