@@ -21,7 +21,8 @@
 // /root/reference by oracle/Makefile) in tests/test_oracle_ref.py; likelihood is checked against the
 // reference's only golden vector for this path, archive/2010-LoopClosure/Tests/TestComputeLikelihood.m
 // (tests/golden/tfidf_golden.json, made by tests/golden/make_tfidf_golden.py).  The NNDR / new-word
-// loop has no golden vector in the reference: parity there is oracle-vs-CUDA only.
+// loop and adjust_likelihood have no golden vector in the reference: PARITY UNPINNED
+// for those two — oracle-vs-CUDA only, plus hand-checked cases in tests/test_oracle_golden.py.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
