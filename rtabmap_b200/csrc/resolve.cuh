@@ -116,7 +116,7 @@ __device__ __forceinline__ void load_desc(const uint32_t * __restrict__ base, in
 #pragma unroll
 	for (int v = 0; v < NW / 4; ++v)
 	{
-		const uint4 x = __ldg(src + v);
+		const uint4 x = src[v]; // plain load: callers pass global or shared memory
 		q[4 * v + 0] = x.x;
 		q[4 * v + 1] = x.y;
 		q[4 * v + 2] = x.z;
@@ -232,6 +232,7 @@ __device__ int resolve_rounds(const uint32_t * __restrict__ fq, int nq, const ui
                               uint16_t * L, uint16_t * rank, uint8_t * flag, uint8_t * flag2, int * s_nL, float nndr, int cmp_new)
 {
 	__shared__ uint32_t s_ext[64];
+	__shared__ uint16_t s_dl[32][34]; // s_dl[e][j] = distance between descriptors c0+e and c0+j of the current chunk
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
 	(void)flag2;
@@ -257,10 +258,23 @@ __device__ int resolve_rounds(const uint32_t * __restrict__ fq, int nq, const ui
 			const int i = c0 + e;
 			if (i >= nq) continue;
 			uint32_t k1 = kKeyNone, k2 = kKeyNone;
+			uint32_t qi[NW];
+			load_desc<NW>(fq, i, qi);
+			{
+				// distances to the chunk-mates (one per lane), for the dependency pass of warp 0 below: computed here by
+				// 32 warps in parallel instead of 1024 shuffled distances by one warp
+				uint32_t qm[NW];
+				const int jm = c0 + lane;
+				if (jm < nq) load_desc<NW>(fq, jm, qm);
+				else
+				{
+#pragma unroll
+					for (int v = 0; v < NW; ++v) qm[v] = 0u;
+				}
+				s_dl[e][lane] = static_cast<uint16_t>(hamming<NW, 2>(qi, qm));
+			}
 			if (nL > 0)
 			{
-				uint32_t qi[NW];
-				load_desc<NW>(fq, i, qi);
 				for (int k = lane; k < nL; k += 32)
 				{
 					uint32_t qj[NW];
@@ -289,22 +303,9 @@ __device__ int resolve_rounds(const uint32_t * __restrict__ fq, int nq, const ui
 		{
 			const int i = c0 + lane;
 			const bool valid = i < nq;
-			uint32_t qi[NW];
-			if (valid) load_desc<NW>(fq, i, qi);
-			else
-			{
-#pragma unroll
-				for (int v = 0; v < NW; ++v) qi[v] = 0u;
-			}
 			uint32_t dl[32]; // distance to chunk-mate j (only j < lane is used)
 #pragma unroll
-			for (int jl = 0; jl < 32; ++jl)
-			{
-				uint32_t d = 0;
-#pragma unroll
-				for (int v = 0; v < NW; ++v) d += __popc(qi[v] ^ __shfl_sync(0xFFFFFFFFu, qi[v], jl));
-				dl[jl] = d;
-			}
+			for (int jl = 0; jl < 32; ++jl) dl[jl] = s_dl[lane][jl];
 			const uint32_t a1 = valid ? sa1[i] : kKeyNone, a2 = valid ? sa2[i] : kKeyNone;
 			const uint32_t e1 = s_ext[2 * lane], e2 = s_ext[2 * lane + 1];
 			int bt;

@@ -51,7 +51,7 @@ struct MatchArgs
 
 __host__ __device__ inline size_t match_smem_bytes(int cap, int nw)
 {
-	return static_cast<size_t>(cap) * (4 + 4 + 4 + 2 + 2 + 1 + 1 + 4 + 4 + 2 + 2) + static_cast<size_t>(cap) * nw * 4 + 128;
+	return static_cast<size_t>(cap) * (4 + 4 + 4 + 2 + 2 + 1 + 1 + 4 + 4 + 2 + 2) + 2 * static_cast<size_t>(cap) * nw * 4 + 128;
 }
 
 __device__ long long g_match_dbg[8];
@@ -64,8 +64,9 @@ pair_match_kernel(const MatchArgs a)
 	MATCH_PHASE(0);
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int cap = a.cap;
-	uint32_t * dict = reinterpret_cast<uint32_t *>(smem_raw);             // [cap][NW]
-	uint32_t * sa1 = dict + static_cast<size_t>(cap) * NW;                // [cap]
+	uint32_t * dict = reinterpret_cast<uint32_t *>(smem_raw);             // [cap][NW] words of the temporary dictionary
+	uint32_t * sdesc = dict + static_cast<size_t>(cap) * NW;              // [cap][NW] the side being quantised (FROM, then TO)
+	uint32_t * sa1 = sdesc + static_cast<size_t>(cap) * NW;               // [cap]
 	uint32_t * sa2 = sa1 + cap;
 	int * res = reinterpret_cast<int *>(sa2 + cap);
 	int * cntF = res + cap;
@@ -90,6 +91,7 @@ pair_match_kernel(const MatchArgs a)
 	const uint32_t * T = a.desc_to + tbase * NW;
 
 	// ---- FROM side: addNewWords(descriptorsFrom, 1) on an empty dictionary -------------------
+	for (int i = tid; i < nf * NW; i += blockDim.x) sdesc[i] = F[i];   // the scans below re-read every descriptor ~nf/32 times
 	for (int i = tid; i < nf; i += blockDim.x)
 	{
 		sa1[i] = kKeyNone;
@@ -99,7 +101,7 @@ pair_match_kernel(const MatchArgs a)
 	}
 	__syncthreads();
 	int n_dict = 0;
-	if (nf > 0) n_dict = resolve_rounds<NW>(F, nf, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
+	if (nf > 0) n_dict = resolve_rounds<NW>(sdesc, nf, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
 	__syncthreads();
 	MATCH_PHASE(1);
 	for (int k = tid; k < n_dict; k += blockDim.x)
@@ -107,7 +109,7 @@ pair_match_kernel(const MatchArgs a)
 		cntF[k] = 0;
 		cntT[k] = 0;
 		uint32_t q[NW];
-		load_desc<NW>(F, L[k], q);
+		load_desc<NW>(sdesc, L[k], q);
 #pragma unroll
 		for (int v = 0; v < NW; ++v) dict[static_cast<size_t>(k) * NW + v] = q[v];
 	}
@@ -123,10 +125,13 @@ pair_match_kernel(const MatchArgs a)
 
 	MATCH_PHASE(2);
 	// ---- TO side: update(); addNewWords(descriptorsTo, 2) --------------------------------------
+	__syncthreads();
+	for (int i = tid; i < nt * NW; i += blockDim.x) sdesc[i] = T[i];
+	__syncthreads();
 	for (int j = tid; j < nt; j += blockDim.x)
 	{
 		uint32_t q[NW];
-		load_desc<NW>(T, j, q);
+		load_desc<NW>(sdesc, j, q);
 		uint32_t k1 = kKeyNone, k2 = kKeyNone;
 		for (int k = 0; k < n_dict; ++k)
 		{
@@ -152,7 +157,7 @@ pair_match_kernel(const MatchArgs a)
 	}
 	__syncthreads();
 	MATCH_PHASE(3);
-	if (nt > 0) resolve_rounds<NW>(T, nt, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
+	if (nt > 0) resolve_rounds<NW>(sdesc, nt, sa1, sa2, res, L, rank, flag, flag2, &s_nL, a.nndr, 1);
 	__syncthreads();
 	MATCH_PHASE(4);
 	for (int j = tid; j < nt; j += blockDim.x)
