@@ -118,3 +118,15 @@ def test_process_frames_full_path_matches_oracle():
         assert res[b]["ok"] == v["ok"] and res[b]["n_matches"] == len(v["matches"]) and res[b]["n_inliers"] == len(v["inliers"])
         assert np.allclose(res[b]["rvec"], v["rvec"], atol=1e-4) and np.allclose(res[b]["tvec"], v["tvec"], atol=1e-4)
         assert res[b]["ok"]
+
+
+def test_orb_1280x720():
+    """BASELINE configs[2] frame size: same bar as 640x480 (keypoints, order, descriptors, 3-D points bit for bit)."""
+    k4 = (910.0, 910.0, 640.0, 360.0)
+    img = synth.make_image(720, 1280, 5)
+    depth = synth.make_depth(720, 1280, 15)
+    eng = Engine()
+    got = eng.orb_detect_describe(img[None], depth[None], Engine.orb_params(k4))[0]
+    want = f2d.detect_describe(img, depth, k4, f2d.OrbParams())
+    assert len(want[0]) == 1000
+    check_frame(got, want)
