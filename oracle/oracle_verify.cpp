@@ -462,6 +462,12 @@ void solve_pnp_iterative_guess(const float * opts, const float * ipts, int n, co
 		double A[36], w[6], vt[36], dx[6] = {0, 0, 0, 0, 0, 0};
 		memcpy(A, JtJ, sizeof(A));
 		for (int i = 0; i < 6; ++i) A[i * 6 + i] *= 1.0 + lambda;
+		if (chol_solve(A, JtErr, 6, dx))
+		{
+			for (int i = 0; i < 6; ++i) param[i] = prev[i] - dx[i];
+			return;
+		}
+		for (int i = 0; i < 6; ++i) dx[i] = 0;
 		sym_eigen_desc(A, 6, w, vt);
 		for (int k = 0; k < 6; ++k)
 		{

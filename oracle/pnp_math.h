@@ -329,6 +329,45 @@ inline void solve_ls(const double * A, const double * b, int m, int n, double * 
 	}
 }
 
+// x = A^-1 b for a symmetric positive definite n x n matrix (n <= 6) by Cholesky, A = L L^T, sums in ascending index order.
+// Returns false (x untouched) when a pivot is not safely positive (<= 1e-12 * the largest diagonal entry): the caller then
+// falls back to the eigen-decomposition pseudo-inverse.  The damped normal equations of the LM step (diag * (1 + lambda)) are
+// positive definite for every non-degenerate pose, where this gives the same step as cv::solve(DECOMP_SVD) to rounding.
+// Same operation sequence as chol_solve in rtabmap_b200/csrc/pnp_device.cuh.
+inline bool chol_solve(const double * A, const double * b, int n, double * x)
+{
+	double L[36], y[6];
+	double dmax = 0;
+	for (int i = 0; i < n; ++i) dmax = std::max(dmax, A[i * n + i]);
+	for (int j = 0; j < n; ++j)
+	{
+		double d = A[j * n + j];
+		for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k];
+		if (!(d > 1e-12 * dmax)) return false;
+		const double ljj = std::sqrt(d);
+		L[j * n + j] = ljj;
+		for (int i = j + 1; i < n; ++i)
+		{
+			double s = A[i * n + j];
+			for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k];
+			L[i * n + j] = s / ljj;
+		}
+	}
+	for (int i = 0; i < n; ++i)
+	{
+		double s = b[i];
+		for (int k = 0; k < i; ++k) s -= L[i * n + k] * y[k];
+		y[i] = s / L[i * n + i];
+	}
+	for (int i = n - 1; i >= 0; --i)
+	{
+		double s = y[i];
+		for (int k = i + 1; k < n; ++k) s -= L[k * n + i] * x[k];
+		x[i] = s / L[i * n + i];
+	}
+	return true;
+}
+
 // Least squares of A x = b (A is m x n row-major, m >= n <= 6, full column rank) by Householder QR — what EPnP's
 // Gauss-Newton refinement of the betas uses (OpenCV epnp.cpp, epnp::qr_solve on the 6x4 Jacobian).  A and b are
 // destroyed.  Returns false (x untouched) when a column is exactly zero.  Same operation sequence as qr_solve in

@@ -292,6 +292,52 @@ __device__ inline void solve_ls(const double * A, const double * b, double * x)
 	}
 }
 
+// x = A^-1 b for a symmetric positive definite N x N matrix by Cholesky — same operation sequence as the oracle's chol_solve
+// (oracle/pnp_math.h).  false: a pivot is not safely positive, the caller falls back to the eigen pseudo-inverse.
+template <int N>
+__device__ inline bool chol_solve(const double * A, const double * b, double * x)
+{
+	double L[N * N], y[N];
+	double dmax = 0;
+#pragma unroll
+	for (int i = 0; i < N; ++i) dmax = fmax(dmax, A[i * N + i]);
+#pragma unroll
+	for (int j = 0; j < N; ++j)
+	{
+		double d = A[j * N + j];
+#pragma unroll
+		for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
+		if (!(d > 1e-12 * dmax)) return false;
+		const double ljj = sqrt(d);
+		L[j * N + j] = ljj;
+#pragma unroll
+		for (int i = j + 1; i < N; ++i)
+		{
+			double s = A[i * N + j];
+#pragma unroll
+			for (int k = 0; k < j; ++k) s -= L[i * N + k] * L[j * N + k];
+			L[i * N + j] = s / ljj;
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < N; ++i)
+	{
+		double s = b[i];
+#pragma unroll
+		for (int k = 0; k < i; ++k) s -= L[i * N + k] * y[k];
+		y[i] = s / L[i * N + i];
+	}
+#pragma unroll
+	for (int i = N - 1; i >= 0; --i)
+	{
+		double s = y[i];
+#pragma unroll
+		for (int k = i + 1; k < N; ++k) s -= L[k * N + i] * x[k];
+		x[i] = s / L[i * N + i];
+	}
+	return true;
+}
+
 // Least squares of A x = b (A is M x N row-major, full column rank) by Householder QR — EPnP's Gauss-Newton step
 // (OpenCV epnp.cpp, epnp::qr_solve).  Same operation sequence as the oracle's qr_solve_ls (oracle/pnp_math.h); every
 // index is a compile-time constant, so it runs out of registers with uniform control flow.

@@ -301,6 +301,12 @@ __device__ inline void lm_step(LmState & s)
 	int ord[6];
 	for (int i = 0; i < 36; ++i) A[i] = s.JtJ[i];
 	for (int i = 0; i < 6; ++i) A[i * 6 + i] *= 1.0 + lambda;
+	if (chol_solve<6>(A, s.JtErr, dx))
+	{
+		for (int i = 0; i < 6; ++i) s.param[i] = s.prev[i] - dx[i];
+		return;
+	}
+	for (int i = 0; i < 6; ++i) dx[i] = 0;
 	sym_eigen<6>(A, v, ord);
 	const double wmax = A[ord[0] * 6 + ord[0]];
 	for (int kk = 0; kk < 6; ++kk)
