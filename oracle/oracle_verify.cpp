@@ -238,7 +238,7 @@ struct Epnp
 			A[4 * i + 2] = l[10 * i + 3];
 			A[4 * i + 3] = l[10 * i + 6];
 		}
-		solve_ls(A, rho, 6, 4, b4);
+		ls_solve(A, rho, 6, 4, b4);
 		if (b4[0] < 0)
 		{
 			betas[0] = std::sqrt(-b4[0]);
@@ -264,7 +264,7 @@ struct Epnp
 			A[3 * i + 1] = l[10 * i + 1];
 			A[3 * i + 2] = l[10 * i + 2];
 		}
-		solve_ls(A, rho, 6, 3, b3);
+		ls_solve(A, rho, 6, 3, b3);
 		if (b3[0] < 0)
 		{
 			betas[0] = std::sqrt(-b3[0]);
@@ -285,7 +285,7 @@ struct Epnp
 		double A[30], b5[5];
 		for (int i = 0; i < 6; ++i)
 			for (int j = 0; j < 5; ++j) A[5 * i + j] = l[10 * i + j];
-		solve_ls(A, rho, 6, 5, b5);
+		ls_solve(A, rho, 6, 5, b5);
 		if (b5[0] < 0)
 		{
 			betas[0] = std::sqrt(-b5[0]);

@@ -372,9 +372,10 @@ inline bool chol_solve(const double * A, const double * b, int n, double * x)
 // Gauss-Newton refinement of the betas uses (OpenCV epnp.cpp, epnp::qr_solve on the 6x4 Jacobian).  A and b are
 // destroyed.  Returns false (x untouched) when a column is exactly zero.  Same operation sequence as qr_solve in
 // rtabmap_b200/csrc/pnp_device.cuh.
-inline bool qr_solve_ls(double * A, double * b, int m, int n, double * x)
+inline bool qr_solve_ls(double * A, double * b, int m, int n, double * x, double rel_tol = 0.0)
 {
 	double rdiag[6], v[12];
+	double amax = 0;
 	for (int k = 0; k < n; ++k)
 	{
 		double sigma = 0;
@@ -382,6 +383,8 @@ inline bool qr_solve_ls(double * A, double * b, int m, int n, double * x)
 		if (sigma == 0.0) return false;
 		const double akk = A[k * n + k];
 		const double alpha = akk > 0 ? -std::sqrt(sigma) : std::sqrt(sigma);
+		if (!(std::fabs(alpha) > rel_tol * amax)) return false; // numerically rank deficient: the caller uses the pseudo-inverse
+		amax = std::max(amax, std::fabs(alpha));
 		const double beta = 1.0 / (sigma - akk * alpha);
 		v[k] = akk - alpha;
 		for (int i = k + 1; i < m; ++i) v[i] = A[i * n + k];
@@ -405,6 +408,17 @@ inline bool qr_solve_ls(double * A, double * b, int m, int n, double * x)
 		x[k] = s / rdiag[k];
 	}
 	return true;
+}
+
+// cvSolve(A, b, x, CV_SVD) of the small systems of EPnP's find_betas_approx_*: Householder QR when the columns are safely
+// independent (|R_kk| > 1e-8 * the largest |R_jj| so far), the eigen pseudo-inverse (minimum-norm solution) otherwise.
+inline void ls_solve(const double * A, const double * b, int m, int n, double * x)
+{
+	double Ac[36], bc[6];
+	memcpy(Ac, A, sizeof(double) * m * n);
+	memcpy(bc, b, sizeof(double) * m);
+	if (qr_solve_ls(Ac, bc, m, n, x, 1e-8)) return;
+	solve_ls(A, b, m, n, x);
 }
 
 // SVD of a 3x3 matrix M = U diag(w) V^T (row-major U and V, columns are singular vectors).

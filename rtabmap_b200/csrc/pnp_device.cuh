@@ -342,9 +342,10 @@ __device__ inline bool chol_solve(const double * A, const double * b, double * x
 // (OpenCV epnp.cpp, epnp::qr_solve).  Same operation sequence as the oracle's qr_solve_ls (oracle/pnp_math.h); every
 // index is a compile-time constant, so it runs out of registers with uniform control flow.
 template <int M, int N>
-__device__ inline bool qr_solve(double * A, double * b, double * x)
+__device__ inline bool qr_solve(double * A, double * b, double * x, double rel_tol = 0.0)
 {
 	double rdiag[N], v[M];
+	double amax = 0;
 #pragma unroll
 	for (int k = 0; k < N; ++k)
 	{
@@ -354,6 +355,8 @@ __device__ inline bool qr_solve(double * A, double * b, double * x)
 		if (sigma == 0.0) return false;
 		const double akk = A[k * N + k];
 		const double alpha = akk > 0 ? -sqrt(sigma) : sqrt(sigma);
+		if (!(fabs(alpha) > rel_tol * amax)) return false;
+		amax = fmax(amax, fabs(alpha));
 		const double beta = 1.0 / (sigma - akk * alpha);
 		v[k] = akk - alpha;
 #pragma unroll
@@ -385,6 +388,19 @@ __device__ inline bool qr_solve(double * A, double * b, double * x)
 		x[k] = s / rdiag[k];
 	}
 	return true;
+}
+
+// cvSolve(A, b, x, CV_SVD) of EPnP's find_betas_approx_*: guarded QR, eigen pseudo-inverse as the fallback (oracle: ls_solve)
+template <int M, int N>
+__device__ inline void ls_solve(const double * A, const double * b, double * x)
+{
+	double Ac[M * N], bc[M];
+#pragma unroll
+	for (int i = 0; i < M * N; ++i) Ac[i] = A[i];
+#pragma unroll
+	for (int i = 0; i < M; ++i) bc[i] = b[i];
+	if (qr_solve<M, N>(Ac, bc, x, 1e-8)) return;
+	solve_ls<M, N>(A, b, x);
 }
 
 // SVD of a 3x3 matrix M = U diag(w) V^T; U, V row-major with singular vectors as columns
@@ -745,7 +761,7 @@ struct Epnp6
 					A[4 * i + 2] = l[10 * i + 3];
 					A[4 * i + 3] = l[10 * i + 6];
 				}
-				solve_ls<6, 4>(A, rho, b4);
+				ls_solve<6, 4>(A, rho, b4);
 				if (b4[0] < 0)
 				{
 					betas[0] = sqrt(-b4[0]);
@@ -770,7 +786,7 @@ struct Epnp6
 					A[3 * i + 1] = l[10 * i + 1];
 					A[3 * i + 2] = l[10 * i + 2];
 				}
-				solve_ls<6, 3>(A, rho, b3);
+				ls_solve<6, 3>(A, rho, b3);
 				if (b3[0] < 0)
 				{
 					betas[0] = sqrt(-b3[0]);
@@ -790,7 +806,7 @@ struct Epnp6
 				double A[30], b5[5];
 				for (int i = 0; i < 6; ++i)
 					for (int j = 0; j < 5; ++j) A[5 * i + j] = l[10 * i + j];
-				solve_ls<6, 5>(A, rho, b5);
+				ls_solve<6, 5>(A, rho, b5);
 				if (b5[0] < 0)
 				{
 					betas[0] = sqrt(-b5[0]);

@@ -572,7 +572,18 @@ pnp_ransac_kernel(const PnpArgs a)
 				const double tv[3] = {h_rt[h * 6 + 3], h_rt[h * 6 + 4], h_rt[h * 6 + 5]};
 				const int i0 = static_cast<int>(static_cast<long long>(n) * part / parts), i1 = static_cast<int>(static_cast<long long>(n) * (part + 1) / parts);
 				int c = 0;
-				for (int i = i0; i < i1; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
+				int i = i0;
+				for (; i + 4 <= i1; i += 4)
+				{
+					// four independent points per trip: the fp64 divide and square root of each projection are long dependent
+					// chains, and a warp here has at most one neighbour on its scheduler to hide them
+					const float e0 = reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i);
+					const float e1 = reproj_err(R, tv, cam, X + 3 * i + 3, uv + 2 * i + 2);
+					const float e2 = reproj_err(R, tv, cam, X + 3 * i + 6, uv + 2 * i + 4);
+					const float e3 = reproj_err(R, tv, cam, X + 3 * i + 9, uv + 2 * i + 6);
+					c += (e0 <= thr2 ? 1 : 0) + (e1 <= thr2 ? 1 : 0) + (e2 <= thr2 ? 1 : 0) + (e3 <= thr2 ? 1 : 0);
+				}
+				for (; i < i1; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
 				if (c) atomicAdd(&cnt[h], c);
 			}
 			if (a.phase_clk && tid == 0 && chunk0 == 0) a.phase_clk[pair * 16 + 8 + 5] = clock64();
