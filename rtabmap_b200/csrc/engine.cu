@@ -209,7 +209,7 @@ struct lcd_engine
 	int st_cap = 0, st_slots = 0;
 	DevBuf<int> d_hyp_id, d_hyp_slot;
 	// ORB workspace
-	DevBuf<uint8_t> o_img, o_gray, o_mask, o_blur, o_desc, o_score;
+	DevBuf<uint8_t> o_img, o_gray, o_mask, o_blur, o_desc;
 	DevBuf<unsigned char> o_depth;
 	DevBuf<uint32_t> o_cand;
 	DevBuf<int> o_cand_count, o_level_n, o_n, o_overflow;
@@ -1458,7 +1458,6 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	LCD_CUDA(e, e->o_level_n.reserve(total_slots, 0, false, s));
 	LCD_CUDA(e, e->o_level_kp.reserve(static_cast<size_t>(total_slots) * level_cap, 0, false, s));
 	if (frame0 == 0) LCD_CUDA(e, e->o_overflow.reserve(1, 0, true, s));
-	LCD_CUDA(e, e->o_score.reserve(pyr, 0, false, s));
 	if (!d_kp)
 	{
 		LCD_CUDA(e, e->o_kp.reserve(static_cast<size_t>(total_frames) * cap, 0, false, s));
@@ -1476,7 +1475,6 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	uint8_t * const w_gray = e->o_gray.p + static_cast<size_t>(frame0) * g.frame_stride;
 	uint8_t * const w_blur = e->o_blur.p + static_cast<size_t>(frame0) * g.frame_stride;
 	uint8_t * const w_mask = use_mask ? e->o_mask.p + static_cast<size_t>(frame0) * g.frame_stride : nullptr;
-	uint8_t * const w_score = e->o_score.p + static_cast<size_t>(frame0) * g.frame_stride;
 	uint32_t * const w_cand = e->o_cand.p + static_cast<size_t>(slot0) * kOrbCandCap;
 	int * const w_cand_count = e->o_cand_count.p + slot0;
 	int * const w_level_n = e->o_level_n.p + slot0;
@@ -1696,7 +1694,6 @@ long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long 
 	{
 	case 0: src = e->o_gray.p; bytes = e->o_gray.cap; break;
 	case 1: src = e->o_mask.p; bytes = e->o_mask.cap; break;
-	case 6: src = e->o_score.p; bytes = e->o_score.cap; break;
 	case 2: src = e->o_blur.p; bytes = e->o_blur.cap; break;
 	case 3: src = e->o_cand.p; bytes = e->o_cand.cap * sizeof(uint32_t); break;
 	case 4: src = e->o_cand_count.p; bytes = e->o_cand_count.cap * sizeof(int); break;
@@ -2235,7 +2232,7 @@ int lcd_process_frames_submit(lcd_engine * e, int n_frames, const uint8_t * imag
 	if (!depth) depth_type = LCD_DEPTH_NONE;
 	const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
 	// upload on the copy stream: the slot's previous batch was waited for, so its staging buffers are free
-	static const int dbg_tl = env_int("LCD_DEBUG_TIMELINE", 0);
+	static const int dbg_tl = env_int("LCD_DEBUG_TIMELINE", 0); // diagnostics: print each batch's upload / compute window at _wait
 	if (dbg_tl && !f.t_h0)
 	{
 		cudaEventCreate(&f.t_h0);
@@ -2249,14 +2246,12 @@ int lcd_process_frames_submit(lcd_engine * e, int n_frames, const uint8_t * imag
 		}
 	}
 	if (dbg_tl) cudaEventRecord(f.t_h0, e->copy_stream);
-	static const int dbg_skip = env_int("LCD_DEBUG_SKIP_UPLOAD", 0); // diagnostics: 1 = reuse the slot's previous upload
-	const bool skip = dbg_skip && f.img.cap >= px * channels;
 	LCD_CUDA(e, f.img.reserve(px * channels, 0, false, e->copy_stream));
-	if (!skip) LCD_CUDA(e, cudaMemcpyAsync(f.img.p, images, px * channels, cudaMemcpyHostToDevice, e->copy_stream));
+	LCD_CUDA(e, cudaMemcpyAsync(f.img.p, images, px * channels, cudaMemcpyHostToDevice, e->copy_stream));
 	if (depth_type != LCD_DEPTH_NONE)
 	{
 		LCD_CUDA(e, f.depth.reserve(px * dbytes, 0, false, e->copy_stream));
-		if (!skip) LCD_CUDA(e, cudaMemcpyAsync(f.depth.p, depth, px * dbytes, cudaMemcpyHostToDevice, e->copy_stream));
+		LCD_CUDA(e, cudaMemcpyAsync(f.depth.p, depth, px * dbytes, cudaMemcpyHostToDevice, e->copy_stream));
 	}
 	// the signature id list rides on the copy stream too: a host -> device copy queued on the compute stream would sit in the
 	// same copy-engine queue as the next batch's images and serialise the two batches (measured)

@@ -152,8 +152,6 @@ __global__ void orb_down_kernel(uint8_t * gray_all, uint8_t * mask_all, const Or
 }
 
 // ---- K2: FAST-9/16 score + 3x3 non-max suppression + border/mask filters -> candidate list --------
-constexpr int kFastTile = 16;
-
 __device__ __forceinline__ int fast_score(const uint8_t * t, int stride, int thr)
 {
 	// t points at the pixel inside a shared tile; d[k] = centre - k-th pixel of the 16-pixel Bresenham circle
@@ -201,46 +199,6 @@ __device__ __forceinline__ int fast_score(const uint8_t * t, int stride, int thr
 		best = static_cast<int>(max(m & 0xFFFFu, m >> 16)) - 256;
 	}
 	return best > thr ? best - 1 : 0;
-}
-
-// FAST score of every pixel of one level -> score plane (0 = not a corner).  Reads straight from the gray
-// plane (L1/L2 resident); the 4-pixel rejection test leaves few pixels that need the whole ring.
-__global__ void __launch_bounds__(256)
-orb_fast_score_kernel(const uint8_t * __restrict__ gray_all, const OrbGeom g, int level, uint8_t * __restrict__ score_all)
-{
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int y = blockIdx.y * blockDim.y + threadIdx.y;
-	const int frame = blockIdx.z;
-	const int w = g.w[level], h = g.h[level];
-	if (x >= w || y >= h) return;
-	const size_t plane = static_cast<size_t>(frame) * g.frame_stride + g.off[level];
-	int s = 0;
-	if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) s = fast_score(gray_all + plane + static_cast<size_t>(y) * w + x, w, g.fast_thr);
-	score_all[plane + static_cast<size_t>(y) * w + x] = static_cast<uint8_t>(s);
-}
-
-// 3x3 strict non-max suppression, then KeyPointsFilter::runByPixelsMask and runByImageBorder -> candidate list
-__global__ void __launch_bounds__(256)
-orb_fast_nms_kernel(const uint8_t * __restrict__ score_all, const uint8_t * __restrict__ mask_all, const OrbGeom g, int level,
-                    uint32_t * __restrict__ cand, int * __restrict__ cand_count)
-{
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int y = blockIdx.y * blockDim.y + threadIdx.y;
-	const int frame = blockIdx.z;
-	const int w = g.w[level], h = g.h[level];
-	// corners exist only in [3, w-3) x [3, h-3); the border filter below is at least as strict
-	if (x < 3 || x >= w - 3 || y < 3 || y >= h - 3) return;
-	if (x < g.edge || x >= w - g.edge || y < g.edge || y >= h - g.edge) return;
-	const size_t plane = static_cast<size_t>(frame) * g.frame_stride + g.off[level];
-	const uint8_t * sc = score_all + plane + static_cast<size_t>(y) * w + x;
-	const int s = sc[0];
-	if (s == 0) return;
-	const bool is_max = s > sc[-w - 1] && s > sc[-w] && s > sc[-w + 1] && s > sc[-1] && s > sc[1] && s > sc[w - 1] && s > sc[w] && s > sc[w + 1];
-	if (!is_max) return;
-	if (mask_all && mask_all[plane + static_cast<size_t>(y) * w + x] == 0) return;
-	const int slot = frame * g.n_levels + level;
-	const int k = atomicAdd(&cand_count[slot], 1);
-	if (k < kOrbCandCap) cand[static_cast<size_t>(slot) * kOrbCandCap + k] = (static_cast<uint32_t>(y * w + x) << 8) | static_cast<uint32_t>(s);
 }
 
 // Fused FAST stage: score + 3x3 non-max suppression + border / mask filters -> candidate list, one 32x16 tile per CTA.
@@ -340,7 +298,8 @@ orb_fast_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restric
 }
 
 // ---- K3: per (frame, level) selection: raster order, retainBest(2N) on FAST score, Harris, retainBest(N),
-//          IC angle.  One CTA; the two retainBest replays are sequential (thread 0). -----------------------
+//          IC angle.  One CTA per frame, one launch per level; the two retainBest replays are block-cooperative
+//          (partition_replay below). ----------------------------------------------------------------------
 // Scratch of the block-cooperative replays below.
 struct SelectScratch
 {
