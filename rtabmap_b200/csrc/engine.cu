@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "nn_hamming.cuh"
 #include "nn_tensor.cuh"
+#include "l2_path.cuh"
 #include "resolve.cuh"
 #include "score.cuh"
 #include "verify.cuh"
@@ -228,6 +229,8 @@ struct lcd_engine
 
 	// tuning knobs (env: LCD_NN_CTAS_PER_SM, LCD_NN_TQ, LCD_NN_VARIANT, LCD_SCORE_BLOCKS)
 	int nn_ctas_per_sm = 2, nn_tq = 8, nn_variant = 2, score_blocks = 32;
+	bool f32 = false;    // LCD_DESC_F32: squared-L2 path (l2_path.cuh)
+	DevBuf<ulonglong2> d_partial64;
 	int nn_tensor = 1;   // 256-bit descriptors: tcgen05 int8 path (nn_tensor.cuh); 0 = POPC kernel (nn_hamming.cuh)
 	int nn_last_tensor = 0; // which kernel the last run_knn used (bench / diagnostics)
 };
@@ -390,6 +393,24 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 {
 	if (e->row_offset + n_rows > kMaxRowsPacked) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d indexed words", kMaxRowsPacked);
 	e->nn_last_tensor = 0;
+	if (e->f32)
+	{
+		// float descriptors: exact squared-L2 2-NN, one query per thread, rows split over blockIdx.y to fill the machine
+		const int q_blocks = (nq_total + kL2Threads - 1) / kL2Threads;
+		int splits = std::max(1, std::min((2 * e->sm_count + q_blocks - 1) / q_blocks, std::max(1, n_rows / (4 * kL2TileRows))));
+		const int rps = std::max(1, (n_rows + splits - 1) / splits);
+		splits = std::max(1, (n_rows + rps - 1) / rps);
+		LCD_CUDA(e, e->d_partial64.reserve(static_cast<size_t>(splits) * nq_total, 0, false, s));
+		const float * v = reinterpret_cast<const float *>(e->vocab.p);
+		const float * q = reinterpret_cast<const float *>(d_q);
+		prof_mark(e, LCD_PROF_NN, s);
+		if (e->nw == 64) knn2_l2_kernel<64><<<dim3(q_blocks, splits), kL2Threads, 0, s>>>(v, n_rows, e->row_offset, q, nq_total, e->d_partial64.p, rps);
+		else knn2_l2_kernel<128><<<dim3(q_blocks, splits), kL2Threads, 0, s>>>(v, n_rows, e->row_offset, q, nq_total, e->d_partial64.p, rps);
+		prof_mark(e, LCD_PROF_NN, s);
+		LCD_CHECK_LAUNCH(e);
+		*n_chunks_out = splits;
+		return LCD_OK;
+	}
 	if (e->nn_tensor && e->nw == 8 && n_rows > 0 && nq_total > 0 && kTcSmemBytes <= static_cast<size_t>(e->smem_optin))
 	{
 		// tensor-core path: expand both operands to the int8 images, then one CTA per (query tile, word split)
@@ -452,6 +473,18 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 
 int launch_resolve(lcd_engine * e, const ResolveArgs & a, int n_frames, cudaStream_t s)
 {
+	if (e->f32)
+	{
+		int nq_pad = 32;
+		while (nq_pad < a.nq) nq_pad <<= 1;
+		const size_t smem32 = static_cast<size_t>(nq_pad) * sizeof(uint32_t);
+		prof_mark(e, LCD_PROF_RESOLVE, s);
+		if (e->nw == 64) resolve_l2_kernel<64><<<n_frames, kL2ResolveThreads, smem32, s>>>(a, e->d_partial64.p);
+		else resolve_l2_kernel<128><<<n_frames, kL2ResolveThreads, smem32, s>>>(a, e->d_partial64.p);
+		prof_mark(e, LCD_PROF_RESOLVE, s);
+		LCD_CHECK_LAUNCH(e);
+		return LCD_OK;
+	}
 	const size_t smem = resolve_smem_bytes(a.nq);
 #define LCD_RES_CASE(NW_)                                                                                               \
 	case NW_:                                                                                                           \
@@ -641,6 +674,12 @@ int add_refs_impl(lcd_engine * e, int sig_id, const int * word_ids, int n)
 	return LCD_OK;
 }
 
+int require_binary(lcd_engine * e, const char * what)
+{
+	if (e->f32) LCD_FAIL(e, LCD_ERR_INVALID, "%s works on binary descriptors only (this engine holds float descriptors)", what);
+	return LCD_OK;
+}
+
 int check_queries(lcd_engine * e, const void * q, int nq)
 {
 	if (!q || nq <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
@@ -721,14 +760,19 @@ lcd_engine * lcd_create(const lcd_config * cfg)
 		g_create_error = "null config";
 		return nullptr;
 	}
-	if (cfg->desc_type != LCD_DESC_U8)
+	if (cfg->desc_type != LCD_DESC_U8 && cfg->desc_type != LCD_DESC_F32)
 	{
-		g_create_error = "only LCD_DESC_U8 (binary descriptors, Hamming) is implemented in this build";
+		g_create_error = "desc_type must be LCD_DESC_U8 (binary, Hamming) or LCD_DESC_F32 (float, squared L2)";
 		return nullptr;
 	}
-	if (cfg->desc_dim != 16 && cfg->desc_dim != 32 && cfg->desc_dim != 64)
+	if (cfg->desc_type == LCD_DESC_U8 && cfg->desc_dim != 16 && cfg->desc_dim != 32 && cfg->desc_dim != 64)
 	{
 		g_create_error = "binary descriptor size must be 16, 32 or 64 bytes";
+		return nullptr;
+	}
+	if (cfg->desc_type == LCD_DESC_F32 && cfg->desc_dim != 64 && cfg->desc_dim != 128)
+	{
+		g_create_error = "float descriptors must have 64 or 128 dimensions (SURF-64, SURF-128 / SIFT)";
 		return nullptr;
 	}
 	int ndev = 0;
@@ -740,7 +784,8 @@ lcd_engine * lcd_create(const lcd_config * cfg)
 	}
 	lcd_engine * e = new lcd_engine();
 	e->cfg = *cfg;
-	e->nw = cfg->desc_dim / 4;
+	e->f32 = cfg->desc_type == LCD_DESC_F32;
+	e->nw = e->f32 ? cfg->desc_dim : cfg->desc_dim / 4; // 32-bit words per descriptor row
 	if ((err = cudaSetDevice(cfg->device)) != cudaSuccess || (err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess)
 	{
 		g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(err);
@@ -1040,15 +1085,23 @@ int lcd_dict_knn2(lcd_engine * e, const void * queries, int nq, int * id1, float
 	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, static_cast<size_t>(nq) * e->nw * 4, cudaMemcpyHostToDevice, s));
 	int n_chunks = 0;
 	LCD_TRY(run_knn(e, e->d_queries.p, nq, e->n_indexed, &n_chunks, s));
-	LCD_CUDA(e, e->d_keys.reserve(2 * static_cast<size_t>(nq), 0, false, s));
-	knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_partial.p, n_chunks, nq, e->d_keys.p);
-	LCD_CHECK_LAUNCH(e);
 	LCD_CUDA(e, e->d_i1.reserve(nq, 0, false, s));
 	LCD_CUDA(e, e->d_i2.reserve(nq, 0, false, s));
 	LCD_CUDA(e, e->d_f1.reserve(nq, 0, false, s));
 	LCD_CUDA(e, e->d_f2.reserve(nq, 0, false, s));
-	knn2_decode_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_keys.p, nq, e->row_ids.p, e->d_i1.p, e->d_f1.p, e->d_i2.p, e->d_f2.p);
-	LCD_CHECK_LAUNCH(e);
+	if (e->f32)
+	{
+		knn2_l2_decode_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_partial64.p, n_chunks, nq, e->row_ids.p, e->d_i1.p, e->d_f1.p, e->d_i2.p, e->d_f2.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	else
+	{
+		LCD_CUDA(e, e->d_keys.reserve(2 * static_cast<size_t>(nq), 0, false, s));
+		knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_partial.p, n_chunks, nq, e->d_keys.p);
+		LCD_CHECK_LAUNCH(e);
+		knn2_decode_kernel<<<(nq + 255) / 256, 256, 0, s>>>(e->d_keys.p, nq, e->row_ids.p, e->d_i1.p, e->d_f1.p, e->d_i2.p, e->d_f2.p);
+		LCD_CHECK_LAUNCH(e);
+	}
 	LCD_CUDA(e, cudaMemcpyAsync(id1, e->d_i1.p, nq * sizeof(int), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaMemcpyAsync(id2, e->d_i2.p, nq * sizeof(int), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaMemcpyAsync(d1, e->d_f1.p, nq * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1911,6 +1964,7 @@ int lcd_match_pairs(lcd_engine * e, int n_pairs, int cap, const void * desc_from
                     const int * n_to, float nndr, int * from_ids, int * to_ids)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_match_pairs"));
 	LCD_TRY(set_device(e));
 	LCD_TRY(check_verify_args(e, n_pairs, cap, desc_from, desc_to, n_from, n_to));
 	cudaStream_t s = e->stream;
@@ -1928,6 +1982,7 @@ int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_fro
                      lcd_verify_result * results, int * match_ids, int * inlier_ids)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_verify_batch"));
 	LCD_TRY(set_device(e));
 	LCD_TRY(check_verify_args(e, n_pairs, cap, desc_from, desc_to, n_from, n_to));
 	if (!xyz_from || !uv_to || !params || !results) LCD_FAIL(e, LCD_ERR_INVALID, "null verification argument");
@@ -1945,6 +2000,7 @@ int lcd_sig_count(const lcd_engine * e) { return e ? e->st_slots - static_cast<i
 int lcd_sig_add_batch(lcd_engine * e, const int * sig_ids, int n_sigs, int cap, const void * desc, const float * xyz, const int * n)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_sig_add_batch"));
 	if (n_sigs <= 0) return LCD_OK;
 	if (!sig_ids || !desc || !xyz || !n || cap <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null signature data");
 	if (cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "at most %d features per signature", kMaxFrameQueries);
@@ -2066,6 +2122,7 @@ int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * 
                           int * d_word_ids_out, float * d_likelihood_out, void * stream)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_process_batch_dev"));
 	LCD_TRY(set_device(e));
 	if (!d_queries || !d_uv || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
 	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
@@ -2318,6 +2375,7 @@ int lcd_verify_top_dev(lcd_engine * e, const void * d_queries, const float * d_u
                        const int * d_sig_ids, int ns, const lcd_verify_params * vp, void * stream)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_verify_top_dev"));
 	LCD_TRY(set_device(e));
 	if (!d_queries || !d_uv || !d_likelihood || !d_sig_ids || n_frames <= 0 || ns <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
 	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
@@ -2343,6 +2401,7 @@ int lcd_process_batch(lcd_engine * e, const void * queries, const float * uv, in
                       int * word_ids_out, float * likelihood_out, int * hypothesis_out, lcd_verify_result * results)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_process_batch"));
 	LCD_TRY(set_device(e));
 	if (!queries || !uv || n_frames <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
 	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
@@ -2379,6 +2438,7 @@ int lcd_shard_set_row_offset(lcd_engine * e, int global_row_offset)
 int lcd_shard_knn2_keys_dev(lcd_engine * e, const void * d_queries, int nq, uint32_t * d_keys_out, void * stream)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_shard_knn2_keys_dev"));
 	LCD_TRY(set_device(e));
 	if (!d_queries || nq <= 0 || !d_keys_out) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
 	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
@@ -2395,6 +2455,7 @@ int lcd_shard_resolve_score_dev(lcd_engine * e, const void * d_queries, int n_fr
                                 int * d_word_ids_out, long long * d_scores_out, void * stream)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_shard_resolve_score_dev"));
 	LCD_TRY(set_device(e));
 	if (!d_queries || !d_keys_gathered || !d_row_ids || n_frames <= 0 || n_ranks <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
 	if (nq_per_frame <= 0 || nq_per_frame > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "1..%d descriptors per frame", kMaxFrameQueries);
@@ -2436,6 +2497,7 @@ int lcd_shard_resolve_frames_dev(lcd_engine * e, const void * d_queries_all, int
                                  float nndr, int new_words_compared_together, const int * d_n_per_frame, int * d_word_ids_out, void * stream)
 {
 	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_shard_resolve_frames_dev"));
 	LCD_TRY(set_device(e));
 	if (!d_queries_all || !d_keys_gathered || !d_row_ids || !d_word_ids_out || n_frames <= 0 || n_ranks <= 0 || frame0 < 0 ||
 	    frame0 + n_frames > n_frames_total)
