@@ -21,8 +21,10 @@
 // /root/reference by oracle/Makefile) in tests/test_oracle_ref.py; likelihood is checked against the
 // reference's only golden vector for this path, archive/2010-LoopClosure/Tests/TestComputeLikelihood.m
 // (tests/golden/tfidf_golden.json, made by tests/golden/make_tfidf_golden.py).  The NNDR / new-word
-// loop and adjust_likelihood have no golden vector in the reference: PARITY UNPINNED
-// for those two — oracle-vs-CUDA only, plus hand-checked cases in tests/test_oracle_golden.py.
+// loop and adjust_likelihood have no golden vector in the reference.  The loop is checked
+// against an independent replay on the reference's own primitives (its compiled rtflann + cv::BFMatcher,
+// tests/test_oracle_ref.py::test_quantiser_loop_against_reference_primitives); adjust_likelihood stays
+// PARITY UNPINNED (oracle-vs-CUDA only).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

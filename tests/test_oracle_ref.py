@@ -41,3 +41,84 @@ def test_l2_matches_rtflann_bit_exact(rows, dim):
     assert np.array_equal(i_ref, i_orc)
     # same float summation order as rtflann::L2 (dist.h:158-166): identical bits
     assert np.array_equal(d_ref.view(np.uint32), d_orc.view(np.uint32))
+
+
+# ---- the quantiser loop, replayed on the reference's own primitives ---------------------------------------------------
+def _replay_add_new_words(index_ids, index_desc, frame, nndr, last_id, incremental=True, cmp_new=True):
+    """VWDictionary::addNewWords "Process results" loop (VWDictionary.cpp:1088-1219) written a second time, independently of
+    oracle/oracle.cpp, on the primitives the reference itself calls: its own rtflann LinearIndex (compiled into oracle/_ref)
+    for the index search and cv::BFMatcher::knnMatch (OpenCV, the installed cv2) for the words created by the same frame.
+    fullResults is a std::multimap<float,int>: a stable sort by distance of the insertion sequence."""
+    import cv2
+
+    binary = frame.dtype == np.uint8
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING if binary else cv2.NORM_L2SQR)
+    idx_all, dist_all = (orc.ref_knn2(index_desc, frame) if len(index_desc) else (None, None))
+    new_desc, new_ids, out = [], [], []
+    for i in range(len(frame)):
+        full = []
+        if idx_all is not None:
+            for j in range(2):
+                if idx_all[i, j] < 0:
+                    break
+                full.append((np.float32(dist_all[i, j]), int(index_ids[idx_all[i, j]])))
+        if cmp_new and new_desc:
+            for mt in bf.knnMatch(frame[i:i + 1], np.stack(new_desc), k=2 if len(new_desc) > 1 else 1)[0]:
+                full.append((np.float32(mt.distance), new_ids[mt.trainIdx]))
+        full.sort(key=lambda t: t[0])                     # stable: equal distances keep insertion order, like the multimap
+        if incremental:
+            bad = len(full) < 2 or full[0][0] > np.float32(nndr) * full[1][0]
+            if bad:
+                last_id += 1
+                new_desc.append(frame[i])
+                new_ids.append(last_id)
+                out.append(last_id)
+            else:
+                out.append(full[0][1])
+        elif full:
+            out.append(full[0][1])
+    return np.array(out, np.int32), last_id
+
+
+@pytest.mark.parametrize("kind", ["hamming", "l2"])
+def test_quantiser_loop_against_reference_primitives(kind):
+    """Pins the NNDR / new-word loop of the oracle (the part of the quantiser the reference has no golden vector for) to an
+    independent replay that gets every distance from the reference's rtflann and from cv::BFMatcher."""
+    rng = np.random.default_rng(31)
+    if kind == "hamming":
+        vocab = rng.integers(0, 256, (1200, 32), dtype=np.uint8)
+
+        def near(rows, k):
+            out = rows.copy()
+            for r in out:
+                for b in rng.integers(0, 256, k):
+                    r[b >> 3] ^= np.uint8(1 << (b & 7))
+            return out
+        o = orc.OracleDictionary(0, 32, True, 0.8, True)
+    else:
+        vocab = rng.standard_normal((1200, 64)).astype(np.float32)
+        vocab /= np.linalg.norm(vocab, axis=1, keepdims=True)
+
+        def near(rows, k):
+            q = rows + 0.004 * k * rng.standard_normal(rows.shape).astype(np.float32)
+            return (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+        o = orc.OracleDictionary(1, 64, True, 0.8, True)
+    ids = np.arange(1, 1201, dtype=np.int32) * 3
+    o.add_words(ids, vocab)
+    o.last_word_id = int(ids.max())
+    o.update()
+    index_ids, index_desc = ids.copy(), vocab.copy()
+    last = int(ids.max())
+    for t in range(1, 5):
+        fresh = rng.integers(0, 256, (120, 32), dtype=np.uint8) if kind == "hamming" else near(rng.standard_normal((120, 64)).astype(np.float32), 0)
+        frame = np.concatenate([near(vocab[rng.integers(0, 1200, 50)], 6), fresh, near(fresh[:40], 4), fresh[5:8]])
+        want, last = _replay_add_new_words(index_ids, index_desc, frame, 0.8, last)
+        got = o.add_new_words(frame, t)
+        assert np.array_equal(got, want), f"{kind} frame {t}"
+        assert o.last_word_id == last
+        # update(): the frame's new words join the index in ascending id order (first occurrence of every new id)
+        new_ids, first = np.unique(want[want > index_ids.max()], return_index=True)
+        pos = np.flatnonzero(want > index_ids.max())[first]
+        index_ids = np.concatenate([index_ids, new_ids.astype(np.int32)])
+        index_desc = np.concatenate([index_desc, frame[pos]])
+        o.update()
