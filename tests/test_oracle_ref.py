@@ -122,3 +122,42 @@ def test_quantiser_loop_against_reference_primitives(kind):
         index_ids = np.concatenate([index_ids, new_ids.astype(np.int32)])
         index_desc = np.concatenate([index_desc, frame[pos]])
         o.update()
+
+
+@pytest.mark.parametrize("kind", ["hamming", "l2"])
+def test_find_nn_against_reference_primitives(kind):
+    """VWDictionary::findNN (VWDictionary.cpp:1273-1552): index hits from the reference's rtflann, hits among the words that are
+    not indexed yet from cv::BFMatcher::knnMatch, multimap order, NNDR — replayed independently and compared with the oracle."""
+    import cv2
+
+    rng = np.random.default_rng(41)
+    if kind == "hamming":
+        vocab = rng.integers(0, 256, (900, 32), dtype=np.uint8)
+        pend = rng.integers(0, 256, (60, 32), dtype=np.uint8)
+        o = orc.OracleDictionary(0, 32, True, 0.8, True)
+        q = np.concatenate([vocab[:40] ^ np.uint8(1), pend[:20] ^ np.uint8(2), rng.integers(0, 256, (30, 32), dtype=np.uint8), pend[3:5]])
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    else:
+        vocab = rng.standard_normal((900, 64)).astype(np.float32)
+        pend = rng.standard_normal((60, 64)).astype(np.float32)
+        o = orc.OracleDictionary(1, 64, True, 0.8, True)
+        q = np.concatenate([vocab[:40] + np.float32(0.01), pend[:20] - np.float32(0.02), rng.standard_normal((30, 64)).astype(np.float32), pend[3:5]])
+        bf = cv2.BFMatcher(cv2.NORM_L2SQR)
+    ids = np.arange(1, 901, dtype=np.int32) * 2
+    pend_ids = np.arange(2001, 2061, dtype=np.int32)
+    o.add_words(ids, vocab)
+    o.update()
+    o.add_words(pend_ids, pend)            # not indexed: no update()
+    o.last_word_id = 2060
+    idx, dist = orc.ref_knn2(vocab, q)
+    mni = bf.knnMatch(q, pend, k=2)
+    want = np.zeros(len(q), np.int32)
+    for i in range(len(q)):
+        full = [(np.float32(dist[i, j]), int(ids[idx[i, j]])) for j in range(2) if idx[i, j] >= 0]
+        full += [(np.float32(m.distance), int(pend_ids[m.trainIdx])) for m in mni[i]]
+        full.sort(key=lambda t: t[0])
+        if len(full) >= 2 and not (full[0][0] > np.float32(0.8) * full[1][0]):
+            want[i] = full[0][1]
+    got = o.find_nn(q)
+    assert np.array_equal(got, want)
+    assert (want > 2000).any() and (want == 0).any() and ((want > 0) & (want <= 1800)).any()
