@@ -142,6 +142,7 @@ struct lcd_engine
 		DevBuf<unsigned char> depth;
 		DevBuf<int> sig_ids;
 		PinBuf<PackedVerifyResult> res;
+		PinBuf<int> overflow;                  // ORB candidate overflow flag of the batch
 		cudaEvent_t uploaded = nullptr, done = nullptr;
 		lcd_verify_result * user_results = nullptr;
 		int n_frames = 0;
@@ -152,6 +153,7 @@ struct lcd_engine
 	int flight_head = 0, flights_busy = 0;
 	DevBuf<PackedVerifyResult> v_packed;
 	PinBuf<PackedVerifyResult> h_packed;
+	PinBuf<int> h_overflow;
 	long long launches = 0;
 	int sm_count = 148;
 	int smem_optin = 0;
@@ -1510,7 +1512,12 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	LCD_CUDA(e, e->o_cand_count.reserve(total_slots, 0, false, s));
 	LCD_CUDA(e, e->o_level_n.reserve(total_slots, 0, false, s));
 	LCD_CUDA(e, e->o_level_kp.reserve(static_cast<size_t>(total_slots) * level_cap, 0, false, s));
-	if (frame0 == 0) LCD_CUDA(e, e->o_overflow.reserve(1, 0, true, s));
+	if (frame0 == 0)
+	{
+		// the "candidate list truncated" flag of this batch: cleared here, read back by the host entry points
+		LCD_CUDA(e, e->o_overflow.reserve(1, 0, true, s));
+		LCD_CUDA(e, zero_fill_async(e->o_overflow.p, sizeof(int), s));
+	}
 	if (!d_kp)
 	{
 		LCD_CUDA(e, e->o_kp.reserve(static_cast<size_t>(total_frames) * cap, 0, false, s));
@@ -2255,8 +2262,12 @@ int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int
 	if (likelihood_out)
 		LCD_CUDA(e, cudaMemcpyAsync(likelihood_out, e->d_like.p, static_cast<size_t>(n_frames) * ns * sizeof(float), cudaMemcpyDeviceToHost, s));
 	if (vp && hypothesis_out) LCD_CUDA(e, cudaMemcpyAsync(hypothesis_out, e->d_hyp_id.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
-	if (vp && results) return verify_download(e, n_frames, 0, results, nullptr, nullptr, s);
+	LCD_CUDA(e, e->h_overflow.reserve(1));
+	LCD_CUDA(e, cudaMemcpyAsync(e->h_overflow.p, e->o_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (vp && results) LCD_TRY(verify_download(e, n_frames, 0, results, nullptr, nullptr, s));
 	LCD_CUDA(e, cudaStreamSynchronize(s));
+	if (*e->h_overflow.p)
+		LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d FAST corners in pyramid level 0 (half as many per further level): raise FAST/Threshold", kOrbCandCap);
 	return LCD_OK;
 }
 
@@ -2342,6 +2353,8 @@ int lcd_process_frames_submit(lcd_engine * e, int n_frames, const uint8_t * imag
 		f.user_results = results;
 	}
 	f.n_frames = n_frames;
+	LCD_CUDA(e, f.overflow.reserve(1));
+	LCD_CUDA(e, cudaMemcpyAsync(f.overflow.p, e->o_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
 	if (dbg_tl) cudaEventRecord(f.t_c1, s);
 	LCD_CUDA(e, cudaEventRecord(f.done, s));
 	++e->flights_busy;
@@ -2368,6 +2381,8 @@ int lcd_process_frames_wait(lcd_engine * e)
 	f.user_results = nullptr;
 	e->flight_head ^= 1;
 	--e->flights_busy;
+	if (f.overflow.p && *f.overflow.p)
+		LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d FAST corners in pyramid level 0 (half as many per further level): raise FAST/Threshold", kOrbCandCap);
 	return LCD_OK;
 }
 
