@@ -20,10 +20,15 @@
  *   - one engine = one VWDictionary instance + its inverted index on one GPU;
  *     several engines may coexist (RegistrationVis builds temporary
  *     dictionaries, RegistrationVis.cpp:1482-1503);
- *   - calls on one engine must be serialised by the caller, except that
- *     lcd_orb_* may run concurrently with lcd_dict_update (the reference runs
- *     VWDictionary::update() on PreUpdateThread beside feature extraction,
- *     Memory.cpp:5284, :5926).
+ *   - calls on one engine must be serialised by the caller, with ONE exception:
+ *     the host-buffer lcd_orb_detect_describe may run on a second thread while
+ *     lcd_dict_update runs (the reference runs VWDictionary::update() on
+ *     PreUpdateThread beside feature extraction, Memory.cpp:5284, :5926).  The two
+ *     calls share no buffers, run on different CUDA streams, and the counters they
+ *     both touch are atomic (tests/test_gpu_concurrency.py).  lcd_profile_enable(1)
+ *     suspends that exception (its event lists are not thread-safe);
+ *   - the *_dev entry points of one engine must all be given the same stream (or
+ *     NULL): scratch buffers are shared between them.
  */
 #ifndef LCD_B200_H
 #define LCD_B200_H
@@ -64,7 +69,7 @@ void lcd_destroy(lcd_engine * e);
 /* last error text of this engine (e may be NULL: error of the last failed lcd_create) */
 const char * lcd_last_error(const lcd_engine * e);
 /* library/ABI version, and the name of the CUDA arch the kernels were built for */
-int lcd_abi_version(void);
+int lcd_abi_version(void); /* 2: lcd_verify_params / lcd_verify_result grew (covariance), lcd_verify_batch takes xyz_to */
 const char * lcd_build_arch(void);
 /* number of kernels this engine has launched since creation (bench "gpu_launches") */
 long long lcd_launch_count(const lcd_engine * e);
@@ -112,6 +117,10 @@ int lcd_orb_detect_describe_dev(lcd_engine * e, int n_frames, const uint8_t * d_
                                 const void * d_depth, int depth_type, const lcd_orb_params * params, int cap,
                                 lcd_keypoint * d_kp_out, uint8_t * d_desc_out, float * d_xyz_out, float * d_uv_out,
                                 int * d_n_out, void * stream);
+/* 1 if the last lcd_orb_* / lcd_process_frames* call on this engine truncated a FAST candidate list (more than 16 384 corners in
+ * level 0, half as many per further level), else 0; synchronises the device.  The host-buffer entry points report the condition
+ * themselves (LCD_ERR_CAPACITY); the *_dev variants return before the kernels ran, so their callers ask here. */
+int lcd_orb_overflow(lcd_engine * e);
 
 /* ---- dictionary: VWDictionary ------------------------------------------------ */
 /* replaces: VWDictionary::addWord (VWDictionary.cpp:1554-1580) for n words whose ids
@@ -230,16 +239,22 @@ typedef struct lcd_verify_params {
 	int refine_iterations; /* Vis/PnPRefineIterations (1)                                   */
 	float refine_sigma;    /* refineSigma of util3d::solvePnPRansac (3.0)                   */
 	double fx, fy, cx, cy; /* CameraModel::K() of the TO signature                          */
+	int var_median_ratio;  /* Vis/PnPVarianceMedianRatio (4, must be > 1)                   */
+	float max_variance;    /* Vis/PnPMaxVariance (0 = off): reject when the linear variance exceeds it */
+	int split_linear_cov;  /* Vis/PnPSplitLinearCovComponents (0)                           */
+	int image_width, image_height; /* CameraModel::imageSize() of the TO camera (0, 0 = not set) */
 } lcd_verify_params;
 
 typedef struct lcd_verify_result {
-	int ok;               /* 1: inliers >= min_inliers, transform valid                      */
+	int ok;               /* 1: inliers >= min_inliers (and variance accepted), transform valid */
 	int n_matches;        /* correspondences given to PnP                                    */
 	int n_inliers;
 	int iterations_run;   /* RANSAC iterations the sequential reference would have executed  */
 	double rvec[3];       /* PnP pose (object -> camera), Rodrigues vector                   */
 	double tvec[3];
 	float transform[12];  /* (localTransform * pnp)^-1 as rtabmap::Transform 3x4             */
+	double covariance[36]; /* RegistrationInfo::covariance, 6x6 row-major (util3d_motion_estimation.cpp:156-258): identity scaled by
+	                          2.1981 x the [n/ratio]-th smallest squared 3-D error (rows 0-2) and angular error (rows 3-5) of the inliers */
 } lcd_verify_result;
 
 /* replaces: the global matching of RegistrationVis::computeTransformationImpl through a temporary
@@ -249,13 +264,46 @@ int lcd_match_pairs(lcd_engine * e, int n_pairs, int cap, const void * desc_from
                     const void * desc_to, const int * n_to, float nndr, int * from_ids, int * to_ids);
 
 /* replaces: Memory::computeTransform -> RegistrationVis (global matching, RegistrationVis.cpp:1482-1546)
- * -> util3d::estimateMotion3DTo2D (util3d_motion_estimation.cpp:59-289) -> util3d::solvePnPRansac
- * (:843-990) -> cv3::solvePnPRansac (opencv/solvepnp.cpp:112-417).  xyz_from: NaN where a keypoint has
- * no depth.  match_ids / inlier_ids [n_pairs*cap] (word ids, ascending / in inlier order) may be NULL. */
-int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const float * xyz_from,
-                     const int * n_from, const void * desc_to, const float * uv_to, const int * n_to,
-                     const lcd_verify_params * params, lcd_verify_result * results, int * match_ids,
-                     int * inlier_ids);
+ * -> util3d::estimateMotion3DTo2D (util3d_motion_estimation.cpp:59-289, incl. the covariance :156-258) -> util3d::solvePnPRansac
+ * (:843-990) -> cv3::solvePnPRansac (opencv/solvepnp.cpp:112-417).  xyz_from: NaN where a keypoint has no depth.  xyz_to: the 3-D
+ * points of the TO signature (words3B; NaN = none) or NULL when it has none — the covariance then comes from the 10 %-depth ray
+ * model (image size set) or from the reprojection RMS (image size 0 x 0), as in the reference.
+ * match_ids / inlier_ids [n_pairs*cap] (word ids, ascending / in inlier order) may be NULL. */
+int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const float * xyz_from, const int * n_from,
+                     const void * desc_to, const float * uv_to, const float * xyz_to, const int * n_to,
+                     const lcd_verify_params * params, lcd_verify_result * results, int * match_ids, int * inlier_ids);
+
+/* replaces: util3d::solvePnPRansac (util3d_motion_estimation.cpp:843-990; argument for argument: objectPoints, imagePoints,
+ * cameraMatrix, distCoeffs, rvec, tvec, useExtrinsicGuess, iterationsCount, reprojectionError, minInliersCount, inliers, flags,
+ * refineIterations, refineSigma) = cv3::solvePnPRansac (opencv/solvepnp.cpp:112-211: EPnP on 6-point samples drawn with
+ * cv::RNG(-1), strict-best model, adaptive iteration count at confidence 0.99, returned pose = best minimal-sample model) followed
+ * by the PCL-style refinement loop (:882-989).  object_points[n*3], image_points[n*2] float; K[9] row-major 3x3 double;
+ * dist_coeffs[n_dist] must be all zero (or NULL): RTAB-Map passes CameraModel::D(), zeros for rectified images — anything else is
+ * rejected with LCD_ERR_INVALID, as are flags != 0 (SOLVEPNP_ITERATIVE) and n == 4 (the reference switches to P3P).
+ * rvec / tvec: in = the extrinsic guess (EPnP ignores it, exactly as in the reference), out = the refined pose; left untouched when
+ * RANSAC finds no model.  inliers_out[n] (indices into the input, ascending), *n_inliers_out. */
+int lcd_pnp_ransac(lcd_engine * e, const float * object_points, const float * image_points, int n, const double K[9],
+                   const double * dist_coeffs, int n_dist, double rvec[3], double tvec[3], int use_extrinsic_guess,
+                   int iterations, float reproj_error, int min_inliers, int flags, int refine_iterations, float refine_sigma,
+                   int * inliers_out, int * n_inliers_out);
+/* n_sets independent problems in one launch (one CTA each): object_points[n_sets][cap][3], image_points[n_sets][cap][2],
+ * n_points[n_sets], rvec / tvec [n_sets][3], inliers_out[n_sets][cap], n_inliers_out / iterations_run_out [n_sets] (may be NULL). */
+int lcd_pnp_ransac_batch(lcd_engine * e, int n_sets, int cap, const float * object_points, const float * image_points, const int * n_points,
+                         const double K[9], const double * dist_coeffs, int n_dist, double * rvec, double * tvec, int use_extrinsic_guess,
+                         int iterations, float reproj_error, int min_inliers, int flags, int refine_iterations, float refine_sigma,
+                         int * inliers_out, int * n_inliers_out, int * iterations_run_out);
+
+/* replaces: cv::BFMatcher on the descriptors of a signature pair (NORM_HAMMING for LCD_DESC_U8 engines, NORM_L2SQR for LCD_DESC_F32):
+ *   LCD_MATCH_KNN2       knnMatch(query, train, k = 2)          (RegistrationVis.cpp:1128-1141, :1280-1300; VWDictionary.cpp:1027-1028)
+ *   LCD_MATCH_CROSSCHECK BFMatcher(norm, crossCheck = true).match(query, train)   (RegistrationVis.cpp:1452-1453, Vis/CorNNType = 5)
+ * for n_pairs independent pairs, [n_pairs][cap] rows each.  idx1 / dist1 [n_pairs*cap]: train index and distance of the best match of
+ * every query row (-1 / -1 = none: in cross-check mode the queries OpenCV returns no DMatch for); idx2 / dist2: second neighbour
+ * (KNN2 only; may be NULL in cross-check mode).  Ties resolve to the lowest index, as in cv::batchDistance.  Float distances are summed in
+ * rtflann's order (dist.h:158-166), which can differ from OpenCV's SIMD order in the last ulp. */
+#define LCD_MATCH_KNN2 0
+#define LCD_MATCH_CROSSCHECK 1
+int lcd_match_bf(lcd_engine * e, int n_pairs, int cap, const void * desc_query, const int * n_query, const void * desc_train,
+                 const int * n_train, int mode, int * idx1, float * dist1, int * idx2, float * dist2);
 
 /* ---- signature store + fused query ----------------------------------------------------------
  * The per-node data Memory keeps for verification (Signature::getWordsDescriptors / getWords3,
@@ -266,6 +314,8 @@ int lcd_sig_add_batch(lcd_engine * e, const int * sig_ids, int n_sigs, int cap, 
                       const float * xyz, const int * n);
 int lcd_sig_remove(lcd_engine * e, int sig_id);
 int lcd_sig_count(const lcd_engine * e);
+/* rows the store has allocated so far (freed rows are reused before it grows) */
+int lcd_sig_slots(const lcd_engine * e);
 
 /* One call = n_frames independent loop-closure queries through quantise -> score -> verify:
  * lcd_localize_batch, then for every frame the signature with the highest likelihood (first maximum,

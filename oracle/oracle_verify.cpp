@@ -845,6 +845,144 @@ int orcv_verify_pair(int desc_type, int dim, const void * desc_from, const float
 	return 1;
 }
 
+// The covariance block of util3d::estimateMotion3DTo2D (util3d_motion_estimation.cpp:156-266) for one accepted pose, single camera,
+// identity localTransform.  obj[n*3] / img[n*2]: the correspondences given to PnP; obj_to[n*3]: the 3-D point of camera B for each
+// correspondence (words3B; NaN = none) or NULL when the TO signature has no 3-D words; inliers[n_inl] index the correspondences.
+// T[12] = transform (float 3x4) as returned; rvec/tvec the PnP pose.  cov[36] row-major.  Returns 0 when Vis/PnPMaxVariance rejects
+// the transform (covariance reset to identity), else 1.  Float arithmetic follows the reference statement by statement
+// (util3d::transformPoint, util3d_transforms.cpp:211-220; util3d::projectDepthTo3DRay, util3d.cpp:246-264; uNormSquared, UMath.h:601-605;
+// pcl::getAngle3D is third party (PCL common: acos of the clamped dot product of the normalised vectors)).
+int orcv_covariance(const float * obj, const float * img, const float * obj_to, int n, const int * inliers, int n_inl, const float T[12],
+                    const double rvec[3], const double tvec[3], const double K[4], int img_w, int img_h, int var_median_ratio,
+                    float max_variance, int split_linear, double cov[36])
+{
+	for (int i = 0; i < 36; ++i) cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+	if (n_inl <= 0) return 1;
+	auto tp = [](const float * M, float x, float y, float z, float out[3]) {
+		out[0] = M[0] * x + M[1] * y + M[2] * z + M[3];
+		out[1] = M[4] * x + M[5] * y + M[6] * z + M[7];
+		out[2] = M[8] * x + M[9] * y + M[10] * z + M[11];
+	};
+	if (obj_to || img_w != 0 || img_h != 0)
+	{
+		// transformCameraFrameInv = (transform * localTransform)^-1: the rigid inverse of T
+		float P[12];
+		for (int i = 0; i < 3; ++i)
+		{
+			for (int j = 0; j < 3; ++j) P[4 * i + j] = T[4 * j + i];
+			P[4 * i + 3] = -(T[0 + i] * T[3] + T[4 + i] * T[7] + T[8 + i] * T[11]);
+		}
+		std::vector<float> eD(n_inl), eA(n_inl), eX(n_inl), eY(n_inl), eZ(n_inl);
+		for (int k = 0; k < n_inl; ++k)
+		{
+			const int i = inliers[k];
+			const float ox = obj[3 * i], oy = obj[3 * i + 1], oz = obj[3 * i + 2];
+			float np_[3];
+			const float * b = obj_to ? obj_to + 3 * i : nullptr;
+			if (b && std::isfinite(b[0]) && std::isfinite(b[1]) && std::isfinite(b[2])) tp(T, b[0], b[1], b[2], np_);
+			else
+			{
+				float cb[3];
+				tp(P, ox, oy, oz, cb);
+				float cx = (float)K[2], cy = (float)K[3];
+				const float fx = (float)K[0], fy = (float)K[1];
+				cx = cx > 0.0f ? cx : float(img_w / 2) - 0.5f;
+				cy = cy > 0.0f ? cy : float(img_h / 2) - 0.5f;
+				const float rx = (img[2 * i] - cx) / fx, ry = (img[2 * i + 1] - cy) / fy;
+				const double sc = cb[2] * 1.1; // float * double literal
+				const float px = (float)(rx * sc), py = (float)(ry * sc), pz = (float)(1.0f * sc);
+				tp(T, px, py, pz, np_);
+			}
+			const float dx = ox - np_[0], dy = oy - np_[1], dz = oz - np_[2];
+			eD[k] = dx * dx + dy * dy + dz * dz;
+			const double ex = dx, ey = dy, ez = dz;
+			eX[k] = (float)(ex * ex);
+			eY[k] = (float)(ey * ey);
+			eZ[k] = (float)(ez * ez);
+			const float n1 = std::sqrt(ox * ox + oz * oz + oy * oy), n2 = std::sqrt(np_[0] * np_[0] + np_[2] * np_[2] + np_[1] * np_[1]);
+			const float ax = ox / n1, ay = oy / n1, az = oz / n1, bx = np_[0] / n2, by = np_[1] / n2, bz = np_[2] / n2;
+			double rad = (double)(ax * bx + az * bz + ay * by);
+			rad = rad < -1.0 ? -1.0 : (rad > 1.0 ? 1.0 : rad);
+			eA[k] = (float)std::acos(rad);
+		}
+		const int kth = n_inl / var_median_ratio;
+		std::sort(eD.begin(), eD.end());
+		std::sort(eA.begin(), eA.end());
+		double lin = 2.1981 * (double)eD[kth];
+		const double ang = 2.1981 * (double)eA[kth];
+		for (int i = 0; i < 3; ++i) cov[7 * i] *= lin;
+		for (int i = 3; i < 6; ++i) cov[7 * i] *= ang;
+		if (split_linear)
+		{
+			std::sort(eX.begin(), eX.end());
+			std::sort(eY.begin(), eY.end());
+			std::sort(eZ.begin(), eZ.end());
+			const double mx = 2.1981 * (double)eX[kth], my = 2.1981 * (double)eY[kth], mz = 2.1981 * (double)eZ[kth];
+			cov[0] = mx;
+			cov[7] = my;
+			cov[14] = mz;
+			lin = std::max(mx, std::max(my, mz));
+		}
+		if (max_variance > 0 && lin > max_variance)
+		{
+			for (int i = 0; i < 36; ++i) cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+			return 0;
+		}
+		return 1;
+	}
+	// rms of the inliers' reprojection errors (:253-266)
+	Cam cam{K[0], K[1], K[2], K[3]};
+	std::vector<double> uvp(2 * n);
+	project(obj, n, rvec, tvec, cam, uvp.data(), nullptr);
+	float err = 0.0f;
+	for (int k = 0; k < n_inl; ++k)
+	{
+		const int i = inliers[k];
+		const float ex = img[2 * i] - (float)uvp[2 * i], ey = img[2 * i + 1] - (float)uvp[2 * i + 1];
+		err += ex * ex + ey * ey;
+	}
+	const double sc = std::sqrt(err / float(n_inl));
+	for (int i = 0; i < 6; ++i) cov[7 * i] *= sc;
+	return 1;
+}
+
+// orcv_verify_pair + the covariance: xyz_to[n_to*3] may be NULL.  cov[36].
+int orcv_verify_pair_cov(int desc_type, int dim, const void * desc_from, const float * xyz_from, int n_from, const void * desc_to,
+                         const float * uv_to, const float * xyz_to, int n_to, const double K[4], float nndr, int min_inliers, int iterations,
+                         float reproj, int refine_iterations, int img_w, int img_h, int var_median_ratio, float max_variance, int split_linear,
+                         int * match_ids, int * n_matches, int * inlier_ids, int * n_inliers, double rvec[3], double tvec[3], float transform[12],
+                         double cov[36])
+{
+	for (int i = 0; i < 36; ++i) cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+	int ok = orcv_verify_pair(desc_type, dim, desc_from, xyz_from, n_from, desc_to, uv_to, n_to, K, nndr, min_inliers, iterations, reproj,
+	                          refine_iterations, match_ids, n_matches, inlier_ids, n_inliers, rvec, tvec, transform);
+	if (!ok) return 0;
+	// rebuild the correspondence arrays in match order (match ids are the temporary dictionary's word ids)
+	std::vector<int> fid(std::max(n_from, 1)), tid(std::max(n_to, 1));
+	orcv_match_pair(desc_type, dim, desc_from, n_from, desc_to, n_to, nndr, fid.data(), tid.data());
+	std::map<int, int> f_of, t_of;
+	for (int i = 0; i < n_from; ++i) f_of[fid[i]] = i;
+	for (int i = 0; i < n_to; ++i) t_of[tid[i]] = i;
+	const int nm = *n_matches, ni = *n_inliers;
+	std::vector<float> obj(3 * nm), img(2 * nm), objt(3 * nm);
+	std::map<int, int> pos;
+	for (int m = 0; m < nm; ++m)
+	{
+		const int id = match_ids[m], fi = f_of[id], ti = t_of[id];
+		pos[id] = m;
+		memcpy(&obj[3 * m], xyz_from + 3 * fi, 3 * sizeof(float));
+		memcpy(&img[2 * m], uv_to + 2 * ti, 2 * sizeof(float));
+		if (xyz_to) memcpy(&objt[3 * m], xyz_to + 3 * ti, 3 * sizeof(float));
+	}
+	std::vector<int> inl(ni);
+	for (int k = 0; k < ni; ++k) inl[k] = pos[inlier_ids[k]];
+	ok = orcv_covariance(obj.data(), img.data(), xyz_to ? objt.data() : nullptr, nm, inl.data(), ni, transform, rvec, tvec, K, img_w, img_h,
+	                     var_median_ratio, max_variance, split_linear, cov);
+	if (!ok)
+		for (int i = 0; i < 12; ++i) transform[i] = 0; // transform.setNull()
+	return ok;
+}
+
 // the restated OpenCV pieces, exposed one by one so tests can pin each against cv2
 int orcv_solve_pnp_epnp(const float * opts, const float * ipts, int n, const double K[4], double rvec[3], double tvec[3])
 {

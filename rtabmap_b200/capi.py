@@ -64,6 +64,11 @@ class VerifyParams(C.Structure):
         ("fy", C.c_double),
         ("cx", C.c_double),
         ("cy", C.c_double),
+        ("var_median_ratio", C.c_int),
+        ("max_variance", C.c_float),
+        ("split_linear_cov", C.c_int),
+        ("image_width", C.c_int),
+        ("image_height", C.c_int),
     ]
 
 
@@ -76,6 +81,7 @@ class VerifyResult(C.Structure):
         ("rvec", C.c_double * 3),
         ("tvec", C.c_double * 3),
         ("transform", C.c_float * 12),
+        ("covariance", C.c_double * 36),
     ]
 
 
@@ -99,6 +105,7 @@ SIGNATURES = {
     "lcd_launch_count": (C.c_longlong, [_P]),
     "lcd_orb_detect_describe": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
     "lcd_orb_detect_describe_dev": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "lcd_orb_overflow": (_I, [_P]),
     "lcd_dict_add_words": (_I, [_P, _P, _P, _I]),
     "lcd_dict_remove_words": (_I, [_P, _P, _I]),
     "lcd_dict_update": (_I, [_P]),
@@ -128,10 +135,14 @@ SIGNATURES = {
     "lcd_localize_batch": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P]),
     "lcd_localize_batch_dev": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
     "lcd_match_pairs": (_I, [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
-    "lcd_verify_batch": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lcd_verify_batch": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "lcd_pnp_ransac": (_I, [_P, _P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _F, _P, _P]),
+    "lcd_pnp_ransac_batch": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _I, _F, _P, _P, _P]),
+    "lcd_match_bf": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
     "lcd_sig_add_batch": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "lcd_sig_remove": (_I, [_P, _I]),
     "lcd_sig_count": (_I, [_P]),
+    "lcd_sig_slots": (_I, [_P]),
     "lcd_process_batch": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "lcd_process_batch_dev": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
     "lcd_process_fetch": (_I, [_P, _I, _P, _P]),
@@ -471,24 +482,74 @@ class Engine:
         return fid, tid
 
     def verify_batch(self, desc_from, xyz_from, desc_to, uv_to, K4, n_from=None, n_to=None, nndr: float = 0.8, min_inliers: int = 20,
-                     iterations: int = 300, reproj_error: float = 2.0, refine_iterations: int = 1, refine_sigma: float = 3.0):
+                     iterations: int = 300, reproj_error: float = 2.0, refine_iterations: int = 1, refine_sigma: float = 3.0, xyz_to=None,
+                     var_median_ratio: int = 4, max_variance: float = 0.0, split_linear_cov: bool = False, image_size=(0, 0)):
         """Memory::computeTransform for a batch of (FROM, TO) pairs; returns a list of dicts."""
         a, b, nf, nt, n_pairs, cap = self._pairs(desc_from, desc_to, n_from, n_to)
         xyz = np.ascontiguousarray(xyz_from, np.float32).reshape(n_pairs, cap, 3)
         uv = np.ascontiguousarray(uv_to, np.float32).reshape(n_pairs, cap, 2)
-        prm = VerifyParams(nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, *[float(k) for k in K4])
+        xt = None if xyz_to is None else np.ascontiguousarray(xyz_to, np.float32).reshape(n_pairs, cap, 3)
+        prm = self.verify_params(K4, nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, var_median_ratio, max_variance,
+                                 split_linear_cov, image_size)
         res = (VerifyResult * n_pairs)()
         mids = np.zeros((n_pairs, cap), np.int32)
         iids = np.zeros((n_pairs, cap), np.int32)
-        self._check(self._lib.lcd_verify_batch(self._h, n_pairs, cap, _ptr(a), _ptr(xyz), _ptr(nf), _ptr(b), _ptr(uv), _ptr(nt),
+        self._check(self._lib.lcd_verify_batch(self._h, n_pairs, cap, _ptr(a), _ptr(xyz), _ptr(nf), _ptr(b), _ptr(uv), _ptr(xt), _ptr(nt),
                                                 C.byref(prm), res, _ptr(mids), _ptr(iids)))
         out = []
         for i in range(n_pairs):
             r = res[i]
             out.append({"ok": bool(r.ok), "matches": mids[i, :r.n_matches].copy(), "inliers": iids[i, :r.n_inliers].copy(),
                         "iterations_run": r.iterations_run, "rvec": np.array(r.rvec[:]), "tvec": np.array(r.tvec[:]),
-                        "transform": np.array(r.transform[:], np.float32).reshape(3, 4)})
+                        "transform": np.array(r.transform[:], np.float32).reshape(3, 4),
+                        "covariance": np.array(r.covariance[:], np.float64).reshape(6, 6)})
         return out
+
+    def pnp_ransac(self, object_points, image_points, K4, rvec=None, tvec=None, use_guess: bool = True, iterations: int = 300,
+                   reproj_error: float = 2.0, min_inliers: int = 20, flags: int = 0, refine_iterations: int = 1, refine_sigma: float = 3.0,
+                   dist_coeffs=None):
+        """util3d::solvePnPRansac: returns (rvec, tvec, inlier indices)."""
+        X = np.ascontiguousarray(object_points, np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(image_points, np.float32).reshape(-1, 2)
+        n = len(X)
+        K = np.array([K4[0], 0, K4[2], 0, K4[1], K4[3], 0, 0, 1], np.float64)
+        D = None if dist_coeffs is None else np.ascontiguousarray(dist_coeffs, np.float64)
+        r = np.zeros(3) if rvec is None else np.array(rvec, np.float64)
+        t = np.zeros(3) if tvec is None else np.array(tvec, np.float64)
+        inl = np.zeros(max(n, 1), np.int32)
+        n_inl = C.c_int(0)
+        self._check(self._lib.lcd_pnp_ransac(self._h, _ptr(X), _ptr(uv), n, _ptr(K), _ptr(D), 0 if D is None else len(D), _ptr(r), _ptr(t),
+                                              int(use_guess), int(iterations), float(reproj_error), int(min_inliers), int(flags),
+                                              int(refine_iterations), float(refine_sigma), _ptr(inl), C.byref(n_inl)))
+        return r, t, inl[:n_inl.value].copy()
+
+    def pnp_ransac_batch(self, object_points, image_points, n_points, K4, iterations: int = 300, reproj_error: float = 2.0,
+                         min_inliers: int = 20, refine_iterations: int = 1, refine_sigma: float = 3.0):
+        X = np.ascontiguousarray(object_points, np.float32)
+        uv = np.ascontiguousarray(image_points, np.float32)
+        n_sets, cap = X.shape[:2]
+        npts = _i32(n_points)
+        K = np.array([K4[0], 0, K4[2], 0, K4[1], K4[3], 0, 0, 1], np.float64)
+        r = np.zeros((n_sets, 3))
+        t = np.zeros((n_sets, 3))
+        inl = np.zeros((n_sets, cap), np.int32)
+        n_inl = np.zeros(n_sets, np.int32)
+        its = np.zeros(n_sets, np.int32)
+        self._check(self._lib.lcd_pnp_ransac_batch(self._h, n_sets, cap, _ptr(X), _ptr(uv), _ptr(npts), _ptr(K), None, 0, _ptr(r), _ptr(t), 1,
+                                                    int(iterations), float(reproj_error), int(min_inliers), 0, int(refine_iterations),
+                                                    float(refine_sigma), _ptr(inl), _ptr(n_inl), _ptr(its)))
+        return r, t, [inl[i, :n_inl[i]].copy() for i in range(n_sets)], its
+
+    def match_bf(self, desc_query, desc_train, n_query=None, n_train=None, cross_check: bool = False):
+        """cv::BFMatcher on [n_pairs, cap, dim] descriptor sets: (idx1, dist1, idx2, dist2); idx2 / dist2 are None with cross_check."""
+        q, t, nq, nt, n_pairs, cap = self._pairs(desc_query, desc_train, n_query, n_train)
+        i1 = np.zeros((n_pairs, cap), np.int32)
+        d1 = np.zeros((n_pairs, cap), np.float32)
+        i2 = None if cross_check else np.zeros((n_pairs, cap), np.int32)
+        d2 = None if cross_check else np.zeros((n_pairs, cap), np.float32)
+        self._check(self._lib.lcd_match_bf(self._h, n_pairs, cap, _ptr(q), _ptr(nq), _ptr(t), _ptr(nt), 1 if cross_check else 0, _ptr(i1), _ptr(d1),
+                                            _ptr(i2), _ptr(d2)))
+        return i1, d1, i2, d2
 
     # -- signature store + fused query -------------------------------------------------------------
     def sig_add_batch(self, sig_ids, desc, xyz, n=None):
@@ -507,9 +568,20 @@ class Engine:
     def sig_count(self) -> int:
         return self._lib.lcd_sig_count(self._h)
 
+    def sig_slots(self) -> int:
+        return self._lib.lcd_sig_slots(self._h)
+
+    def orb_overflow(self) -> bool:
+        r = self._lib.lcd_orb_overflow(self._h)
+        if r < 0:
+            self._check(r)
+        return bool(r)
+
     @staticmethod
-    def verify_params(K4, nndr=0.8, min_inliers=20, iterations=300, reproj_error=2.0, refine_iterations=1, refine_sigma=3.0):
-        return VerifyParams(nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, *[float(k) for k in K4])
+    def verify_params(K4, nndr=0.8, min_inliers=20, iterations=300, reproj_error=2.0, refine_iterations=1, refine_sigma=3.0, var_median_ratio=4,
+                      max_variance=0.0, split_linear_cov=False, image_size=(0, 0)):
+        return VerifyParams(nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, *[float(k) for k in K4],
+                            int(var_median_ratio), float(max_variance), int(bool(split_linear_cov)), int(image_size[0]), int(image_size[1]))
 
     @staticmethod
     def _results(res, n):
@@ -517,7 +589,8 @@ class Engine:
         for i in range(n):
             r = res[i]
             out.append({"ok": bool(r.ok), "n_matches": r.n_matches, "n_inliers": r.n_inliers, "iterations_run": r.iterations_run,
-                        "rvec": np.array(r.rvec[:]), "tvec": np.array(r.tvec[:]), "transform": np.array(r.transform[:], np.float32).reshape(3, 4)})
+                        "rvec": np.array(r.rvec[:]), "tvec": np.array(r.tvec[:]), "transform": np.array(r.transform[:], np.float32).reshape(3, 4),
+                        "covariance": np.array(r.covariance[:], np.float64).reshape(6, 6)})
         return out
 
     def process_batch(self, queries, uv, n_frames: int, sig_ids, n_total: int, vp: "VerifyParams", incremental: bool = True, nndr: float = 0.8,

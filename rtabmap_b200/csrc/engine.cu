@@ -17,12 +17,16 @@
 #include "resolve.cuh"
 #include "score.cuh"
 #include "verify.cuh"
+#include "match_bf.cuh"
 #include "orb.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -47,7 +51,9 @@ struct DevBuf
 		p = nullptr;
 		cap = 0;
 	}
-	// grow to at least n elements; keep the first `keep` elements; zero the rest if asked
+	// grow to at least n elements; keep the first `keep` elements; zero the rest if asked.
+	// A re-growth replaces a buffer that kernels on ANY stream of the engine (caller streams of the _dev entry points, the ORB side
+	// streams) may still be reading or writing: the device is drained first, so the copy sees final data and the free is safe.
 	cudaError_t reserve(size_t n, size_t keep, bool zero_new, cudaStream_t s)
 	{
 		if (n <= cap) return cudaSuccess;
@@ -55,21 +61,16 @@ struct DevBuf
 		T * np = nullptr;
 		cudaError_t err = cudaMalloc(&np, ncap * sizeof(T));
 		if (err != cudaSuccess) return err;
-		if (zero_new)
+		if (p) err = cudaDeviceSynchronize();
+		if (err == cudaSuccess && zero_new) err = cudaMemsetAsync(np, 0, ncap * sizeof(T), s);
+		if (err == cudaSuccess && p && keep) err = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+		if (err == cudaSuccess && p) err = cudaStreamSynchronize(s);
+		if (err != cudaSuccess)
 		{
-			err = cudaMemsetAsync(np, 0, ncap * sizeof(T), s);
-			if (err != cudaSuccess) return err;
+			cudaFree(np);
+			return err;
 		}
-		if (p && keep)
-		{
-			err = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
-			if (err != cudaSuccess) return err;
-		}
-		if (p)
-		{
-			cudaStreamSynchronize(s);
-			cudaFree(p);
-		}
+		if (p) cudaFree(p);
 		p = np;
 		cap = ncap;
 		return cudaSuccess;
@@ -129,7 +130,9 @@ struct lcd_engine
 	lcd_config cfg{};
 	int nw = 0; // 32-bit words per descriptor
 	mutable std::string err;
+	mutable std::mutex err_mu;                // lcd_orb_* may fail on another thread than the dictionary calls
 	cudaStream_t stream = nullptr;
+	cudaStream_t orb_stream = nullptr;        // host-buffer lcd_orb_detect_describe: its own stream, so that it overlaps lcd_dict_update
 	cudaStream_t copy_stream = nullptr;       // host -> device image chunks of lcd_process_frames
 	std::vector<cudaEvent_t> copy_events;     // one per chunk
 	cudaEvent_t copy_fence = nullptr;
@@ -154,7 +157,7 @@ struct lcd_engine
 	DevBuf<PackedVerifyResult> v_packed;
 	PinBuf<PackedVerifyResult> h_packed;
 	PinBuf<int> h_overflow;
-	long long launches = 0;
+	std::atomic<long long> launches{0};
 	int sm_count = 148;
 	int smem_optin = 0;
 
@@ -200,7 +203,10 @@ struct lcd_engine
 	DevBuf<int> d_perm;
 	// verification scratch
 	DevBuf<uint32_t> v_df, v_dt;
-	DevBuf<float> v_xyz, v_uv, v_obj, v_img, v_T;
+	DevBuf<float> v_xyz, v_uv, v_obj, v_img, v_T, v_xyz_to, v_obj_to;
+	DevBuf<double> v_cov6;
+	DevBuf<ulonglong2> bf_keys_a, bf_keys_b;
+	DevBuf<unsigned long long> bf_best;
 	DevBuf<long long> v_clk;
 	DevBuf<int> v_nf, v_nt, v_mid, v_mfrom, v_mto, v_nm, v_fid, v_tid, v_inl, v_ninl, v_iters, v_ok, v_inl_ids;
 	DevBuf<double> v_rvec, v_tvec;
@@ -235,6 +241,8 @@ struct lcd_engine
 	DevBuf<ulonglong2> d_partial64;
 	int nn_tensor = 1;   // 256-bit descriptors: tcgen05 int8 path (nn_tensor.cuh); 0 = POPC kernel (nn_hamming.cuh)
 	int nn_last_tensor = 0; // which kernel the last run_knn used (bench / diagnostics)
+	bool match_has_xyz_to = false; // verify_upload staged xyz_to for the next launch_match
+	bool pnp_has_obj_to = false;   // the last launch_match gathered obj_to for launch_pnp
 };
 
 #define LCD_FAIL(e, code, ...)                          \
@@ -242,7 +250,10 @@ struct lcd_engine
 	{                                                   \
 		char _b[512];                                   \
 		snprintf(_b, sizeof(_b), __VA_ARGS__);          \
-		(e)->err = _b;                                  \
+		{                                               \
+			std::lock_guard<std::mutex> _g((e)->err_mu); \
+			(e)->err = _b;                              \
+		}                                               \
 		return (code);                                  \
 	} while (0)
 
@@ -682,6 +693,14 @@ int require_binary(lcd_engine * e, const char * what)
 	return LCD_OK;
 }
 
+// entry points that translate local rows through e->row_ids are only valid on an unsharded engine
+int require_unsharded(lcd_engine * e, const char * what)
+{
+	if (e->row_offset != 0)
+		LCD_FAIL(e, LCD_ERR_STATE, "%s needs an unsharded engine (lcd_shard_set_row_offset(%d) is set: use the lcd_shard_* calls)", what, e->row_offset);
+	return LCD_OK;
+}
+
 int check_queries(lcd_engine * e, const void * q, int nq)
 {
 	if (!q || nq <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "Descriptors size is null!");
@@ -695,6 +714,7 @@ int localize_dev(lcd_engine * e, const uint32_t * d_q, int n_frames, int nq, int
                  const int * d_nq_frame = nullptr)
 {
 	if (e->n_indexed == 0 && !incremental) LCD_FAIL(e, LCD_ERR_STATE, "Dictionary mode is set to fixed but no words are in it!");
+	LCD_TRY(require_unsharded(e, "localisation on one engine"));
 	const int nq_total = n_frames * nq;
 	int n_chunks = 0;
 	LCD_TRY(run_knn(e, d_q, nq_total, e->n_indexed, &n_chunks, s));
@@ -738,11 +758,11 @@ int localize_dev(lcd_engine * e, const uint32_t * d_q, int n_frames, int nq, int
 // ============================================================================ C ABI ====
 extern "C" {
 
-int lcd_abi_version(void) { return 1; }
+int lcd_abi_version(void) { return 2; }
 const char * lcd_build_arch(void) { return "sm_100a"; }
 
 const char * lcd_last_error(const lcd_engine * e) { return e ? e->err.c_str() : g_create_error.c_str(); }
-long long lcd_launch_count(const lcd_engine * e) { return e ? e->launches : 0; }
+long long lcd_launch_count(const lcd_engine * e) { return e ? e->launches.load() : 0; }
 
 int lcd_nn_select(lcd_engine * e, int kernel)
 {
@@ -788,7 +808,8 @@ lcd_engine * lcd_create(const lcd_config * cfg)
 	e->cfg = *cfg;
 	e->f32 = cfg->desc_type == LCD_DESC_F32;
 	e->nw = e->f32 ? cfg->desc_dim : cfg->desc_dim / 4; // 32-bit words per descriptor row
-	if ((err = cudaSetDevice(cfg->device)) != cudaSuccess || (err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess)
+	if ((err = cudaSetDevice(cfg->device)) != cudaSuccess || (err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (err = cudaStreamCreateWithFlags(&e->orb_stream, cudaStreamNonBlocking)) != cudaSuccess)
 	{
 		g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(err);
 		delete e;
@@ -818,6 +839,11 @@ void lcd_destroy(lcd_engine * e)
 	if (e->stream)
 	{
 		cudaStreamSynchronize(e->stream);
+		if (e->orb_stream)
+		{
+			cudaStreamSynchronize(e->orb_stream);
+			cudaStreamDestroy(e->orb_stream);
+		}
 		if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
 		for (cudaEvent_t ev : e->copy_events) cudaEventDestroy(ev);
 		if (e->copy_fence) cudaEventDestroy(e->copy_fence);
@@ -930,7 +956,22 @@ int lcd_dict_remove_words(lcd_engine * e, const int * ids, int n)
 		e->id2row.erase(it);
 		if (ids[i] < static_cast<int>(e->h_len.size()) && e->h_len[ids[i]] > 0)
 		{
-			e->total_refs -= 0; // references of a removed word are dropped with it (caller removes only unused words)
+			// The reference only removes unused words (VWDictionary::deleteUnusedWords, VWDictionary.cpp:1595-1607); a word that still
+			// has references takes them with it here: its posting list is read back once so that the per-signature word lists and
+			// the reference total stay consistent with the device (a later lcd_index_remove_sig must not count them again).
+			const int len = e->h_len[ids[i]];
+			std::vector<int2> post(len);
+			LCD_CUDA(e, cudaMemcpyAsync(post.data(), e->postings.p + e->h_off[ids[i]], len * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+			LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+			for (const int2 & pc : post)
+			{
+				e->total_refs -= pc.y;
+				auto sw = e->sig_words.find(pc.x);
+				if (sw == e->sig_words.end()) continue;
+				auto & v = sw->second;
+				auto pos = std::lower_bound(v.begin(), v.end(), std::make_pair(ids[i], 0));
+				if (pos != v.end() && pos->first == ids[i]) v.erase(pos);
+			}
 			e->h_len[ids[i]] = 0;
 			zero_ids.push_back(ids[i]);
 		}
@@ -1082,6 +1123,7 @@ int lcd_dict_knn2(lcd_engine * e, const void * queries, int nq, int * id1, float
 	if (!e) return LCD_ERR_INVALID;
 	LCD_TRY(set_device(e));
 	if (!queries || nq <= 0 || !id1 || !d1 || !id2 || !d2) LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	LCD_TRY(require_unsharded(e, "lcd_dict_knn2"));
 	cudaStream_t s = e->stream;
 	LCD_CUDA(e, e->d_queries.reserve(static_cast<size_t>(nq) * e->nw, 0, false, s));
 	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, static_cast<size_t>(nq) * e->nw * 4, cudaMemcpyHostToDevice, s));
@@ -1120,6 +1162,7 @@ int lcd_dict_quantize(lcd_engine * e, const void * queries, int nq, int sig_id, 
 	LCD_TRY(check_queries(e, queries, nq));
 	if (!word_ids_out) LCD_FAIL(e, LCD_ERR_INVALID, "null output");
 	if (!incremental && e->id2row.empty()) LCD_FAIL(e, LCD_ERR_STATE, "Dictionary mode is set to fixed but no words are in it!");
+	LCD_TRY(require_unsharded(e, "lcd_dict_quantize"));
 	cudaStream_t s = e->stream;
 	const int rows0 = total_rows(e);
 	LCD_TRY(ensure_rows(e, rows0 + nq));
@@ -1178,6 +1221,7 @@ int lcd_dict_find_nn(lcd_engine * e, const void * queries, int nq, int increment
 		memset(word_ids_out, 0, nq * sizeof(int));
 		return LCD_OK;
 	}
+	LCD_TRY(require_unsharded(e, "lcd_dict_find_nn"));
 	LCD_TRY(sort_pending(e));
 	cudaStream_t s = e->stream;
 	LCD_CUDA(e, e->d_queries.reserve(static_cast<size_t>(nq) * e->nw, 0, false, s));
@@ -1276,10 +1320,20 @@ int lcd_index_load_csr(lcd_engine * e, const int * word_ids, int nw, const int64
 	LCD_TRY(set_device(e));
 	const int64_t total = row_ptr[nw] - row_ptr[0];
 	int max_word = 0, max_sig = 0;
+	// the whole input is validated before any state changes
+	if (total < 0) LCD_FAIL(e, LCD_ERR_INVALID, "row_ptr must be non-decreasing");
 	for (int k = 0; k < nw; ++k)
 	{
 		if (e->id2row.find(word_ids[k]) == e->id2row.end()) LCD_FAIL(e, LCD_ERR_INVALID, "word %d is not in the dictionary", word_ids[k]);
+		if (row_ptr[k + 1] < row_ptr[k]) LCD_FAIL(e, LCD_ERR_INVALID, "row_ptr must be non-decreasing");
+		if (word_ids[k] < static_cast<int>(e->h_len.size()) && e->h_len[word_ids[k]] != 0)
+			LCD_FAIL(e, LCD_ERR_STATE, "word %d already has references; bulk load needs empty lists", word_ids[k]);
 		max_word = std::max(max_word, word_ids[k]);
+	}
+	{
+		std::unordered_set<int> seen;
+		for (int k = 0; k < nw; ++k)
+			if (!seen.insert(word_ids[k]).second) LCD_FAIL(e, LCD_ERR_INVALID, "word %d appears twice in the table", word_ids[k]);
 	}
 	for (int64_t p = row_ptr[0]; p < row_ptr[nw]; ++p)
 	{
@@ -1294,7 +1348,6 @@ int lcd_index_load_csr(lcd_engine * e, const int * word_ids, int nw, const int64
 	for (int k = 0; k < nw; ++k)
 	{
 		const int word = word_ids[k];
-		if (e->h_len[word] != 0) LCD_FAIL(e, LCD_ERR_STATE, "word %d already has references; bulk load needs empty lists", word);
 		const int len = static_cast<int>(row_ptr[k + 1] - row_ptr[k]);
 		e->h_off[word] = static_cast<uint32_t>(e->post_used + w);
 		e->h_len[word] = len;
@@ -1715,7 +1768,7 @@ int lcd_orb_detect_describe(lcd_engine * e, int n_frames, const uint8_t * images
 	LCD_TRY(set_device(e));
 	if (!images || n_frames <= 0 || width <= 0 || height <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "null image");
 	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap must be 1..%d", kMaxFrameQueries);
-	cudaStream_t s = e->stream;
+	cudaStream_t s = e->orb_stream; // not the dictionary's stream: this call may overlap lcd_dict_update (Memory.cpp:5284)
 	const size_t px = static_cast<size_t>(n_frames) * width * height;
 	LCD_CUDA(e, e->o_img.reserve(px * channels, 0, false, s));
 	LCD_CUDA(e, cudaMemcpyAsync(e->o_img.p, images, px * channels, cudaMemcpyHostToDevice, s));
@@ -1744,6 +1797,17 @@ int lcd_orb_detect_describe(lcd_engine * e, int n_frames, const uint8_t * images
 	return LCD_OK;
 }
 
+int lcd_orb_overflow(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!e->o_overflow.p) return 0;
+	int flag = 0;
+	LCD_CUDA(e, cudaDeviceSynchronize());
+	LCD_CUDA(e, cudaMemcpy(&flag, e->o_overflow.p, sizeof(int), cudaMemcpyDeviceToHost));
+	return flag ? 1 : 0;
+}
+
 long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long cap_bytes)
 {
 	if (!e || !out) return LCD_ERR_INVALID;
@@ -1759,6 +1823,7 @@ long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long 
 	case 4: src = e->o_cand_count.p; bytes = e->o_cand_count.cap * sizeof(int); break;
 	case 5: src = e->o_level_n.p; bytes = e->o_level_n.cap * sizeof(int); break;
 	case 7: src = e->v_clk.p; bytes = e->v_clk.cap * sizeof(long long); break;
+#ifdef LCD_DEBUG_PHASES
 	case 9:
 	{
 		void * sym = nullptr;
@@ -1767,6 +1832,7 @@ long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long 
 		bytes = sizeof(long long) * 8;
 		break;
 	}
+#endif
 	case 8:
 	{
 		void * sym = nullptr;
@@ -1785,7 +1851,7 @@ long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long 
 
 // ---- geometric verification ------------------------------------------------------------------
 static int verify_upload(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const float * xyz_from, const int * n_from,
-                         const void * desc_to, const float * uv_to, const int * n_to, cudaStream_t s)
+                         const void * desc_to, const float * uv_to, const int * n_to, cudaStream_t s, const float * xyz_to = nullptr)
 {
 	const size_t rows = static_cast<size_t>(n_pairs) * cap;
 	LCD_CUDA(e, e->v_df.reserve(rows * e->nw, 0, false, s));
@@ -1802,6 +1868,11 @@ static int verify_upload(lcd_engine * e, int n_pairs, int cap, const void * desc
 	else LCD_CUDA(e, cudaMemsetAsync(e->v_uv.p, 0, rows * 2 * sizeof(float), s));
 	LCD_CUDA(e, cudaMemcpyAsync(e->v_nf.p, n_from, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
 	LCD_CUDA(e, cudaMemcpyAsync(e->v_nt.p, n_to, n_pairs * sizeof(int), cudaMemcpyHostToDevice, s));
+	if (xyz_to)
+	{
+		LCD_CUDA(e, e->v_xyz_to.reserve(rows * 3, 0, false, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->v_xyz_to.p, xyz_to, rows * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	}
 	return LCD_OK;
 }
 
@@ -1817,6 +1888,7 @@ struct MatchSrc
 	const int * n_to;
 	int n_to_all;
 	int cap_to;
+	const float * xyz_to; // 3-D points of the TO side (words3B) or nullptr
 };
 
 static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool want_ids, cudaStream_t s, const MatchSrc * src = nullptr)
@@ -1846,6 +1918,7 @@ static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool w
 		a.n_to = src->n_to;
 		a.n_to_all = src->n_to_all;
 		a.cap_to = src->cap_to;
+		a.xyz_to = src->xyz_to;
 	}
 	else
 	{
@@ -1859,7 +1932,11 @@ static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool w
 		a.n_to = e->v_nt.p;
 		a.n_to_all = 0;
 		a.cap_to = cap;
+		a.xyz_to = e->match_has_xyz_to ? e->v_xyz_to.p : nullptr;
 	}
+	if (a.xyz_to) LCD_CUDA(e, e->v_obj_to.reserve(rows * 3, 0, false, s));
+	a.obj_to = a.xyz_to ? e->v_obj_to.p : nullptr;
+	e->pnp_has_obj_to = a.xyz_to != nullptr;
 	a.cap = cap;
 	a.nndr = nndr;
 	a.obj = e->v_obj.p;
@@ -1895,9 +1972,12 @@ static int launch_match(lcd_engine * e, int n_pairs, int cap, float nndr, bool w
 	return LCD_OK;
 }
 
-static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_params * p, cudaStream_t s)
+static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_params * p, cudaStream_t s, bool gate_min_matches = true,
+                      bool want_cov = true)
 {
 	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	if (want_cov && p->var_median_ratio <= 1) LCD_FAIL(e, LCD_ERR_INVALID, "Vis/PnPVarianceMedianRatio must be > 1 (UASSERT in estimateMotion3DTo2D)");
+	LCD_CUDA(e, e->v_cov6.reserve(n_pairs * 6, 0, false, s));
 	LCD_CUDA(e, e->v_rvec.reserve(n_pairs * 3, 0, false, s));
 	LCD_CUDA(e, e->v_tvec.reserve(n_pairs * 3, 0, false, s));
 	LCD_CUDA(e, e->v_inl.reserve(rows, 0, false, s));
@@ -1917,6 +1997,14 @@ static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_par
 	a.min_inliers = p->min_inliers;
 	a.refine_iterations = p->refine_iterations;
 	a.refine_sigma = p->refine_sigma;
+	a.gate_min_matches = gate_min_matches ? 1 : 0;
+	a.obj_to = (want_cov && e->pnp_has_obj_to) ? e->v_obj_to.p : nullptr;
+	a.var_median_ratio = p->var_median_ratio;
+	a.max_variance = p->max_variance;
+	a.split_linear = p->split_linear_cov;
+	a.img_w = p->image_width;
+	a.img_h = p->image_height;
+	a.cov6 = want_cov ? e->v_cov6.p : nullptr;
 	a.rvec = e->v_rvec.p;
 	a.tvec = e->v_tvec.p;
 	a.inliers = e->v_inl.p;
@@ -1924,7 +2012,8 @@ static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_par
 	a.iters_run = e->v_iters.p;
 	a.ok = e->v_ok.p;
 	a.transform = e->v_T.p;
-	a.phase_clk = e->v_clk.p;
+	static const int pnp_clocks = env_int("LCD_PNP_CLOCKS", 0); // diagnostics: phase clocks of the RANSAC kernel (lcd_debug_orb_buffer 7)
+	a.phase_clk = pnp_clocks ? e->v_clk.p : nullptr;
 	const size_t smem = pnp_smem_bytes(cap);
 	if (smem > static_cast<size_t>(e->smem_optin)) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap %d needs %zu B of shared memory", cap, smem);
 	if (smem > 48 * 1024)
@@ -1949,7 +2038,7 @@ static int verify_download(lcd_engine * e, int n_pairs, int cap, lcd_verify_resu
 	LCD_CUDA(e, e->v_packed.reserve(n_pairs, 0, false, s));
 	LCD_CUDA(e, e->h_packed.reserve(n_pairs));
 	pack_verify_results_kernel<<<(n_pairs + 127) / 128, 128, 0, s>>>(n_pairs, e->v_ok.p, e->v_nm.p, e->v_ninl.p, e->v_iters.p, e->v_rvec.p, e->v_tvec.p,
-	                                                                e->v_T.p, e->v_packed.p);
+	                                                                e->v_T.p, e->v_cov6.p, e->v_packed.p);
 	LCD_CHECK_LAUNCH(e);
 	LCD_CUDA(e, cudaMemcpyAsync(e->h_packed.p, e->v_packed.p, n_pairs * sizeof(PackedVerifyResult), cudaMemcpyDeviceToHost, s));
 	if (cap > 0 && match_ids) LCD_CUDA(e, cudaMemcpyAsync(match_ids, e->v_mid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1976,6 +2065,7 @@ int lcd_match_pairs(lcd_engine * e, int n_pairs, int cap, const void * desc_from
 	LCD_TRY(check_verify_args(e, n_pairs, cap, desc_from, desc_to, n_from, n_to));
 	cudaStream_t s = e->stream;
 	LCD_TRY(verify_upload(e, n_pairs, cap, desc_from, nullptr, n_from, desc_to, nullptr, n_to, s));
+	e->match_has_xyz_to = false;
 	LCD_TRY(launch_match(e, n_pairs, cap, nndr, true, s));
 	const size_t rows = static_cast<size_t>(n_pairs) * cap;
 	if (from_ids) LCD_CUDA(e, cudaMemcpyAsync(from_ids, e->v_fid.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1985,7 +2075,7 @@ int lcd_match_pairs(lcd_engine * e, int n_pairs, int cap, const void * desc_from
 }
 
 int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_from, const float * xyz_from, const int * n_from,
-                     const void * desc_to, const float * uv_to, const int * n_to, const lcd_verify_params * params,
+                     const void * desc_to, const float * uv_to, const float * xyz_to, const int * n_to, const lcd_verify_params * params,
                      lcd_verify_result * results, int * match_ids, int * inlier_ids)
 {
 	if (!e) return LCD_ERR_INVALID;
@@ -1995,14 +2085,204 @@ int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_fro
 	if (!xyz_from || !uv_to || !params || !results) LCD_FAIL(e, LCD_ERR_INVALID, "null verification argument");
 	if (params->iterations > kMaxRansacIters) LCD_FAIL(e, LCD_ERR_CAPACITY, "Vis/Iterations > %d", kMaxRansacIters);
 	cudaStream_t s = e->stream;
-	LCD_TRY(verify_upload(e, n_pairs, cap, desc_from, xyz_from, n_from, desc_to, uv_to, n_to, s));
+	LCD_TRY(verify_upload(e, n_pairs, cap, desc_from, xyz_from, n_from, desc_to, uv_to, n_to, s, xyz_to));
+	e->match_has_xyz_to = xyz_to != nullptr;
 	LCD_TRY(launch_match(e, n_pairs, cap, params->nndr, false, s));
 	LCD_TRY(launch_pnp(e, n_pairs, cap, params, s));
 	return verify_download(e, n_pairs, cap, results, match_ids, inlier_ids, s);
 }
 
+// ---- stand-alone PnP RANSAC: util3d::solvePnPRansac ------------------------------------------------
+static int check_pnp_camera(lcd_engine * e, const double K[9], const double * dist_coeffs, int n_dist, int flags)
+{
+	if (!K) LCD_FAIL(e, LCD_ERR_INVALID, "null camera matrix");
+	if (K[1] != 0.0 || K[3] != 0.0 || K[6] != 0.0 || K[7] != 0.0 || K[8] != 1.0 || !(K[0] > 0.0) || !(K[4] > 0.0))
+		LCD_FAIL(e, LCD_ERR_INVALID, "camera matrix must be [fx 0 cx; 0 fy cy; 0 0 1]");
+	for (int i = 0; i < n_dist; ++i)
+		if (dist_coeffs && dist_coeffs[i] != 0.0)
+			LCD_FAIL(e, LCD_ERR_INVALID, "distortion coefficients are not supported: rectify first (CameraModel::D() is zero for rectified images, CameraModel.h:111)");
+	if (flags != 0) LCD_FAIL(e, LCD_ERR_INVALID, "Vis/PnPFlags=%d is not implemented (0 = cv::SOLVEPNP_ITERATIVE only)", flags);
+	return LCD_OK;
+}
+
+int lcd_pnp_ransac_batch(lcd_engine * e, int n_sets, int cap, const float * object_points, const float * image_points, const int * n_points,
+                         const double K[9], const double * dist_coeffs, int n_dist, double * rvec, double * tvec, int use_extrinsic_guess,
+                         int iterations, float reproj_error, int min_inliers, int flags, int refine_iterations, float refine_sigma,
+                         int * inliers_out, int * n_inliers_out, int * iterations_run_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (n_sets <= 0 || cap <= 0 || !object_points || !image_points || !n_points || !rvec || !tvec) LCD_FAIL(e, LCD_ERR_INVALID, "null or empty PnP input");
+	if (cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "at most %d correspondences per set", kMaxFrameQueries);
+	LCD_TRY(check_pnp_camera(e, K, dist_coeffs, n_dist, flags));
+	if (iterations > kMaxRansacIters) LCD_FAIL(e, LCD_ERR_CAPACITY, "iterationsCount > %d", kMaxRansacIters);
+	for (int i = 0; i < n_sets; ++i)
+	{
+		if (n_points[i] < 0 || n_points[i] > cap) LCD_FAIL(e, LCD_ERR_INVALID, "set %d has %d points (cap %d)", i, n_points[i], cap);
+		// cv3::solvePnPRansac switches to P3P on exactly four points (opencv/solvepnp.cpp:150-154): not implemented
+		if (n_points[i] == 4) LCD_FAIL(e, LCD_ERR_INVALID, "set %d has exactly 4 points: the reference solves it with P3P, which is not implemented", i);
+	}
+	(void)use_extrinsic_guess; // the RANSAC kernel is EPnP on 6 points, which ignores the guess; on failure rvec / tvec are left untouched
+	cudaStream_t s = e->stream;
+	const size_t rows = static_cast<size_t>(n_sets) * cap;
+	LCD_CUDA(e, e->v_obj.reserve(rows * 3, 0, false, s));
+	LCD_CUDA(e, e->v_img.reserve(rows * 2, 0, false, s));
+	LCD_CUDA(e, e->v_nm.reserve(n_sets, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->v_obj.p, object_points, rows * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->v_img.p, image_points, rows * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->v_nm.p, n_points, n_sets * sizeof(int), cudaMemcpyHostToDevice, s));
+	lcd_verify_params vp{};
+	vp.min_inliers = min_inliers;
+	vp.iterations = iterations;
+	vp.reproj_error = reproj_error;
+	vp.refine_iterations = refine_iterations;
+	vp.refine_sigma = refine_sigma;
+	vp.fx = K[0];
+	vp.fy = K[4];
+	vp.cx = K[2];
+	vp.cy = K[5];
+	vp.var_median_ratio = 2;
+	LCD_TRY(launch_pnp(e, n_sets, cap, &vp, s, false, false));
+	std::vector<double> hr(static_cast<size_t>(n_sets) * 3), ht(static_cast<size_t>(n_sets) * 3);
+	std::vector<int> hn(n_sets), hit(n_sets);
+	LCD_CUDA(e, cudaMemcpyAsync(hr.data(), e->v_rvec.p, hr.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ht.data(), e->v_tvec.p, ht.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(hn.data(), e->v_ninl.p, n_sets * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(hit.data(), e->v_iters.p, n_sets * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (inliers_out) LCD_CUDA(e, cudaMemcpyAsync(inliers_out, e->v_inl.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	for (int i = 0; i < n_sets; ++i)
+	{
+		// a model was found (the kernel zeroes the pose first and writes the final model last): rvec / tvec of the (refined) model;
+		// otherwise the caller's values stay, as when cv3::solvePnPRansac returns false (solvepnp.cpp:183-192)
+		bool found = hn[i] > 0;
+		for (int k = 0; k < 3; ++k) found = found || hr[3 * i + k] != 0.0 || ht[3 * i + k] != 0.0;
+		if (found)
+		{
+			for (int k = 0; k < 3; ++k)
+			{
+				rvec[3 * i + k] = hr[3 * i + k];
+				tvec[3 * i + k] = ht[3 * i + k];
+			}
+		}
+		if (n_inliers_out) n_inliers_out[i] = hn[i];
+		if (iterations_run_out) iterations_run_out[i] = hit[i];
+	}
+	return LCD_OK;
+}
+
+int lcd_pnp_ransac(lcd_engine * e, const float * object_points, const float * image_points, int n, const double K[9], const double * dist_coeffs,
+                   int n_dist, double rvec[3], double tvec[3], int use_extrinsic_guess, int iterations, float reproj_error, int min_inliers,
+                   int flags, int refine_iterations, float refine_sigma, int * inliers_out, int * n_inliers_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	if (n <= 0)
+	{
+		if (n_inliers_out) *n_inliers_out = 0;
+		return LCD_OK;
+	}
+	return lcd_pnp_ransac_batch(e, 1, n, object_points, image_points, &n, K, dist_coeffs, n_dist, rvec, tvec, use_extrinsic_guess, iterations,
+	                            reproj_error, min_inliers, flags, refine_iterations, refine_sigma, inliers_out, n_inliers_out, nullptr);
+}
+
+// ---- brute-force matching of two descriptor sets: cv::BFMatcher ----------------------------------------
+} // extern "C"
+template <int NW, bool F32>
+static int launch_bf(lcd_engine * e, int n_pairs, int cap, const uint32_t * A, const int * nA, const uint32_t * B, const int * nB, ulonglong2 * keys,
+                     cudaStream_t s)
+{
+	dim3 grid((cap + kBfThreads - 1) / kBfThreads, n_pairs);
+	prof_mark(e, LCD_PROF_MATCH, s);
+	bf_knn2_kernel<NW, F32><<<grid, kBfThreads, 0, s>>>(A, nA, B, nB, cap, keys);
+	prof_mark(e, LCD_PROF_MATCH, s);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+static int launch_bf_any(lcd_engine * e, int n_pairs, int cap, const uint32_t * A, const int * nA, const uint32_t * B, const int * nB,
+                         ulonglong2 * keys, cudaStream_t s)
+{
+	if (e->f32) return e->nw == 64 ? launch_bf<64, true>(e, n_pairs, cap, A, nA, B, nB, keys, s) : launch_bf<128, true>(e, n_pairs, cap, A, nA, B, nB, keys, s);
+	switch (e->nw)
+	{
+	case 4: return launch_bf<4, false>(e, n_pairs, cap, A, nA, B, nB, keys, s);
+	case 8: return launch_bf<8, false>(e, n_pairs, cap, A, nA, B, nB, keys, s);
+	case 16: return launch_bf<16, false>(e, n_pairs, cap, A, nA, B, nB, keys, s);
+	default: LCD_FAIL(e, LCD_ERR_INVALID, "unsupported descriptor size");
+	}
+}
+
+extern "C" {
+int lcd_match_bf(lcd_engine * e, int n_pairs, int cap, const void * desc_query, const int * n_query, const void * desc_train, const int * n_train,
+                 int mode, int * idx1, float * dist1, int * idx2, float * dist2)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_TRY(check_verify_args(e, n_pairs, cap, desc_query, desc_train, n_query, n_train));
+	if (mode != LCD_MATCH_KNN2 && mode != LCD_MATCH_CROSSCHECK) LCD_FAIL(e, LCD_ERR_INVALID, "mode must be LCD_MATCH_KNN2 or LCD_MATCH_CROSSCHECK");
+	if (!idx1 || !dist1 || (mode == LCD_MATCH_KNN2 && (!idx2 || !dist2))) LCD_FAIL(e, LCD_ERR_INVALID, "null output");
+	cudaStream_t s = e->stream;
+	const size_t rows = static_cast<size_t>(n_pairs) * cap;
+	// FROM buffers hold the train side, TO buffers the query side (cv::BFMatcher::match(queryDescriptors = TO, trainDescriptors = FROM))
+	LCD_TRY(verify_upload(e, n_pairs, cap, desc_train, nullptr, n_train, desc_query, nullptr, n_query, s));
+	LCD_CUDA(e, e->bf_keys_a.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->d_i1.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->d_f1.reserve(rows, 0, false, s));
+	const int nb = static_cast<int>((rows + 255) / 256);
+	if (mode == LCD_MATCH_KNN2)
+	{
+		LCD_TRY(launch_bf_any(e, n_pairs, cap, e->v_dt.p, e->v_nt.p, e->v_df.p, e->v_nf.p, e->bf_keys_a.p, s));
+		LCD_CUDA(e, e->d_i2.reserve(rows, 0, false, s));
+		LCD_CUDA(e, e->d_f2.reserve(rows, 0, false, s));
+		const unsigned long long * k = reinterpret_cast<const unsigned long long *>(e->bf_keys_a.p);
+		if (e->f32)
+		{
+			bf_decode_kernel<true><<<nb, 256, 0, s>>>(k, 2, 0, static_cast<int>(rows), e->d_i1.p, e->d_f1.p);
+			bf_decode_kernel<true><<<nb, 256, 0, s>>>(k, 2, 1, static_cast<int>(rows), e->d_i2.p, e->d_f2.p);
+		}
+		else
+		{
+			bf_decode_kernel<false><<<nb, 256, 0, s>>>(k, 2, 0, static_cast<int>(rows), e->d_i1.p, e->d_f1.p);
+			bf_decode_kernel<false><<<nb, 256, 0, s>>>(k, 2, 1, static_cast<int>(rows), e->d_i2.p, e->d_f2.p);
+		}
+		LCD_CHECK_LAUNCH(e);
+		++e->launches;
+		LCD_CUDA(e, cudaMemcpyAsync(idx2, e->d_i2.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+		LCD_CUDA(e, cudaMemcpyAsync(dist2, e->d_f2.p, rows * sizeof(float), cudaMemcpyDeviceToHost, s));
+	}
+	else
+	{
+		// every train row picks its nearest query; every query keeps the nearest train row that picked it
+		LCD_TRY(launch_bf_any(e, n_pairs, cap, e->v_df.p, e->v_nf.p, e->v_dt.p, e->v_nt.p, e->bf_keys_a.p, s));
+		LCD_CUDA(e, e->bf_best.reserve(rows, 0, false, s));
+		bf_cross_fill_kernel<<<nb, 256, 0, s>>>(e->bf_best.p, cap, n_pairs);
+		LCD_CHECK_LAUNCH(e);
+		bf_cross_scatter_kernel<<<dim3((cap + 255) / 256, n_pairs), 256, 0, s>>>(e->bf_keys_a.p, e->v_nf.p, cap, e->bf_best.p);
+		LCD_CHECK_LAUNCH(e);
+		if (e->f32) bf_decode_kernel<true><<<nb, 256, 0, s>>>(e->bf_best.p, 1, 0, static_cast<int>(rows), e->d_i1.p, e->d_f1.p);
+		else bf_decode_kernel<false><<<nb, 256, 0, s>>>(e->bf_best.p, 1, 0, static_cast<int>(rows), e->d_i1.p, e->d_f1.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	LCD_CUDA(e, cudaMemcpyAsync(idx1, e->d_i1.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(dist1, e->d_f1.p, rows * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	if (mode == LCD_MATCH_KNN2)
+	{
+		// rows past a pair's query count were not written by the kernel: report them as "no match"
+		for (int p = 0; p < n_pairs; ++p)
+			for (int i = std::max(0, std::min(n_query[p], cap)); i < cap; ++i)
+			{
+				const size_t r = static_cast<size_t>(p) * cap + i;
+				idx1[r] = idx2[r] = -1;
+				dist1[r] = dist2[r] = -1.0f;
+			}
+	}
+	return LCD_OK;
+}
+
 // ---- signature store + fused query -------------------------------------------------------------
 int lcd_sig_count(const lcd_engine * e) { return e ? e->st_slots - static_cast<int>(e->free_slots.size()) : 0; }
+int lcd_sig_slots(const lcd_engine * e) { return e ? e->st_slots : 0; }
 
 int lcd_sig_add_batch(lcd_engine * e, const int * sig_ids, int n_sigs, int cap, const void * desc, const float * xyz, const int * n)
 {
@@ -2027,7 +2307,8 @@ int lcd_sig_add_batch(lcd_engine * e, const int * sig_ids, int n_sigs, int cap, 
 		const size_t ncap = std::max<size_t>(max_id + 1, old + old / 2 + 1024);
 		e->h_slot_of_sig.resize(ncap, -1);
 	}
-	// slots: contiguous fresh slots when possible so that the bulk copy is one transfer
+	// slots: freed slots are reused first (one add + one remove per frame is what the WM -> LTM transfer produces: the store must
+	// not grow); the bulk copy is used when the slots happen to be consecutive
 	const size_t prev_slots = static_cast<size_t>(e->st_slots);
 	std::vector<int> slots(n_sigs);
 	bool contiguous = true;
@@ -2036,7 +2317,7 @@ int lcd_sig_add_batch(lcd_engine * e, const int * sig_ids, int n_sigs, int cap, 
 		int slot = e->h_slot_of_sig[sig_ids[i]];
 		if (slot < 0)
 		{
-			if (!e->free_slots.empty() && !contiguous)
+			if (!e->free_slots.empty())
 			{
 				slot = e->free_slots.back();
 				e->free_slots.pop_back();
@@ -2088,7 +2369,8 @@ int lcd_sig_remove(lcd_engine * e, int sig_id)
 }
 
 static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, const float * d_like,
-                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s, const int * d_nq_frame = nullptr);
+                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s, const int * d_nq_frame = nullptr,
+                          const float * d_xyz_to = nullptr);
 
 static int process_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, int incremental, float nndr, int cmp_new,
                        const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp, int * d_words, float * d_like, cudaStream_t s)
@@ -2107,7 +2389,7 @@ static int process_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv,
 }
 
 static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_uv, int n_frames, int nq, const float * d_like,
-                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s, const int * d_nq_frame)
+                          const int * d_sig_ids, int ns, const lcd_verify_params * vp, cudaStream_t s, const int * d_nq_frame, const float * d_xyz_to)
 {
 	if (!vp) LCD_FAIL(e, LCD_ERR_INVALID, "null verification parameters");
 	if (vp->iterations > kMaxRansacIters) LCD_FAIL(e, LCD_ERR_CAPACITY, "Vis/Iterations > %d", kMaxRansacIters);
@@ -2118,7 +2400,7 @@ static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_
 	                                                  e->d_hyp_id.p, e->d_hyp_slot.p);
 	LCD_CHECK_LAUNCH(e);
 	const int cap = std::max(e->st_cap, nq);
-	MatchSrc src{e->st_desc.p, e->st_xyz.p, e->st_n.p, e->d_hyp_slot.p, e->st_cap, d_q, d_uv, d_nq_frame, nq, nq};
+	MatchSrc src{e->st_desc.p, e->st_xyz.p, e->st_n.p, e->d_hyp_slot.p, e->st_cap, d_q, d_uv, d_nq_frame, nq, nq, d_xyz_to};
 	LCD_TRY(launch_match(e, n_frames, cap, vp->nndr, false, s, &src));
 	LCD_TRY(launch_pnp(e, n_frames, cap, vp, s));
 	return LCD_OK;
@@ -2210,7 +2492,7 @@ static int process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_im
 	}
 	const uint32_t * d_q = reinterpret_cast<const uint32_t *>(e->o_desc.p);
 	LCD_TRY(localize_dev(e, d_q, n_frames, cap, incremental, nndr, cmp_new, d_sig_ids, ns, n_total, d_words, d_like, s, e->o_n.p));
-	if (vp) LCD_TRY(verify_top_dev(e, d_q, e->o_uv.p, n_frames, cap, d_like, d_sig_ids, ns, vp, s, e->o_n.p));
+	if (vp) LCD_TRY(verify_top_dev(e, d_q, e->o_uv.p, n_frames, cap, d_like, d_sig_ids, ns, vp, s, e->o_n.p, e->o_xyz.p));
 	return LCD_OK;
 }
 
@@ -2347,7 +2629,7 @@ int lcd_process_frames_submit(lcd_engine * e, int n_frames, const uint8_t * imag
 		LCD_CUDA(e, e->v_packed.reserve(n_frames, 0, false, s));
 		LCD_CUDA(e, f.res.reserve(n_frames));
 		pack_verify_results_kernel<<<(n_frames + 127) / 128, 128, 0, s>>>(n_frames, e->v_ok.p, e->v_nm.p, e->v_ninl.p, e->v_iters.p, e->v_rvec.p,
-		                                                                 e->v_tvec.p, e->v_T.p, e->v_packed.p);
+		                                                                 e->v_tvec.p, e->v_T.p, e->v_cov6.p, e->v_packed.p);
 		LCD_CHECK_LAUNCH(e);
 		LCD_CUDA(e, cudaMemcpyAsync(f.res.p, e->v_packed.p, n_frames * sizeof(PackedVerifyResult), cudaMemcpyDeviceToHost, s));
 		f.user_results = results;

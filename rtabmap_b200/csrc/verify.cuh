@@ -33,6 +33,7 @@ struct MatchArgs
 	int cap_from;               // row stride of the FROM arrays
 	const uint32_t * desc_to;   // [n_pairs][cap_to][NW]
 	const float * uv_to;        // [n_pairs][cap_to][2]
+	const float * xyz_to;       // [n_pairs][cap_to][3] or nullptr: Signature::getWords3 of the TO side (words3B of estimateMotion3DTo2D)
 	const int * n_to;           // [n_pairs] or nullptr (= n_to_all)
 	int n_to_all;
 	int cap_to;                 // row stride of the TO arrays
@@ -41,6 +42,7 @@ struct MatchArgs
 	// outputs
 	float * obj;       // [n_pairs][cap][3]
 	float * img;       // [n_pairs][cap][2]
+	float * obj_to;    // [n_pairs][cap][3] 3-D point of the TO side for each correspondence (NaN = none); nullptr when xyz_to is
 	int * match_id;    // [n_pairs][cap]  word id of the correspondence (ascending)
 	int * match_from;  // [n_pairs][cap]  descriptor index in FROM
 	int * match_to;    // [n_pairs][cap]  descriptor index in TO
@@ -54,8 +56,13 @@ __host__ __device__ inline size_t match_smem_bytes(int cap, int nw)
 	return static_cast<size_t>(cap) * (4 + 4 + 4 + 2 + 2 + 1 + 1 + 4 + 4 + 2 + 2) + 2 * static_cast<size_t>(cap) * nw * 4 + 128;
 }
 
+// phase clocks of the matching kernel: diagnostics only, compiled in with -DLCD_DEBUG_PHASES
+#ifdef LCD_DEBUG_PHASES
 __device__ long long g_match_dbg[8];
 #define MATCH_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_match_dbg[k] = clock64(); } while (0)
+#else
+#define MATCH_PHASE(k) do { } while (0)
+#endif
 
 template <int NW>
 __global__ void __launch_bounds__(kResolveThreads)
@@ -209,6 +216,13 @@ pair_match_kernel(const MatchArgs a)
 		a.obj[(base + m) * 3 + 2] = p[2];
 		a.img[(base + m) * 2 + 0] = q[0];
 		a.img[(base + m) * 2 + 1] = q[1];
+		if (a.obj_to)
+		{
+			const float * r = a.xyz_to + (tbase + ti) * 3;
+			a.obj_to[(base + m) * 3 + 0] = r[0];
+			a.obj_to[(base + m) * 3 + 1] = r[1];
+			a.obj_to[(base + m) * 3 + 2] = r[2];
+		}
 		a.match_id[base + m] = k + 1;
 		a.match_from[base + m] = fi;
 		a.match_to[base + m] = ti;
@@ -229,6 +243,15 @@ struct PnpArgs
 	int min_inliers;       // Vis/MinInliers
 	int refine_iterations; // Vis/PnPRefineIterations
 	float refine_sigma;    // 3.0
+	int gate_min_matches;  // 1: util3d::estimateMotion3DTo2D semantics (PnP only with >= min_inliers correspondences, :111);
+	                       // 0: util3d::solvePnPRansac alone (lcd_pnp_ransac)
+	// covariance of util3d::estimateMotion3DTo2D (util3d_motion_estimation.cpp:156-258); cov6 == nullptr: skipped
+	const float * obj_to;  // [n_pairs][cap][3] words3B of each correspondence (NaN = none) or nullptr (words3B empty)
+	int var_median_ratio;  // Vis/PnPVarianceMedianRatio (> 1)
+	float max_variance;    // Vis/PnPMaxVariance (0 = off)
+	int split_linear;      // Vis/PnPSplitLinearCovComponents
+	int img_w, img_h;      // CameraModel::imageSize() of the TO camera (0 x 0 = not set)
+	double * cov6;         // [n_pairs][6] diagonal of the 6x6 covariance (the reference only ever scales the identity)
 	// outputs
 	double * rvec;      // [n_pairs][3]
 	double * tvec;      // [n_pairs][3]
@@ -242,7 +265,7 @@ struct PnpArgs
 
 __host__ __device__ inline size_t pnp_smem_bytes(int cap)
 {
-	return static_cast<size_t>(cap) * (12 + 8 + 4 + 2 + 2 + 1) + kMaxRansacIters * (6 * 2) + kPnpChunk * (4 + 6 * 8) + (28 * 32 + 32) * 8 + 1024;
+	return static_cast<size_t>(cap) * (12 + 8 + 4 + 4 + 2 + 2 + 1) + kMaxRansacIters * (6 * 2) + kPnpChunk * (4 + 6 * 8) + (28 * 32 + 32) * 8 + 1024;
 }
 
 __device__ inline int ransac_update_num_iters(double p, double ep, int modelPoints, int maxIters)
@@ -453,7 +476,8 @@ pnp_ransac_kernel(const PnpArgs a)
 	float * X = reinterpret_cast<float *>(s_out + 32);                       // [cap][3]
 	float * uv = X + static_cast<size_t>(cap) * 3;                           // [cap][2]
 	float * errs = uv + static_cast<size_t>(cap) * 2;                        // [cap]
-	int * cnt = reinterpret_cast<int *>(errs + cap);                         // [kPnpChunk]
+	float * cbuf = errs + cap;                                               // [cap] covariance pass: per-inlier error values
+	int * cnt = reinterpret_cast<int *>(cbuf + cap);                         // [kPnpChunk]
 	uint16_t * sidx = reinterpret_cast<uint16_t *>(cnt + kPnpChunk);    // [kMaxRansacIters][6]
 	uint16_t * listA = sidx + kMaxRansacIters * 6;                           // [cap]
 	uint16_t * listB = listA + cap;                                          // [cap]
@@ -484,8 +508,9 @@ pnp_ransac_kernel(const PnpArgs a)
 		a.iters_run[pair] = 0;
 		a.ok[pair] = 0;
 	}
+	if (a.cov6 && tid < 6) a.cov6[pair * 6 + tid] = 1.0; // *covariance = cv::Mat::eye(6,6,CV_64FC1) (:83)
 	// util3d::estimateMotion3DTo2D runs PnP only with >= Vis/MinInliers correspondences; RANSAC needs >= 6
-	if (n < a.min_inliers || n < 6) return;
+	if ((a.gate_min_matches && n < a.min_inliers) || n < 6) return;
 
 	for (int i = tid; i < n * 3; i += blockDim.x) X[i] = a.obj[base * 3 + i];
 	for (int i = tid; i < n * 2; i += blockDim.x) uv[i] = a.img[base * 2 + i];
@@ -756,11 +781,14 @@ pnp_ransac_kernel(const PnpArgs a)
 		a.tvec[pair * 3 + tid] = lm.param[3 + tid];
 	}
 	for (int k = tid; k < n_fin; k += blockDim.x) a.inliers[base + k] = fin[k];
+	__shared__ float s_T[12], s_P[12]; // transform = (localTransform * pnp)^-1 and pnp itself (= transformCameraFrameInv), 3x4 float
+	__shared__ int s_acc;
+	__shared__ double s_med[5];
 	if (tid == 0)
 	{
 		a.n_inliers[pair] = n_fin;
 		const int accepted = n_fin >= a.min_inliers ? 1 : 0;
-		a.ok[pair] = accepted;
+		s_acc = accepted;
 		if (accepted)
 		{
 			double R[9];
@@ -768,14 +796,150 @@ pnp_ransac_kernel(const PnpArgs a)
 			float Rf[9], tf[3];
 			for (int i = 0; i < 9; ++i) Rf[i] = static_cast<float>(R[i]);
 			for (int i = 0; i < 3; ++i) tf[i] = static_cast<float>(lm.param[3 + i]);
-			float * T = a.transform + pair * 12;
 			for (int i = 0; i < 3; ++i)
 			{
-				for (int j = 0; j < 3; ++j) T[4 * i + j] = Rf[3 * j + i];
-				T[4 * i + 3] = -(Rf[0 + i] * tf[0] + Rf[3 + i] * tf[1] + Rf[6 + i] * tf[2]);
+				for (int j = 0; j < 3; ++j)
+				{
+					s_T[4 * i + j] = Rf[3 * j + i];
+					s_P[4 * i + j] = Rf[3 * i + j];
+				}
+				s_T[4 * i + 3] = -(Rf[0 + i] * tf[0] + Rf[3 + i] * tf[1] + Rf[6 + i] * tf[2]);
+				s_P[4 * i + 3] = tf[i];
 			}
 		}
 	}
+	__syncthreads();
+	int accepted = s_acc;
+	if (accepted && a.cov6)
+	{
+		// ---- covariance (util3d_motion_estimation.cpp:156-258), localTransform = identity --------------------
+		const bool have3B = a.obj_to != nullptr;
+		if (have3B || a.img_w != 0 || a.img_h != 0)
+		{
+			// channels: 0 squared 3-D distance, 1 angle (pcl::getAngle3D), 2..4 squared x / y / z error (split components)
+			const int n_ch = a.split_linear ? 5 : 2;
+			const int kth = n_fin / max(a.var_median_ratio, 2);
+			for (int ch = 0; ch < n_ch; ++ch)
+			{
+				for (int k = tid; k < n_fin; k += blockDim.x)
+				{
+					const int i = fin[k];
+					const float ox = X[3 * i], oy = X[3 * i + 1], oz = X[3 * i + 2];
+					float nx, ny, nz;
+					bool from3B = false;
+					if (have3B)
+					{
+						const float * p = a.obj_to + (base + i) * 3;
+						if (isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]))
+						{
+							// util3d::transformPoint(words3B, transform) (util3d_transforms.cpp:211-220), float, left to right
+							nx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_T[0], p[0]), __fmul_rn(s_T[1], p[1])), __fmul_rn(s_T[2], p[2])), s_T[3]);
+							ny = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_T[4], p[0]), __fmul_rn(s_T[5], p[1])), __fmul_rn(s_T[6], p[2])), s_T[7]);
+							nz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_T[8], p[0]), __fmul_rn(s_T[9], p[1])), __fmul_rn(s_T[10], p[2])), s_T[11]);
+							from3B = true;
+						}
+					}
+					if (!from3B)
+					{
+						// depth of the object point in camera B, ray through the image point, 10 % error (:186-203)
+						const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_P[8], ox), __fmul_rn(s_P[9], oy)), __fmul_rn(s_P[10], oz)), s_P[11]);
+						const float fx = static_cast<float>(cam.fu), fy = static_cast<float>(cam.fv);
+						float cx = static_cast<float>(cam.uc), cy = static_cast<float>(cam.vc);
+						cx = cx > 0.0f ? cx : static_cast<float>(a.img_w / 2) - 0.5f;
+						cy = cy > 0.0f ? cy : static_cast<float>(a.img_h / 2) - 0.5f;
+						const float rx = __fdiv_rn(__fsub_rn(uv[2 * i], cx), fx), ry = __fdiv_rn(__fsub_rn(uv[2 * i + 1], cy), fy);
+						// cv::Point3f * (float * double): the scale is a double product converted back to float per component
+						const double sc = static_cast<double>(zc) * 1.1;
+						const float px = static_cast<float>(static_cast<double>(rx) * sc), py = static_cast<float>(static_cast<double>(ry) * sc),
+						            pz = static_cast<float>(sc);
+						nx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_T[0], px), __fmul_rn(s_T[1], py)), __fmul_rn(s_T[2], pz)), s_T[3]);
+						ny = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_T[4], px), __fmul_rn(s_T[5], py)), __fmul_rn(s_T[6], pz)), s_T[7]);
+						nz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_T[8], px), __fmul_rn(s_T[9], py)), __fmul_rn(s_T[10], pz)), s_T[11]);
+					}
+					const float dx = __fsub_rn(ox, nx), dy = __fsub_rn(oy, ny), dz = __fsub_rn(oz, nz);
+					float v;
+					if (ch == 0) v = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+					else if (ch == 1)
+					{
+						// pcl::getAngle3D(v1, v2): acos of the clamped dot product of the normalised vectors (Eigen::Vector4f, w = 0)
+						const float n1 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oz, oz)), __fmul_rn(oy, oy)));
+						const float n2 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(nz, nz)), __fmul_rn(ny, ny)));
+						const float ax = __fdiv_rn(ox, n1), ay = __fdiv_rn(oy, n1), az = __fdiv_rn(oz, n1);
+						const float bx = __fdiv_rn(nx, n2), by = __fdiv_rn(ny, n2), bz = __fdiv_rn(nz, n2);
+						double rad = static_cast<double>(__fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(az, bz)), __fmul_rn(ay, by)));
+						rad = rad < -1.0 ? -1.0 : (rad > 1.0 ? 1.0 : rad);
+						v = static_cast<float>(acos(rad));
+					}
+					else
+					{
+						const double e = static_cast<double>(ch == 2 ? dx : (ch == 3 ? dy : dz));
+						v = static_cast<float>(e * e);
+					}
+					cbuf[k] = v;
+				}
+				__syncthreads();
+				// the element std::sort would leave at index kth: rank by (value, position)
+				for (int k = tid; k < n_fin; k += blockDim.x)
+				{
+					const float v = cbuf[k];
+					int r = 0;
+					for (int j = 0; j < n_fin; ++j)
+					{
+						const float w = cbuf[j];
+						r += (w < v || (w == v && j < k)) ? 1 : 0;
+					}
+					if (r == kth) s_med[ch] = 2.1981 * static_cast<double>(v);
+				}
+				__syncthreads();
+			}
+			if (tid == 0)
+			{
+				double lin = s_med[0];
+				double d[6] = {lin, lin, lin, s_med[1], s_med[1], s_med[1]};
+				if (a.split_linear)
+				{
+					d[0] = s_med[2];
+					d[1] = s_med[3];
+					d[2] = s_med[4];
+					lin = fmax(fmax(s_med[2], s_med[3]), s_med[4]);
+				}
+				if (a.max_variance > 0.f && lin > static_cast<double>(a.max_variance))
+				{
+					// "Rejected PnP transform, variance is too high": covariance back to identity, transform null (:246-251)
+					for (int k = 0; k < 6; ++k) d[k] = 1.0;
+					s_acc = 0;
+				}
+				for (int k = 0; k < 6; ++k) a.cov6[pair * 6 + k] = d[k];
+			}
+		}
+		else
+		{
+			// no 3-D points of B and no image size: covariance *= sqrt(mean squared reprojection error of the inliers) (:253-266);
+			// cv::projectPoints with the final pose, K and no distortion; float accumulation in inlier order
+			if (tid == 0) rodrigues_v2m(lm.param, lm.R, nullptr);
+			__syncthreads();
+			for (int k = tid; k < n_fin; k += blockDim.x)
+			{
+				const int i = fin[k];
+				double pu, pv;
+				project_point(lm.R, lm.param + 3, cam, X + 3 * i, pu, pv);
+				const float ex = __fsub_rn(uv[2 * i], static_cast<float>(pu)), ey = __fsub_rn(uv[2 * i + 1], static_cast<float>(pv));
+				cbuf[k] = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+			}
+			__syncthreads();
+			if (tid == 0)
+			{
+				float err = 0.0f;
+				for (int k = 0; k < n_fin; ++k) err = __fadd_rn(err, cbuf[k]);
+				const double sc = static_cast<double>(sqrtf(__fdiv_rn(err, static_cast<float>(n_fin))));
+				for (int k = 0; k < 6; ++k) a.cov6[pair * 6 + k] = sc;
+			}
+		}
+		__syncthreads();
+		accepted = s_acc;
+	}
+	if (tid == 0) a.ok[pair] = accepted;
+	if (accepted && tid < 12) a.transform[pair * 12 + tid] = s_T[tid];
 }
 
 // Pack the per-pair verification outputs into lcd_verify_result records (one device->host copy instead of seven).
@@ -784,10 +948,11 @@ struct PackedVerifyResult // layout of lcd_verify_result (include/lcd_b200.h)
 	int ok, n_matches, n_inliers, iterations_run;
 	double rvec[3], tvec[3];
 	float transform[12];
+	double covariance[36];
 };
 __global__ void pack_verify_results_kernel(int n_pairs, const int * __restrict__ ok, const int * __restrict__ n_match, const int * __restrict__ n_inl,
                                            const int * __restrict__ iters, const double * __restrict__ rvec, const double * __restrict__ tvec,
-                                           const float * __restrict__ T, PackedVerifyResult * __restrict__ out)
+                                           const float * __restrict__ T, const double * __restrict__ cov6, PackedVerifyResult * __restrict__ out)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_pairs) return;
@@ -802,6 +967,8 @@ __global__ void pack_verify_results_kernel(int n_pairs, const int * __restrict__
 		r.tvec[k] = tvec[3 * i + k];
 	}
 	for (int k = 0; k < 12; ++k) r.transform[k] = T[12 * i + k];
+	for (int k = 0; k < 36; ++k) r.covariance[k] = 0.0;
+	for (int k = 0; k < 6; ++k) r.covariance[7 * k] = cov6 ? cov6[6 * i + k] : 1.0;
 	out[i] = r;
 }
 

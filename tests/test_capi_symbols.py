@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = rtabmap_b200.load_library()
     for s in declared_symbols():
         assert hasattr(lib, s), f"liblcd_b200.so does not export {s}"
-    assert lib.lcd_abi_version() == 1
+    assert lib.lcd_abi_version() == 2
     assert lib.lcd_build_arch() == b"sm_100a"
 
 
