@@ -30,6 +30,19 @@ def make_binary_vocabulary(n_words: int, dim_bytes: int = 32, seed: int = 1, chi
     return np.ascontiguousarray(vocab[:n_words])
 
 
+def make_float_vocabulary(n_words: int, dim: int = 64, seed: int = 1) -> np.ndarray:
+    """SURF-like float vocabulary: unit L2 norm, Laplacian-distributed components, generated in chunks so that a
+    million rows stay cheap."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n_words, dim), np.float32)
+    for r0 in range(0, n_words, 1 << 16):
+        r1 = min(n_words, r0 + (1 << 16))
+        v = rng.laplace(0.0, 1.0, (r1 - r0, dim)).astype(np.float32)
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        out[r0:r1] = v
+    return out
+
+
 def flip_bits(desc: np.ndarray, p: float, rng: np.random.Generator) -> np.ndarray:
     flips = rng.random((desc.shape[0], desc.shape[1] * 8)) < p
     return desc ^ np.packbits(flips, axis=1)
@@ -298,14 +311,53 @@ def make_place_world(orb_fn, n_places: int = 50, n_words: int = 49152, n_signatu
     return PlaceWorld(images, depths, vocab, word_ids, smap, SynthStore(np.ascontiguousarray(sdesc), sxyz.astype(np.float32)), sig_place)
 
 
-def make_view_frames(world: PlaceWorld, n_frames: int, seed: int = 3, max_shift: int = 6, noise_sigma: float = 2.0):
-    """Query frames: noisy, slightly shifted views of random places. Returns images [n,H,W,3], depths [n,H,W], places [n]."""
+def warp_view(image: np.ndarray, depth: np.ndarray, angle_deg: float, scale: float, dx: float, dy: float, noise_sigma: float,
+              rng: np.random.Generator):
+    """A revisit from a different viewpoint ("rotated / homography views"): the frame rotated about its centre,
+    scaled and shifted (bilinear for the image, nearest for the depth, which is divided by the scale: closer = larger)."""
+    import cv2  # input synthesis only
+
+    h, w = depth.shape
+    M = cv2.getRotationMatrix2D((w * 0.5, h * 0.5), angle_deg, scale)
+    M[0, 2] += dx
+    M[1, 2] += dy
+    img = cv2.warpAffine(image, M, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    dep = cv2.warpAffine(depth, M, (w, h), flags=cv2.INTER_NEAREST, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    dep = np.where(dep > 0, np.clip(dep.astype(np.float32) / np.float32(scale), 1, 65000), 0).astype(np.uint16)
+    if noise_sigma > 0:
+        img = np.clip(img.astype(np.float32) + rng.normal(0, noise_sigma, img.shape), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(img), np.ascontiguousarray(dep)
+
+
+def make_view_frames(world: PlaceWorld, n_frames: int, seed: int = 3, max_shift: int = 6, noise_sigma: float = 2.0, mode: str = "revisit",
+                     new_place_frac: float = 0.3, warp_frac: float = 0.4):
+    """Query frames.  mode "revisit": noisy, slightly shifted views of random places (every query is a true loop closure).
+    mode "mixed" (the harder workload SURVEY.md §8(d) specifies): `new_place_frac` of the frames show places that are NOT in the map
+    (no loop closure: the likelihood is flat, verification runs all its RANSAC iterations and rejects), `warp_frac` are rotated
+    (+-12 deg) / scaled (0.85-1.15) / shifted views, the rest plain shifted revisits.
+    Returns images [n,H,W,3], depths [n,H,W], places [n] (-1 = never-seen place)."""
     rng = np.random.default_rng(seed)
     P = len(world.images)
     places = rng.integers(0, P, n_frames)
     imgs = np.empty((n_frames,) + world.images.shape[1:], np.uint8)
     deps = np.empty((n_frames,) + world.depths.shape[1:], np.uint16)
+    h, w = world.depths.shape[1:]
+    kind = np.zeros(n_frames, np.int64)
+    if mode == "mixed":
+        u = rng.random(n_frames)
+        kind = np.where(u < new_place_frac, 2, np.where(u < new_place_frac + warp_frac, 1, 0))
+    elif mode != "revisit":
+        raise ValueError(mode)
     for f in range(n_frames):
         dx, dy = rng.integers(-max_shift, max_shift + 1, 2)
-        imgs[f], deps[f] = render_view(world.images[places[f]], world.depths[places[f]], int(dx), int(dy), noise_sigma, rng)
+        if kind[f] == 2:
+            places[f] = -1
+            img = make_image(h, w, 100000 + seed * 1000 + f, bgr=True)
+            dep = make_depth(h, w, 200000 + seed * 1000 + f, zero_frac=0.01)
+            imgs[f], deps[f] = render_view(img, dep, int(dx), int(dy), noise_sigma, rng)
+        elif kind[f] == 1:
+            imgs[f], deps[f] = warp_view(world.images[places[f]], world.depths[places[f]], float(rng.uniform(-12, 12)), float(rng.uniform(0.85, 1.15)),
+                                         float(rng.uniform(-20, 20)), float(rng.uniform(-20, 20)), noise_sigma, rng)
+        else:
+            imgs[f], deps[f] = render_view(world.images[places[f]], world.depths[places[f]], int(dx), int(dy), noise_sigma, rng)
     return imgs, deps, places
