@@ -14,6 +14,7 @@
 #include "nn_hamming.cuh"
 #include "nn_tensor.cuh"
 #include "l2_path.cuh"
+#include "nn_tensor_f32.cuh"
 #include "resolve.cuh"
 #include "score.cuh"
 #include "verify.cuh"
@@ -239,6 +240,16 @@ struct lcd_engine
 	int nn_ctas_per_sm = 2, nn_tq = 8, nn_variant = 2, score_blocks = 32;
 	bool f32 = false;    // LCD_DESC_F32: squared-L2 path (l2_path.cuh)
 	DevBuf<ulonglong2> d_partial64;
+	// float descriptors on the tensor cores (nn_tensor_f32.cuh): cached fp16 image of rows [0, tf_rows) + their norms
+	DevBuf<uint4> tf_words, tf_queries;
+	DevBuf<float> tf_norms, tf_qn;
+	DevBuf<uint32_t> tf_tau, tf_cand, tf_wmax2;  // tf_wmax2[0] = bits of the largest |w|^2 seen
+	DevBuf<int> tf_cand_count, tf_fb_list, tf_flags; // tf_flags[0] = fallback count, tf_flags[1] = "a row does not fit fp16"
+	int tf_rows = 0;            // rows of the vocabulary whose image is current
+	bool tf_disabled = false;   // a dictionary row does not fit fp16: exact CUDA-core path from then on
+	int nn_f32_tensor = 1;      // LCD_NN_F32_TENSOR=0 forces the exact CUDA-core kernel
+	int nn_last_f32_tensor = 0;
+	long long tf_img_builds = 0; // rows expanded so far (diagnostics: the image is built once per dictionary change)
 	int nn_tensor = 1;   // 256-bit descriptors: tcgen05 int8 path (nn_tensor.cuh); 0 = POPC kernel (nn_hamming.cuh)
 	int nn_last_tensor = 0; // which kernel the last run_knn used (bench / diagnostics)
 	bool match_has_xyz_to = false; // verify_upload staged xyz_to for the next launch_match
@@ -401,11 +412,124 @@ int launch_knn_nw(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows
 	return launch_knn_t<NW, 4, 0>(e, d_q, nq_total, n_rows, n_chunks, rows_per_cta, d_partial, s);
 }
 
+// ---- float descriptors on the tensor cores ------------------------------------------------------------------------
+// rows of the vocabulary changed from `row` on (compaction, re-sorted tail): their image is stale
+void tf_invalidate_from(lcd_engine * e, int row) { e->tf_rows = std::min(e->tf_rows, std::max(row, 0)); }
+
+template <int DIM>
+int tf_search(lcd_engine * e, const float * d_q, int nq, int n_rows, cudaStream_t s)
+{
+	using Cfg = TfCfg<DIM>;
+	const int n_tiles = (n_rows + kTfBN - 1) / kTfBN, n_qtiles = (nq + kTfBM - 1) / kTfBM;
+	const float * vocab = reinterpret_cast<const float *>(e->vocab.p);
+	LCD_CUDA(e, e->tf_flags.reserve(4, 0, true, s));
+	LCD_CUDA(e, e->tf_wmax2.reserve(1, 0, true, s));
+	// (1) the cached word image: only rows that are new since the last search are converted
+	if (e->tf_rows < n_rows)
+	{
+		const size_t tile16 = static_cast<size_t>(kTfBN) * (DIM / 8);
+		const int old_tiles = static_cast<int>(e->tf_words.cap / tile16);
+		if (n_tiles > old_tiles)
+		{
+			const int want = std::max(n_tiles, old_tiles + old_tiles / 2 + 64);
+			LCD_CUDA(e, e->tf_words.reserve(static_cast<size_t>(want) * tile16, static_cast<size_t>(e->tf_rows / kTfBN) * tile16, false, s));
+			LCD_CUDA(e, e->tf_norms.reserve(static_cast<size_t>(want) * kTfBN, static_cast<size_t>(e->tf_rows / kTfBN) * kTfBN, false, s));
+		}
+		const int t0 = e->tf_rows / kTfBN;
+		const size_t rows_todo = static_cast<size_t>(n_tiles - t0) * kTfBN, chunks = rows_todo * (DIM / 8);
+		tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_words.p, e->tf_flags.p + 1);
+		LCD_CHECK_LAUNCH(e);
+		tf_norms_kernel<DIM><<<static_cast<unsigned>((rows_todo + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_norms.p, e->tf_wmax2.p);
+		LCD_CHECK_LAUNCH(e);
+		e->tf_img_builds += n_rows - e->tf_rows;
+		e->tf_rows = n_rows;
+	}
+	// (2) per-call query image and per-query state
+	const size_t qtile16 = static_cast<size_t>(kTfBM) * (DIM / 8);
+	LCD_CUDA(e, e->tf_queries.reserve(static_cast<size_t>(n_qtiles) * qtile16, 0, false, s));
+	LCD_CUDA(e, e->tf_qn.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->tf_tau.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->tf_cand_count.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->tf_cand.reserve(static_cast<size_t>(nq) * kTfCandCap, 0, false, s));
+	LCD_CUDA(e, e->tf_fb_list.reserve(nq, 0, false, s));
+	LCD_CUDA(e, e->d_partial64.reserve(nq, 0, false, s));
+	LCD_CUDA(e, zero_fill_async(e->tf_flags.p, sizeof(int), s)); // fallback count
+	{
+		const size_t chunks = static_cast<size_t>(n_qtiles) * kTfBM * (DIM / 8);
+		tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(d_q, 0, nq, kTfBM, e->tf_queries.p, nullptr);
+		LCD_CHECK_LAUNCH(e);
+		tf_query_init_kernel<DIM><<<(nq + 255) / 256, 256, 0, s>>>(d_q, nq, e->tf_qn.p, e->tf_cand_count.p, e->tf_tau.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	// (3) bound-only pre-pass over the first rows, then the emitting pass over all rows
+	LCD_CUDA(e, cudaFuncSetAttribute(knn2_tensor_f32_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::smem)));
+	TfArgs a{};
+	a.word_img = e->tf_words.p;
+	a.word_norms = e->tf_norms.p;
+	a.n_rows = n_rows;
+	a.query_img = e->tf_queries.p;
+	a.qn = e->tf_qn.p;
+	a.nq = nq;
+	a.wmax2_bits = e->tf_wmax2.p;
+	a.tau = e->tf_tau.p;
+	a.cand = e->tf_cand.p;
+	a.cand_count = e->tf_cand_count.p;
+	prof_mark(e, LCD_PROF_NN, s);
+	a.tile_begin = 0;
+	a.tile_end = std::min(n_tiles, kTfPrepassTiles);
+	a.tiles_per_split = a.tile_end;
+	a.emit = 0;
+	knn2_tensor_f32_kernel<DIM><<<dim3(n_qtiles, 1), kTfThreads, Cfg::smem, s>>>(a);
+	LCD_CHECK_LAUNCH(e);
+	// splits: a split's slice of the word image should sit in L2 while the query tiles of that split stream it (CTAs with the same
+	// blockIdx.y are scheduled together), and small query batches still have to fill the machine
+	const int tiles_l2 = std::max(1, static_cast<int>((24u << 20) / Cfg::b_bytes));
+	int splits = std::max((n_tiles + tiles_l2 - 1) / tiles_l2, (2 * e->sm_count + n_qtiles - 1) / n_qtiles);
+	splits = std::max(1, std::min(splits, n_tiles));
+	const int tps = (n_tiles + splits - 1) / splits;
+	splits = (n_tiles + tps - 1) / tps;
+	a.tile_begin = 0;
+	a.tile_end = n_tiles;
+	a.tiles_per_split = tps;
+	a.emit = 1;
+	knn2_tensor_f32_kernel<DIM><<<dim3(n_qtiles, splits), kTfThreads, Cfg::smem, s>>>(a);
+	LCD_CHECK_LAUNCH(e);
+	// (4) exact re-rank of the candidates; overflowed lists are redone by an exact scan
+	rerank_l2_kernel<DIM><<<(nq + 7) / 8, 256, 0, s>>>(vocab, e->row_offset, d_q, nq, e->tf_cand.p, e->tf_cand_count.p, e->d_partial64.p, e->tf_fb_list.p,
+	                                                   e->tf_flags.p);
+	LCD_CHECK_LAUNCH(e);
+	knn2_l2_fallback_kernel<DIM><<<e->sm_count, 256, 0, s>>>(vocab, n_rows, e->row_offset, d_q, e->tf_fb_list.p, e->tf_flags.p, e->d_partial64.p);
+	prof_mark(e, LCD_PROF_NN, s);
+	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+// A dictionary row outside the fp16 range switches the engine to the exact kernel; read wherever the host synchronises anyway.
+int tf_poll_bad_rows(lcd_engine * e)
+{
+	if (!e->f32 || e->tf_disabled || !e->tf_flags.p) return LCD_OK;
+	int bad = 0;
+	LCD_CUDA(e, cudaMemcpyAsync(&bad, e->tf_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
+	if (bad) e->tf_disabled = true;
+	return LCD_OK;
+}
+
 // exact 2-NN of nq_total queries over rows [0,n_rows): fills e->d_partial, returns chunk count
 int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int * n_chunks_out, cudaStream_t s)
 {
 	if (e->row_offset + n_rows > kMaxRowsPacked) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d indexed words", kMaxRowsPacked);
 	e->nn_last_tensor = 0;
+	e->nn_last_f32_tensor = 0;
+	if (e->f32 && e->nn_f32_tensor && !e->tf_disabled && n_rows >= kTfMinRows && nq_total > 0 &&
+	    TfCfg<64>::smem <= static_cast<size_t>(e->smem_optin))
+	{
+		// float descriptors, large dictionary: distance matrix on the tensor cores as a filter + exact re-rank (nn_tensor_f32.cuh)
+		const float * q = reinterpret_cast<const float *>(d_q);
+		e->nn_last_f32_tensor = 1;
+		*n_chunks_out = 1;
+		return e->nw == 64 ? tf_search<64>(e, q, nq_total, n_rows, s) : tf_search<128>(e, q, nq_total, n_rows, s);
+	}
 	if (e->f32)
 	{
 		// float descriptors: exact squared-L2 2-NN, one query per thread, rows split over blockIdx.y to fill the machine
@@ -596,6 +720,7 @@ int sort_pending(lcd_engine * e)
 	LCD_CUDA(e, cudaMemcpyAsync(e->row_ids.p + base, ids.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
 	e->pending_sorted = true;
+	tf_invalidate_from(e, base);
 	return LCD_OK;
 }
 
@@ -767,12 +892,13 @@ long long lcd_launch_count(const lcd_engine * e) { return e ? e->launches.load()
 int lcd_nn_select(lcd_engine * e, int kernel)
 {
 	if (!e) return LCD_ERR_INVALID;
-	if (kernel != 0 && kernel != 1) LCD_FAIL(e, LCD_ERR_INVALID, "kernel must be 0 (popcount) or 1 (tensor)");
-	e->nn_tensor = kernel;
+	if (kernel != 0 && kernel != 1) LCD_FAIL(e, LCD_ERR_INVALID, "kernel must be 0 (popcount / exact L2 on the CUDA cores) or 1 (tensor)");
+	if (e->f32) e->nn_f32_tensor = kernel;
+	else e->nn_tensor = kernel;
 	return LCD_OK;
 }
 
-int lcd_nn_last_kernel(const lcd_engine * e) { return e ? e->nn_last_tensor : LCD_ERR_INVALID; }
+int lcd_nn_last_kernel(const lcd_engine * e) { return e ? (e->f32 ? e->nn_last_f32_tensor : e->nn_last_tensor) : LCD_ERR_INVALID; }
 void * lcd_stream(lcd_engine * e) { return e ? static_cast<void *>(e->stream) : nullptr; }
 
 lcd_engine * lcd_create(const lcd_config * cfg)
@@ -821,6 +947,7 @@ lcd_engine * lcd_create(const lcd_config * cfg)
 	e->nn_tq = env_int("LCD_NN_TQ", e->nn_tq);
 	e->nn_variant = env_int("LCD_NN_VARIANT", e->nn_variant);
 	e->nn_tensor = env_int("LCD_NN_TENSOR", e->nn_tensor);
+	e->nn_f32_tensor = env_int("LCD_NN_F32_TENSOR", e->nn_f32_tensor);
 	e->score_blocks = std::max(1, env_int("LCD_SCORE_BLOCKS", e->score_blocks));
 	if (ensure_rows(e, std::max(cfg->max_words, 1024)) != LCD_OK || ensure_ids(e, std::max(cfg->max_words, 1024)) != LCD_OK ||
 	    ensure_sigs(e, std::max(cfg->max_signatures, 1024)) != LCD_OK)
@@ -1011,6 +1138,7 @@ int lcd_dict_remove_words(lcd_engine * e, const int * ids, int n)
 		}
 		if (nk) LCD_CUDA(e, cudaMemcpyAsync(e->row_ids.p + base, kid.data(), nk * sizeof(int), cudaMemcpyHostToDevice, e->stream));
 		e->n_pending = nk;
+		tf_invalidate_from(e, base);
 	}
 	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
 	return LCD_OK;
@@ -1058,7 +1186,9 @@ int lcd_dict_update(lcd_engine * e)
 		e->n_pending = nk - kept_indexed;
 		e->n_indexed = kept_indexed;
 		e->removed_rows.clear();
+		tf_invalidate_from(e, 0); // rows moved: the fp16 image is rebuilt at the next search
 	}
+	LCD_TRY(tf_poll_bad_rows(e));
 	e->n_indexed += e->n_pending;
 	e->n_pending = 0;
 	e->pending_sorted = true;
@@ -1086,6 +1216,10 @@ int lcd_dict_clear(lcd_engine * e)
 	e->post_used = 0;
 	e->sig_words.clear();
 	e->total_refs = 0;
+	e->tf_rows = 0;
+	e->tf_disabled = false;
+	if (e->tf_wmax2.p) LCD_CUDA(e, cudaMemsetAsync(e->tf_wmax2.p, 0, sizeof(uint32_t), e->stream));
+	if (e->tf_flags.p) LCD_CUDA(e, cudaMemsetAsync(e->tf_flags.p, 0, 4 * sizeof(int), e->stream));
 	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
 	return LCD_OK;
 }
@@ -2252,12 +2386,12 @@ int lcd_match_bf(lcd_engine * e, int n_pairs, int cap, const void * desc_query, 
 	}
 	else
 	{
-		// every train row picks its nearest query; every query keeps the nearest train row that picked it
-		LCD_TRY(launch_bf_any(e, n_pairs, cap, e->v_df.p, e->v_nf.p, e->v_dt.p, e->v_nt.p, e->bf_keys_a.p, s));
+		// nearest train row of every query, nearest query of every train row, then the mutual test
+		LCD_TRY(launch_bf_any(e, n_pairs, cap, e->v_dt.p, e->v_nt.p, e->v_df.p, e->v_nf.p, e->bf_keys_a.p, s));
+		LCD_CUDA(e, e->bf_keys_b.reserve(rows, 0, false, s));
+		LCD_TRY(launch_bf_any(e, n_pairs, cap, e->v_df.p, e->v_nf.p, e->v_dt.p, e->v_nt.p, e->bf_keys_b.p, s));
 		LCD_CUDA(e, e->bf_best.reserve(rows, 0, false, s));
-		bf_cross_fill_kernel<<<nb, 256, 0, s>>>(e->bf_best.p, cap, n_pairs);
-		LCD_CHECK_LAUNCH(e);
-		bf_cross_scatter_kernel<<<dim3((cap + 255) / 256, n_pairs), 256, 0, s>>>(e->bf_keys_a.p, e->v_nf.p, cap, e->bf_best.p);
+		bf_cross_kernel<<<dim3((cap + 255) / 256, n_pairs), 256, 0, s>>>(e->bf_keys_a.p, e->bf_keys_b.p, e->v_nt.p, cap, e->bf_best.p);
 		LCD_CHECK_LAUNCH(e);
 		if (e->f32) bf_decode_kernel<true><<<nb, 256, 0, s>>>(e->bf_best.p, 1, 0, static_cast<int>(rows), e->d_i1.p, e->d_f1.p);
 		else bf_decode_kernel<false><<<nb, 256, 0, s>>>(e->bf_best.p, 1, 0, static_cast<int>(rows), e->d_i1.p, e->d_f1.p);

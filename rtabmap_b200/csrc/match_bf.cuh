@@ -6,11 +6,11 @@
 // norm = NORM_HAMMING for CV_8U rows, NORM_L2SQR for CV_32F rows.  cv::BFMatcher is third-party (OpenCV features2d, not under
 // /root/reference); its published behaviour restated here:
 //   knnMatch   : per query the k nearest train rows, ties -> lowest train index (cv::batchDistance keeps the first minimum);
-//   crossCheck : cv::batchDistance(..., crosscheck = true) first finds for every TRAIN row its nearest QUERY row (ties -> lowest
-//                query index), then gives every query q the nearest of the train rows that chose q (strict '<' while scanning train
-//                rows in ascending order: ties -> lowest train index); queries no train row chose stay unmatched.
+//   crossCheck : a query q is matched to its nearest train row t (ties -> lowest t) only if q is in turn the nearest query of t
+//                (ties -> lowest q); other queries get no DMatch.  Verified against cv2 4.13 on tie-heavy random sets
+//                (tests/test_gpu_boundary.py).
 // Sizes are those of one signature pair (<= 4096 rows each), so one thread scans one row of one side against a shared-memory
-// tile of the other; the two sides of the cross check meet through an atomicMin on a packed (distance, index) key.
+// tile of the other.
 #pragma once
 #include "common.cuh"
 #include "nn_hamming.cuh"
@@ -74,22 +74,25 @@ bf_knn2_kernel(const uint32_t * __restrict__ A, const int * __restrict__ n_a, co
 	if (i < na) keys[static_cast<size_t>(pair) * cap + i] = make_ulonglong2(k1, k2);
 }
 
-// cross check, second half: train row t chose query q = index(key_of_train[t].x); query q keeps the nearest such t.
-__global__ void bf_cross_fill_kernel(unsigned long long * __restrict__ best /* [n_pairs][cap] */, int cap, int n_pairs)
-{
-	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i < static_cast<size_t>(n_pairs) * cap) best[i] = kKey64None;
-}
-__global__ void bf_cross_scatter_kernel(const ulonglong2 * __restrict__ train_keys, const int * __restrict__ n_train, int cap,
-                                        unsigned long long * __restrict__ best)
+// cross check: query q keeps its nearest train row t only if q is also the nearest query of t (ties -> lowest index on both sides).
+// query_keys[pair][q].x = (distance, t), train_keys[pair][t].x = (distance, q).
+__global__ void bf_cross_kernel(const ulonglong2 * __restrict__ query_keys, const ulonglong2 * __restrict__ train_keys, const int * __restrict__ n_query,
+                                int cap, unsigned long long * __restrict__ best)
 {
 	const int pair = blockIdx.y;
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= min(n_train[pair], cap)) return;
-	const unsigned long long k = train_keys[static_cast<size_t>(pair) * cap + t].x;
-	if (k == kKey64None) return;
-	const uint32_t q = static_cast<uint32_t>(k);
-	atomicMin(&best[static_cast<size_t>(pair) * cap + q], (k & 0xFFFFFFFF00000000ull) | static_cast<unsigned long long>(t));
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= cap) return;
+	unsigned long long out = kKey64None;
+	if (q < min(n_query[pair], cap))
+	{
+		const unsigned long long k = query_keys[static_cast<size_t>(pair) * cap + q].x;
+		if (k != kKey64None)
+		{
+			const unsigned long long kt = train_keys[static_cast<size_t>(pair) * cap + static_cast<uint32_t>(k)].x;
+			if (kt != kKey64None && static_cast<uint32_t>(kt) == static_cast<uint32_t>(q)) out = k;
+		}
+	}
+	best[static_cast<size_t>(pair) * cap + q] = out;
 }
 
 // decode packed keys into (index, distance as float); index -1 / distance -1 = none

@@ -1,0 +1,451 @@
+// nn_tensor_f32.cuh — exact squared-L2 2-NN of FLOAT descriptors (SURF-64 / SIFT-128 sized rows) with the distance matrix on the
+// 5th-generation tensor cores (sm_100a): BASELINE configs[3], "tensor cores ... if SURF/float descriptors make it a true dense GEMM".
+//
+// Replaces, for CV_32F descriptors: FlannIndex::knnSearch(k = 2) on a LinearIndex (corelib/src/FlannIndex.cpp:701-745 ->
+// rtflann::L2<float>::operator(), rtflann/algorithms/dist.h:133-180, KNNSimpleResultSet, rtflann/util/result_set.h:151-172), whose
+// result — ids AND fp32 distances in rtflann's summation order — must be reproduced bit for bit.  A tensor-core GEMM cannot reproduce
+// an fp32 summation order, so it is used as a FILTER with a proven bound, followed by an exact re-rank:
+//
+//   1. operands rounded to fp16 (round to nearest, no scaling; |x| < 65504 is checked) in pre-tiled, 128-byte-swizzled K-major
+//      images: the word image is built once per dictionary change and CACHED (half the bytes of the fp32 rows: the 1M x 64
+//      vocabulary streams as 128 MB), the query image per call;
+//   2. knn2_tensor_f32_kernel: tcgen05.mma kind::f16 (M128 N256 K16, fp32 accumulators in TMEM) gives acc ~ q.w; the epilogue forms
+//      v = |w|^2 - 2 acc (= approximate squared distance minus |q|^2) and appends to the query's CANDIDATE LIST every row with
+//      v <= t2 + 2 eps, where t2 is the second-smallest v this thread has seen so far (initialised from a shared per-query bound);
+//   3. rerank_l2_kernel computes the exact rtflann-order distance of every candidate from the fp32 rows and keeps the best two by
+//      (distance, row) — the same packed 64-bit keys as the exact kernel of l2_path.cuh, consumed by the same resolve kernel;
+//   4. a query whose list overflowed (or whose values do not fit fp16) is redone by an exact scan (knn2_l2_fallback_kernel).
+//
+// Why the filter cannot lose a true neighbour.  Let d(w) be the distance rtflann computes, e1, e2 the true two nearest rows, and
+// |v(w) + |q|^2 - d(w)| <= eps for every row w.  t2 is always the larger of the v's of two DISTINCT rows, hence
+// t2 + |q|^2 >= d(e2) - eps; and v(e_i) + |q|^2 <= d(e_i) + eps <= d(e2) + eps.  So v(e_i) <= t2 + 2 eps whenever e_i is examined:
+// both true neighbours (and every row tying with them) reach the list, and the exact re-rank then orders them as rtflann does.
+// eps bounds (a) fp16 rounding of both operands: |q^.w^ - q.w| <= 2^-10 (1 + 2^-11) |q| |w| + subnormal terms (Cauchy-Schwarz on the
+// element-wise relative errors 2^-11), doubled by the factor 2 in the distance; (b) fp32 accumulation in the tensor core, the fma
+// of the epilogue, the float norms and rtflann's own rounding, all far below 2^-15 (|q|^2 + |w|^2):
+//     eps(q) = 1.02 * 2^-9 * |q| * Wmax + 2^-15 * (|q|^2 + Wmax^2),      Wmax = largest |w| in the dictionary.
+// For unit-length descriptors eps ~ 2.1e-3 against nearest-neighbour distances of 1e-2 .. 1: the lists stay a few dozen rows long.
+#pragma once
+#include "common.cuh"
+#include "l2_path.cuh"
+#include "nn_tensor.cuh"
+#include <cuda_fp16.h>
+
+namespace lcd {
+
+constexpr int kTfBM = 128;          // queries per CTA tile (UMMA M)
+constexpr int kTfBN = 256;          // words per tile (UMMA N)
+constexpr int kTfEpiGroups = 4;     // column groups of a tile, one set of 4 epilogue warps each
+constexpr int kTfEpiCols = kTfBN / kTfEpiGroups;
+constexpr int kTfThreads = 128 + 128 * kTfEpiGroups;
+constexpr int kTfNormSlots = 4;     // ring of per-tile norm vectors (1 KB each)
+constexpr int kTfCandCap = 96;      // candidate rows kept per query; more -> exact fallback for that query
+constexpr int kTfMinRows = 4096;    // below this the exact CUDA-core kernel is used
+constexpr int kTfPrepassTiles = 16; // rows [0, 4096): the bound-only pre-pass that initialises the per-query bound
+
+template <int DIM>
+struct TfCfg
+{
+	static constexpr int atoms = DIM / 64;                 // 64 halves = one 128-byte swizzle atom
+	static constexpr uint32_t a_bytes = kTfBM * DIM * 2;
+	static constexpr uint32_t b_bytes = kTfBN * DIM * 2;
+	static constexpr int stages = DIM == 64 ? 5 : 2;
+	static constexpr size_t smem = 1024 + a_bytes + stages * b_bytes + kTfNormSlots * kTfBN * 4 + 512;
+};
+
+// order-preserving float <-> uint mapping (v can be negative), for atomicMin on the shared per-query bound
+__device__ __forceinline__ uint32_t f2ord(float f)
+{
+	const uint32_t b = __float_as_uint(f);
+	return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u)
+{
+	return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// ---- operand images ----------------------------------------------------------------------------------------------
+// One thread converts 8 consecutive floats of a row into one 16-byte chunk.  Rows >= n_rows of the last tile are zero.
+// Layout: [tile][atom][tile_rows][128 B], chunk c of row r at c ^ (r & 7) (canonical K-major SWIZZLE_128B).
+// bad_row[row] (may be null) is set when a value is not finite or does not fit fp16.
+template <int DIM>
+__global__ void tf_expand_kernel(const float * __restrict__ src, int row_begin, int n_rows, int tile_rows, uint4 * __restrict__ dst,
+                                 int * __restrict__ bad_flag)
+{
+	constexpr int chunks = DIM / 8;
+	const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	const int tile0 = row_begin / tile_rows;
+	const size_t row = static_cast<size_t>(tile0) * tile_rows + gid / chunks;
+	const int chunk = static_cast<int>(gid % chunks);
+	const size_t row_end = (static_cast<size_t>(n_rows) + tile_rows - 1) / tile_rows * tile_rows;
+	if (row >= row_end) return;
+	uint4 o = make_uint4(0, 0, 0, 0);
+	if (row < static_cast<size_t>(n_rows))
+	{
+		const float4 a = *reinterpret_cast<const float4 *>(src + row * DIM + chunk * 8);
+		const float4 b = *reinterpret_cast<const float4 *>(src + row * DIM + chunk * 8 + 4);
+		const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+		                      fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+		if (!(m < 65504.0f) && bad_flag) *bad_flag = 1; // also true for NaN
+		const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y),
+		              h3 = __floats2half2_rn(b.z, b.w);
+		o.x = *reinterpret_cast<const uint32_t *>(&h0);
+		o.y = *reinterpret_cast<const uint32_t *>(&h1);
+		o.z = *reinterpret_cast<const uint32_t *>(&h2);
+		o.w = *reinterpret_cast<const uint32_t *>(&h3);
+	}
+	const int tile = static_cast<int>(row / tile_rows), r = static_cast<int>(row % tile_rows);
+	const int atom = chunk >> 3, c = chunk & 7;
+	const size_t off16 = static_cast<size_t>(tile) * (static_cast<size_t>(tile_rows) * chunks) + static_cast<size_t>(atom) * (tile_rows * 8) +
+	                     static_cast<size_t>(r) * 8 + static_cast<size_t>(c ^ (r & 7));
+	dst[off16] = o;
+}
+
+// |w|^2 of rows [row_begin rounded down to a tile, n_rows rounded up): +inf for the padding rows; the largest one into *wmax2_bits.
+template <int DIM>
+__global__ void tf_norms_kernel(const float * __restrict__ src, int row_begin, int n_rows, int tile_rows, float * __restrict__ norms,
+                                uint32_t * __restrict__ wmax2_bits)
+{
+	const size_t row = static_cast<size_t>(row_begin / tile_rows) * tile_rows + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	const size_t row_end = (static_cast<size_t>(n_rows) + tile_rows - 1) / tile_rows * tile_rows;
+	if (row >= row_end) return;
+	float s = INFINITY;
+	if (row < static_cast<size_t>(n_rows))
+	{
+		s = 0.0f;
+		for (int i = 0; i < DIM; i += 4)
+		{
+			const float4 a = *reinterpret_cast<const float4 *>(src + row * DIM + i);
+			s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+		}
+		if (wmax2_bits && s == s) atomicMax(wmax2_bits, __float_as_uint(s)); // s >= 0: unsigned order of the bits = float order
+	}
+	norms[row] = s;
+}
+
+// per-query state of one search: norm, empty candidate list (or "overflowed" for queries that do not fit fp16), loose bound
+template <int DIM>
+__global__ void tf_query_init_kernel(const float * __restrict__ q, int nq, float * __restrict__ qn, int * __restrict__ cand_count,
+                                     uint32_t * __restrict__ tau)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nq) return;
+	float s = 0.0f, m = 0.0f;
+	for (int k = 0; k < DIM; k += 4)
+	{
+		const float4 a = *reinterpret_cast<const float4 *>(q + static_cast<size_t>(i) * DIM + k);
+		s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+		m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+	}
+	const bool ok = (m < 65504.0f) && (s == s) && (s < INFINITY);
+	qn[i] = ok ? s : 0.0f;
+	cand_count[i] = ok ? 0 : (kTfCandCap + 1);
+	tau[i] = 0xFFFFFFFFu;
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, f16 x f16 -> f32, M128 x N256 x K16
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"setp.ne.b32 p, %4, 0;\n"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+		"}\n" ::"r"(tmem_d),
+		"l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+// instruction descriptor: f32 accumulator, f16 x f16, both K-major
+__device__ __forceinline__ constexpr uint32_t tc_idesc_f16(int m, int n)
+{
+	return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct TfArgs
+{
+	const uint4 * word_img;      // fp16 word image
+	const float * word_norms;    // [tiles * 256] |w|^2, +inf in padding rows
+	int n_rows;                  // rows of this search
+	const uint4 * query_img;
+	const float * qn;            // [nq] |q|^2
+	int nq;
+	int tile_begin, tile_end;    // tile range of the whole launch; blockIdx.y * tiles_per_split selects the CTA's share
+	int tiles_per_split;
+	const uint32_t * wmax2_bits; // largest |w|^2 of the dictionary (float bits)
+	uint32_t * tau;              // [nq] shared bound on the second-smallest v (ordered-uint encoding)
+	uint32_t * cand;             // [nq][kTfCandCap] candidate rows (local to this engine)
+	int * cand_count;            // [nq]
+	int emit;                    // 0: bound-only pre-pass
+};
+
+// grid = (query tiles, splits).  Roles as in knn2_tensor_kernel (nn_tensor.cuh): warp 0 producer (bulk copies of the word tiles and
+// of their norm vectors), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 epilogue (thread = one query = one TMEM lane,
+// column group (warp - 4) / 4).
+template <int DIM>
+__global__ void __launch_bounds__(kTfThreads, 1)
+knn2_tensor_f32_kernel(const TfArgs a)
+{
+	using Cfg = TfCfg<DIM>;
+	constexpr int kStages = Cfg::stages;
+	extern __shared__ unsigned char smem_dyn[];
+	unsigned char * smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+	unsigned char * sA = smem;
+	unsigned char * sB = smem + Cfg::a_bytes;
+	float * sN = reinterpret_cast<float *>(sB + kStages * Cfg::b_bytes); // [kTfNormSlots][256]
+	uint64_t * bars = reinterpret_cast<uint64_t *>(sN + kTfNormSlots * kTfBN);
+	uint64_t * full = bars;                     // [kStages] word tile landed
+	uint64_t * empty = full + kStages;          // [kStages] word tile consumed by the MMAs
+	uint64_t * tfull = empty + kStages;         // [2] accumulator stage complete
+	uint64_t * tempty = tfull + 2;              // [2] accumulator stage drained
+	uint64_t * nfull = tempty + 2;              // [kTfNormSlots] norm vector landed
+	uint64_t * nempty = nfull + kTfNormSlots;   // [kTfNormSlots] norm vector read by all epilogue warps
+	uint64_t * afull = nempty + kTfNormSlots;   // [1] query tile landed
+	uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(afull + 1);
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int tile_begin = a.tile_begin + blockIdx.y * a.tiles_per_split;
+	const int tile_end = min(a.tile_end, tile_begin + a.tiles_per_split);
+	const int n_tiles = max(0, tile_end - tile_begin);
+	const int qtile = blockIdx.x;
+
+	if (tid == 0)
+	{
+		for (int s = 0; s < kStages; ++s)
+		{
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], 1);
+		}
+		for (int s = 0; s < 2; ++s)
+		{
+			mbar_init(&tfull[s], 1);
+			mbar_init(&tempty[s], 4 * kTfEpiGroups);
+		}
+		for (int s = 0; s < kTfNormSlots; ++s)
+		{
+			mbar_init(&nfull[s], 1);
+			mbar_init(&nempty[s], 4 * kTfEpiGroups);
+		}
+		mbar_init(afull, 1);
+		mbar_fence_init();
+	}
+	if (warp == 2) tc_alloc(tmem_slot, 512);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp == 0)
+	{
+		if (lane == 0 && n_tiles > 0)
+		{
+			mbar_arrive_expect_tx(afull, Cfg::a_bytes);
+			bulk_g2s(sA, reinterpret_cast<const unsigned char *>(a.query_img) + static_cast<size_t>(qtile) * Cfg::a_bytes, Cfg::a_bytes, afull);
+			for (int t = 0; t < n_tiles; ++t)
+			{
+				const int s = t % kStages, ns = t % kTfNormSlots;
+				if (t >= kTfNormSlots) mbar_wait(&nempty[ns], ((t / kTfNormSlots) - 1) & 1);
+				mbar_arrive_expect_tx(&nfull[ns], kTfBN * 4);
+				bulk_g2s(sN + ns * kTfBN, a.word_norms + static_cast<size_t>(tile_begin + t) * kTfBN, kTfBN * 4, &nfull[ns]);
+				if (t >= kStages) mbar_wait(&empty[s], ((t / kStages) - 1) & 1);
+				mbar_arrive_expect_tx(&full[s], Cfg::b_bytes);
+				const unsigned char * src = reinterpret_cast<const unsigned char *>(a.word_img) + static_cast<size_t>(tile_begin + t) * Cfg::b_bytes;
+				bulk_g2s(sB + s * Cfg::b_bytes, src, Cfg::b_bytes / 2, &full[s]);
+				bulk_g2s(sB + s * Cfg::b_bytes + Cfg::b_bytes / 2, src + Cfg::b_bytes / 2, Cfg::b_bytes / 2, &full[s]);
+			}
+		}
+	}
+	else if (warp == 1)
+	{
+		if (lane == 0 && n_tiles > 0)
+		{
+			constexpr uint32_t idesc = tc_idesc_f16(kTfBM, kTfBN);
+			const uint32_t a_base = smem_u32(sA);
+			mbar_wait(afull, 0);
+			for (int t = 0; t < n_tiles; ++t)
+			{
+				const int s = t % kStages, acc = t & 1;
+				if (t >= 2) mbar_wait(&tempty[acc], ((t >> 1) - 1) & 1);
+				mbar_wait(&full[s], (t / kStages) & 1);
+				tc_fence_after();
+				const uint32_t b_base = smem_u32(sB + s * Cfg::b_bytes);
+				const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kTfBN);
+#pragma unroll
+				for (int ks = 0; ks < DIM / 16; ++ks)
+				{
+					const uint32_t atom = ks >> 2, koff = (ks & 3) * 32; // 16 halves = 32 bytes per K step, 4 steps per 128-byte atom
+					const uint64_t ad = tc_smem_desc(a_base + atom * (kTfBM * 128) + koff);
+					const uint64_t bd = tc_smem_desc(b_base + atom * (kTfBN * 128) + koff);
+					tc_mma_f16(d_addr, ad, bd, idesc, ks > 0 ? 1u : 0u);
+				}
+				tc_commit(&empty[s]);
+				tc_commit(&tfull[acc]);
+			}
+		}
+	}
+	else if (warp >= 4)
+	{
+		const int quarter = warp & 3;
+		const int cg = (warp - 4) >> 2;
+		const int qi = qtile * kTfBM + quarter * 32 + lane;
+		const bool live = qi < a.nq;
+		float margin = 0.0f, t1 = INFINITY, t2 = INFINITY;
+		if (live)
+		{
+			const float q2 = a.qn[qi], w2 = __uint_as_float(*a.wmax2_bits);
+			const float eps = 1.02f * 0.001953125f * sqrtf(q2) * sqrtf(w2) + 3.0517578125e-05f * (q2 + w2);
+			margin = 2.0f * eps;
+			t2 = ord2f(a.tau[qi]);
+		}
+		const int emit = a.emit;
+		for (int t = 0; t < n_tiles; ++t)
+		{
+			const int acc = t & 1, ns = t % kTfNormSlots;
+			mbar_wait(&nfull[ns], (t / kTfNormSlots) & 1);
+			mbar_wait(&tfull[acc], (t >> 1) & 1);
+			tc_fence_after();
+			const int row0 = (tile_begin + t) * kTfBN + cg * kTfEpiCols;
+			const float4 * wn4 = reinterpret_cast<const float4 *>(sN + ns * kTfBN + cg * kTfEpiCols);
+			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTfBN + cg * kTfEpiCols);
+#pragma unroll
+			for (int c0 = 0; c0 < kTfEpiCols; c0 += 32)
+			{
+				int v[32];
+				tc_ld32(taddr + c0, v);
+				tc_wait_ld();
+				float f[32];
+				float m = INFINITY;
+#pragma unroll
+				for (int j = 0; j < 32; j += 4)
+				{
+					const float4 w = wn4[(c0 + j) >> 2];
+					f[j] = fmaf(__int_as_float(v[j]), -2.0f, w.x);
+					f[j + 1] = fmaf(__int_as_float(v[j + 1]), -2.0f, w.y);
+					f[j + 2] = fmaf(__int_as_float(v[j + 2]), -2.0f, w.z);
+					f[j + 3] = fmaf(__int_as_float(v[j + 3]), -2.0f, w.w);
+					m = fminf(m, fminf(fminf(f[j], f[j + 1]), fminf(f[j + 2], f[j + 3])));
+				}
+				if (live && m <= t2 + margin)
+				{
+					// rare: some column of this chunk may belong to the two nearest rows
+#pragma unroll
+					for (int j = 0; j < 32; ++j)
+					{
+						const float x = f[j];
+						if (x <= t2 + margin && x < INFINITY)
+						{
+							if (emit)
+							{
+								const int pos = atomicAdd(&a.cand_count[qi], 1);
+								if (pos < kTfCandCap) a.cand[static_cast<size_t>(qi) * kTfCandCap + pos] = static_cast<uint32_t>(row0 + c0 + j);
+							}
+							if (x < t1)
+							{
+								t2 = t1;
+								t1 = x;
+							}
+							else if (x < t2) t2 = x;
+						}
+					}
+				}
+			}
+			// accumulator stage and norm slot are free once every lane of the warp is done with them
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0)
+			{
+				mbar_arrive(&tempty[acc]);
+				mbar_arrive(&nempty[ns]);
+			}
+		}
+		if (live && t2 < INFINITY) atomicMin(&a.tau[qi], f2ord(t2));
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 2) tc_dealloc(tmem_base, 512);
+}
+
+// ---- exact re-rank of the candidate lists: one warp per query -----------------------------------------------------------------
+// partial[q] = (best key, second key) with keys (float bits of rtflann's distance << 32 | row_offset + row); queries whose list
+// overflowed go to the fallback list instead.
+template <int DIM>
+__global__ void rerank_l2_kernel(const float * __restrict__ vocab, int row_offset, const float * __restrict__ queries, int nq,
+                                 const uint32_t * __restrict__ cand, const int * __restrict__ cand_count, ulonglong2 * __restrict__ partial,
+                                 int * __restrict__ fb_list, int * __restrict__ fb_count)
+{
+	const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (qi >= nq) return;
+	const int n = cand_count[qi];
+	if (n > kTfCandCap)
+	{
+		if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = qi;
+		return;
+	}
+	unsigned long long k1 = kKey64None, k2 = kKey64None;
+	const float * q = queries + static_cast<size_t>(qi) * DIM;
+	for (int c = lane; c < n; c += 32)
+	{
+		const uint32_t row = cand[static_cast<size_t>(qi) * kTfCandCap + c];
+		const float d = l2_rtflann<DIM>(q, vocab + static_cast<size_t>(row) * DIM);
+		top2_insert64(k1, k2, pack64(d, static_cast<uint32_t>(row_offset) + row));
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		const unsigned long long o1 = __shfl_down_sync(0xFFFFFFFFu, k1, o);
+		const unsigned long long o2 = __shfl_down_sync(0xFFFFFFFFu, k2, o);
+		top2_insert64(k1, k2, o1);
+		top2_insert64(k1, k2, o2);
+	}
+	if (lane == 0) partial[qi] = make_ulonglong2(k1, k2);
+}
+
+// exact scan for the queries of the fallback list (list overflow, values outside fp16): one CTA per query at a time
+template <int DIM>
+__global__ void __launch_bounds__(256)
+knn2_l2_fallback_kernel(const float * __restrict__ vocab, int n_rows, int row_offset, const float * __restrict__ queries,
+                        const int * __restrict__ fb_list, const int * __restrict__ fb_count, ulonglong2 * __restrict__ partial)
+{
+	__shared__ float s_q[DIM];
+	__shared__ unsigned long long s_k1[8], s_k2[8];
+	const int n_fb = *fb_count;
+	for (int k = blockIdx.x; k < n_fb; k += gridDim.x)
+	{
+		const int qi = fb_list[k];
+		__syncthreads();
+		for (int i = threadIdx.x; i < DIM; i += blockDim.x) s_q[i] = queries[static_cast<size_t>(qi) * DIM + i];
+		__syncthreads();
+		unsigned long long k1 = kKey64None, k2 = kKey64None;
+		for (int r = threadIdx.x; r < n_rows; r += blockDim.x)
+		{
+			const float d = l2_rtflann<DIM>(s_q, vocab + static_cast<size_t>(r) * DIM);
+			top2_insert64(k1, k2, pack64(d, static_cast<uint32_t>(row_offset + r)));
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			const unsigned long long o1 = __shfl_down_sync(0xFFFFFFFFu, k1, o);
+			const unsigned long long o2 = __shfl_down_sync(0xFFFFFFFFu, k2, o);
+			top2_insert64(k1, k2, o1);
+			top2_insert64(k1, k2, o2);
+		}
+		if ((threadIdx.x & 31) == 0)
+		{
+			s_k1[threadIdx.x >> 5] = k1;
+			s_k2[threadIdx.x >> 5] = k2;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			for (int w = 1; w < 8; ++w)
+			{
+				top2_insert64(k1, k2, s_k1[w]);
+				top2_insert64(k1, k2, s_k2[w]);
+			}
+			partial[qi] = make_ulonglong2(k1, k2);
+		}
+	}
+}
+
+} // namespace lcd

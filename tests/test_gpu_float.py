@@ -108,3 +108,92 @@ def test_float_engine_rejects_binary_only_calls():
     eng = Engine(desc_type=LCD_DESC_F32, desc_dim=64)
     with pytest.raises(Exception):
         eng.match_pairs(np.zeros((1, 8, 64), np.float32), np.zeros((1, 8, 64), np.float32), [8], [8])
+
+
+# ---------------------------------------------------------------- tensor-core filter + exact re-rank (nn_tensor_f32.cuh) ----------
+@pytest.mark.parametrize("dim,n_words", [(64, 4096), (64, 20000), (64, 70001), (128, 9000)])
+def test_tensor_filter_is_bit_identical_to_the_exact_kernel(dim, n_words):
+    """Dictionaries of >= 4096 float rows go through the tcgen05 fp16 GEMM filter + exact re-rank; ids and fp32 distances must equal
+    the exact CUDA-core scan (and the rtflann-pinned oracle) bit for bit."""
+    eng, o, vocab, ids = pair(n_words, dim, seed=3 * dim + n_words)
+    rng = np.random.default_rng(17)
+    q = float_vocab(700, dim, 5)
+    q[:300] = noisy(vocab[rng.integers(0, n_words, 300)], 0.05, rng)
+    q[300:330] = vocab[rng.integers(0, n_words, 30)]          # exact copies: distance 0
+    q[330] = 0.0                                              # zero vector
+    q[331:340] *= 30.0                                        # long vectors: large distances, large error bound
+    eng.nn_select(1)
+    g = eng.knn2(q)
+    assert eng.nn_last_kernel == 1, "the tensor-core filter did not run"
+    eng.nn_select(0)
+    x = eng.knn2(q)
+    assert eng.nn_last_kernel == 0
+    for a, b in zip(g, x):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    w = o.knn2(q[:200])
+    assert np.array_equal(g[0][:200], w[0]) and np.array_equal(g[2][:200], w[2])
+    assert np.array_equal(g[1][:200].view(np.uint32), w[1].view(np.uint32)) and np.array_equal(g[3][:200].view(np.uint32), w[3].view(np.uint32))
+
+
+def test_tensor_filter_overflowing_lists_and_out_of_range_values_fall_back_to_the_exact_scan():
+    dim, n_words = 64, 12000
+    vocab = float_vocab(n_words, dim, 31)
+    vocab[2000:2400] = vocab[7]                 # 401 identical rows: every one of them ties for nearest -> the list overflows
+    vocab[5000:5200] = vocab[8] * np.float32(1.0 + 1e-4)  # 200 rows within the error bound of each other
+    ids = np.arange(1, n_words + 1, dtype=np.int32)
+    eng = Engine(desc_type=LCD_DESC_F32, desc_dim=dim)
+    eng.add_words(ids, vocab)
+    eng.last_word_id = n_words
+    eng.update()
+    rng = np.random.default_rng(32)
+    q = noisy(vocab[rng.integers(0, n_words, 64)], 0.03, rng)
+    q[0] = vocab[7]
+    q[1] = noisy(vocab[7:8], 0.01, rng)[0]
+    q[2] = vocab[8]
+    q[3] = 1.0e6                                 # does not fit fp16: exact scan for this query
+    q[4, 5] = np.float32(7.0e4)
+    eng.nn_select(1)
+    g = eng.knn2(q)
+    assert eng.nn_last_kernel == 1
+    eng.nn_select(0)
+    x = eng.knn2(q)
+    for a, b in zip(g, x):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert g[0][0] == 8 and g[2][0] == 2001      # ties resolve to the lowest rows: row 7 (id 8), then row 2000 (id 2001)
+    # a dictionary row outside the fp16 range: the engine notices at the next synchronising call and stays on the exact kernel
+    big = float_vocab(1, dim, 33) * np.float32(1.0e5)
+    eng.nn_select(1)
+    eng.add_words([n_words + 1], big)
+    eng.update()
+    g1 = eng.knn2(q)          # this search still builds the image (and raises the flag)
+    eng.update()
+    g2 = eng.knn2(q)
+    assert eng.nn_last_kernel == 0
+    eng.nn_select(0)
+    x2 = eng.knn2(q)
+    for a, b in zip(g2, x2):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_tensor_filter_incremental_stream_matches_oracle():
+    """Mapping mode on a float dictionary large enough for the tensor path: new words join the cached fp16 image row by row."""
+    eng, o, vocab, ids = pair(6000, 64, seed=77)
+    rng = np.random.default_rng(78)
+    for t in range(1, 7):
+        frame = np.concatenate([noisy(vocab[rng.integers(0, 6000, 150)], 0.04, rng), float_vocab(60, 64, 1000 + t)])
+        frame[200:205] = frame[195:200] + np.float32(1e-3)   # near copies of descriptors that become new words in this frame
+        eng.update()
+        o.update()
+        g, n_new = eng.quantize(frame, t)
+        w = o.add_new_words(frame, t)
+        assert eng.nn_last_kernel == 1
+        assert np.array_equal(g, w), f"frame {t}"
+        if t == 3:  # forget some indexed words: the compaction rebuilds the image
+            victims = np.asarray(ids[100:140])
+            eng.remove_words(victims)
+            o.remove_words(victims)
+    q = noisy(vocab[rng.integers(0, 6000, 50)], 0.05, rng)
+    assert np.array_equal(eng.find_nn(q, True, 0.8), o.find_nn(q))
+    eng.update()
+    o.update()
+    assert np.array_equal(eng.find_nn(q, True, 0.8), o.find_nn(q))
