@@ -565,7 +565,25 @@ int orc_localize(void * h, const void * desc, int n, int sig_id, const int * sig
 // same float arithmetic, but the words the frame would create live in local vectors and the query's
 // own reference is accounted for as nw = refs.size() + 1 instead of being inserted and rolled back.
 // tests/test_oracle_golden.py checks it against orc_localize.  Safe to call from many threads.
+static int localize_ro_impl(void * h, const void * desc_, int n, const int * sig_ids, int ns, int n_total, int * out_words, float * out_like,
+                            const long long * knn_idx, const float * knn_dist);
+
 int orc_localize_ro(void * h, const void * desc_, int n, const int * sig_ids, int ns, int n_total, int * out_words, float * out_like)
+{
+	return localize_ro_impl(h, desc_, n, sig_ids, ns, n_total, out_words, out_like, nullptr, nullptr);
+}
+
+// Same, with the index search of every descriptor done by the caller — bench.py's CPU arm passes the output of the REFERENCE'S OWN
+// compiled rtflann (oracle/_ref, FlannIndex::knnSearch on the LinearIndex): knn_idx[n][2] rows in search order (-1 = none),
+// knn_dist[n][2].  Everything after the search (multimap, NNDR, new words, TF-IDF) is the restatement.
+int orc_localize_ro_knn(void * h, const void * desc_, int n, const long long * knn_idx, const float * knn_dist, const int * sig_ids, int ns,
+                        int n_total, int * out_words, float * out_like)
+{
+	return localize_ro_impl(h, desc_, n, sig_ids, ns, n_total, out_words, out_like, knn_idx, knn_dist);
+}
+
+static int localize_ro_impl(void * h, const void * desc_, int n, const int * sig_ids, int ns, int n_total, int * out_words, float * out_like,
+                            const long long * knn_idx, const float * knn_dist)
 {
 	const OracleDict & d = *(const OracleDict *)h;
 	const uint8_t * desc = (const uint8_t *)desc_;
@@ -579,7 +597,16 @@ int orc_localize_ro(void * h, const void * desc_, int n, const int * sig_ids, in
 	{
 		const uint8_t * q = desc + (size_t)i * rb;
 		std::multimap<float, int> full;
-		if (!rowptr.empty())
+		if (knn_idx)
+		{
+			for (int j = 0; j < 2; ++j)
+			{
+				const long long r = knn_idx[2 * (size_t)i + j];
+				if (r < 0) break;
+				full.insert(std::make_pair(knn_dist[2 * (size_t)i + j], d.rows[(size_t)r]));
+			}
+		}
+		else if (!rowptr.empty())
 		{
 			Top2 t;
 			knn2_rows(d, rowptr, q, t);

@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
         L.orc_localize.restype = _I
         L.orc_localize_ro.argtypes = [_P, _P, _I, _P, _I, _I, _P, _P]
         L.orc_localize_ro.restype = _I
+        L.orc_localize_ro_knn.argtypes = [_P, _P, _I, _P, _P, _P, _I, _I, _P, _P]
+        L.orc_localize_ro_knn.restype = _I
         L.orc_adjust_likelihood.argtypes = [_P, _I, _I]
         _lib = L
     return _lib
@@ -259,6 +261,17 @@ class OracleDictionary:
         words = np.zeros(len(desc), np.int32)
         like = np.zeros(len(s), np.float32) if want_like else None
         n = self.L.orc_localize_ro(self.h, _p(desc), len(desc), _p(s), len(s), int(n_total), _p(words), _p(like))
+        return words[:n], like
+
+    def localize_ro_knn(self, desc, knn_idx, knn_dist, sig_ids, n_total, want_like=True):
+        """localize_ro with the index search done by the caller (bench.py: the reference's own compiled rtflann, ref_knn2)."""
+        desc = self._d(desc)
+        s = _i32(sig_ids)
+        ki = np.ascontiguousarray(knn_idx, np.int64)
+        kd = np.ascontiguousarray(knn_dist, np.float32)
+        words = np.zeros(len(desc), np.int32)
+        like = np.zeros(len(s), np.float32) if want_like else None
+        n = self.L.orc_localize_ro_knn(self.h, _p(desc), len(desc), _p(ki), _p(kd), _p(s), len(s), int(n_total), _p(words), _p(like))
         return words[:n], like
 
 

@@ -416,34 +416,46 @@ int launch_knn_nw(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows
 // rows of the vocabulary changed from `row` on (compaction, re-sorted tail): their image is stale
 void tf_invalidate_from(lcd_engine * e, int row) { e->tf_rows = std::min(e->tf_rows, std::max(row, 0)); }
 
+// (1) the cached word image: only rows that are new since the last search are converted.  When rows were converted, the "does not
+// fit fp16" flag is read back at once (a synchronisation that only happens right after the dictionary changed): such a dictionary
+// stays on the exact kernel.
+template <int DIM>
+int tf_prepare_words(lcd_engine * e, int n_rows, cudaStream_t s)
+{
+	if (e->tf_rows >= n_rows) return LCD_OK;
+	const int n_tiles = (n_rows + kTfBN - 1) / kTfBN;
+	const float * vocab = reinterpret_cast<const float *>(e->vocab.p);
+	LCD_CUDA(e, e->tf_flags.reserve(4, 0, true, s));
+	LCD_CUDA(e, e->tf_wmax2.reserve(1, 0, true, s));
+	const size_t tile16 = static_cast<size_t>(kTfBN) * (DIM / 8);
+	const int old_tiles = static_cast<int>(e->tf_words.cap / tile16);
+	if (n_tiles > old_tiles)
+	{
+		const int want = std::max(n_tiles, old_tiles + old_tiles / 2 + 64);
+		LCD_CUDA(e, e->tf_words.reserve(static_cast<size_t>(want) * tile16, static_cast<size_t>(e->tf_rows / kTfBN) * tile16, false, s));
+		LCD_CUDA(e, e->tf_norms.reserve(static_cast<size_t>(want) * kTfBN, static_cast<size_t>(e->tf_rows / kTfBN) * kTfBN, false, s));
+	}
+	const int t0 = e->tf_rows / kTfBN;
+	const size_t rows_todo = static_cast<size_t>(n_tiles - t0) * kTfBN, chunks = rows_todo * (DIM / 8);
+	tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_words.p, e->tf_flags.p + 1);
+	LCD_CHECK_LAUNCH(e);
+	tf_norms_kernel<DIM><<<static_cast<unsigned>((rows_todo + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_norms.p, e->tf_wmax2.p);
+	LCD_CHECK_LAUNCH(e);
+	e->tf_img_builds += n_rows - e->tf_rows;
+	e->tf_rows = n_rows;
+	int bad = 0;
+	LCD_CUDA(e, cudaMemcpyAsync(&bad, e->tf_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	if (bad) e->tf_disabled = true;
+	return LCD_OK;
+}
+
 template <int DIM>
 int tf_search(lcd_engine * e, const float * d_q, int nq, int n_rows, cudaStream_t s)
 {
 	using Cfg = TfCfg<DIM>;
 	const int n_tiles = (n_rows + kTfBN - 1) / kTfBN, n_qtiles = (nq + kTfBM - 1) / kTfBM;
 	const float * vocab = reinterpret_cast<const float *>(e->vocab.p);
-	LCD_CUDA(e, e->tf_flags.reserve(4, 0, true, s));
-	LCD_CUDA(e, e->tf_wmax2.reserve(1, 0, true, s));
-	// (1) the cached word image: only rows that are new since the last search are converted
-	if (e->tf_rows < n_rows)
-	{
-		const size_t tile16 = static_cast<size_t>(kTfBN) * (DIM / 8);
-		const int old_tiles = static_cast<int>(e->tf_words.cap / tile16);
-		if (n_tiles > old_tiles)
-		{
-			const int want = std::max(n_tiles, old_tiles + old_tiles / 2 + 64);
-			LCD_CUDA(e, e->tf_words.reserve(static_cast<size_t>(want) * tile16, static_cast<size_t>(e->tf_rows / kTfBN) * tile16, false, s));
-			LCD_CUDA(e, e->tf_norms.reserve(static_cast<size_t>(want) * kTfBN, static_cast<size_t>(e->tf_rows / kTfBN) * kTfBN, false, s));
-		}
-		const int t0 = e->tf_rows / kTfBN;
-		const size_t rows_todo = static_cast<size_t>(n_tiles - t0) * kTfBN, chunks = rows_todo * (DIM / 8);
-		tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_words.p, e->tf_flags.p + 1);
-		LCD_CHECK_LAUNCH(e);
-		tf_norms_kernel<DIM><<<static_cast<unsigned>((rows_todo + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_norms.p, e->tf_wmax2.p);
-		LCD_CHECK_LAUNCH(e);
-		e->tf_img_builds += n_rows - e->tf_rows;
-		e->tf_rows = n_rows;
-	}
 	// (2) per-call query image and per-query state
 	const size_t qtile16 = static_cast<size_t>(kTfBM) * (DIM / 8);
 	LCD_CUDA(e, e->tf_queries.reserve(static_cast<size_t>(n_qtiles) * qtile16, 0, false, s));
@@ -504,23 +516,15 @@ int tf_search(lcd_engine * e, const float * d_q, int nq, int n_rows, cudaStream_
 	return LCD_OK;
 }
 
-// A dictionary row outside the fp16 range switches the engine to the exact kernel; read wherever the host synchronises anyway.
-int tf_poll_bad_rows(lcd_engine * e)
-{
-	if (!e->f32 || e->tf_disabled || !e->tf_flags.p) return LCD_OK;
-	int bad = 0;
-	LCD_CUDA(e, cudaMemcpyAsync(&bad, e->tf_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-	LCD_CUDA(e, cudaStreamSynchronize(e->stream));
-	if (bad) e->tf_disabled = true;
-	return LCD_OK;
-}
-
 // exact 2-NN of nq_total queries over rows [0,n_rows): fills e->d_partial, returns chunk count
 int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int * n_chunks_out, cudaStream_t s)
 {
 	if (e->row_offset + n_rows > kMaxRowsPacked) LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d indexed words", kMaxRowsPacked);
 	e->nn_last_tensor = 0;
 	e->nn_last_f32_tensor = 0;
+	if (e->f32 && e->nn_f32_tensor && !e->tf_disabled && n_rows >= kTfMinRows && nq_total > 0 &&
+	    TfCfg<64>::smem <= static_cast<size_t>(e->smem_optin))
+		LCD_TRY(e->nw == 64 ? tf_prepare_words<64>(e, n_rows, s) : tf_prepare_words<128>(e, n_rows, s));
 	if (e->f32 && e->nn_f32_tensor && !e->tf_disabled && n_rows >= kTfMinRows && nq_total > 0 &&
 	    TfCfg<64>::smem <= static_cast<size_t>(e->smem_optin))
 	{
@@ -1188,7 +1192,6 @@ int lcd_dict_update(lcd_engine * e)
 		e->removed_rows.clear();
 		tf_invalidate_from(e, 0); // rows moved: the fp16 image is rebuilt at the next search
 	}
-	LCD_TRY(tf_poll_bad_rows(e));
 	e->n_indexed += e->n_pending;
 	e->n_pending = 0;
 	e->pending_sorted = true;

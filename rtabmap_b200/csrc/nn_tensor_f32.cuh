@@ -140,7 +140,7 @@ __global__ void tf_query_init_kernel(const float * __restrict__ q, int nq, float
 	const bool ok = (m < 65504.0f) && (s == s) && (s < INFINITY);
 	qn[i] = ok ? s : 0.0f;
 	cand_count[i] = ok ? 0 : (kTfCandCap + 1);
-	tau[i] = 0xFFFFFFFFu;
+	tau[i] = 0xFF800000u; // f2ord(+inf): no bound yet
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, f16 x f16 -> f32, M128 x N256 x K16

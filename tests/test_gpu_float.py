@@ -160,12 +160,10 @@ def test_tensor_filter_overflowing_lists_and_out_of_range_values_fall_back_to_th
     for a, b in zip(g, x):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert g[0][0] == 8 and g[2][0] == 2001      # ties resolve to the lowest rows: row 7 (id 8), then row 2000 (id 2001)
-    # a dictionary row outside the fp16 range: the engine notices at the next synchronising call and stays on the exact kernel
-    big = float_vocab(1, dim, 33) * np.float32(1.0e5)
+    # a dictionary row outside the fp16 range: noticed while its image is built, the engine stays on the exact kernel
+    big = float_vocab(1, dim, 33) * np.float32(1.0e7)
     eng.nn_select(1)
     eng.add_words([n_words + 1], big)
-    eng.update()
-    g1 = eng.knn2(q)          # this search still builds the image (and raises the flag)
     eng.update()
     g2 = eng.knn2(q)
     assert eng.nn_last_kernel == 0
