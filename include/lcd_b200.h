@@ -100,6 +100,8 @@ typedef struct lcd_orb_params {
 #define LCD_DEPTH_NONE 0
 #define LCD_DEPTH_U16_MM 1 /* CV_16UC1, millimetres */
 #define LCD_DEPTH_F32_M 2  /* CV_32FC1, metres     */
+#define LCD_DEPTH_MASK_U8 3 /* not a depth image: the CV_8UC1 mask (0 / 255) Feature2D::generateKeypoints hands to
+                               generateKeypointsImpl (Features2d.cpp:783-857); no 3-D points are produced */
 
 /* replaces, for Kp/DetectorStrategy=2: cv::cvtColor(BGR2GRAY) (Memory.cpp:5447),
  * Feature2D::generateKeypoints incl. the depth mask and limitKeypoints (Features2d.cpp:775-878, :356-399)

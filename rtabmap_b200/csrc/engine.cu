@@ -118,6 +118,8 @@ static cudaError_t zero_fill_async(void * p, size_t bytes, cudaStream_t s)
 	return cudaGetLastError();
 }
 
+size_t depth_elem_bytes(int depth_type) { return depth_type == LCD_DEPTH_U16_MM ? 2 : (depth_type == LCD_DEPTH_MASK_U8 ? 1 : 4); }
+
 int env_int(const char * name, int def)
 {
 	const char * v = getenv(name);
@@ -1690,7 +1692,8 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	if (channels != 1 && channels != 3) LCD_FAIL(e, LCD_ERR_INVALID, "images must be 8UC1 or 8UC3 (BGR)");
 	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap must be 1..%d", kMaxFrameQueries);
 	if (!d_depth) depth_type = LCD_DEPTH_NONE;
-	const bool use_mask = depth_type != LCD_DEPTH_NONE && p->depth_as_mask;
+	if (depth_type < LCD_DEPTH_NONE || depth_type > LCD_DEPTH_MASK_U8) LCD_FAIL(e, LCD_ERR_INVALID, "unknown depth type %d", depth_type);
+	const bool use_mask = depth_type == LCD_DEPTH_MASK_U8 || (depth_type != LCD_DEPTH_NONE && p->depth_as_mask);
 	const size_t pyr = static_cast<size_t>(total_frames) * g.frame_stride;
 	LCD_CUDA(e, e->o_gray.reserve(pyr, 0, false, s));
 	LCD_CUDA(e, e->o_blur.reserve(pyr, 0, false, s));
@@ -1721,7 +1724,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	// pointers of the range
 	const size_t px = static_cast<size_t>(width) * height;
 	d_images += static_cast<size_t>(frame0) * px * channels;
-	if (d_depth) d_depth = static_cast<const unsigned char *>(d_depth) + static_cast<size_t>(frame0) * px * (depth_type == LCD_DEPTH_U16_MM ? 2 : 4);
+	if (d_depth) d_depth = static_cast<const unsigned char *>(d_depth) + static_cast<size_t>(frame0) * px * (depth_elem_bytes(depth_type));
 	uint8_t * const w_gray = e->o_gray.p + static_cast<size_t>(frame0) * g.frame_stride;
 	uint8_t * const w_blur = e->o_blur.p + static_cast<size_t>(frame0) * g.frame_stride;
 	uint8_t * const w_mask = use_mask ? e->o_mask.p + static_cast<size_t>(frame0) * g.frame_stride : nullptr;
@@ -1855,7 +1858,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		if (d_xyz)
 		{
 			OrbXyzArgs a{};
-			a.depth = depth_type != LCD_DEPTH_NONE ? d_depth : nullptr;
+			a.depth = (depth_type != LCD_DEPTH_NONE && depth_type != LCD_DEPTH_MASK_U8) ? d_depth : nullptr;
 			a.depth_type = depth_type;
 			a.w = width;
 			a.h = height;
@@ -1910,7 +1913,7 @@ int lcd_orb_detect_describe(lcd_engine * e, int n_frames, const uint8_t * images
 	LCD_CUDA(e, e->o_img.reserve(px * channels, 0, false, s));
 	LCD_CUDA(e, cudaMemcpyAsync(e->o_img.p, images, px * channels, cudaMemcpyHostToDevice, s));
 	if (!depth) depth_type = LCD_DEPTH_NONE;
-	const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+	const size_t dbytes = depth_elem_bytes(depth_type);
 	if (depth_type != LCD_DEPTH_NONE)
 	{
 		LCD_CUDA(e, e->o_depth.reserve(px * dbytes, 0, false, s));
@@ -2599,7 +2602,7 @@ static int process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_im
 			e->copy_events.push_back(ev);
 		}
 		const size_t px = static_cast<size_t>(width) * height;
-		const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+		const size_t dbytes = depth_elem_bytes(depth_type);
 		// the device staging buffers may still be read by work queued on s (a previous call): order the copies after it
 		LCD_CUDA(e, cudaEventRecord(e->copy_fence, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->copy_fence, 0));
@@ -2663,7 +2666,7 @@ int lcd_process_frames(lcd_engine * e, int n_frames, const uint8_t * images, int
 	if (!depth) depth_type = LCD_DEPTH_NONE;
 	if (depth_type != LCD_DEPTH_NONE)
 	{
-		const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+		const size_t dbytes = depth_elem_bytes(depth_type);
 		LCD_CUDA(e, e->o_depth.reserve(px * dbytes, 0, false, s));
 	}
 	// the frames themselves are uploaded chunk by chunk inside process_frames_dev, overlapped with detect + describe
@@ -2717,7 +2720,7 @@ int lcd_process_frames_submit(lcd_engine * e, int n_frames, const uint8_t * imag
 	}
 	const size_t px = static_cast<size_t>(n_frames) * width * height;
 	if (!depth) depth_type = LCD_DEPTH_NONE;
-	const size_t dbytes = depth_type == LCD_DEPTH_U16_MM ? 2 : 4;
+	const size_t dbytes = depth_elem_bytes(depth_type);
 	// upload on the copy stream: the slot's previous batch was waited for, so its staging buffers are free
 	static const int dbg_tl = env_int("LCD_DEBUG_TIMELINE", 0); // diagnostics: print each batch's upload / compute window at _wait
 	if (dbg_tl && !f.t_h0)

@@ -65,7 +65,7 @@ struct OrbPrepArgs
 	const uint8_t * images; // [n_frames][h][w][channels]
 	int channels;
 	const void * depth;     // [n_frames][h][w] u16 (mm) or f32 (m), or nullptr
-	int depth_type;         // 0 none, 1 u16, 2 f32
+	int depth_type;         // 0 none, 1 u16, 2 f32, 3 u8 mask
 	float min_depth, max_depth;
 	uint8_t * gray;         // pyramids
 	uint8_t * mask;         // pyramids or nullptr
@@ -75,6 +75,7 @@ struct OrbPrepArgs
 __device__ __forceinline__ uint8_t depth_to_mask(const void * depth, int type, size_t idx, float min_depth, float max_depth)
 {
 	float value = 0.0f;
+	if (type == 3) return static_cast<const uint8_t *>(depth)[idx] ? 255 : 0; // a ready-made CV_8UC1 mask (0 / 255)
 	if (type == 1)
 	{
 		const unsigned short d = static_cast<const unsigned short *>(depth)[idx];
