@@ -872,6 +872,7 @@ def run_c4(args):
     prof = {name: eng.profile_read(i) for i, name in enumerate(["nn", "resolve", "score"])}
     eng.profile_enable(False)
     value = B * args.steps / (dev_ms * 1e-3)
+    n_fallback, n_cand, rows_conv = eng.nn_f32_stats(nq)
     like_last = d_like.view(B, S).argmax(1).cpu().numpy()
     last_pool = (args.steps - 1) % n_pool
     hit = float(np.mean(smap.sig_ids[like_last] == smap.sig_ids[places[last_pool * B:(last_pool + 1) * B]]))
@@ -912,6 +913,8 @@ def run_c4(args):
                 "peak_source": peak_src, "note": "algorithmic bytes of ONE step (vocabulary read once per batch of frames); the kernel is epilogue / tensor bound, "
                                                  "not HBM bound: the fp16 word image streams once per step (DESIGN.md 4.4)"},
         "step_share_ms": {k + "_ms": v[0] / args.steps for k, v in prof.items()},
+        "filter": {"candidates_per_query": n_cand / nq, "queries_redone_by_exact_scan": n_fallback, "queries": nq,
+                   "dictionary_rows_converted_to_fp16_since_start": rows_conv},
     }
 
     cpu = None

@@ -156,6 +156,11 @@ int lcd_dict_get_indexed(lcd_engine * e, int * ids, void * desc, int cap_rows);
  * (VWDictionary::setNNStrategy, VWDictionary.cpp:316-338).  lcd_nn_last_kernel: which one the last search used. */
 int lcd_nn_select(lcd_engine * e, int kernel);
 int lcd_nn_last_kernel(const lcd_engine * e);
+/* Float engines (LCD_DESC_F32) with >= 4096 rows search through the fp16 tensor-core filter + exact re-rank (kernel 1; kernel 0 = the
+ * exact CUDA-core scan; results are bit-identical).  Diagnostics of the LAST search of nq queries: how many queries were redone by
+ * the exact fallback scan, how many candidate rows the filter passed to the re-rank in total, and how many dictionary rows have been
+ * converted to the cached fp16 image since the engine was created (it is converted once per dictionary change, not per search). */
+int lcd_nn_f32_stats(lcd_engine * e, int nq, int * n_fallback, long long * n_candidates, long long * rows_converted);
 
 /* replaces: FlannIndex::knnSearch(k=2) on a LinearIndex (FlannIndex.cpp:701-745 ->
  * rtflann linear_index.h:129-146 + result_set.h:151-172): exact 2-NN of every query
@@ -207,6 +212,25 @@ int lcd_index_get_refs(lcd_engine * e, int word_id, int * sig, int * cnt, int ca
  * n_total = N = Memory::getSignatures().size().  likelihood_out[ns] float. */
 int lcd_index_score(lcd_engine * e, const int * query_word_ids, int nq,
                     const int * sig_ids, int ns, int n_total, float * likelihood_out);
+
+/* ---- Bayes filter over the loop-closure hypotheses ---------------------------
+ * replaces: BayesFilter::computePosterior (BayesFilter.cpp:145-270): prior = prediction x last posterior, posterior = likelihood .* prior,
+ * normalised; the prediction is the matrix of generatePrediction / addNeighborProb / normalize (:272-505) kept in its sparse form (the
+ * reference builds it dense: S x S floats).  The engine keeps the last posterior by place id between calls (updatePosterior, :712-737);
+ * lcd_bayes_reset = BayesFilter::reset.
+ *   ids[n]         uKeys(likelihood): ascending place ids, ids[0] < 0 = the virtual place (Rtabmap::adjustLikelihood adds it)
+ *   likelihood[n]  the adjusted likelihood of each id
+ *   col_ptr[n+1], nbr_row[nnz], nbr_level[nnz]   for every place (column) the places its probability mass spreads to:
+ *                  Memory::getNeighborsId(id, n_lc - 1, ...) restricted to the places of this call and outside the short-term memory,
+ *                  as (position in ids, graph margin) pairs in ascending id order; the place itself (margin 0) must be listed — the
+ *                  graph walk is the caller's (Memory), the probability model is computed here.  Columns of loop-closure partners that
+ *                  share a neighbour tree (BayesFilter.cpp:378-391) simply carry the same list.  The virtual place has an empty list.
+ *   prediction_lc[n_lc]  Bayes/PredictionLC {virtual place, loop closure, level 1, level 2, ...}, virtual_place_prior = Bayes/VirtualPlacePriorThr
+ *   posterior_out[n]
+ * Float results agree with the reference's dense float product to ~1e-6 relative. */
+int lcd_bayes_compute_posterior(lcd_engine * e, const int * ids, const float * likelihood, int n, const int64_t * col_ptr, const int * nbr_row,
+                                const int * nbr_level, const double * prediction_lc, int n_lc, float virtual_place_prior, float * posterior_out);
+int lcd_bayes_reset(lcd_engine * e);
 
 /* ---- fused, batched localisation query (frozen dictionary + frozen map) ---------
  * One call = B independent queries of the quantise -> score half of the hot path with

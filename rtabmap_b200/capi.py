@@ -119,6 +119,7 @@ SIGNATURES = {
     "lcd_dict_get_indexed": (_I, [_P, _P, _P, _I]),
     "lcd_nn_select": (_I, [_P, _I]),
     "lcd_nn_last_kernel": (_I, [_P]),
+    "lcd_nn_f32_stats": (_I, [_P, _I, _P, _P, _P]),
     "lcd_dict_knn2": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "lcd_dict_quantize": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
     "lcd_dict_find_nn": (_I, [_P, _P, _I, _I, _F, _P]),
@@ -132,6 +133,8 @@ SIGNATURES = {
     "lcd_index_score": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "lcd_adjust_likelihood": (_I, [_P, _P, _I, _I, _I, _P]),
     "lcd_adjust_likelihood_dev": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "lcd_bayes_compute_posterior": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _F, _P]),
+    "lcd_bayes_reset": (_I, [_P]),
     "lcd_localize_batch": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P]),
     "lcd_localize_batch_dev": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P]),
     "lcd_match_pairs": (_I, [_P, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
@@ -356,6 +359,14 @@ class Engine:
         """0 = XOR/POPC kernel, 1 = tensor-core kernel (default for 32-byte descriptors)."""
         self._check(self._lib.lcd_nn_select(self._h, int(kernel)))
 
+    def nn_f32_stats(self, nq: int):
+        """(queries redone by the exact fallback, candidate rows re-ranked, dictionary rows converted to fp16 so far) of the last float search."""
+        fb = C.c_int(0)
+        cand = C.c_longlong(0)
+        conv = C.c_longlong(0)
+        self._check(self._lib.lcd_nn_f32_stats(self._h, int(nq), C.byref(fb), C.byref(cand), C.byref(conv)))
+        return fb.value, cand.value, conv.value
+
     @property
     def nn_last_kernel(self) -> int:
         return int(self._lib.lcd_nn_last_kernel(self._h))
@@ -436,6 +447,22 @@ class Engine:
         out = np.zeros((l2.shape[0], l2.shape[1] + 1), np.float32)
         self._check(self._lib.lcd_adjust_likelihood(self._h, _ptr(l2), l2.shape[0], l2.shape[1], int(virtual_place_ratio), _ptr(out)))
         return out[0] if one else out
+
+    def bayes_reset(self):
+        self._check(self._lib.lcd_bayes_reset(self._h))
+
+    def bayes_compute_posterior(self, ids, likelihood, col_ptr, nbr_row, nbr_level, prediction_lc, virtual_place_prior: float = 0.9) -> np.ndarray:
+        """BayesFilter::computePosterior with the prediction in sparse form (see lcd_b200.h)."""
+        i = _i32(ids)
+        l = np.ascontiguousarray(likelihood, np.float32)
+        cp = np.ascontiguousarray(col_ptr, np.int64)
+        r = _i32(nbr_row)
+        lv = _i32(nbr_level)
+        lc = np.ascontiguousarray(prediction_lc, np.float64)
+        out = np.zeros(len(i), np.float32)
+        self._check(self._lib.lcd_bayes_compute_posterior(self._h, _ptr(i), _ptr(l), len(i), _ptr(cp), _ptr(r), _ptr(lv), _ptr(lc), len(lc),
+                                                           float(virtual_place_prior), _ptr(out)))
+        return out
 
     def localize_batch(self, queries, n_frames: int, sig_ids, n_total: int, incremental: bool = True, nndr: float = 0.8,
                        cmp_new: bool = True, want_words: bool = True, want_likelihood: bool = True,

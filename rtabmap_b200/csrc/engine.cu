@@ -17,6 +17,7 @@
 #include "nn_tensor_f32.cuh"
 #include "resolve.cuh"
 #include "score.cuh"
+#include "bayes.cuh"
 #include "verify.cuh"
 #include "match_bf.cuh"
 #include "orb.cuh"
@@ -204,6 +205,11 @@ struct lcd_engine
 	DevBuf<RefOp> d_ops;
 	DevBuf<MoveOp> d_moves;
 	DevBuf<int> d_perm;
+	// Bayes filter (bayes.cuh): the last posterior by place id + per-call scratch
+	DevBuf<int> by_ids, by_colptr, by_row, by_level, by_entry_col, by_state_ids;
+	DevBuf<float> by_like, by_last, by_u, by_scale, by_delta, by_post, by_state_post;
+	DevBuf<double> by_lc, by_prior, by_sums;
+	int by_n_state = 0;
 	// verification scratch
 	DevBuf<uint32_t> v_df, v_dt;
 	DevBuf<float> v_xyz, v_uv, v_obj, v_img, v_T, v_xyz_to, v_obj_to;
@@ -512,7 +518,9 @@ int tf_search(lcd_engine * e, const float * d_q, int nq, int n_rows, cudaStream_
 	rerank_l2_kernel<DIM><<<(nq + 7) / 8, 256, 0, s>>>(vocab, e->row_offset, d_q, nq, e->tf_cand.p, e->tf_cand_count.p, e->d_partial64.p, e->tf_fb_list.p,
 	                                                   e->tf_flags.p);
 	LCD_CHECK_LAUNCH(e);
-	knn2_l2_fallback_kernel<DIM><<<e->sm_count, 256, 0, s>>>(vocab, n_rows, e->row_offset, d_q, e->tf_fb_list.p, e->tf_flags.p, e->d_partial64.p);
+	LCD_CUDA(e, cudaFuncSetAttribute(knn2_l2_fallback_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fallback_smem_bytes<DIM>())));
+	knn2_l2_fallback_kernel<DIM><<<e->sm_count, 256, fallback_smem_bytes<DIM>(), s>>>(vocab, n_rows, e->row_offset, d_q, e->tf_fb_list.p, e->tf_flags.p,
+	                                                                                e->d_partial64.p);
 	prof_mark(e, LCD_PROF_NN, s);
 	LCD_CHECK_LAUNCH(e);
 	return LCD_OK;
@@ -901,6 +909,26 @@ int lcd_nn_select(lcd_engine * e, int kernel)
 	if (kernel != 0 && kernel != 1) LCD_FAIL(e, LCD_ERR_INVALID, "kernel must be 0 (popcount / exact L2 on the CUDA cores) or 1 (tensor)");
 	if (e->f32) e->nn_f32_tensor = kernel;
 	else e->nn_tensor = kernel;
+	return LCD_OK;
+}
+
+int lcd_nn_f32_stats(lcd_engine * e, int nq, int * n_fallback, long long * n_candidates, long long * rows_converted)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (n_fallback) *n_fallback = 0;
+	if (n_candidates) *n_candidates = 0;
+	if (rows_converted) *rows_converted = e->tf_img_builds;
+	if (!e->f32 || !e->tf_flags.p || !e->tf_cand_count.p || nq <= 0) return LCD_OK;
+	LCD_CUDA(e, cudaDeviceSynchronize());
+	int fb = 0;
+	LCD_CUDA(e, cudaMemcpy(&fb, e->tf_flags.p, sizeof(int), cudaMemcpyDeviceToHost));
+	std::vector<int> cnt(std::min<size_t>(nq, e->tf_cand_count.cap));
+	LCD_CUDA(e, cudaMemcpy(cnt.data(), e->tf_cand_count.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+	long long tot = 0;
+	for (int c : cnt) tot += std::min(c, kTfCandCap);
+	if (n_fallback) *n_fallback = fb;
+	if (n_candidates) *n_candidates = tot;
 	return LCD_OK;
 }
 
@@ -1594,6 +1622,134 @@ int lcd_adjust_likelihood(lcd_engine * e, const float * likelihood, int n_frames
 	LCD_TRY(lcd_adjust_likelihood_dev(e, e->d_f1.p, n_frames, ns, virtual_place_ratio, e->d_f2.p, s));
 	LCD_CUDA(e, cudaMemcpyAsync(adjusted_out, e->d_f2.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaStreamSynchronize(s));
+	return LCD_OK;
+}
+
+// ---- Bayes filter over the loop-closure hypotheses ----------------------------------------------------
+int lcd_bayes_reset(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	e->by_n_state = 0;
+	return LCD_OK;
+}
+
+int lcd_bayes_compute_posterior(lcd_engine * e, const int * ids, const float * likelihood, int n, const int64_t * col_ptr, const int * nbr_row,
+                                const int * nbr_level, const double * prediction_lc, int n_lc, float virtual_place_prior, float * posterior_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!ids || !likelihood || n <= 0 || !posterior_out) LCD_FAIL(e, LCD_ERR_INVALID, "likelihood is empty!");
+	if (!prediction_lc || n_lc < 2) LCD_FAIL(e, LCD_ERR_INVALID, "Prediction is not valid!");
+	if (!col_ptr) LCD_FAIL(e, LCD_ERR_INVALID, "null neighbour table");
+	if (!(virtual_place_prior >= 0.f && virtual_place_prior <= 1.f)) LCD_FAIL(e, LCD_ERR_INVALID, "Bayes/VirtualPlacePriorThr must be in [0, 1]");
+	for (int i = 1; i < n; ++i)
+		if (ids[i] <= ids[i - 1] || ids[i] <= 0) LCD_FAIL(e, LCD_ERR_INVALID, "ids must ascend and only ids[0] may be the (negative) virtual place");
+	if (ids[0] == 0) LCD_FAIL(e, LCD_ERR_INVALID, "id 0 is invalid");
+	const int64_t nnz = col_ptr[n];
+	if (col_ptr[0] != 0 || nnz < 0 || nnz > 0x7FFFFFFF) LCD_FAIL(e, LCD_ERR_INVALID, "bad neighbour table");
+	std::vector<int> cp(n + 1), ecol(static_cast<size_t>(nnz));
+	for (int c = 0; c < n; ++c)
+	{
+		if (col_ptr[c + 1] < col_ptr[c]) LCD_FAIL(e, LCD_ERR_INVALID, "col_ptr must be non-decreasing");
+		cp[c] = static_cast<int>(col_ptr[c]);
+		bool diag = ids[c] < 0;
+		for (int64_t k = col_ptr[c]; k < col_ptr[c + 1]; ++k)
+		{
+			if (nbr_row[k] < 0 || nbr_row[k] >= n || nbr_level[k] < 0 || nbr_level[k] + 1 >= n_lc)
+				LCD_FAIL(e, LCD_ERR_INVALID, "neighbour %lld of column %d is out of range", static_cast<long long>(k - col_ptr[c]), c);
+			if (k > col_ptr[c] && nbr_row[k] <= nbr_row[k - 1]) LCD_FAIL(e, LCD_ERR_INVALID, "neighbours of a column must ascend");
+			diag = diag || nbr_row[k] == c;
+			ecol[static_cast<size_t>(k)] = c;
+		}
+		// generatePrediction: "No 0 margin neighbor for signature" is fatal in the reference (BayesFilter.cpp:371-374)
+		if (!diag) LCD_FAIL(e, LCD_ERR_INVALID, "column %d (place %d) does not list the place itself", c, ids[c]);
+	}
+	cp[n] = static_cast<int>(nnz);
+	// _totalPredictionLCValues / _predictionEpsilon as setPredictionLC computes them (float sum of the doubles, smallest value)
+	float total = 0.f;
+	double eps = prediction_lc[0];
+	for (int j = 0; j < n_lc; ++j)
+	{
+		if (prediction_lc[j] < 0.0 || prediction_lc[j] > 1.0) LCD_FAIL(e, LCD_ERR_INVALID, "The prediction is not valid (values must be between >0 && <=1)");
+		if (prediction_lc[j] < eps) eps = prediction_lc[j];
+	}
+	total = 0.f;
+	for (int j = 0; j < n_lc; ++j) total = static_cast<float>(static_cast<double>(total) + prediction_lc[j]); // float += double
+	cudaStream_t s = e->stream;
+	const size_t nz = static_cast<size_t>(std::max<int64_t>(nnz, 1));
+	LCD_CUDA(e, e->by_ids.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_like.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_colptr.reserve(n + 1, 0, false, s));
+	LCD_CUDA(e, e->by_row.reserve(nz, 0, false, s));
+	LCD_CUDA(e, e->by_level.reserve(nz, 0, false, s));
+	LCD_CUDA(e, e->by_entry_col.reserve(nz, 0, false, s));
+	LCD_CUDA(e, e->by_lc.reserve(n_lc, 0, false, s));
+	LCD_CUDA(e, e->by_last.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_u.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_scale.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_delta.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_post.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_prior.reserve(n, 0, false, s));
+	LCD_CUDA(e, e->by_sums.reserve(4, 0, false, s));
+	// the previous state is read while the new one is written: double-buffer by size (state arrays hold max(n, n_state) entries twice)
+	const size_t st_need = static_cast<size_t>(std::max(n, e->by_n_state)) * 2;
+	LCD_CUDA(e, e->by_state_ids.reserve(st_need, static_cast<size_t>(e->by_n_state), false, s));
+	LCD_CUDA(e, e->by_state_post.reserve(st_need, static_cast<size_t>(e->by_n_state), false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->by_ids.p, ids, n * sizeof(int), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->by_like.p, likelihood, n * sizeof(float), cudaMemcpyHostToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->by_colptr.p, cp.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+	if (nnz)
+	{
+		LCD_CUDA(e, cudaMemcpyAsync(e->by_row.p, nbr_row, nnz * sizeof(int), cudaMemcpyHostToDevice, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->by_level.p, nbr_level, nnz * sizeof(int), cudaMemcpyHostToDevice, s));
+		LCD_CUDA(e, cudaMemcpyAsync(e->by_entry_col.p, ecol.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, s));
+	}
+	LCD_CUDA(e, cudaMemcpyAsync(e->by_lc.p, prediction_lc, n_lc * sizeof(double), cudaMemcpyHostToDevice, s));
+	BayesArgs a{};
+	a.n = n;
+	a.vp_used = ids[0] < 0 ? 1 : 0;
+	a.ids = e->by_ids.p;
+	a.like = e->by_like.p;
+	a.col_ptr = e->by_colptr.p;
+	a.nbr_row = e->by_row.p;
+	a.nbr_level = e->by_level.p;
+	a.lc = e->by_lc.p;
+	a.n_lc = n_lc;
+	a.total = total;
+	a.eps = static_cast<float>(eps);
+	a.vpp = virtual_place_prior;
+	// the state lives in the first half of the state arrays, the new one is written to the second half and copied down
+	a.prev_ids = e->by_state_ids.p;
+	a.prev_post = e->by_state_post.p;
+	a.n_prev = e->by_n_state;
+	a.last = e->by_last.p;
+	a.col_u = e->by_u.p;
+	a.col_scale = e->by_scale.p;
+	a.col_delta = e->by_delta.p;
+	a.prior = e->by_prior.p;
+	a.sums = e->by_sums.p;
+	a.post = e->by_post.p;
+	const int nb = (n + 255) / 256;
+	bayes_last_kernel<<<nb, 256, 0, s>>>(a);
+	LCD_CHECK_LAUNCH(e);
+	bayes_columns_kernel<<<nb, 256, 0, s>>>(a);
+	LCD_CHECK_LAUNCH(e);
+	if (nnz)
+	{
+		bayes_scatter_kernel<<<static_cast<unsigned>((nnz + 255) / 256), 256, 0, s>>>(a, static_cast<int>(nnz), e->by_entry_col.p);
+		LCD_CHECK_LAUNCH(e);
+	}
+	bayes_update_kernel<<<nb, 256, 0, s>>>(a);
+	LCD_CHECK_LAUNCH(e);
+	int * st_i = e->by_state_ids.p + std::max(n, e->by_n_state);
+	float * st_p = e->by_state_post.p + std::max(n, e->by_n_state);
+	bayes_normalize_kernel<<<nb, 256, 0, s>>>(a, st_i, st_p);
+	LCD_CHECK_LAUNCH(e);
+	LCD_CUDA(e, cudaMemcpyAsync(e->by_state_ids.p, st_i, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->by_state_post.p, st_p, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+	LCD_CUDA(e, cudaMemcpyAsync(posterior_out, e->by_post.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaStreamSynchronize(s));
+	e->by_n_state = n;
 	return LCD_OK;
 }
 

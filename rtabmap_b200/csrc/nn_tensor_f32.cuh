@@ -338,9 +338,10 @@ knn2_tensor_f32_kernel(const TfArgs a)
 								const int pos = atomicAdd(&a.cand_count[qi], 1);
 								if (pos < kTfCandCap) a.cand[static_cast<size_t>(qi) * kTfCandCap + pos] = static_cast<uint32_t>(row0 + c0 + j);
 							}
+							// t2 only ever tightens: it starts as the shared bound while t1 is still unknown (+inf)
 							if (x < t1)
 							{
-								t2 = t1;
+								t2 = fminf(t2, t1);
 								t1 = x;
 							}
 							else if (x < t2) t2 = x;
@@ -401,49 +402,88 @@ __global__ void rerank_l2_kernel(const float * __restrict__ vocab, int row_offse
 	if (lane == 0) partial[qi] = make_ulonglong2(k1, k2);
 }
 
-// exact scan for the queries of the fallback list (list overflow, values outside fp16): one CTA per query at a time
+// exact scan for the queries of the fallback list (list overflow, values outside fp16).  A CTA takes kFbQueries queries at a time and
+// streams the vocabulary once for all of them: 256-row tiles are loaded coalesced into (padded) shared memory, thread t then computes
+// row t against every query in rtflann's summation order.  Dynamic shared memory: 256 * (DIM + 1) + kFbQueries * DIM floats.
+constexpr int kFbQueries = 4;
+template <int DIM>
+__host__ __device__ constexpr size_t fallback_smem_bytes() { return (256 * (DIM + 1) + kFbQueries * DIM) * sizeof(float); }
+
 template <int DIM>
 __global__ void __launch_bounds__(256)
 knn2_l2_fallback_kernel(const float * __restrict__ vocab, int n_rows, int row_offset, const float * __restrict__ queries,
                         const int * __restrict__ fb_list, const int * __restrict__ fb_count, ulonglong2 * __restrict__ partial)
 {
-	__shared__ float s_q[DIM];
-	__shared__ unsigned long long s_k1[8], s_k2[8];
+	extern __shared__ __align__(16) float fb_smem[];
+	float * s_rows = fb_smem;                    // [256][DIM + 1]
+	float * s_q = fb_smem + 256 * (DIM + 1);     // [kFbQueries][DIM]
+	__shared__ unsigned long long s_k1[kFbQueries][8], s_k2[kFbQueries][8];
 	const int n_fb = *fb_count;
-	for (int k = blockIdx.x; k < n_fb; k += gridDim.x)
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int n_groups = (n_fb + kFbQueries - 1) / kFbQueries;
+	for (int g = blockIdx.x; g < n_groups; g += gridDim.x)
 	{
-		const int qi = fb_list[k];
+		const int nqg = min(kFbQueries, n_fb - g * kFbQueries);
 		__syncthreads();
-		for (int i = threadIdx.x; i < DIM; i += blockDim.x) s_q[i] = queries[static_cast<size_t>(qi) * DIM + i];
-		__syncthreads();
-		unsigned long long k1 = kKey64None, k2 = kKey64None;
-		for (int r = threadIdx.x; r < n_rows; r += blockDim.x)
+		for (int i = tid; i < nqg * DIM; i += 256) s_q[i] = queries[static_cast<size_t>(fb_list[g * kFbQueries + i / DIM]) * DIM + (i % DIM)];
+		unsigned long long k1[kFbQueries], k2[kFbQueries];
+#pragma unroll
+		for (int j = 0; j < kFbQueries; ++j) k1[j] = k2[j] = kKey64None;
+		for (int r0 = 0; r0 < n_rows; r0 += 256)
 		{
-			const float d = l2_rtflann<DIM>(s_q, vocab + static_cast<size_t>(r) * DIM);
-			top2_insert64(k1, k2, pack64(d, static_cast<uint32_t>(row_offset + r)));
+			const int nr = min(256, n_rows - r0);
+			__syncthreads();
+			for (int i = tid; i < nr * (DIM / 4); i += 256)
+			{
+				const int r = i / (DIM / 4), c = (i % (DIM / 4)) * 4;
+				const float4 v = *reinterpret_cast<const float4 *>(vocab + static_cast<size_t>(r0 + r) * DIM + c);
+				float * d = s_rows + r * (DIM + 1) + c;
+				d[0] = v.x;
+				d[1] = v.y;
+				d[2] = v.z;
+				d[3] = v.w;
+			}
+			__syncthreads();
+			if (tid < nr)
+			{
+#pragma unroll
+				for (int j = 0; j < kFbQueries; ++j)
+				{
+					if (j < nqg)
+					{
+						const float d = l2_rtflann<DIM>(s_q + j * DIM, s_rows + tid * (DIM + 1));
+						top2_insert64(k1[j], k2[j], pack64(d, static_cast<uint32_t>(row_offset + r0 + tid)));
+					}
+				}
+			}
 		}
 #pragma unroll
-		for (int o = 16; o > 0; o >>= 1)
+		for (int j = 0; j < kFbQueries; ++j)
 		{
-			const unsigned long long o1 = __shfl_down_sync(0xFFFFFFFFu, k1, o);
-			const unsigned long long o2 = __shfl_down_sync(0xFFFFFFFFu, k2, o);
-			top2_insert64(k1, k2, o1);
-			top2_insert64(k1, k2, o2);
-		}
-		if ((threadIdx.x & 31) == 0)
-		{
-			s_k1[threadIdx.x >> 5] = k1;
-			s_k2[threadIdx.x >> 5] = k2;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+			{
+				const unsigned long long o1 = __shfl_down_sync(0xFFFFFFFFu, k1[j], o);
+				const unsigned long long o2 = __shfl_down_sync(0xFFFFFFFFu, k2[j], o);
+				top2_insert64(k1[j], k2[j], o1);
+				top2_insert64(k1[j], k2[j], o2);
+			}
+			if (lane == 0)
+			{
+				s_k1[j][warp] = k1[j];
+				s_k2[j][warp] = k2[j];
+			}
 		}
 		__syncthreads();
-		if (threadIdx.x == 0)
+		if (tid < nqg)
 		{
-			for (int w = 1; w < 8; ++w)
+			unsigned long long a1 = kKey64None, a2 = kKey64None;
+			for (int w = 0; w < 8; ++w)
 			{
-				top2_insert64(k1, k2, s_k1[w]);
-				top2_insert64(k1, k2, s_k2[w]);
+				top2_insert64(a1, a2, s_k1[tid][w]);
+				top2_insert64(a1, a2, s_k2[tid][w]);
 			}
-			partial[qi] = make_ulonglong2(k1, k2);
+			partial[fb_list[g * kFbQueries + tid]] = make_ulonglong2(a1, a2);
 		}
 	}
 }

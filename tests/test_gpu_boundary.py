@@ -225,8 +225,8 @@ def test_signature_store_reuses_freed_rows():
         eng.sig_remove(1 + k)
         eng.sig_add_batch([9 + k], d[k % 8][None], x[k % 8][None])
         assert eng.sig_slots() == 8 and eng.sig_count() == 8
-    eng.sig_remove(20)
-    eng.sig_remove(30)
+    eng.sig_remove(42)
+    eng.sig_remove(45)
     eng.sig_add_batch([100, 101, 102], d[:3], x[:3])  # two freed rows + one fresh
     assert eng.sig_slots() == 9 and eng.sig_count() == 9
     # the reused rows hold the right data: verify signature 101 against itself through the fused call
@@ -299,6 +299,7 @@ def test_orb_detection_runs_beside_dictionary_update():
     for out in outs:
         for (kp, d, x), (kp0, d0, x0) in zip(out, ref):
             assert np.array_equal(kp, kp0) and np.array_equal(d, d0)
+    eng.update()  # the rows removed after the last update leave the index now
     assert eng.indexed_size() + eng.not_indexed_size() == eng.size() == 60000 - 10 * 500
     q = words[59000:59010]
     i1, dd1, _, _ = eng.knn2(q)
