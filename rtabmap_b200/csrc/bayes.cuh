@@ -36,7 +36,7 @@ struct BayesArgs
 	float * col_scale;        // [n]
 	float * col_delta;        // [n] mass added to the diagonal
 	double * prior;           // [n]
-	double * sums;            // [0] U, [1] sum of real-place posteriors (for the virtual-place row), [2] posterior sum
+	double * sums;            // [0] U, [1] sum of the real places' last posterior (for the virtual-place row), [2] posterior sum
 	float * post;             // [n] output
 };
 
@@ -155,7 +155,7 @@ __global__ void bayes_update_kernel(const BayesArgs a)
 		{
 			// row 0: P[0][0] = vpp (or 1 for a single place, or 1/n when vpp == 0), P[0][c] = lc[0] for every real place
 			float p00 = a.vpp > 0.f ? (a.n > 1 ? a.vpp : 1.0f) : (a.n > 1 ? static_cast<float>(1.0 / a.n) : 1.0f);
-			prior = static_cast<double>(p00) * last0 + static_cast<double>(static_cast<float>(a.lc[0])) * (a.sums[1] - last0);
+			prior = static_cast<double>(p00) * last0 + static_cast<double>(static_cast<float>(a.lc[0])) * a.sums[1]; // sums[1]: real places only
 		}
 		else
 		{

@@ -247,7 +247,7 @@ struct lcd_engine
 	// tuning knobs (env: LCD_NN_CTAS_PER_SM, LCD_NN_TQ, LCD_NN_VARIANT, LCD_SCORE_BLOCKS)
 	int nn_ctas_per_sm = 2, nn_tq = 8, nn_variant = 2, score_blocks = 32;
 	bool f32 = false;    // LCD_DESC_F32: squared-L2 path (l2_path.cuh)
-	DevBuf<ulonglong2> d_partial64;
+	DevBuf<ulonglong2> d_partial64, tf_fb_scratch;
 	// float descriptors on the tensor cores (nn_tensor_f32.cuh): cached fp16 image of rows [0, tf_rows) + their norms
 	DevBuf<uint4> tf_words, tf_queries;
 	DevBuf<float> tf_norms, tf_qn;
@@ -518,9 +518,13 @@ int tf_search(lcd_engine * e, const float * d_q, int nq, int n_rows, cudaStream_
 	rerank_l2_kernel<DIM><<<(nq + 7) / 8, 256, 0, s>>>(vocab, e->row_offset, d_q, nq, e->tf_cand.p, e->tf_cand_count.p, e->d_partial64.p, e->tf_fb_list.p,
 	                                                   e->tf_flags.p);
 	LCD_CHECK_LAUNCH(e);
+	const int fb_slots = std::max(4 * nq, 1 << 18), fb_ctas = 2 * e->sm_count;
+	LCD_CUDA(e, e->tf_fb_scratch.reserve(static_cast<size_t>(fb_slots), 0, false, s));
 	LCD_CUDA(e, cudaFuncSetAttribute(knn2_l2_fallback_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fallback_smem_bytes<DIM>())));
-	knn2_l2_fallback_kernel<DIM><<<e->sm_count, 256, fallback_smem_bytes<DIM>(), s>>>(vocab, n_rows, e->row_offset, d_q, e->tf_fb_list.p, e->tf_flags.p,
-	                                                                                e->d_partial64.p);
+	knn2_l2_fallback_kernel<DIM><<<fb_ctas, 256, fallback_smem_bytes<DIM>(), s>>>(vocab, n_rows, e->row_offset, d_q, e->tf_fb_list.p, e->tf_flags.p,
+	                                                                              e->tf_fb_scratch.p, fb_slots);
+	LCD_CHECK_LAUNCH(e);
+	knn2_l2_fallback_merge_kernel<<<64, 256, 0, s>>>(e->tf_fb_list.p, e->tf_flags.p, e->tf_fb_scratch.p, fb_slots, fb_ctas, e->d_partial64.p);
 	prof_mark(e, LCD_PROF_NN, s);
 	LCD_CHECK_LAUNCH(e);
 	return LCD_OK;
@@ -626,9 +630,12 @@ int launch_resolve(lcd_engine * e, const ResolveArgs & a, int n_frames, cudaStre
 {
 	if (e->f32)
 	{
-		int nq_pad = 32;
-		while (nq_pad < a.nq) nq_pad <<= 1;
-		const size_t smem32 = static_cast<size_t>(nq_pad) * sizeof(uint32_t);
+		const size_t smem32 = resolve_l2_smem_bytes(a.nq);
+		if (smem32 > 48 * 1024)
+		{
+			if (e->nw == 64) LCD_CUDA(e, cudaFuncSetAttribute(resolve_l2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem32)));
+			else LCD_CUDA(e, cudaFuncSetAttribute(resolve_l2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem32)));
+		}
 		prof_mark(e, LCD_PROF_RESOLVE, s);
 		if (e->nw == 64) resolve_l2_kernel<64><<<n_frames, kL2ResolveThreads, smem32, s>>>(a, e->d_partial64.p);
 		else resolve_l2_kernel<128><<<n_frames, kL2ResolveThreads, smem32, s>>>(a, e->d_partial64.p);

@@ -11,10 +11,9 @@
 // with them every tie-break and every NNDR decision — equal the CPU's.  Keys are 64-bit: (float bits of the distance << 32) |
 // row; distances are >= 0, so unsigned order of the key is (distance, lowest row) order.
 //
-// This path is exact, not fast: a CUDA-core kernel (one query per thread, rows staged through shared memory) and a per-frame
-// sequential replay of the new-word loop with the candidate scan spread over the CTA.  The float GEMM formulation on the
-// tensor cores (BASELINE configs[3]) cannot reproduce fp32 summation order and is left for a filter + exact
-// re-check design.
+// knn2_l2_kernel is the exact CUDA-core scan (one query per thread, rows staged through shared memory), used for small dictionaries
+// and as the cross-check of the tensor-core filter + exact re-rank of nn_tensor_f32.cuh (dictionaries of >= 4096 rows).
+// resolve_l2_kernel settles the new-word loop with the chunked scheme of the binary path (parallel inside a frame, exact).
 #pragma once
 #include "common.cuh"
 #include "resolve.cuh"
@@ -133,127 +132,214 @@ __device__ __forceinline__ bool nndr_decide64(unsigned long long a1, unsigned lo
 	return cnt < 2 || bd > __fmul_rn(nndr, sd);
 }
 
-// One CTA per frame: the reference's sequential loop, descriptor by descriptor; the scan of the words this frame has created
-// so far is spread over the CTA.  Dynamic shared memory: nq_pad uint32 (TF-IDF preparation buffer).
+// Intra-frame new-word resolution for one frame of FLOAT descriptors: the chunked scheme of resolve_rounds (resolve.cuh) with exact
+// squared-L2 distances in rtflann's order.  The reference decides descriptor i after descriptors 0..i-1 (VWDictionary.cpp:1139-1219);
+// here the frame is walked in chunks of 32: (A) one warp per descriptor of the chunk finds its two nearest among the words created by
+// EARLIER chunks (already final) and its distances to the 32 chunk-mates, all warps in parallel; (B) one warp settles the dependencies
+// inside the chunk by fixed-point iteration over a ballot mask; (C) the chunk's new words join the list.
+// sa1 / sa2: each descriptor's two best index hits (64-bit keys).  Returns the number of created words; flag / rank / L / res as in
+// resolve_rounds.
+template <int DIM>
+__device__ int resolve_rounds_l2(const float * __restrict__ fq, int nq, const unsigned long long * sa1, const unsigned long long * sa2, int * res,
+                                 uint16_t * L, uint16_t * rank, uint8_t * flag, int * s_nL, float nndr, int cmp_new)
+{
+	__shared__ unsigned long long s_ext[64];
+	__shared__ float s_dl[32][33]; // s_dl[e][j] = distance between descriptors c0+e and c0+j of the current chunk
+	const int tid = threadIdx.x;
+	const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+	if (!cmp_new)
+	{
+		if (tid < 32)
+		{
+			const int n = warp0_compact(flag, nq, L, rank);
+			if (tid == 0) *s_nL = n;
+		}
+		__syncthreads();
+		return *s_nL;
+	}
+	if (tid == 0) *s_nL = 0;
+	__syncthreads();
+	for (int c0 = 0; c0 < nq; c0 += 32)
+	{
+		const int nL = *s_nL;
+		for (int e = warp; e < 32; e += nwarps)
+		{
+			const int i = c0 + e;
+			if (i >= nq) continue;
+			const float * qi = fq + static_cast<size_t>(i) * DIM;
+			const int jm = c0 + lane;
+			s_dl[e][lane] = jm < nq ? l2_rtflann<DIM>(qi, fq + static_cast<size_t>(jm) * DIM) : INFINITY;
+			unsigned long long k1 = kKey64None, k2 = kKey64None;
+			if (nL > 0)
+			{
+				for (int k = lane; k < nL; k += 32)
+				{
+					const float d = l2_rtflann<DIM>(qi, fq + static_cast<size_t>(L[k]) * DIM);
+					top2_insert64(k1, k2, pack64(d, static_cast<uint32_t>(k)));
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+				{
+					const unsigned long long o1 = __shfl_down_sync(0xFFFFFFFFu, k1, o);
+					const unsigned long long o2 = __shfl_down_sync(0xFFFFFFFFu, k2, o);
+					top2_insert64(k1, k2, o1);
+					top2_insert64(k1, k2, o2);
+				}
+			}
+			if (lane == 0)
+			{
+				s_ext[2 * e] = k1;
+				s_ext[2 * e + 1] = k2;
+			}
+		}
+		__syncthreads();
+		if (warp == 0)
+		{
+			const int i = c0 + lane;
+			const bool valid = i < nq;
+			float dl[32];
+#pragma unroll
+			for (int jl = 0; jl < 32; ++jl) dl[jl] = s_dl[lane][jl];
+			const unsigned long long a1 = valid ? sa1[i] : kKey64None, a2 = valid ? sa2[i] : kKey64None;
+			const unsigned long long e1 = s_ext[2 * lane], e2 = s_ext[2 * lane + 1];
+			int bt;
+			bool bad = valid && nndr_decide64(a1, a2, e1, e2, nndr, bt);
+			unsigned long long n1 = e1;
+			uint32_t mask = __ballot_sync(0xFFFFFFFFu, bad);
+			for (int r = 0; r < 33; ++r)
+			{
+				n1 = e1;
+				unsigned long long n2 = e2;
+#pragma unroll
+				for (int jl = 0; jl < 32; ++jl)
+				{
+					if (jl < lane && ((mask >> jl) & 1u))
+					{
+						const uint32_t kidx = static_cast<uint32_t>(nL) + __popc(mask & ((1u << jl) - 1u));
+						top2_insert64(n1, n2, pack64(dl[jl], kidx));
+					}
+				}
+				bad = valid && nndr_decide64(a1, a2, n1, n2, nndr, bt);
+				const uint32_t nm = __ballot_sync(0xFFFFFFFFu, bad);
+				if (nm == mask) break;
+				mask = nm;
+			}
+			if (valid)
+			{
+				flag[i] = bad ? 1 : 0;
+				if (bad)
+				{
+					const int k = nL + __popc(mask & ((1u << lane) - 1u));
+					rank[i] = static_cast<uint16_t>(k);
+					L[k] = static_cast<uint16_t>(i);
+				}
+				else res[i] = bt >= 2 ? -1 - static_cast<int>(key64_row(n1)) : static_cast<int>(key64_row(a1));
+			}
+			if (lane == 0) *s_nL = nL + __popc(mask);
+		}
+		__syncthreads();
+	}
+	return *s_nL;
+}
+
+__host__ __device__ inline size_t resolve_l2_smem_bytes(int cap)
+{
+	int nq_pad = 32;
+	while (nq_pad < cap) nq_pad <<= 1;
+	return static_cast<size_t>(cap) * (8 + 8 + 4 + 2 + 2 + 1) + static_cast<size_t>(nq_pad) * 4 + 64;
+}
+
+// One CTA per frame.  Dynamic shared memory: resolve_l2_smem_bytes(a.nq).
 template <int DIM>
 __global__ void __launch_bounds__(kL2ResolveThreads)
 resolve_l2_kernel(const ResolveArgs a, const ulonglong2 * __restrict__ partial64)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	uint32_t * sbuf = reinterpret_cast<uint32_t *>(smem_raw);
-	__shared__ float s_q[DIM];
-	__shared__ unsigned long long s_k1[kL2ResolveThreads / 32], s_k2[kL2ResolveThreads / 32];
-	__shared__ int s_nL, s_wid;
-	__shared__ uint16_t s_new[kMaxFrameQueries]; // descriptor index of the k-th word created by this frame
-
 	const int cap = a.nq;
 	int nq_pad = 32;
 	while (nq_pad < cap) nq_pad <<= 1;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned long long * sa1 = reinterpret_cast<unsigned long long *>(smem_raw);
+	unsigned long long * sa2 = sa1 + cap;
+	uint32_t * sbuf = reinterpret_cast<uint32_t *>(sa2 + cap); // [nq_pad]
+	int * res = reinterpret_cast<int *>(sbuf + nq_pad);        // >=0 row, -1-k new word k, INT_MIN none
+	uint16_t * L = reinterpret_cast<uint16_t *>(res + cap);
+	uint16_t * rank = L + cap;
+	uint8_t * flag = reinterpret_cast<uint8_t *>(rank + cap);
+	__shared__ int s_nL;
+
+	const int tid = threadIdx.x;
 	const int frame = blockIdx.x;
 	const int nq = a.nq_frame ? min(max(a.nq_frame[frame], 0), cap) : cap;
 	const float * fq = reinterpret_cast<const float *>(a.queries) + static_cast<size_t>(frame) * cap * DIM;
 	const size_t pbase = static_cast<size_t>(frame) * cap;
-	if (tid == 0) s_nL = 0;
+
+	// 1. merge the per-split top-2 keys (FlannIndex::knnSearch result of this descriptor) and take the index-only decision
+	for (int i = tid; i < nq; i += blockDim.x)
+	{
+		unsigned long long k1 = kKey64None, k2 = kKey64None;
+		for (int c = 0; c < a.n_chunks; ++c)
+		{
+			const ulonglong2 p = partial64[static_cast<size_t>(c) * a.nq_total + pbase + i];
+			top2_insert64(k1, k2, p.x);
+			top2_insert64(k1, k2, p.y);
+		}
+		sa1[i] = k1;
+		sa2[i] = k2;
+		int bt;
+		const bool bad = nndr_decide64(k1, k2, kKey64None, kKey64None, a.nndr, bt);
+		if (a.incremental)
+		{
+			flag[i] = bad ? 1 : 0;
+			res[i] = static_cast<int>(key64_row(k1));
+		}
+		else
+		{
+			// fixed dictionary: nearest word, no NNDR (VWDictionary.cpp:1211-1218)
+			flag[i] = 0;
+			res[i] = k1 != kKey64None ? static_cast<int>(key64_row(k1)) : INT_MIN;
+		}
+	}
 	__syncthreads();
 
-	for (int i = 0; i < nq; ++i)
+	int n_new = 0;
+	if (a.incremental)
 	{
-		for (int v = tid; v < DIM; v += blockDim.x) s_q[v] = fq[static_cast<size_t>(i) * DIM + v];
-		__syncthreads();
-		const int nL = s_nL;
-		// hits among the words created by descriptors 0..i-1 of this frame (cv::BFMatcher::knnMatch on newWords)
-		unsigned long long k1 = kKey64None, k2 = kKey64None;
-		if (a.incremental && a.cmp_new)
-		{
-			for (int k = tid; k < nL; k += blockDim.x)
-			{
-				const float d = l2_rtflann<DIM>(s_q, fq + static_cast<size_t>(s_new[k]) * DIM);
-				top2_insert64(k1, k2, pack64(d, static_cast<uint32_t>(k)));
-			}
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-			{
-				const unsigned long long o1 = __shfl_down_sync(0xFFFFFFFFu, k1, o);
-				const unsigned long long o2 = __shfl_down_sync(0xFFFFFFFFu, k2, o);
-				top2_insert64(k1, k2, o1);
-				top2_insert64(k1, k2, o2);
-			}
-			if (lane == 0)
-			{
-				s_k1[warp] = k1;
-				s_k2[warp] = k2;
-			}
-		}
-		__syncthreads();
-		if (tid == 0)
-		{
-			unsigned long long n1 = kKey64None, n2 = kKey64None;
-			if (a.incremental && a.cmp_new)
-			{
-				for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w)
-				{
-					top2_insert64(n1, n2, s_k1[w]);
-					top2_insert64(n1, n2, s_k2[w]);
-				}
-			}
-			unsigned long long a1 = kKey64None, a2 = kKey64None;
-			for (int c = 0; c < a.n_chunks; ++c)
-			{
-				const ulonglong2 p = partial64[static_cast<size_t>(c) * a.nq_total + pbase + i];
-				top2_insert64(a1, a2, p.x);
-				top2_insert64(a1, a2, p.y);
-			}
-			int wid = 0;
-			uint32_t sv = kSortNone;
-			if (a.incremental)
-			{
-				int bt;
-				const bool bad = nndr_decide64(a1, a2, n1, n2, a.nndr, bt);
-				if (bad)
-				{
-					if (!a.find_only)
-					{
-						wid = a.last_word_id + 1 + nL;
-						s_new[nL] = static_cast<uint16_t>(i);
-						s_nL = nL + 1;
-					}
-				}
-				else if (bt >= 2) wid = a.last_word_id + 1 + static_cast<int>(key64_row(bt == 2 ? n1 : n2));
-				else
-				{
-					wid = a.row_ids[key64_row(bt == 0 ? a1 : a2)];
-					sv = static_cast<uint32_t>(wid);
-				}
-			}
-			else if (a1 != kKey64None)
-			{
-				// fixed dictionary: nearest word, no NNDR (VWDictionary.cpp:1211-1218)
-				wid = a.row_ids[key64_row(a1)];
-				sv = static_cast<uint32_t>(wid);
-			}
-			if (a.word_ids_out) a.word_ids_out[pbase + i] = wid;
-			sbuf[i] = sv;
-		}
-		__syncthreads();
+		// 2. intra-frame dependency among the words this frame creates (findNN creates none: every descriptor stands alone)
+		n_new = resolve_rounds_l2<DIM>(fq, nq, sa1, sa2, res, L, rank, flag, &s_nL, a.nndr, a.find_only ? 0 : a.cmp_new);
 	}
-	const int n_new = s_nL;
+
+	// 3. word ids in creation order, and the created words into the not-indexed tail of the vocabulary (single-frame quantise)
+	for (int i = tid; i < nq; i += blockDim.x)
+	{
+		int wid;
+		uint32_t sv = kSortNone;
+		if (flag[i]) wid = a.find_only ? 0 : a.last_word_id + 1 + rank[i];
+		else if (res[i] == INT_MIN) wid = 0;
+		else if (res[i] < 0) wid = a.last_word_id + 1 + (-1 - res[i]);
+		else
+		{
+			wid = a.row_ids[res[i]];
+			sv = static_cast<uint32_t>(wid);
+		}
+		if (a.word_ids_out) a.word_ids_out[pbase + i] = wid;
+		sbuf[i] = sv;
+	}
 	for (int i = nq + tid; i < nq_pad; i += blockDim.x)
 	{
 		sbuf[i] = kSortNone;
 		if (i < cap && a.word_ids_out) a.word_ids_out[pbase + i] = 0; // padding rows of a short frame
 	}
-	// commit the created words into the not-indexed tail of the vocabulary (single-frame quantise)
 	if (a.pending_desc && !a.find_only)
 	{
 		float * dst = reinterpret_cast<float *>(a.pending_desc);
+		const int lane = tid & 31, warp = tid >> 5;
 		for (int k = warp; k < n_new; k += static_cast<int>(blockDim.x >> 5))
 		{
-			for (int v = lane; v < DIM; v += 32) dst[static_cast<size_t>(k) * DIM + v] = fq[static_cast<size_t>(s_new[k]) * DIM + v];
+			for (int v = lane; v < DIM; v += 32) dst[static_cast<size_t>(k) * DIM + v] = fq[static_cast<size_t>(L[k]) * DIM + v];
 			if (lane == 0) a.pending_ids[k] = a.last_word_id + 1 + k;
 		}
 	}
-	if (tid == 0 && a.n_new_out) a.n_new_out[frame] = n_new;
+	if (tid == 0 && a.n_new_out) a.n_new_out[frame] = (a.find_only ? 0 : n_new);
 	__syncthreads();
 	if (a.do_prep) score_prep(sbuf, nq_pad, cap, a, frame);
 }

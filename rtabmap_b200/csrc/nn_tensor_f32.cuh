@@ -402,26 +402,35 @@ __global__ void rerank_l2_kernel(const float * __restrict__ vocab, int row_offse
 	if (lane == 0) partial[qi] = make_ulonglong2(k1, k2);
 }
 
-// exact scan for the queries of the fallback list (list overflow, values outside fp16).  A CTA takes kFbQueries queries at a time and
-// streams the vocabulary once for all of them: 256-row tiles are loaded coalesced into (padded) shared memory, thread t then computes
-// row t against every query in rtflann's summation order.  Dynamic shared memory: 256 * (DIM + 1) + kFbQueries * DIM floats.
+// exact scan for the queries of the fallback list (list overflow, values outside fp16), spread over the whole machine: the CTAs form
+// S row-splits x G query-group slots (S as large as the scratch allows: one overflowing query still uses every SM).  A CTA takes
+// kFbQueries queries at a time and streams its share of the vocabulary once for all of them: 256-row tiles are loaded coalesced
+// into (padded) shared memory, thread t then computes row t against every query in rtflann's summation order.  The per-split results
+// are merged by knn2_l2_fallback_merge_kernel.  Dynamic shared memory: 256 * (DIM + 1) + kFbQueries * DIM floats.
 constexpr int kFbQueries = 4;
 template <int DIM>
 __host__ __device__ constexpr size_t fallback_smem_bytes() { return (256 * (DIM + 1) + kFbQueries * DIM) * sizeof(float); }
 
+__device__ __forceinline__ int fallback_splits(int n_fb, int n_ctas, int slots) { return max(1, min(n_ctas, slots / max(n_fb, 1))); }
+
 template <int DIM>
 __global__ void __launch_bounds__(256)
 knn2_l2_fallback_kernel(const float * __restrict__ vocab, int n_rows, int row_offset, const float * __restrict__ queries,
-                        const int * __restrict__ fb_list, const int * __restrict__ fb_count, ulonglong2 * __restrict__ partial)
+                        const int * __restrict__ fb_list, const int * __restrict__ fb_count, ulonglong2 * __restrict__ scratch, int slots)
 {
 	extern __shared__ __align__(16) float fb_smem[];
 	float * s_rows = fb_smem;                    // [256][DIM + 1]
 	float * s_q = fb_smem + 256 * (DIM + 1);     // [kFbQueries][DIM]
 	__shared__ unsigned long long s_k1[kFbQueries][8], s_k2[kFbQueries][8];
 	const int n_fb = *fb_count;
+	if (n_fb <= 0) return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int S = fallback_splits(n_fb, gridDim.x, slots);
+	const int split = blockIdx.x % S, gslot = blockIdx.x / S, n_gslots = gridDim.x / S;
+	if (gslot >= n_gslots) return;
 	const int n_groups = (n_fb + kFbQueries - 1) / kFbQueries;
-	for (int g = blockIdx.x; g < n_groups; g += gridDim.x)
+	const int n_tiles = (n_rows + 255) / 256;
+	for (int g = gslot; g < n_groups; g += n_gslots)
 	{
 		const int nqg = min(kFbQueries, n_fb - g * kFbQueries);
 		__syncthreads();
@@ -429,8 +438,9 @@ knn2_l2_fallback_kernel(const float * __restrict__ vocab, int n_rows, int row_of
 		unsigned long long k1[kFbQueries], k2[kFbQueries];
 #pragma unroll
 		for (int j = 0; j < kFbQueries; ++j) k1[j] = k2[j] = kKey64None;
-		for (int r0 = 0; r0 < n_rows; r0 += 256)
+		for (int t = split; t < n_tiles; t += S)
 		{
+			const int r0 = t * 256;
 			const int nr = min(256, n_rows - r0);
 			__syncthreads();
 			for (int i = tid; i < nr * (DIM / 4); i += 256)
@@ -483,8 +493,26 @@ knn2_l2_fallback_kernel(const float * __restrict__ vocab, int n_rows, int row_of
 				top2_insert64(a1, a2, s_k1[tid][w]);
 				top2_insert64(a1, a2, s_k2[tid][w]);
 			}
-			partial[fb_list[g * kFbQueries + tid]] = make_ulonglong2(a1, a2);
+			scratch[static_cast<size_t>(g * kFbQueries + tid) * S + split] = make_ulonglong2(a1, a2);
 		}
+	}
+}
+
+__global__ void knn2_l2_fallback_merge_kernel(const int * __restrict__ fb_list, const int * __restrict__ fb_count, const ulonglong2 * __restrict__ scratch,
+                                              int slots, int n_ctas, ulonglong2 * __restrict__ partial)
+{
+	const int n_fb = *fb_count;
+	const int S = fallback_splits(n_fb, n_ctas, slots);
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_fb; k += gridDim.x * blockDim.x)
+	{
+		unsigned long long a1 = kKey64None, a2 = kKey64None;
+		for (int sp = 0; sp < S; ++sp)
+		{
+			const ulonglong2 p = scratch[static_cast<size_t>(k) * S + sp];
+			top2_insert64(a1, a2, p.x);
+			top2_insert64(a1, a2, p.y);
+		}
+		partial[fb_list[k]] = make_ulonglong2(a1, a2);
 	}
 }
 

@@ -75,7 +75,7 @@ def test_large_map_is_sparse_work():
     like = np.ones(n + 1, np.float32)
     like[777] = 40.0
     post = None
-    for _ in range(3):
+    for _ in range(8):
         post = eng.bayes_compute_posterior(ids, like, col_ptr, rows, levels, DEFAULT_PREDICTION_LC, 0.9)
     assert abs(float(post.sum()) - 1.0) < 1e-4 and int(np.argmax(post)) == 777 and post[777] > 0.5
 
