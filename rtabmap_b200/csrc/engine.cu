@@ -22,6 +22,10 @@
 #include "match_bf.cuh"
 #include "orb.cuh"
 
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -120,6 +124,91 @@ static cudaError_t zero_fill_async(void * p, size_t bytes, cudaStream_t s)
 }
 
 size_t depth_elem_bytes(int depth_type) { return depth_type == LCD_DEPTH_U16_MM ? 2 : (depth_type == LCD_DEPTH_MASK_U8 ? 1 : 4); }
+
+// NCCL is loaded at run time (dlopen): single-GPU users of liblcd_b200.so need no NCCL, and a host that already carries one
+// (PyTorch's bundled libnccl.so.2, or the system's) shares it with the library.
+struct NcclApi
+{
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char * (*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+	std::string why;
+};
+const NcclApi & nccl_api()
+{
+	static NcclApi api = []() {
+		NcclApi a;
+		void * h = nullptr;
+		for (const char * name : {"libnccl.so.2", "libnccl.so"})
+		{
+			h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if (h) break;
+		}
+		if (!h)
+		{
+			a.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+			return a;
+		}
+#define LCD_NCCL_SYM(field, sym)                                         \
+	a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, sym));       \
+	if (!a.field)                                                        \
+	{                                                                    \
+		a.why = std::string("NCCL symbol missing: ") + sym;              \
+		return a;                                                        \
+	}
+		LCD_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+		LCD_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+		LCD_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+		LCD_NCCL_SYM(AllGather, "ncclAllGather")
+		LCD_NCCL_SYM(ReduceScatter, "ncclReduceScatter")
+		LCD_NCCL_SYM(Send, "ncclSend")
+		LCD_NCCL_SYM(Recv, "ncclRecv")
+		LCD_NCCL_SYM(GroupStart, "ncclGroupStart")
+		LCD_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+		LCD_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef LCD_NCCL_SYM
+		a.ok = true;
+		return a;
+	}();
+	return api;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder()
+{
+	static EncodeTiledFn fn = []() -> EncodeTiledFn {
+		void * p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+		return reinterpret_cast<EncodeTiledFn>(p);
+	}();
+	return fn;
+}
+
+// 3-D tensor map over the u8 planes [frames][h][w] of one pyramid level (frame pitch `frame_stride` bytes), box = box_w x box_h x 1,
+// zero fill outside.  false: the geometry does not meet the TMA alignment rules (or the driver lacks the call): plain loads instead.
+static_assert(sizeof(CUtensorMap) == sizeof(lcd::OrbTensorMap), "tensor map size");
+bool make_plane_tensor_map(lcd::OrbTensorMap * out, const uint8_t * base, int w, int h, int n_frames, size_t frame_stride, int box_w, int box_h)
+{
+	EncodeTiledFn enc = tensor_map_encoder();
+	if (!enc || (w % 16) || (frame_stride % 16) || (reinterpret_cast<uintptr_t>(base) % 16) || n_frames <= 0) return false;
+	const cuuint64_t dims[3] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n_frames)};
+	const cuuint64_t strides[2] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(frame_stride)};
+	const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
+	const cuuint32_t estr[3] = {1u, 1u, 1u};
+	return enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(base), dims, strides, box, estr,
+	           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 int env_int(const char * name, int def)
 {
@@ -234,6 +323,7 @@ struct lcd_engine
 	DevBuf<OrbKeypoint> o_level_kp, o_kp;
 	DevBuf<float> o_xyz, o_uv;
 	float gauss_sigma_loaded = -1.f;
+	int orb_tma_used = 0; // the last FAST launch staged its tiles through a tensor map
 	DevBuf<float> d_uv;
 
 	// measurement hooks (lcd_profile_*)
@@ -249,8 +339,8 @@ struct lcd_engine
 	bool f32 = false;    // LCD_DESC_F32: squared-L2 path (l2_path.cuh)
 	DevBuf<ulonglong2> d_partial64, tf_fb_scratch;
 	// float descriptors on the tensor cores (nn_tensor_f32.cuh): cached fp16 image of rows [0, tf_rows) + their norms
-	DevBuf<uint4> tf_words, tf_queries;
-	DevBuf<float> tf_norms, tf_qn;
+	DevBuf<uint4> tf_words, tf_queries, tf_words_aug, tf_queries_aug;
+	DevBuf<float> tf_qn;
 	DevBuf<uint32_t> tf_tau, tf_cand, tf_wmax2;  // tf_wmax2[0] = bits of the largest |w|^2 seen
 	DevBuf<int> tf_cand_count, tf_fb_list, tf_flags; // tf_flags[0] = fallback count, tf_flags[1] = "a row does not fit fp16"
 	int tf_rows = 0;            // rows of the vocabulary whose image is current
@@ -260,6 +350,16 @@ struct lcd_engine
 	long long tf_img_builds = 0; // rows expanded so far (diagnostics: the image is built once per dictionary change)
 	int nn_tensor = 1;   // 256-bit descriptors: tcgen05 int8 path (nn_tensor.cuh); 0 = POPC kernel (nn_hamming.cuh)
 	int nn_last_tensor = 0; // which kernel the last run_knn used (bench / diagnostics)
+	// word-range sharding across GPUs (lcd_shard_*): NCCL communicator + exchange buffers of the fused sharded step
+	ncclComm_t comm = nullptr;
+	bool comm_owned = false;
+	int sh_rank = 0, sh_ranks = 1;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t sh_ev[2][8] = {};
+	DevBuf<uint8_t> sh_desc_all[2];
+	DevBuf<int> sh_n_all, sh_words_loc[2], sh_words_all[2];
+	DevBuf<uint32_t> sh_keys[2], sh_keys_mine[2];
+	DevBuf<long long> sh_scores[2], sh_scores_loc[2];
 	bool match_has_xyz_to = false; // verify_upload staged xyz_to for the next launch_match
 	bool pnp_has_obj_to = false;   // the last launch_match gathered obj_to for launch_pnp
 };
@@ -284,6 +384,13 @@ struct lcd_engine
 		{                                                                                          \
 			LCD_FAIL(e, LCD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_c), __FILE__, __LINE__); \
 		}                                                                                          \
+	} while (0)
+
+#define LCD_NCCL(e, call)                                                                                     \
+	do                                                                                                        \
+	{                                                                                                         \
+		ncclResult_t _n = (call);                                                                             \
+		if (_n != ncclSuccess) LCD_FAIL(e, LCD_ERR_CUDA, "%s failed: %s", #call, nccl_api().GetErrorString(_n)); \
 	} while (0)
 
 #define LCD_CHECK_LAUNCH(e)                 \
@@ -441,13 +548,14 @@ int tf_prepare_words(lcd_engine * e, int n_rows, cudaStream_t s)
 	{
 		const int want = std::max(n_tiles, old_tiles + old_tiles / 2 + 64);
 		LCD_CUDA(e, e->tf_words.reserve(static_cast<size_t>(want) * tile16, static_cast<size_t>(e->tf_rows / kTfBN) * tile16, false, s));
-		LCD_CUDA(e, e->tf_norms.reserve(static_cast<size_t>(want) * kTfBN, static_cast<size_t>(e->tf_rows / kTfBN) * kTfBN, false, s));
+		LCD_CUDA(e, e->tf_words_aug.reserve(static_cast<size_t>(want) * kTfBN * 2, static_cast<size_t>(e->tf_rows / kTfBN) * kTfBN * 2, false, s));
 	}
 	const int t0 = e->tf_rows / kTfBN;
 	const size_t rows_todo = static_cast<size_t>(n_tiles - t0) * kTfBN, chunks = rows_todo * (DIM / 8);
-	tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_words.p, e->tf_flags.p + 1);
+	tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_words.p, e->tf_flags.p + 1, -2.0f);
 	LCD_CHECK_LAUNCH(e);
-	tf_norms_kernel<DIM><<<static_cast<unsigned>((rows_todo + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_norms.p, e->tf_wmax2.p);
+	tf_aug_kernel<DIM><<<static_cast<unsigned>((rows_todo + 255) / 256), 256, 0, s>>>(vocab, t0 * kTfBN, n_rows, kTfBN, e->tf_words_aug.p, 0, e->tf_wmax2.p,
+	                                                                                  e->tf_flags.p + 1);
 	LCD_CHECK_LAUNCH(e);
 	e->tf_img_builds += n_rows - e->tf_rows;
 	e->tf_rows = n_rows;
@@ -476,7 +584,10 @@ int tf_search(lcd_engine * e, const float * d_q, int nq, int n_rows, cudaStream_
 	LCD_CUDA(e, zero_fill_async(e->tf_flags.p, sizeof(int), s)); // fallback count
 	{
 		const size_t chunks = static_cast<size_t>(n_qtiles) * kTfBM * (DIM / 8);
-		tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(d_q, 0, nq, kTfBM, e->tf_queries.p, nullptr);
+		tf_expand_kernel<DIM><<<static_cast<unsigned>((chunks + 255) / 256), 256, 0, s>>>(d_q, 0, nq, kTfBM, e->tf_queries.p, nullptr, 1.0f);
+		LCD_CHECK_LAUNCH(e);
+		LCD_CUDA(e, e->tf_queries_aug.reserve(static_cast<size_t>(n_qtiles) * kTfBM * 2, 0, false, s));
+		tf_aug_kernel<DIM><<<(n_qtiles * kTfBM + 255) / 256, 256, 0, s>>>(d_q, 0, nq, kTfBM, e->tf_queries_aug.p, 1, nullptr, nullptr);
 		LCD_CHECK_LAUNCH(e);
 		tf_query_init_kernel<DIM><<<(nq + 255) / 256, 256, 0, s>>>(d_q, nq, e->tf_qn.p, e->tf_cand_count.p, e->tf_tau.p);
 		LCD_CHECK_LAUNCH(e);
@@ -485,7 +596,8 @@ int tf_search(lcd_engine * e, const float * d_q, int nq, int n_rows, cudaStream_
 	LCD_CUDA(e, cudaFuncSetAttribute(knn2_tensor_f32_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::smem)));
 	TfArgs a{};
 	a.word_img = e->tf_words.p;
-	a.word_norms = e->tf_norms.p;
+	a.word_aug = e->tf_words_aug.p;
+	a.query_aug = e->tf_queries_aug.p;
 	a.n_rows = n_rows;
 	a.query_img = e->tf_queries.p;
 	a.qn = e->tf_qn.p;
@@ -1007,6 +1119,11 @@ void lcd_destroy(lcd_engine * e)
 	if (e->stream)
 	{
 		cudaStreamSynchronize(e->stream);
+		if (e->comm && e->comm_owned && nccl_api().ok) nccl_api().CommDestroy(e->comm);
+		if (e->comm_stream) cudaStreamDestroy(e->comm_stream);
+		for (auto & half : e->sh_ev)
+			for (cudaEvent_t ev : half)
+				if (ev) cudaEventDestroy(ev);
 		if (e->orb_stream)
 		{
 			cudaStreamSynchronize(e->orb_stream);
@@ -1962,10 +2079,23 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		}
 		LCD_CUDA(e, cudaEventRecord(e->aux_blur_done, bs));
 	}
+	static const int orb_tma = env_int("LCD_ORB_TMA", 1);
 	for (int l = 0; l < g.n_levels; ++l)
 	{
-		dim3 grd((g.w[l] + kFastTW - 1) / kFastTW, (g.h[l] + kFastTH - 1) / kFastTH, n_frames);
-		orb_fast_kernel<<<grd, 256, 0, s>>>(w_gray, w_mask, g, l, w_cand, w_cand_count);
+		OrbTensorMap tm;
+		if (orb_tma && make_plane_tensor_map(&tm, w_gray + g.off[l], g.w[l], g.h[l], n_frames, static_cast<size_t>(g.frame_stride), kFastTmaGW, kFastTmaGH))
+		{
+			// gray tile + halo staged by the TMA engine (one cp.async.bulk.tensor per CTA), byte-SIMD compass test and suppression
+			dim3 grd((g.w[l] + kFastTmaTW - 1) / kFastTmaTW, (g.h[l] + kFastTmaTH - 1) / kFastTmaTH, n_frames);
+			orb_fast_tma_kernel<<<grd, 256, 0, s>>>(tm, w_mask, g, l, w_cand, w_cand_count);
+			e->orb_tma_used = 1;
+		}
+		else
+		{
+			dim3 grd((g.w[l] + kFastTW - 1) / kFastTW, (g.h[l] + kFastTH - 1) / kFastTH, n_frames);
+			orb_fast_kernel<<<grd, 256, 0, s>>>(w_gray, w_mask, g, l, w_cand, w_cand_count);
+			e->orb_tma_used = 0;
+		}
 		LCD_CHECK_LAUNCH(e);
 	}
 	{
@@ -3144,6 +3274,225 @@ int lcd_shard_score_ids_dev(lcd_engine * e, const int * d_word_ids_all, int n_fr
 	dim3 grid((ns + 255) / 256, n_frames);
 	gather_fixed_kernel<<<grid, 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), d_sig_ids, ns, d_scores_out);
 	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+// ---- NCCL inside the library: communicator + the fused sharded step ------------------------------------------------
+int lcd_shard_unique_id(char id_out[128])
+{
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	if (!id_out) return LCD_ERR_INVALID;
+	if (!nccl_api().ok)
+	{
+		g_create_error = nccl_api().why;
+		return LCD_ERR_STATE;
+	}
+	ncclUniqueId id;
+	if (nccl_api().GetUniqueId(&id) != ncclSuccess)
+	{
+		g_create_error = "ncclGetUniqueId failed";
+		return LCD_ERR_CUDA;
+	}
+	memcpy(id_out, &id, 128);
+	return LCD_OK;
+}
+
+static int shard_comm_common(lcd_engine * e, int rank, int n_ranks)
+{
+	if (!e->comm_stream) LCD_CUDA(e, cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
+	for (auto & half : e->sh_ev)
+		for (cudaEvent_t & ev : half)
+			if (!ev) LCD_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	e->sh_rank = rank;
+	e->sh_ranks = n_ranks;
+	return LCD_OK;
+}
+
+int lcd_shard_comm_init(lcd_engine * e, const char id[128], int rank, int n_ranks)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) LCD_FAIL(e, LCD_ERR_INVALID, "bad rank %d of %d", rank, n_ranks);
+	if (!nccl_api().ok) LCD_FAIL(e, LCD_ERR_STATE, "%s", nccl_api().why.c_str());
+	if (e->comm) LCD_FAIL(e, LCD_ERR_STATE, "the engine already has a communicator");
+	ncclUniqueId uid;
+	memcpy(&uid, id, 128);
+	LCD_NCCL(e, nccl_api().CommInitRank(&e->comm, n_ranks, uid, rank));
+	e->comm_owned = true;
+	return shard_comm_common(e, rank, n_ranks);
+}
+
+int lcd_shard_comm_adopt(lcd_engine * e, void * nccl_comm, int rank, int n_ranks)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!nccl_comm || n_ranks < 1 || rank < 0 || rank >= n_ranks) LCD_FAIL(e, LCD_ERR_INVALID, "bad communicator / rank");
+	if (!nccl_api().ok) LCD_FAIL(e, LCD_ERR_STATE, "%s", nccl_api().why.c_str());
+	if (e->comm) LCD_FAIL(e, LCD_ERR_STATE, "the engine already has a communicator");
+	e->comm = static_cast<ncclComm_t>(nccl_comm);
+	e->comm_owned = false;
+	return shard_comm_common(e, rank, n_ranks);
+}
+
+int lcd_shard_comm_destroy(lcd_engine * e)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (e->comm)
+	{
+		LCD_CUDA(e, cudaDeviceSynchronize());
+		if (e->comm_owned) nccl_api().CommDestroy(e->comm);
+		e->comm = nullptr;
+	}
+	e->sh_ranks = 1;
+	e->sh_rank = 0;
+	return LCD_OK;
+}
+
+int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
+                                 int depth_type, const lcd_orb_params * op, int incremental, float nndr, int new_words_compared_together,
+                                 const int * d_sig_ids, int ns, int n_total, const int * d_row_ids_global, int last_word_id,
+                                 const lcd_verify_params * vp, int * d_word_ids_out, float * d_likelihood_out, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(require_binary(e, "lcd_shard_process_frames_dev"));
+	LCD_TRY(set_device(e));
+	if (!e->comm) LCD_FAIL(e, LCD_ERR_STATE, "no communicator: call lcd_shard_comm_init first");
+	if (!d_images || n_frames <= 0 || !op || !d_sig_ids || ns <= 0 || !d_row_ids_global || !d_likelihood_out)
+		LCD_FAIL(e, LCD_ERR_INVALID, "null argument");
+	if (e->cfg.desc_dim != 32) LCD_FAIL(e, LCD_ERR_INVALID, "ORB descriptors need an engine with 32-byte binary descriptors");
+	const int cap = op->n_features;
+	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "Kp/MaxFeatures must be 1..%d", kMaxFrameQueries);
+	const NcclApi & nc = nccl_api();
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	cudaStream_t c = e->comm_stream;
+	const int G = e->sh_ranks, R = e->sh_rank;
+	// the local batch is processed as two halves so that the exchanges of one half run under the kernels of the other
+	const int n_parts = n_frames >= 2 ? 2 : 1;
+	const int part_frames[2] = {n_parts == 2 ? (n_frames + 1) / 2 : n_frames, n_parts == 2 ? n_frames / 2 : 0};
+	const int part_f0[2] = {0, part_frames[0]};
+	const size_t rows = static_cast<size_t>(n_frames) * cap;
+	LCD_CUDA(e, e->o_kp.reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->o_desc.reserve(rows * 32, 0, false, s));
+	LCD_CUDA(e, e->o_xyz.reserve(rows * 3, 0, false, s));
+	LCD_CUDA(e, e->o_uv.reserve(rows * 2, 0, false, s));
+	LCD_CUDA(e, e->o_n.reserve(n_frames, 0, false, s));
+	LCD_CUDA(e, e->sh_n_all.reserve(static_cast<size_t>(G) * n_frames, 0, false, s));
+	LCD_CUDA(e, e->d_like.reserve(static_cast<size_t>(n_frames) * ns, 0, false, s));
+	for (int h = 0; h < n_parts; ++h)
+	{
+		const size_t pr = static_cast<size_t>(part_frames[h]) * cap; // descriptor rows of this part on one rank
+		LCD_CUDA(e, e->sh_desc_all[h].reserve(pr * 32 * G, 0, false, s));
+		LCD_CUDA(e, e->sh_keys[h].reserve(pr * 2 * G, 0, false, s));
+		LCD_CUDA(e, e->sh_keys_mine[h].reserve(pr * 2 * G, 0, false, s));
+		LCD_CUDA(e, e->sh_words_loc[h].reserve(pr, 0, false, s));
+		LCD_CUDA(e, e->sh_words_all[h].reserve(pr * G, 0, false, s));
+		LCD_CUDA(e, e->sh_scores[h].reserve(static_cast<size_t>(part_frames[h]) * G * ns, 0, false, s));
+		LCD_CUDA(e, e->sh_scores_loc[h].reserve(static_cast<size_t>(part_frames[h]) * ns, 0, false, s));
+	}
+	LCD_CUDA(e, zero_fill_async(e->o_desc.p, rows * 32, s)); // padding rows of short frames must hold defined bytes
+	// the communication stream starts behind everything already queued on the compute stream
+	LCD_CUDA(e, cudaEventRecord(e->sh_ev[0][7], s));
+	LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[0][7], 0));
+
+	// phase 1: detect + describe the part, all-gather its descriptors (and the keypoint counts)
+	for (int h = 0; h < n_parts; ++h)
+	{
+		LCD_TRY(orb_run(e, part_frames[h], d_images, width, height, channels, d_depth, depth_type, op, cap, e->o_kp.p, e->o_desc.p, e->o_xyz.p, e->o_uv.p,
+		                e->o_n.p, s, part_f0[h], n_frames));
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][0], s));
+		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][0], 0));
+		const size_t pr = static_cast<size_t>(part_frames[h]) * cap;
+		LCD_NCCL(e, nc.GroupStart());
+		LCD_NCCL(e, nc.AllGather(e->o_desc.p + static_cast<size_t>(part_f0[h]) * cap * 32, e->sh_desc_all[h].p, pr * 32, ncclUint8, e->comm, c));
+		if (h == n_parts - 1) LCD_NCCL(e, nc.AllGather(e->o_n.p, e->sh_n_all.p, n_frames, ncclInt32, e->comm, c));
+		LCD_NCCL(e, nc.GroupEnd());
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][1], c));
+	}
+	// phase 2: top-2 keys of every rank's descriptors over the local word range; every rank gets back the keys of ITS frames
+	for (int h = 0; h < n_parts; ++h)
+	{
+		const size_t pr = static_cast<size_t>(part_frames[h]) * cap;
+		const int nq_all = static_cast<int>(pr) * G;
+		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][1], 0));
+		int n_chunks = 0;
+		LCD_TRY(run_knn(e, reinterpret_cast<const uint32_t *>(e->sh_desc_all[h].p), nq_all, e->n_indexed, &n_chunks, s));
+		knn2_merge_kernel<<<(nq_all + 255) / 256, 256, 0, s>>>(e->d_partial.p, n_chunks, nq_all, e->sh_keys[h].p);
+		LCD_CHECK_LAUNCH(e);
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][2], s));
+		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][2], 0));
+		LCD_NCCL(e, nc.GroupStart());
+		for (int p = 0; p < G; ++p)
+		{
+			LCD_NCCL(e, nc.Send(e->sh_keys[h].p + static_cast<size_t>(p) * pr * 2, pr * 2, ncclUint32, p, e->comm, c));
+			LCD_NCCL(e, nc.Recv(e->sh_keys_mine[h].p + static_cast<size_t>(p) * pr * 2, pr * 2, ncclUint32, p, e->comm, c));
+		}
+		LCD_NCCL(e, nc.GroupEnd());
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][3], c));
+	}
+	// phase 3: merge + NNDR / new-word pass of the local frames, all-gather of their word ids
+	for (int h = 0; h < n_parts; ++h)
+	{
+		const size_t pr = static_cast<size_t>(part_frames[h]) * cap;
+		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][3], 0));
+		ResolveArgs a{};
+		a.queries = reinterpret_cast<const uint32_t *>(e->o_desc.p) + static_cast<size_t>(part_f0[h]) * cap * e->nw;
+		a.nq = cap;
+		a.nq_total = static_cast<int>(pr);                         // stride between the G key sets
+		a.partial = reinterpret_cast<const uint2 *>(e->sh_keys_mine[h].p);
+		a.n_chunks = G;
+		a.row_ids = d_row_ids_global;
+		a.incremental = incremental;
+		a.nndr = nndr;
+		a.cmp_new = new_words_compared_together;
+		a.last_word_id = last_word_id;
+		a.word_ids_out = e->sh_words_loc[h].p;
+		a.nq_frame = e->o_n.p + part_f0[h];
+		LCD_TRY(launch_resolve(e, a, part_frames[h], s));
+		if (d_word_ids_out)
+			LCD_CUDA(e, cudaMemcpyAsync(d_word_ids_out + static_cast<size_t>(part_f0[h]) * cap, e->sh_words_loc[h].p, pr * sizeof(int), cudaMemcpyDeviceToDevice, s));
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][4], s));
+		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][4], 0));
+		LCD_NCCL(e, nc.AllGather(e->sh_words_loc[h].p, e->sh_words_all[h].p, pr, ncclInt32, e->comm, c));
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][5], c));
+	}
+	// phase 4: TF-IDF of every rank's frames over the local word range, reduce-scatter of the exact fixed-point sums
+	for (int h = 0; h < n_parts; ++h)
+	{
+		const int nf_all = part_frames[h] * G;
+		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][5], 0));
+		LCD_TRY(ensure_uq(e, nf_all, cap, s));
+		LCD_TRY(ensure_acc(e, nf_all));
+		LCD_CUDA(e, zero_fill_async(e->acc.p, static_cast<size_t>(e->acc_stride) * nf_all * sizeof(long long), s));
+		ResolveArgs a{};
+		a.nq = cap;
+		fill_prep(e, a, static_cast<float>(n_total), 1);
+		int nq_pad = 32;
+		while (nq_pad < cap) nq_pad <<= 1;
+		prof_mark(e, LCD_PROF_RESOLVE, s);
+		prep_from_ids_kernel<<<nf_all, kResolveThreads, nq_pad * sizeof(uint32_t), s>>>(e->sh_words_all[h].p, a);
+		prof_mark(e, LCD_PROF_RESOLVE, s);
+		LCD_CHECK_LAUNCH(e);
+		LCD_TRY(launch_score(e, nf_all, cap, s));
+		gather_fixed_kernel<<<dim3((ns + 255) / 256, nf_all), 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), d_sig_ids, ns, e->sh_scores[h].p);
+		LCD_CHECK_LAUNCH(e);
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][6], s));
+		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][6], 0));
+		LCD_NCCL(e, nc.ReduceScatter(e->sh_scores[h].p, e->sh_scores_loc[h].p, static_cast<size_t>(part_frames[h]) * ns, ncclInt64, ncclSum, e->comm, c));
+		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][7], c));
+	}
+	// phase 5: likelihood of the local frames, verification of their top hypothesis
+	for (int h = 0; h < n_parts; ++h)
+	{
+		const int n = part_frames[h] * ns;
+		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][7], 0));
+		fixed_to_float_kernel<<<(n + 255) / 256, 256, 0, s>>>(e->sh_scores_loc[h].p, n, d_likelihood_out + static_cast<size_t>(part_f0[h]) * ns);
+		LCD_CHECK_LAUNCH(e);
+	}
+	if (vp)
+		LCD_TRY(verify_top_dev(e, reinterpret_cast<const uint32_t *>(e->o_desc.p), e->o_uv.p, n_frames, cap, d_likelihood_out, d_sig_ids, ns, vp, s, e->o_n.p,
+		                       e->o_xyz.p));
+	(void)R;
 	return LCD_OK;
 }
 

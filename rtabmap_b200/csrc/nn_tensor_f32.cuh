@@ -9,9 +9,11 @@
 //   1. operands rounded to fp16 (round to nearest, no scaling; |x| < 65504 is checked) in pre-tiled, 128-byte-swizzled K-major
 //      images: the word image is built once per dictionary change and CACHED (half the bytes of the fp32 rows: the 1M x 64
 //      vocabulary streams as 128 MB), the query image per call;
-//   2. knn2_tensor_f32_kernel: tcgen05.mma kind::f16 (M128 N256 K16, fp32 accumulators in TMEM) gives acc ~ q.w; the epilogue forms
-//      v = |w|^2 - 2 acc (= approximate squared distance minus |q|^2) and appends to the query's CANDIDATE LIST every row with
-//      v <= t2 + 2 eps, where t2 is the second-smallest v this thread has seen so far (initialised from a shared per-query bound);
+//   2. knn2_tensor_f32_kernel: tcgen05.mma kind::f16 (M128 N256 K16, fp32 accumulators in TMEM).  The word image holds -2 w and one
+//      extra K-step holds |w|^2 (as an fp16 hi + lo pair against a constant column of the query image), so the accumulator IS
+//      v = |w|^2 - 2 q.w (= approximate squared distance minus |q|^2): the epilogue is a running minimum over the columns (one
+//      three-input FMNMX per two columns) and appends to the query's CANDIDATE LIST every row with v <= t2 + 2 eps, where t2 is the
+//      second-smallest v this thread has seen so far (initialised from a shared per-query bound);
 //   3. rerank_l2_kernel computes the exact rtflann-order distance of every candidate from the fp32 rows and keeps the best two by
 //      (distance, row) — the same packed 64-bit keys as the exact kernel of l2_path.cuh, consumed by the same resolve kernel;
 //   4. a query whose list overflowed (or whose values do not fit fp16) is redone by an exact scan (knn2_l2_fallback_kernel).
@@ -22,8 +24,9 @@
 // both true neighbours (and every row tying with them) reach the list, and the exact re-rank then orders them as rtflann does.
 // eps bounds (a) fp16 rounding of both operands: |q^.w^ - q.w| <= 2^-10 (1 + 2^-11) |q| |w| + subnormal terms (Cauchy-Schwarz on the
 // element-wise relative errors 2^-11), doubled by the factor 2 in the distance; (b) fp32 accumulation in the tensor core, the fma
-// of the epilogue, the float norms and rtflann's own rounding, all far below 2^-15 (|q|^2 + |w|^2):
-//     eps(q) = 1.02 * 2^-9 * |q| * Wmax + 2^-15 * (|q|^2 + Wmax^2),      Wmax = largest |w| in the dictionary.
+// the fp16 hi + lo split of |w|^2 (relative 2^-21, plus 2^-19 absolute for its subnormal tail), the float norms and rtflann's own
+// rounding, all far below 2^-15 (|q|^2 + |w|^2) + 4e-6:
+//     eps(q) = 1.02 * 2^-9 * |q| * Wmax + 2^-15 * (|q|^2 + Wmax^2) + 4e-6,      Wmax = largest |w| in the dictionary.
 // For unit-length descriptors eps ~ 2.1e-3 against nearest-neighbour distances of 1e-2 .. 1: the lists stay a few dozen rows long.
 #pragma once
 #include "common.cuh"
@@ -38,10 +41,12 @@ constexpr int kTfBN = 256;          // words per tile (UMMA N)
 constexpr int kTfEpiGroups = 4;     // column groups of a tile, one set of 4 epilogue warps each
 constexpr int kTfEpiCols = kTfBN / kTfEpiGroups;
 constexpr int kTfThreads = 128 + 128 * kTfEpiGroups;
-constexpr int kTfNormSlots = 4;     // ring of per-tile norm vectors (1 KB each)
 constexpr int kTfCandCap = 96;      // candidate rows kept per query; more -> exact fallback for that query
 constexpr int kTfMinRows = 4096;    // below this the exact CUDA-core kernel is used
 constexpr int kTfPrepassTiles = 16; // rows [0, 4096): the bound-only pre-pass that initialises the per-query bound
+constexpr float kTfAugScale = 64.0f; // the constant of the query image's augmentation columns; |w|^2 is stored divided by it
+constexpr float kTfMaxAbs = 32752.0f; // -2 w must fit fp16
+constexpr float kTfMaxNorm2 = 65504.0f * kTfAugScale;
 
 template <int DIM>
 struct TfCfg
@@ -49,8 +54,10 @@ struct TfCfg
 	static constexpr int atoms = DIM / 64;                 // 64 halves = one 128-byte swizzle atom
 	static constexpr uint32_t a_bytes = kTfBM * DIM * 2;
 	static constexpr uint32_t b_bytes = kTfBN * DIM * 2;
+	static constexpr uint32_t a_aug_bytes = kTfBM * 32;    // one K-step (16 halves) per row, un-swizzled core-matrix layout
+	static constexpr uint32_t b_aug_bytes = kTfBN * 32;
 	static constexpr int stages = DIM == 64 ? 5 : 2;
-	static constexpr size_t smem = 1024 + a_bytes + stages * b_bytes + kTfNormSlots * kTfBN * 4 + 512;
+	static constexpr size_t smem = 1024 + a_bytes + a_aug_bytes + stages * (b_bytes + b_aug_bytes) + 512;
 };
 
 // order-preserving float <-> uint mapping (v can be negative), for atomicMin on the shared per-query bound
@@ -70,7 +77,7 @@ __device__ __forceinline__ float ord2f(uint32_t u)
 // bad_row[row] (may be null) is set when a value is not finite or does not fit fp16.
 template <int DIM>
 __global__ void tf_expand_kernel(const float * __restrict__ src, int row_begin, int n_rows, int tile_rows, uint4 * __restrict__ dst,
-                                 int * __restrict__ bad_flag)
+                                 int * __restrict__ bad_flag, float scale)
 {
 	constexpr int chunks = DIM / 8;
 	const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -86,9 +93,10 @@ __global__ void tf_expand_kernel(const float * __restrict__ src, int row_begin, 
 		const float4 b = *reinterpret_cast<const float4 *>(src + row * DIM + chunk * 8 + 4);
 		const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
 		                      fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
-		if (!(m < 65504.0f) && bad_flag) *bad_flag = 1; // also true for NaN
-		const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y),
-		              h3 = __floats2half2_rn(b.z, b.w);
+		if (!(m < kTfMaxAbs) && bad_flag) *bad_flag = 1; // also true for NaN
+		// scale = -2 for the word image (exact in fp16), 1 for the query image
+		const __half2 h0 = __floats2half2_rn(a.x * scale, a.y * scale), h1 = __floats2half2_rn(a.z * scale, a.w * scale),
+		              h2 = __floats2half2_rn(b.x * scale, b.y * scale), h3 = __floats2half2_rn(b.z * scale, b.w * scale);
 		o.x = *reinterpret_cast<const uint32_t *>(&h0);
 		o.y = *reinterpret_cast<const uint32_t *>(&h1);
 		o.z = *reinterpret_cast<const uint32_t *>(&h2);
@@ -101,26 +109,48 @@ __global__ void tf_expand_kernel(const float * __restrict__ src, int row_begin, 
 	dst[off16] = o;
 }
 
-// |w|^2 of rows [row_begin rounded down to a tile, n_rows rounded up): +inf for the padding rows; the largest one into *wmax2_bits.
+// The augmentation K-step of rows [row_begin rounded down to a tile, n_rows rounded up): 16 halves per row in the un-swizzled K-major
+// core-matrix layout ([8-row group][k-chunk 0..1][8 rows][8 halves], 256 B per group), image = [tile][tile_rows / 8 groups].
+//   words  : (hi, lo, 0...) with hi + lo = |w|^2 / kTfAugScale (+inf in the padding rows); the largest |w|^2 into *wmax2_bits
+//   queries: (kTfAugScale, kTfAugScale, 0...)
 template <int DIM>
-__global__ void tf_norms_kernel(const float * __restrict__ src, int row_begin, int n_rows, int tile_rows, float * __restrict__ norms,
-                                uint32_t * __restrict__ wmax2_bits)
+__global__ void tf_aug_kernel(const float * __restrict__ src, int row_begin, int n_rows, int tile_rows, uint4 * __restrict__ aug, int is_query,
+                              uint32_t * __restrict__ wmax2_bits, int * __restrict__ bad_flag)
 {
 	const size_t row = static_cast<size_t>(row_begin / tile_rows) * tile_rows + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	const size_t row_end = (static_cast<size_t>(n_rows) + tile_rows - 1) / tile_rows * tile_rows;
 	if (row >= row_end) return;
-	float s = INFINITY;
-	if (row < static_cast<size_t>(n_rows))
+	__half h0, h1;
+	if (is_query)
 	{
-		s = 0.0f;
-		for (int i = 0; i < DIM; i += 4)
-		{
-			const float4 a = *reinterpret_cast<const float4 *>(src + row * DIM + i);
-			s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-		}
-		if (wmax2_bits && s == s) atomicMax(wmax2_bits, __float_as_uint(s)); // s >= 0: unsigned order of the bits = float order
+		h0 = __float2half_rn(kTfAugScale);
+		h1 = h0;
 	}
-	norms[row] = s;
+	else
+	{
+		float s = INFINITY;
+		if (row < static_cast<size_t>(n_rows))
+		{
+			s = 0.0f;
+			for (int i = 0; i < DIM; i += 4)
+			{
+				const float4 a = *reinterpret_cast<const float4 *>(src + row * DIM + i);
+				s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+			}
+			if (!(s < kTfMaxNorm2) && bad_flag) *bad_flag = 1;
+			if (wmax2_bits && s == s) atomicMax(wmax2_bits, __float_as_uint(s)); // s >= 0: unsigned order of the bits = float order
+		}
+		const float t = s / kTfAugScale;
+		h0 = __float2half_rn(t);
+		h1 = (t < INFINITY) ? __float2half_rn(t - __half2float(h0)) : __float2half_rn(0.0f);
+	}
+	// row r of the image: group r / 8, core-matrix row r % 8; k-chunk 0 holds halves 0..7 (hi, lo, 0 x 6), k-chunk 1 is zero
+	const size_t grp = row / 8;
+	const int rr = static_cast<int>(row % 8);
+	uint4 c0 = make_uint4(0, 0, 0, 0);
+	c0.x = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+	aug[grp * 16 + rr] = c0;
+	aug[grp * 16 + 8 + rr] = make_uint4(0, 0, 0, 0);
 }
 
 // per-query state of one search: norm, empty candidate list (or "overflowed" for queries that do not fit fp16), loose bound
@@ -161,12 +191,25 @@ __device__ __forceinline__ constexpr uint32_t tc_idesc_f16(int m, int n)
 	return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// shared-memory matrix descriptor of an UN-swizzled K-major operand slab of one K-step (16 halves): 8 x 16-byte core matrices, the two
+// k-chunks of a row group 128 B apart (leading byte offset), row groups 256 B apart (stride byte offset)
+__device__ __forceinline__ uint64_t tc_smem_desc_noswz(uint32_t saddr)
+{
+	uint64_t d = 0;
+	d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
+	d |= static_cast<uint64_t>(128 >> 4) << 16;                  // leading byte offset [16,30): next core matrix along K
+	d |= static_cast<uint64_t>(256 >> 4) << 32;                  // stride byte offset [32,46): next 8-row group
+	d |= static_cast<uint64_t>(1) << 46;                         // descriptor version (sm_100)
+	return d;                                                    // layout type 0: no swizzle
+}
+
 struct TfArgs
 {
-	const uint4 * word_img;      // fp16 word image
-	const float * word_norms;    // [tiles * 256] |w|^2, +inf in padding rows
+	const uint4 * word_img;      // fp16 image of -2 w
+	const uint4 * word_aug;      // augmentation K-step of the words (|w|^2 as hi + lo)
 	int n_rows;                  // rows of this search
 	const uint4 * query_img;
+	const uint4 * query_aug;
 	const float * qn;            // [nq] |q|^2
 	int nq;
 	int tile_begin, tile_end;    // tile range of the whole launch; blockIdx.y * tiles_per_split selects the CTA's share
@@ -179,7 +222,7 @@ struct TfArgs
 };
 
 // grid = (query tiles, splits).  Roles as in knn2_tensor_kernel (nn_tensor.cuh): warp 0 producer (bulk copies of the word tiles and
-// of their norm vectors), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 epilogue (thread = one query = one TMEM lane,
+// their augmentation slabs), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 epilogue (thread = one query = one TMEM lane,
 // column group (warp - 4) / 4).
 template <int DIM>
 __global__ void __launch_bounds__(kTfThreads, 1)
@@ -187,19 +230,17 @@ knn2_tensor_f32_kernel(const TfArgs a)
 {
 	using Cfg = TfCfg<DIM>;
 	constexpr int kStages = Cfg::stages;
+	constexpr uint32_t kStageBytes = Cfg::b_bytes + Cfg::b_aug_bytes;
 	extern __shared__ unsigned char smem_dyn[];
 	unsigned char * smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
-	unsigned char * sA = smem;
-	unsigned char * sB = smem + Cfg::a_bytes;
-	float * sN = reinterpret_cast<float *>(sB + kStages * Cfg::b_bytes); // [kTfNormSlots][256]
-	uint64_t * bars = reinterpret_cast<uint64_t *>(sN + kTfNormSlots * kTfBN);
+	unsigned char * sA = smem;                                   // query tile, then its augmentation slab
+	unsigned char * sB = smem + Cfg::a_bytes + Cfg::a_aug_bytes; // stages of (word tile, augmentation slab)
+	uint64_t * bars = reinterpret_cast<uint64_t *>(sB + kStages * kStageBytes);
 	uint64_t * full = bars;                     // [kStages] word tile landed
 	uint64_t * empty = full + kStages;          // [kStages] word tile consumed by the MMAs
 	uint64_t * tfull = empty + kStages;         // [2] accumulator stage complete
 	uint64_t * tempty = tfull + 2;              // [2] accumulator stage drained
-	uint64_t * nfull = tempty + 2;              // [kTfNormSlots] norm vector landed
-	uint64_t * nempty = nfull + kTfNormSlots;   // [kTfNormSlots] norm vector read by all epilogue warps
-	uint64_t * afull = nempty + kTfNormSlots;   // [1] query tile landed
+	uint64_t * afull = tempty + 2;              // [1] query tile landed
 	uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(afull + 1);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -220,11 +261,6 @@ knn2_tensor_f32_kernel(const TfArgs a)
 			mbar_init(&tfull[s], 1);
 			mbar_init(&tempty[s], 4 * kTfEpiGroups);
 		}
-		for (int s = 0; s < kTfNormSlots; ++s)
-		{
-			mbar_init(&nfull[s], 1);
-			mbar_init(&nempty[s], 4 * kTfEpiGroups);
-		}
 		mbar_init(afull, 1);
 		mbar_fence_init();
 	}
@@ -238,19 +274,21 @@ knn2_tensor_f32_kernel(const TfArgs a)
 	{
 		if (lane == 0 && n_tiles > 0)
 		{
-			mbar_arrive_expect_tx(afull, Cfg::a_bytes);
+			mbar_arrive_expect_tx(afull, Cfg::a_bytes + Cfg::a_aug_bytes);
 			bulk_g2s(sA, reinterpret_cast<const unsigned char *>(a.query_img) + static_cast<size_t>(qtile) * Cfg::a_bytes, Cfg::a_bytes, afull);
+			bulk_g2s(sA + Cfg::a_bytes, reinterpret_cast<const unsigned char *>(a.query_aug) + static_cast<size_t>(qtile) * Cfg::a_aug_bytes,
+			         Cfg::a_aug_bytes, afull);
 			for (int t = 0; t < n_tiles; ++t)
 			{
-				const int s = t % kStages, ns = t % kTfNormSlots;
-				if (t >= kTfNormSlots) mbar_wait(&nempty[ns], ((t / kTfNormSlots) - 1) & 1);
-				mbar_arrive_expect_tx(&nfull[ns], kTfBN * 4);
-				bulk_g2s(sN + ns * kTfBN, a.word_norms + static_cast<size_t>(tile_begin + t) * kTfBN, kTfBN * 4, &nfull[ns]);
+				const int s = t % kStages;
 				if (t >= kStages) mbar_wait(&empty[s], ((t / kStages) - 1) & 1);
-				mbar_arrive_expect_tx(&full[s], Cfg::b_bytes);
+				mbar_arrive_expect_tx(&full[s], kStageBytes);
 				const unsigned char * src = reinterpret_cast<const unsigned char *>(a.word_img) + static_cast<size_t>(tile_begin + t) * Cfg::b_bytes;
-				bulk_g2s(sB + s * Cfg::b_bytes, src, Cfg::b_bytes / 2, &full[s]);
-				bulk_g2s(sB + s * Cfg::b_bytes + Cfg::b_bytes / 2, src + Cfg::b_bytes / 2, Cfg::b_bytes / 2, &full[s]);
+				unsigned char * dst = sB + s * kStageBytes;
+				bulk_g2s(dst, src, Cfg::b_bytes / 2, &full[s]);
+				bulk_g2s(dst + Cfg::b_bytes / 2, src + Cfg::b_bytes / 2, Cfg::b_bytes / 2, &full[s]);
+				bulk_g2s(dst + Cfg::b_bytes, reinterpret_cast<const unsigned char *>(a.word_aug) + static_cast<size_t>(tile_begin + t) * Cfg::b_aug_bytes,
+				         Cfg::b_aug_bytes, &full[s]);
 			}
 		}
 	}
@@ -260,6 +298,7 @@ knn2_tensor_f32_kernel(const TfArgs a)
 		{
 			constexpr uint32_t idesc = tc_idesc_f16(kTfBM, kTfBN);
 			const uint32_t a_base = smem_u32(sA);
+			const uint64_t a_aug = tc_smem_desc_noswz(a_base + Cfg::a_bytes);
 			mbar_wait(afull, 0);
 			for (int t = 0; t < n_tiles; ++t)
 			{
@@ -267,7 +306,7 @@ knn2_tensor_f32_kernel(const TfArgs a)
 				if (t >= 2) mbar_wait(&tempty[acc], ((t >> 1) - 1) & 1);
 				mbar_wait(&full[s], (t / kStages) & 1);
 				tc_fence_after();
-				const uint32_t b_base = smem_u32(sB + s * Cfg::b_bytes);
+				const uint32_t b_base = smem_u32(sB + s * kStageBytes);
 				const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kTfBN);
 #pragma unroll
 				for (int ks = 0; ks < DIM / 16; ++ks)
@@ -277,6 +316,8 @@ knn2_tensor_f32_kernel(const TfArgs a)
 					const uint64_t bd = tc_smem_desc(b_base + atom * (kTfBN * 128) + koff);
 					tc_mma_f16(d_addr, ad, bd, idesc, ks > 0 ? 1u : 0u);
 				}
+				// the augmentation K-step: + kTfAugScale * (hi + lo) = + |w|^2
+				tc_mma_f16(d_addr, a_aug, tc_smem_desc_noswz(b_base + Cfg::b_bytes), idesc, 1u);
 				tc_commit(&empty[s]);
 				tc_commit(&tfull[acc]);
 			}
@@ -292,71 +333,54 @@ knn2_tensor_f32_kernel(const TfArgs a)
 		if (live)
 		{
 			const float q2 = a.qn[qi], w2 = __uint_as_float(*a.wmax2_bits);
-			const float eps = 1.02f * 0.001953125f * sqrtf(q2) * sqrtf(w2) + 3.0517578125e-05f * (q2 + w2);
+			const float eps = 1.02f * 0.001953125f * sqrtf(q2) * sqrtf(w2) + 3.0517578125e-05f * (q2 + w2) + 4.0e-6f;
 			margin = 2.0f * eps;
 			t2 = ord2f(a.tau[qi]);
 		}
 		const int emit = a.emit;
 		for (int t = 0; t < n_tiles; ++t)
 		{
-			const int acc = t & 1, ns = t % kTfNormSlots;
-			mbar_wait(&nfull[ns], (t / kTfNormSlots) & 1);
+			const int acc = t & 1;
 			mbar_wait(&tfull[acc], (t >> 1) & 1);
 			tc_fence_after();
 			const int row0 = (tile_begin + t) * kTfBN + cg * kTfEpiCols;
-			const float4 * wn4 = reinterpret_cast<const float4 *>(sN + ns * kTfBN + cg * kTfEpiCols);
 			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTfBN + cg * kTfEpiCols);
+			int v[kTfEpiCols];
 #pragma unroll
-			for (int c0 = 0; c0 < kTfEpiCols; c0 += 32)
+			for (int c0 = 0; c0 < kTfEpiCols; c0 += 32) tc_ld32(taddr + c0, *reinterpret_cast<int(*)[32]>(&v[c0]));
+			tc_wait_ld();
+			// the accumulator stage is free as soon as the values are in registers
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&tempty[acc]);
+			float m = INFINITY;
+#pragma unroll
+			for (int j = 0; j < kTfEpiCols; j += 2) m = fminf(m, fminf(__int_as_float(v[j]), __int_as_float(v[j + 1])));
+			if (live && m <= t2 + margin)
 			{
-				int v[32];
-				tc_ld32(taddr + c0, v);
-				tc_wait_ld();
-				float f[32];
-				float m = INFINITY;
+				// rare: some column of this tile may belong to the two nearest rows
 #pragma unroll
-				for (int j = 0; j < 32; j += 4)
+				for (int j = 0; j < kTfEpiCols; ++j)
 				{
-					const float4 w = wn4[(c0 + j) >> 2];
-					f[j] = fmaf(__int_as_float(v[j]), -2.0f, w.x);
-					f[j + 1] = fmaf(__int_as_float(v[j + 1]), -2.0f, w.y);
-					f[j + 2] = fmaf(__int_as_float(v[j + 2]), -2.0f, w.z);
-					f[j + 3] = fmaf(__int_as_float(v[j + 3]), -2.0f, w.w);
-					m = fminf(m, fminf(fminf(f[j], f[j + 1]), fminf(f[j + 2], f[j + 3])));
-				}
-				if (live && m <= t2 + margin)
-				{
-					// rare: some column of this chunk may belong to the two nearest rows
-#pragma unroll
-					for (int j = 0; j < 32; ++j)
+					const float x = __int_as_float(v[j]);
+					if (x <= t2 + margin && x < INFINITY)
 					{
-						const float x = f[j];
-						if (x <= t2 + margin && x < INFINITY)
+						if (emit)
 						{
-							if (emit)
-							{
-								const int pos = atomicAdd(&a.cand_count[qi], 1);
-								if (pos < kTfCandCap) a.cand[static_cast<size_t>(qi) * kTfCandCap + pos] = static_cast<uint32_t>(row0 + c0 + j);
-							}
-							// t2 only ever tightens: it starts as the shared bound while t1 is still unknown (+inf)
-							if (x < t1)
-							{
-								t2 = fminf(t2, t1);
-								t1 = x;
-							}
-							else if (x < t2) t2 = x;
+							const int pos = atomicAdd(&a.cand_count[qi], 1);
+							if (pos < kTfCandCap) a.cand[static_cast<size_t>(qi) * kTfCandCap + pos] = static_cast<uint32_t>(row0 + j);
 						}
+						// t2 only ever tightens: it starts as the shared bound while t1 is still unknown (+inf)
+						if (x < t1)
+						{
+							t2 = fminf(t2, t1);
+							t1 = x;
+						}
+						else if (x < t2) t2 = x;
 					}
 				}
 			}
-			// accumulator stage and norm slot are free once every lane of the warp is done with them
-			tc_fence_before();
 			__syncwarp();
-			if (lane == 0)
-			{
-				mbar_arrive(&tempty[acc]);
-				mbar_arrive(&nempty[ns]);
-			}
 		}
 		if (live && t2 < INFINITY) atomicMin(&a.tau[qi], f2ord(t2));
 	}
