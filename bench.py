@@ -331,42 +331,23 @@ def run_b200(args):
     img_bytes = IMG_W * IMG_H * 3
     dep_bytes = IMG_W * IMG_H * 2
     if world_size > 1:
-        d_desc_loc = torch.zeros(nf * F_FEATS * DESC_BYTES, dtype=torch.uint8, device="cuda")
-        d_uv_loc = torch.zeros(nf * F_FEATS * 2, dtype=torch.float32, device="cuda")
-        d_n_loc = torch.zeros(nf, dtype=torch.int32, device="cuda")
-        d_desc = torch.zeros(nq * DESC_BYTES, dtype=torch.uint8, device="cuda")
-        d_uv = torch.zeros(nq * 2, dtype=torch.float32, device="cuda")
-        d_keys = torch.zeros(nq * 2, dtype=torch.int32, device="cuda")
-        d_keys_all = torch.zeros(world_size * nq * 2, dtype=torch.int32, device="cuda")
+        # the exchanges live behind the C ABI (lcd_shard_process_frames_dev): the library's own NCCL communicator, bootstrapped like any
+        # NCCL program — rank 0 creates the unique id, the host (here: torch.distributed) hands it to the other ranks
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Engine.shard_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.shard_comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world_size)
         d_rowids = torch.from_numpy(ids).cuda()
-        d_scores = torch.zeros(B * S_SIGS, dtype=torch.int64, device="cuda")
-        d_n_all = torch.zeros(B, dtype=torch.int32, device="cuda")
-        d_scores_loc = torch.zeros(nf * S_SIGS, dtype=torch.int64, device="cuda")
-        d_words_loc = torch.zeros(nf * F_FEATS, dtype=torch.int32, device="cuda")
+        d_words = torch.zeros(nf * F_FEATS, dtype=torch.int32, device="cuda")   # this rank's frames only
+        d_like = torch.zeros(nf * S_SIGS, dtype=torch.float32, device="cuda")
+        h_words = torch.zeros((nf, F_FEATS), dtype=torch.int32).pin_memory()
+        h_like = torch.zeros((nf, S_SIGS), dtype=torch.float32).pin_memory()
 
     def sharded_step(img_t, dep_t):
-        # detect: frames sharded; quantise: words sharded; score: words sharded; verify: frames sharded
-        d_desc_loc.zero_()
-        eng._check(eng._lib.lcd_orb_detect_describe_dev(eng.handle, nf, ctypes.c_void_p(img_t.data_ptr()), IMG_W, IMG_H, 3,
-                                                         ctypes.c_void_p(dep_t.data_ptr()), 1, ctypes.byref(op), F_FEATS, None,
-                                                         ctypes.c_void_p(d_desc_loc.data_ptr()), None, ctypes.c_void_p(d_uv_loc.data_ptr()),
-                                                         ctypes.c_void_p(d_n_loc.data_ptr()), None))
-        dist.all_gather_into_tensor(d_desc, d_desc_loc)
-        dist.all_gather_into_tensor(d_uv, d_uv_loc)
-        dist.all_gather_into_tensor(d_n_all, d_n_loc)
-        eng.shard_knn2_keys_dev(d_desc.data_ptr(), nq, d_keys.data_ptr())
-        dist.all_gather_into_tensor(d_keys_all, d_keys)
-        # stage 2 sharded by frame: resolve the local frames, all-gather their word ids, score every frame on the local word range
-        eng.shard_resolve_frames_dev(d_desc.data_ptr(), f0, nf, B, F_FEATS, d_keys_all.data_ptr(), world_size, d_rowids.data_ptr(), W_WORDS,
-                                     d_n_all.data_ptr(), d_words_loc.data_ptr(), True, NNDR, True)
-        dist.all_gather_into_tensor(d_words, d_words_loc)
-        eng.shard_score_ids_dev(d_words.data_ptr(), B, F_FEATS, d_sig.data_ptr(), S_SIGS, S_SIGS + 1, d_scores.data_ptr())
-        # every rank only needs the likelihood rows of the frames it verifies: reduce-scatter (half the traffic of an all-reduce);
-        # the int64 fixed-point sums are exact, so the result does not depend on the reduction order
-        dist.reduce_scatter_tensor(d_scores_loc, d_scores, op=dist.ReduceOp.SUM)
-        eng.shard_finalize_dev(d_scores_loc.data_ptr(), nf * S_SIGS, d_like.data_ptr() + f0 * S_SIGS * 4)
-        eng.verify_top_dev(d_desc.data_ptr() + f0 * F_FEATS * DESC_BYTES, d_uv.data_ptr() + f0 * F_FEATS * 8, nf, F_FEATS,
-                           d_like.data_ptr() + f0 * S_SIGS * 4, d_sig.data_ptr(), S_SIGS, vp)
+        # detect: frames sharded; quantise: words sharded; score: words sharded; verify: frames sharded — one library call per step
+        eng.shard_process_frames_dev(img_t.data_ptr(), nf, IMG_W, IMG_H, 3, dep_t.data_ptr(), 1, op, d_sig.data_ptr(), S_SIGS, S_SIGS + 1,
+                                     d_rowids.data_ptr(), W_WORDS, vp, d_words.data_ptr(), d_like.data_ptr(), True, NNDR, True)
 
     def step_dev(k):
         if world_size == 1:
@@ -506,8 +487,8 @@ def run_b200(args):
             flush.fill_(k & 0xFF)
             ext.wait_event(up_ev[k & 1])
             sharded_step(d_img[k & 1], d_dep[k & 1])
-            h_words.view(-1)[f0 * F_FEATS:f1 * F_FEATS].copy_(d_words[f0 * F_FEATS:f1 * F_FEATS], non_blocking=True)
-            h_like.view(-1)[f0 * S_SIGS:f1 * S_SIGS].copy_(d_like[f0 * S_SIGS:f1 * S_SIGS], non_blocking=True)
+            h_words.view(-1).copy_(d_words, non_blocking=True)
+            h_like.view(-1).copy_(d_like, non_blocking=True)
             if k + 1 < args.steps:
                 prefetch(k + 1)
             hyp_h, res_h = eng.process_fetch(nf)  # device-wide synchronisation + results of this rank's frames
@@ -625,9 +606,9 @@ def run_b200(args):
         nchk = 2
         for b in range(nchk):
             kp, d, words, like, hyp_o, v, x = ref.one(h_img[kpool][b].numpy(), h_dep[kpool][b].numpy().view(np.uint16))
-            wg = h_words[f0 + b].numpy()
+            wg = h_words[b].numpy()
             assert np.array_equal(wg[:len(words)], words), "sharded run: GPU/oracle word ids differ"
-            assert np.allclose(h_like[f0 + b].numpy(), like, atol=1e-4, rtol=1e-4), "sharded run: GPU/oracle likelihood differ"
+            assert np.allclose(h_like[b].numpy(), like, atol=1e-4, rtol=1e-4), "sharded run: GPU/oracle likelihood differ"
             assert hyp_o == int(hyp_h[b]) and v["ok"] == res_h[b]["ok"], "sharded run: GPU/oracle verification differ"
             if v["ok"]:
                 assert len(v["inliers"]) == res_h[b]["n_inliers"]
@@ -655,7 +636,7 @@ def run_b200(args):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (img_bytes + dep_bytes) + S_SIGS * 4),
                 "d2h_bytes_per_step": int(nq * 4 + B * S_SIGS * 4 + B * (4 + 4 + 124 + 288)),
-                "api": "lcd_process_frames_submit/_wait (pinned host buffers, 2 batches in flight, L2 flush between steps inside the timed region)" if world_size == 1 else "sharded *_dev calls, double-buffered pinned uploads on a side stream, results copied back every step",
+                "api": "lcd_process_frames_submit/_wait (pinned host buffers, 2 batches in flight, L2 flush between steps inside the timed region)" if world_size == 1 else "lcd_shard_process_frames_dev (exchanges inside the library), double-buffered pinned uploads on a side stream, results copied back every step",
                 "top1_place_hit_rate": e2e_hit, "verified_rate": e2e_verified},
         "roofline": roofline, "cpu_baseline": cpu, "top1_place_hit_rate": hit, "verified_rate": verified, "ransac_iterations_hist_50": iters_hist,
         "wall_s_timed_region": t_wall, "frames_pool": f"{n_pool} batches of {BL} frames cycled", "oracle_check": sharded_check, **extra,

@@ -439,6 +439,28 @@ int lcd_shard_resolve_score_dev(lcd_engine * e, const void * d_queries, int n_fr
 int lcd_shard_finalize_dev(lcd_engine * e, const long long * d_scores, int n, float * d_likelihood_out,
                            void * stream);
 
+/* ---- the exchanges behind the C ABI: one engine = one rank of a word-range-sharded job ----------------------------------
+ * NCCL is loaded at run time (dlopen of libnccl.so.2: the host's own copy when it has one).  Bootstrap as any NCCL program: rank 0 calls
+ * lcd_shard_unique_id, the host sends the 128 bytes to the other ranks over whatever channel it has (MPI, sockets, a file), every rank
+ * calls lcd_shard_comm_init; or hand over a communicator the host already owns with lcd_shard_comm_adopt (ncclComm_t as void *). */
+int lcd_shard_unique_id(char id_out[128]);
+int lcd_shard_comm_init(lcd_engine * e, const char id[128], int rank, int n_ranks);
+int lcd_shard_comm_adopt(lcd_engine * e, void * nccl_comm, int rank, int n_ranks);
+int lcd_shard_comm_destroy(lcd_engine * e);
+/* One step of the sharded job on this rank, entirely on the device: detect + describe the n_frames LOCAL frames, all-gather of the
+ * descriptors, top-2 keys of every rank's descriptors over the local word range (lcd_shard_set_row_offset), all-to-all so that every rank
+ * receives the keys of ITS frames, merge + NNDR / new-word pass of the local frames, all-gather of their word ids, TF-IDF of all frames
+ * over the local word range, reduce-scatter of the exact 64-bit fixed-point sums, likelihood + verification of the local frames'
+ * top hypotheses (results through lcd_process_fetch).  The local batch runs as two halves so that the exchanges of one half (on the
+ * engine's communication stream) overlap the kernels of the other.  d_row_ids_global: global row -> word id of the WHOLE dictionary
+ * (rows of all ranks in ascending id order); d_word_ids_out[n_frames * n_features] (may be NULL), d_likelihood_out[n_frames * ns].
+ * Every rank must call it with the same n_frames.  Results equal the unsharded engine's: word ids bit for bit, likelihood from the same
+ * exact sums. */
+int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_images, int width, int height, int channels, const void * d_depth,
+                                 int depth_type, const lcd_orb_params * params, int incremental, float nndr, int new_words_compared_together,
+                                 const int * d_sig_ids, int ns, int n_total, const int * d_row_ids_global, int last_word_id,
+                                 const lcd_verify_params * vp, int * d_word_ids_out, float * d_likelihood_out, void * stream);
+
 /* ---- measurement hooks ---------------------------------------------------------------
  * Optional per-kernel timing with CUDA events recorded on the launching stream around
  * every launch of kernel class `which` (0 = dictionary NN, 1 = resolve, 2 = score, 3 = pair

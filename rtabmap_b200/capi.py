@@ -14,6 +14,7 @@ import numpy as np
 
 from . import build as _build
 
+LCD_OK = 0
 LCD_DESC_U8 = 0
 LCD_DESC_F32 = 1
 
@@ -160,6 +161,11 @@ SIGNATURES = {
     "lcd_shard_resolve_frames_dev": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _F, _I, _P, _P, _P]),
     "lcd_shard_score_ids_dev": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P]),
     "lcd_shard_finalize_dev": (_I, [_P, _P, _I, _P, _P]),
+    "lcd_shard_unique_id": (_I, [_P]),
+    "lcd_shard_comm_init": (_I, [_P, _P, _I, _I]),
+    "lcd_shard_comm_adopt": (_I, [_P, _P, _I, _I]),
+    "lcd_shard_comm_destroy": (_I, [_P]),
+    "lcd_shard_process_frames_dev": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
     "lcd_profile_enable": (_I, [_P, _I]),
     "lcd_profile_read": (_I, [_P, _I, _P, _P]),
     "lcd_profile_reset": (_I, [_P]),
@@ -702,6 +708,29 @@ class Engine:
         return hyp, self._results(res, n_frames)
 
     # -- word-range sharding ----------------------------------------------------------------------
+    @staticmethod
+    def shard_unique_id() -> bytes:
+        """ncclGetUniqueId through the library (rank 0); broadcast the 128 bytes to the other ranks."""
+        buf = C.create_string_buffer(128)
+        rc = load_library().lcd_shard_unique_id(buf)
+        if rc != LCD_OK:
+            raise LcdError(rc, (load_library().lcd_last_error(None) or b"").decode())
+        return buf.raw
+
+    def shard_comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        self._check(self._lib.lcd_shard_comm_init(self._h, C.create_string_buffer(unique_id, 128), int(rank), int(n_ranks)))
+
+    def shard_comm_destroy(self):
+        self._check(self._lib.lcd_shard_comm_destroy(self._h))
+
+    def shard_process_frames_dev(self, d_images: int, n_frames: int, w: int, h: int, ch: int, d_depth: int, depth_type: int, op: "OrbParams", d_sig_ids: int,
+                                 ns: int, n_total: int, d_row_ids_global: int, last_word_id: int, vp: "VerifyParams", d_words_out: int, d_like_out: int,
+                                 incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True, stream: int = 0):
+        self._check(self._lib.lcd_shard_process_frames_dev(self._h, n_frames, C.c_void_p(d_images), w, h, ch, C.c_void_p(d_depth or None), depth_type,
+                                                            C.byref(op), int(incremental), float(nndr), int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total),
+                                                            C.c_void_p(d_row_ids_global), int(last_word_id), C.byref(vp) if vp is not None else None,
+                                                            C.c_void_p(d_words_out or None), C.c_void_p(d_like_out), C.c_void_p(stream or None)))
+
     def shard_set_row_offset(self, off: int):
         self._check(self._lib.lcd_shard_set_row_offset(self._h, int(off)))
 

@@ -113,3 +113,48 @@ def test_two_word_range_shards_equal_one_engine(by_frame):
             assert np.allclose(got_l[b], want_l[b], rtol=1e-6, atol=1e-7), f"frame {b}"
         if by_frame:
             assert not got_w[b, n_valid[b]:].any()
+
+
+def test_fused_sharded_step_with_a_single_rank_communicator_equals_the_unsharded_call():
+    """lcd_shard_process_frames_dev (the exchanges inside the library, NCCL loaded at run time) on a communicator of ONE rank: every
+    collective degenerates to a copy, the two-half pipeline and all the bookkeeping still run, and the result must equal
+    lcd_process_frames_dev on the same engine — word ids, likelihood, hypotheses, verification."""
+    import torch
+
+    eng = Engine(max_words=8192, max_signatures=400)
+    op = Engine.orb_params(synth.CAMERA_K4, n_features=300)
+    world = synth.make_place_world(lambda im, dp: eng.orb_detect_describe(im[None], dp[None], op, cap=300)[0], 6, 1500, 120, 300, 240, 320)
+    sm = world.smap
+    eng.add_words(world.word_ids, world.vocab)
+    eng.last_word_id = int(world.word_ids.max())
+    eng.update()
+    eng.load_csr(sm.word_ids, sm.row_ptr, sm.sig, sm.cnt)
+    eng.set_ni(sm.sig_ids, sm.ni)
+    eng.sig_add_batch(sm.sig_ids, world.store.desc, world.store.xyz, sm.ni)
+    imgs, deps, places = synth.make_view_frames(world, 5, seed=4)   # an odd count: halves of 3 and 2 frames
+    vp = Engine.verify_params(synth.CAMERA_K4, image_size=(320, 240))
+    nf, ns = len(imgs), len(sm.sig_ids)
+    d_img = torch.from_numpy(imgs).cuda()
+    d_dep = torch.from_numpy(deps.view(np.int16)).cuda()
+    d_sig = torch.from_numpy(sm.sig_ids).cuda()
+    d_rowids = torch.from_numpy(world.word_ids).cuda()
+    ext = torch.cuda.ExternalStream(eng.stream)
+    with torch.cuda.stream(ext):
+        w0 = torch.zeros(nf * 300, dtype=torch.int32, device="cuda")
+        l0 = torch.zeros(nf * ns, dtype=torch.float32, device="cuda")
+        eng.process_frames_dev(d_img.data_ptr(), nf, 320, 240, 3, d_dep.data_ptr(), 1, op, d_sig.data_ptr(), ns, ns + 1, vp, w0.data_ptr(), l0.data_ptr(),
+                               True, 0.8, True)
+        hyp0, res0 = eng.process_fetch(nf)
+        eng.shard_comm_init(Engine.shard_unique_id(), 0, 1)
+        w1 = torch.zeros(nf * 300, dtype=torch.int32, device="cuda")
+        l1 = torch.zeros(nf * ns, dtype=torch.float32, device="cuda")
+        for _ in range(2):  # twice: the exchange buffers and events are reused
+            eng.shard_process_frames_dev(d_img.data_ptr(), nf, 320, 240, 3, d_dep.data_ptr(), 1, op, d_sig.data_ptr(), ns, ns + 1, d_rowids.data_ptr(),
+                                         int(world.word_ids.max()), vp, w1.data_ptr(), l1.data_ptr(), True, 0.8, True)
+        hyp1, res1 = eng.process_fetch(nf)
+        eng.shard_comm_destroy()
+    assert torch.equal(w0, w1)
+    assert torch.equal(l0, l1)
+    assert np.array_equal(hyp0, hyp1) and (hyp0 > 0).all()
+    for a, b in zip(res0, res1):
+        assert a["ok"] == b["ok"] and a["n_inliers"] == b["n_inliers"] and np.array_equal(a["rvec"], b["rvec"])
