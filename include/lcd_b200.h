@@ -397,6 +397,21 @@ int lcd_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d_image
                            const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp,
                            int * d_word_ids_out, float * d_likelihood_out, void * stream);
 
+/* ---- mapping mode: Memory::update + Memory::computeLikelihood for a STREAM of frames (Rtabmap.cpp:1470, :2117) --------------------------
+ * Frame t+1 depends on frame t (its new words, its references), so the frames of one map cannot be batched; what can overlap is the
+ * detection of the next frame.  lcd_map_detect_async uploads one image (+ depth) and runs ORB detect + describe + 3-D lifting on the
+ * engine's ORB stream and returns at once (two detections may be in flight; host buffers must stay valid until the matching
+ * lcd_map_frame).  lcd_map_frame takes the OLDEST detection and does, in the reference's order: VWDictionary::update (Memory::preUpdate,
+ * Memory.cpp:1004-1016), addNewWords of the frame's descriptors for sig_id incl. the references (the descriptors never leave the device),
+ * and — when wm_sig_ids is given — the TF-IDF likelihood against those signatures (n_total = Memory::getSignatures().size()).
+ * Outputs: *n_kp_out, kp_out / desc_out / xyz_out [n_kp] (any may be NULL), word_ids_out[Kp/MaxFeatures] (first n_kp valid), *n_new_out,
+ * likelihood_out[ns].  Identical, call for call, to lcd_orb_detect_describe + lcd_dict_update + lcd_dict_quantize + lcd_index_score. */
+int lcd_map_detect_async(lcd_engine * e, const uint8_t * image, int width, int height, int channels, const void * depth, int depth_type,
+                         const lcd_orb_params * params);
+int lcd_map_frame(lcd_engine * e, int sig_id, int incremental, float nndr, int new_words_compared_together, const int * wm_sig_ids, int ns,
+                  int n_total, int * n_kp_out, lcd_keypoint * kp_out, uint8_t * desc_out, float * xyz_out, int * word_ids_out, int * n_new_out,
+                  float * likelihood_out);
+
 /* The verification half alone, for likelihood rows that already exist on the device (the sharded
  * multi-GPU path all-reduces the scores first, then every rank verifies its share of the frames):
  * arg-max hypothesis of each of the n_frames rows of d_likelihood[n_frames][ns], then

@@ -154,6 +154,8 @@ SIGNATURES = {
     "lcd_process_frames_submit": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "lcd_process_frames_wait": (_I, [_P]),
     "lcd_process_frames_dev": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "lcd_map_detect_async": (_I, [_P, _P, _I, _I, _I, _P, _I, _P]),
+    "lcd_map_frame": (_I, [_P, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "lcd_verify_top_dev": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "lcd_shard_set_row_offset": (_I, [_P, _I]),
     "lcd_shard_knn2_keys_dev": (_I, [_P, _P, _I, _P, _P]),
@@ -696,6 +698,41 @@ class Engine:
                                                       C.byref(op), int(incremental), float(nndr), int(cmp_new), C.c_void_p(d_sig_ids), ns, int(n_total),
                                                       C.byref(vp) if vp is not None else None, C.c_void_p(d_words_out or None),
                                                       C.c_void_p(d_like_out or None), C.c_void_p(stream or None)))
+
+    def map_detect_async(self, image, depth, op: "OrbParams"):
+        """Queue the upload + ORB of ONE frame (image [h,w] or [h,w,3] uint8, depth [h,w] or None); buffers must stay alive until map_frame."""
+        img = np.ascontiguousarray(image, np.uint8)
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        dtype, dptr = 0, None
+        if depth is not None:
+            if depth.dtype == np.uint16:
+                dtype, depth = 1, np.ascontiguousarray(depth)
+            else:
+                dtype, depth = 2, np.ascontiguousarray(depth, np.float32)
+            dptr = _ptr(depth)
+        self._map_keep = getattr(self, "_map_keep", [])[-1:] + [(img, depth)]
+        self._map_cap = op.n_features
+        self._check(self._lib.lcd_map_detect_async(self._h, _ptr(img), w, h, ch, dptr, dtype, C.byref(op)))
+
+    def map_frame(self, sig_id: int, wm_sig_ids=None, n_total: int = 0, incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True,
+                  want_features: bool = False):
+        """Memory::update + computeLikelihood of the oldest detected frame: (n_kp, word ids [n_kp], n_new, likelihood or None[, kp, desc, xyz])."""
+        cap = self._map_cap
+        words = np.zeros(cap, np.int32)
+        n_kp = C.c_int(0)
+        n_new = C.c_int(0)
+        s = None if wm_sig_ids is None or len(wm_sig_ids) == 0 else _i32(wm_sig_ids)
+        like = None if s is None else np.zeros(len(s), np.float32)
+        kp = (Keypoint * cap)() if want_features else None
+        desc = np.zeros((cap, 32), np.uint8) if want_features else None
+        xyz = np.zeros((cap, 3), np.float32) if want_features else None
+        self._check(self._lib.lcd_map_frame(self._h, int(sig_id), int(incremental), float(nndr), int(cmp_new), _ptr(s), 0 if s is None else len(s),
+                                             int(n_total), C.byref(n_kp), kp, _ptr(desc), _ptr(xyz), _ptr(words), C.byref(n_new), _ptr(like)))
+        n = n_kp.value
+        if want_features:
+            return n, words[:n], n_new.value, like, kp, desc[:n], xyz[:n]
+        return n, words[:n], n_new.value, like
 
     def verify_top_dev(self, d_queries: int, d_uv: int, n_frames: int, nq: int, d_like: int, d_sig_ids: int, ns: int, vp: "VerifyParams", stream: int = 0):
         self._check(self._lib.lcd_verify_top_dev(self._h, C.c_void_p(d_queries), C.c_void_p(d_uv), n_frames, nq, C.c_void_p(d_like),

@@ -350,6 +350,22 @@ struct lcd_engine
 	long long tf_img_builds = 0; // rows expanded so far (diagnostics: the image is built once per dictionary change)
 	int nn_tensor = 1;   // 256-bit descriptors: tcgen05 int8 path (nn_tensor.cuh); 0 = POPC kernel (nn_hamming.cuh)
 	int nn_last_tensor = 0; // which kernel the last run_knn used (bench / diagnostics)
+	// mapping mode (lcd_map_*): detection of frame t+1 on the ORB stream while frame t is quantised and scored
+	struct MapSlot
+	{
+		DevBuf<uint8_t> img, desc;
+		DevBuf<unsigned char> depth;
+		DevBuf<OrbKeypoint> kp;
+		DevBuf<float> xyz;
+		DevBuf<int> n;
+		PinBuf<int> h_n, h_overflow;
+		cudaEvent_t done = nullptr;
+		int cap = 0;
+		bool busy = false;
+	};
+	MapSlot map_slots[2];
+	int map_head = 0, map_busy = 0;
+	PinBuf<int> map_h_words, map_h_scalars;
 	// word-range sharding across GPUs (lcd_shard_*): NCCL communicator + exchange buffers of the fused sharded step
 	ncclComm_t comm = nullptr;
 	bool comm_owned = false;
@@ -1119,6 +1135,8 @@ void lcd_destroy(lcd_engine * e)
 	if (e->stream)
 	{
 		cudaStreamSynchronize(e->stream);
+		for (auto & ms : e->map_slots)
+			if (ms.done) cudaEventDestroy(ms.done);
 		if (e->comm && e->comm_owned && nccl_api().ok) nccl_api().CommDestroy(e->comm);
 		if (e->comm_stream) cudaStreamDestroy(e->comm_stream);
 		for (auto & half : e->sh_ev)
@@ -1445,34 +1463,33 @@ int lcd_dict_knn2(lcd_engine * e, const void * queries, int nq, int * id1, float
 	return LCD_OK;
 }
 
-int lcd_dict_quantize(lcd_engine * e, const void * queries, int nq, int sig_id, int incremental, float nndr,
-                      int new_words_compared_together, int * word_ids_out, int * n_new_out)
+} // extern "C"
+
+// VWDictionary::addNewWords on descriptors that are already on the device: d_q holds `rows` descriptor rows of which the first
+// n_valid (host value, or the device counter d_n_valid when n_valid < 0) are real.  Word ids of all rows -> word_ids_out (host),
+// *n_new_out = words created, *n_valid_out = the device counter's value.
+static int quantize_dev(lcd_engine * e, const uint32_t * d_q, int rows, int n_valid, const int * d_n_valid, int sig_id, int incremental, float nndr,
+                        int cmp_new, int * word_ids_out, int * n_new_out, int * n_valid_out, cudaStream_t s)
 {
-	if (!e) return LCD_ERR_INVALID;
-	LCD_TRY(set_device(e));
-	LCD_TRY(check_queries(e, queries, nq));
-	if (!word_ids_out) LCD_FAIL(e, LCD_ERR_INVALID, "null output");
 	if (!incremental && e->id2row.empty()) LCD_FAIL(e, LCD_ERR_STATE, "Dictionary mode is set to fixed but no words are in it!");
 	LCD_TRY(require_unsharded(e, "lcd_dict_quantize"));
-	cudaStream_t s = e->stream;
 	const int rows0 = total_rows(e);
-	LCD_TRY(ensure_rows(e, rows0 + nq));
-	LCD_CUDA(e, e->d_queries.reserve(static_cast<size_t>(nq) * e->nw, 0, false, s));
-	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, static_cast<size_t>(nq) * e->nw * 4, cudaMemcpyHostToDevice, s));
+	LCD_TRY(ensure_rows(e, rows0 + rows));
 	int n_chunks = 0;
-	LCD_TRY(run_knn(e, e->d_queries.p, nq, e->n_indexed, &n_chunks, s));
-	LCD_CUDA(e, e->d_word_ids.reserve(nq, 0, false, s));
+	LCD_TRY(run_knn(e, d_q, rows, e->n_indexed, &n_chunks, s));
+	LCD_CUDA(e, e->d_word_ids.reserve(rows, 0, false, s));
 	LCD_CUDA(e, e->d_n_new.reserve(1, 0, false, s));
 	ResolveArgs a{};
-	a.queries = e->d_queries.p;
-	a.nq = nq;
-	a.nq_total = nq;
+	a.queries = d_q;
+	a.nq = rows;
+	a.nq_total = rows;
+	a.nq_frame = n_valid < 0 ? d_n_valid : nullptr;
 	a.partial = e->d_partial.p;
 	a.n_chunks = n_chunks;
 	a.row_ids = e->row_ids.p;
 	a.incremental = incremental;
 	a.nndr = nndr;
-	a.cmp_new = new_words_compared_together;
+	a.cmp_new = cmp_new;
 	a.last_word_id = e->last_word_id;
 	a.word_ids_out = e->d_word_ids.p;
 	a.n_new_out = e->d_n_new.p;
@@ -1480,9 +1497,10 @@ int lcd_dict_quantize(lcd_engine * e, const void * queries, int nq, int sig_id, 
 	a.pending_ids = e->row_ids.p + rows0;
 	a.do_prep = 0;
 	LCD_TRY(launch_resolve(e, a, 1, s));
-	int n_new = 0;
-	LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, nq * sizeof(int), cudaMemcpyDeviceToHost, s));
+	int n_new = 0, nv = n_valid;
+	LCD_CUDA(e, cudaMemcpyAsync(word_ids_out, e->d_word_ids.p, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaMemcpyAsync(&n_new, e->d_n_new.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (n_valid < 0) LCD_CUDA(e, cudaMemcpyAsync(&nv, d_n_valid, sizeof(int), cudaMemcpyDeviceToHost, s));
 	LCD_CUDA(e, cudaStreamSynchronize(s));
 	if (n_new > 0)
 	{
@@ -1497,8 +1515,24 @@ int lcd_dict_quantize(lcd_engine * e, const void * queries, int nq, int sig_id, 
 		e->last_word_id += n_new;
 	}
 	if (n_new_out) *n_new_out = n_new;
-	if (sig_id > 0) LCD_TRY(add_refs_impl(e, sig_id, word_ids_out, nq));
+	if (n_valid_out) *n_valid_out = nv;
+	if (sig_id > 0) LCD_TRY(add_refs_impl(e, sig_id, word_ids_out, std::min(std::max(nv, 0), rows)));
 	return LCD_OK;
+}
+
+extern "C" {
+
+int lcd_dict_quantize(lcd_engine * e, const void * queries, int nq, int sig_id, int incremental, float nndr,
+                      int new_words_compared_together, int * word_ids_out, int * n_new_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	LCD_TRY(check_queries(e, queries, nq));
+	if (!word_ids_out) LCD_FAIL(e, LCD_ERR_INVALID, "null output");
+	cudaStream_t s = e->stream;
+	LCD_CUDA(e, e->d_queries.reserve(static_cast<size_t>(nq) * e->nw, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(e->d_queries.p, queries, static_cast<size_t>(nq) * e->nw * 4, cudaMemcpyHostToDevice, s));
+	return quantize_dev(e, e->d_queries.p, nq, nq, nullptr, sig_id, incremental, nndr, new_words_compared_together, word_ids_out, n_new_out, nullptr, s);
 }
 
 int lcd_dict_find_nn(lcd_engine * e, const void * queries, int nq, int incremental, float nndr, int * word_ids_out)
@@ -3274,6 +3308,82 @@ int lcd_shard_score_ids_dev(lcd_engine * e, const int * d_word_ids_all, int n_fr
 	dim3 grid((ns + 255) / 256, n_frames);
 	gather_fixed_kernel<<<grid, 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), d_sig_ids, ns, d_scores_out);
 	LCD_CHECK_LAUNCH(e);
+	return LCD_OK;
+}
+
+// ---- mapping mode: Memory::update for a stream of frames ------------------------------------------------------------------
+int lcd_map_detect_async(lcd_engine * e, const uint8_t * image, int width, int height, int channels, const void * depth, int depth_type,
+                         const lcd_orb_params * params)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (!image || width <= 0 || height <= 0 || !params) LCD_FAIL(e, LCD_ERR_INVALID, "null image");
+	if (e->cfg.desc_type != LCD_DESC_U8 || e->cfg.desc_dim != 32) LCD_FAIL(e, LCD_ERR_INVALID, "ORB descriptors need an engine with 32-byte binary descriptors");
+	if (e->map_busy >= 2) LCD_FAIL(e, LCD_ERR_STATE, "two detections are already in flight: call lcd_map_frame first");
+	const int cap = params->n_features;
+	if (cap <= 0 || cap > kMaxFrameQueries) LCD_FAIL(e, LCD_ERR_CAPACITY, "Kp/MaxFeatures must be 1..%d", kMaxFrameQueries);
+	lcd_engine::MapSlot & ms = e->map_slots[(e->map_head + e->map_busy) & 1];
+	cudaStream_t s = e->orb_stream;
+	if (!ms.done) LCD_CUDA(e, cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+	const size_t px = static_cast<size_t>(width) * height;
+	if (!depth) depth_type = LCD_DEPTH_NONE;
+	LCD_CUDA(e, ms.img.reserve(px * channels, 0, false, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ms.img.p, image, px * channels, cudaMemcpyHostToDevice, s));
+	if (depth_type != LCD_DEPTH_NONE)
+	{
+		LCD_CUDA(e, ms.depth.reserve(px * depth_elem_bytes(depth_type), 0, false, s));
+		LCD_CUDA(e, cudaMemcpyAsync(ms.depth.p, depth, px * depth_elem_bytes(depth_type), cudaMemcpyHostToDevice, s));
+	}
+	LCD_CUDA(e, ms.kp.reserve(cap, 0, false, s));
+	LCD_CUDA(e, ms.desc.reserve(static_cast<size_t>(cap) * 32, 0, false, s));
+	LCD_CUDA(e, ms.xyz.reserve(static_cast<size_t>(cap) * 3, 0, false, s));
+	LCD_CUDA(e, ms.n.reserve(1, 0, false, s));
+	LCD_CUDA(e, ms.h_n.reserve(1));
+	LCD_CUDA(e, ms.h_overflow.reserve(1));
+	LCD_CUDA(e, zero_fill_async(ms.desc.p, static_cast<size_t>(cap) * 32, s)); // padding rows feed the NN kernel: defined bytes
+	LCD_TRY(orb_run(e, 1, ms.img.p, width, height, channels, depth_type != LCD_DEPTH_NONE ? ms.depth.p : nullptr, depth_type, params, cap, ms.kp.p, ms.desc.p,
+	                ms.xyz.p, nullptr, ms.n.p, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ms.h_n.p, ms.n.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaMemcpyAsync(ms.h_overflow.p, e->o_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+	LCD_CUDA(e, cudaEventRecord(ms.done, s));
+	ms.cap = cap;
+	ms.busy = true;
+	++e->map_busy;
+	return LCD_OK;
+}
+
+int lcd_map_frame(lcd_engine * e, int sig_id, int incremental, float nndr, int new_words_compared_together, const int * wm_sig_ids, int ns,
+                  int n_total, int * n_kp_out, lcd_keypoint * kp_out, uint8_t * desc_out, float * xyz_out, int * word_ids_out, int * n_new_out,
+                  float * likelihood_out)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (e->map_busy <= 0) LCD_FAIL(e, LCD_ERR_STATE, "no detection in flight: call lcd_map_detect_async first");
+	if (!word_ids_out) LCD_FAIL(e, LCD_ERR_INVALID, "null output");
+	lcd_engine::MapSlot & ms = e->map_slots[e->map_head];
+	cudaStream_t s = e->stream;
+	// Memory::preUpdate: the words of the previous frame join the index (VWDictionary::update)
+	LCD_TRY(lcd_dict_update(e));
+	LCD_CUDA(e, cudaStreamWaitEvent(s, ms.done, 0));
+	const int cap = ms.cap;
+	int n_new = 0, n_kp = 0;
+	// Memory::createSignature: quantise the frame's descriptors (they never leave the device), references for sig_id
+	int rc = quantize_dev(e, reinterpret_cast<const uint32_t *>(ms.desc.p), cap, -1, ms.n.p, sig_id, incremental, nndr, new_words_compared_together,
+	                      word_ids_out, &n_new, &n_kp, s);
+	e->map_head ^= 1;
+	--e->map_busy;
+	ms.busy = false;
+	if (rc != LCD_OK) return rc;
+	if (*ms.h_overflow.p)
+		LCD_FAIL(e, LCD_ERR_CAPACITY, "more than %d FAST corners in pyramid level 0 (half as many per further level): raise FAST/Threshold", kOrbCandCap);
+	if (n_kp_out) *n_kp_out = n_kp;
+	if (n_new_out) *n_new_out = n_new;
+	if (kp_out) LCD_CUDA(e, cudaMemcpyAsync(kp_out, ms.kp.p, static_cast<size_t>(n_kp) * sizeof(OrbKeypoint), cudaMemcpyDeviceToHost, s));
+	if (desc_out) LCD_CUDA(e, cudaMemcpyAsync(desc_out, ms.desc.p, static_cast<size_t>(n_kp) * 32, cudaMemcpyDeviceToHost, s));
+	if (xyz_out) LCD_CUDA(e, cudaMemcpyAsync(xyz_out, ms.xyz.p, static_cast<size_t>(n_kp) * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+	// Memory::computeLikelihood against the working memory
+	if (likelihood_out && wm_sig_ids && ns > 0 && n_kp > 0) return lcd_index_score(e, word_ids_out, n_kp, wm_sig_ids, ns, n_total, likelihood_out);
+	LCD_CUDA(e, cudaStreamSynchronize(s));
 	return LCD_OK;
 }
 
