@@ -269,6 +269,9 @@ typedef struct lcd_verify_params {
 	float max_variance;    /* Vis/PnPMaxVariance (0 = off): reject when the linear variance exceeds it */
 	int split_linear_cov;  /* Vis/PnPSplitLinearCovComponents (0)                           */
 	int image_width, image_height; /* CameraModel::imageSize() of the TO camera (0, 0 = not set) */
+	int repeat_once;       /* Reg/RepeatOnce (1 in the reference): after a successful first pass, register again with its transform as
+	                          the guess (projection + window matching); needs the image size */
+	int guess_win_size;    /* Vis/CorGuessWinSize (40 pixels; 0 = no second pass) */
 } lcd_verify_params;
 
 typedef struct lcd_verify_result {

@@ -295,6 +295,11 @@ def _vlib():
         L.orcv_verify_pair_cov.argtypes = [_I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _F, _I, _I, _F, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P,
                                            _P, _P]
         L.orcv_verify_pair_cov.restype = _I
+        L.orcv_verify_pair_repeat.argtypes = [_I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _F, _I, _I, _F, _I, _I, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P,
+                                              _P, _P, _P, _P]
+        L.orcv_verify_pair_repeat.restype = _I
+        L.orcv_guess_match.argtypes = [_I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _I, _F, _F, _P]
+        L.orcv_guess_match.restype = _I
         L._verify_ready = True
     return L
 
@@ -409,3 +414,33 @@ def verify_pair_cov(desc_from, xyz_from, desc_to, uv_to, K4, xyz_to=None, nndr=0
                                 _p(cov))
     return {"ok": bool(ok), "matches": mids[:nm.value].copy(), "inliers": iids[:ni.value].copy(), "rvec": r, "tvec": tv,
             "transform": T.reshape(3, 4), "covariance": cov.reshape(6, 6)}
+
+
+def verify_pair_repeat(desc_from, xyz_from, desc_to, uv_to, K4, xyz_to=None, nndr=0.8, min_inliers=20, iterations=300, reproj=2.0, refine_iterations=1,
+                       image_size=(640, 480), var_median_ratio=4, max_variance=0.0, split_linear_cov=False, repeat_once=True, guess_win_size=40):
+    """Memory::computeTransform as Registration::computeTransformationMod runs it by default: global matching pass, then (Reg/RepeatOnce) the
+    pass with the first result as the guess.  Returns the dict of verify_pair_cov plus "second_pass" (bool)."""
+    L = _vlib()
+    t = 0 if desc_from.dtype == np.uint8 else 1
+    a = np.ascontiguousarray(desc_from)
+    b = np.ascontiguousarray(desc_to)
+    xa = np.ascontiguousarray(xyz_from, np.float32)
+    ub = np.ascontiguousarray(uv_to, np.float32)
+    xb = None if xyz_to is None else np.ascontiguousarray(xyz_to, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float64)
+    cap = max(len(a), len(b), 1)
+    mids = np.zeros(cap, np.int32)
+    iids = np.zeros(cap, np.int32)
+    nm = C.c_int(0)
+    ni = C.c_int(0)
+    sp = C.c_int(0)
+    r = np.zeros(3)
+    tv = np.zeros(3)
+    T = np.zeros(12, np.float32)
+    cov = np.zeros(36)
+    ok = L.orcv_verify_pair_repeat(t, a.shape[1], _p(a), _p(xa), len(a), _p(b), _p(ub), _p(xb), len(b), _p(K4), nndr, int(min_inliers), int(iterations),
+                                   reproj, int(refine_iterations), int(image_size[0]), int(image_size[1]), int(var_median_ratio), max_variance,
+                                   int(bool(split_linear_cov)), int(bool(repeat_once)), float(guess_win_size), _p(mids), C.byref(nm), _p(iids),
+                                   C.byref(ni), _p(r), _p(tv), _p(T), _p(cov), C.byref(sp))
+    return {"ok": bool(ok), "matches": mids[:nm.value].copy(), "inliers": iids[:ni.value].copy(), "rvec": r, "tvec": tv, "transform": T.reshape(3, 4),
+            "covariance": cov.reshape(6, 6), "second_pass": bool(sp.value)}

@@ -946,6 +946,16 @@ int orcv_covariance(const float * obj, const float * img, const float * obj_to, 
 	return 1;
 }
 
+static double g_cov_lin_eps = 0.00000001, g_cov_ang_eps = 0.00000003; // Registration::COVARIANCE_LINEAR / ANGULAR_EPSILON (Registration.cpp:36-37)
+static void covariance_floor(double cov[36])
+{
+	// Registration::computeTransformationMod (Registration.cpp:239-250)
+	for (int i = 0; i < 3; ++i)
+		if (cov[7 * i] <= g_cov_lin_eps) cov[7 * i] = g_cov_lin_eps;
+	for (int i = 3; i < 6; ++i)
+		if (cov[7 * i] <= g_cov_ang_eps) cov[7 * i] = g_cov_ang_eps;
+}
+
 // orcv_verify_pair + the covariance: xyz_to[n_to*3] may be NULL.  cov[36].
 int orcv_verify_pair_cov(int desc_type, int dim, const void * desc_from, const float * xyz_from, int n_from, const void * desc_to,
                          const float * uv_to, const float * xyz_to, int n_to, const double K[4], float nndr, int min_inliers, int iterations,
@@ -980,6 +990,167 @@ int orcv_verify_pair_cov(int desc_type, int dim, const void * desc_from, const f
 	                     var_median_ratio, max_variance, split_linear, cov);
 	if (!ok)
 		for (int i = 0; i < 12; ++i) transform[i] = 0; // transform.setNull()
+	covariance_floor(cov);
+	return ok;
+}
+
+// ---- second registration pass (Reg/RepeatOnce, Registration.cpp:221-229) ------------------------------------------------------
+// RegistrationVis::computeTransformationImpl WITH a guess, default branch Vis/CorGuessMatchToProjection = false
+// (RegistrationVis.cpp:1017-1070 projection, :1225-1370 matching): the 3-D points of FROM are projected into TO's image with the guess
+// (cv::projectPoints, no distortion), the TO keypoints within Vis/CorGuessWinSize pixels of each projection are its candidates, the
+// candidate set is ranked by cv::BFMatcher::knnMatch(k = 2) + the strict Vis/CorNNDR test (a single candidate is taken as it is), every TO
+// keypoint goes to the first FROM point (ascending index) that selects it; ids = FROM indices.
+// The reference finds the candidates with a randomised kd-tree limited to 32 checks (rtflann::KDTreeIndexParams(), SearchParams(32, 0,
+// false)): approximate and unordered, i.e. not a deterministic function of the inputs.  This restatement — and the
+// CUDA kernel it checks — use the EXACT radius search (squared distance < r^2 as RadiusResultSet::addPoint, rtflann/util/result_set.h:475-479)
+// with candidates in ascending TO index: a superset of what the kd-tree can return, same rule otherwise.  Parity for this pass is
+// therefore oracle-vs-CUDA only ("unpinned").
+// sel_to[n_from]: TO index matched to FROM i (-1 none).  Returns the number of projected FROM points.
+int orcv_guess_match(int desc_type, int dim, const void * desc_from, const float * xyz_from, int n_from, const void * desc_to, const float * uv_to,
+                     int n_to, const double K[4], const double rvec[3], const double tvec[3], int img_w, int img_h, float win, float nndr, int * sel_to)
+{
+	Cam cam{K[0], K[1], K[2], K[3]};
+	std::vector<double> uvp(2 * (size_t)std::max(n_from, 1));
+	// projectPoints on the float points; NaN points give NaN pixels and fail the bounds test
+	project(xyz_from, n_from, rvec, tvec, cam, uvp.data(), nullptr);
+	double R[9];
+	rodrigues_v2m(rvec, R, nullptr);
+	const size_t rb = desc_type == 0 ? (size_t)dim : (size_t)dim * 4;
+	std::vector<int> claim(std::max(n_to, 1), -1);
+	int n_proj = 0;
+	for (int i = 0; i < n_from; ++i) sel_to[i] = -1;
+	for (int i = 0; i < n_from; ++i)
+	{
+		const float px = (float)uvp[2 * i], py = (float)uvp[2 * i + 1];
+		const float * X = xyz_from + 3 * i;
+		// util3d::transformPoint(kptsFrom3D[i], guessCameraRef).z with the float Transform of the guess
+		const float zc = (float)R[6] * X[0] + (float)R[7] * X[1] + (float)R[8] * X[2] + (float)tvec[2];
+		const bool inb = std::isfinite(px) && !(px < 0.0f) && !(px >= float(img_w - 1)) && std::isfinite(py) && !(py < 0.0f) && !(py >= float(img_h - 1));
+		if (!(inb && zc > 0.0f)) continue;
+		++n_proj;
+		if (!(std::isfinite(X[0]) && std::isfinite(X[1]) && std::isfinite(X[2]))) continue;
+		// candidates: exact radius search, ascending TO index; k = 2 brute force among them
+		const float r2 = win * win;
+		int cnt = 0, b1 = -1;
+		float d1 = INFINITY, d2 = INFINITY;
+		const uint8_t * qd = (const uint8_t *)desc_from + rb * i;
+		for (int j = 0; j < n_to; ++j)
+		{
+			float dist = 0.0f;
+			const float dx = px - uv_to[2 * j], dy = py - uv_to[2 * j + 1];
+			dist += dx * dx;
+			dist += dy * dy;
+			if (!(dist < r2)) continue;
+			++cnt;
+			float d;
+			const uint8_t * td = (const uint8_t *)desc_to + rb * j;
+			if (desc_type == 0)
+			{
+				int h = 0;
+				for (int k = 0; k < dim; ++k) h += __builtin_popcount((unsigned)(qd[k] ^ td[k]));
+				d = (float)h;
+			}
+			else
+			{
+				const float * a = (const float *)qd;
+				const float * b = (const float *)td;
+				float acc = 0.0f;
+				for (int k = 0; k < dim; k += 4)
+				{
+					const float e0 = a[k] - b[k], e1 = a[k + 1] - b[k + 1], e2 = a[k + 2] - b[k + 2], e3 = a[k + 3] - b[k + 3];
+					acc += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+				}
+				d = acc;
+			}
+			if (d < d1)
+			{
+				d2 = d1;
+				d1 = d;
+				b1 = j;
+			}
+			else if (d < d2) d2 = d;
+		}
+		int m = -1;
+		if (cnt >= 2)
+		{
+			if (d1 < nndr * d2) m = b1;
+		}
+		else if (cnt == 1) m = b1;
+		if (m >= 0 && claim[m] < 0)
+		{
+			claim[m] = i;
+			sel_to[i] = m;
+		}
+	}
+	return n_proj;
+}
+
+
+// Memory::computeTransform as Registration::computeTransformationMod runs it by default: pass 1 without a guess (global matching), then
+// — Reg/RepeatOnce, only when pass 1 succeeded — pass 2 with pass 1's transform as the guess; its outputs replace pass 1's.
+int orcv_verify_pair_repeat(int desc_type, int dim, const void * desc_from, const float * xyz_from, int n_from, const void * desc_to,
+                            const float * uv_to, const float * xyz_to, int n_to, const double K[4], float nndr, int min_inliers, int iterations,
+                            float reproj, int refine_iterations, int img_w, int img_h, int var_median_ratio, float max_variance, int split_linear,
+                            int repeat_once, float guess_win, int * match_ids, int * n_matches, int * inlier_ids, int * n_inliers, double rvec[3],
+                            double tvec[3], float transform[12], double cov[36], int * second_pass_ran)
+{
+	*second_pass_ran = 0;
+	int ok = orcv_verify_pair_cov(desc_type, dim, desc_from, xyz_from, n_from, desc_to, uv_to, xyz_to, n_to, K, nndr, min_inliers, iterations, reproj,
+	                              refine_iterations, img_w, img_h, var_median_ratio, max_variance, split_linear, match_ids, n_matches, inlier_ids,
+	                              n_inliers, rvec, tvec, transform, cov);
+	if (ok && repeat_once && guess_win > 0 && img_w > 0 && img_h > 0)
+	{
+		*second_pass_ran = 1;
+		std::vector<int> sel(std::max(n_from, 1));
+		orcv_guess_match(desc_type, dim, desc_from, xyz_from, n_from, desc_to, uv_to, n_to, K, rvec, tvec, img_w, img_h, guess_win, nndr, sel.data());
+		std::vector<float> obj, img, objt;
+		std::vector<int> ids;
+		for (int i = 0; i < n_from; ++i)
+		{
+			if (sel[i] < 0) continue;
+			const float * p = xyz_from + 3 * i;
+			obj.insert(obj.end(), p, p + 3);
+			img.push_back(uv_to[2 * sel[i]]);
+			img.push_back(uv_to[2 * sel[i] + 1]);
+			if (xyz_to) objt.insert(objt.end(), xyz_to + 3 * sel[i], xyz_to + 3 * sel[i] + 3);
+			ids.push_back(i);
+		}
+		const int nm = (int)ids.size();
+		*n_matches = nm;
+		for (int m = 0; m < nm; ++m) match_ids[m] = ids[m];
+		*n_inliers = 0;
+		for (int i = 0; i < 12; ++i) transform[i] = 0;
+		for (int i = 0; i < 36; ++i) cov[i] = (i % 7 == 0) ? 1.0 : 0.0;
+		ok = 0;
+		if (nm >= min_inliers)
+		{
+			Cam cam{K[0], K[1], K[2], K[3]};
+			const double guess[6] = {rvec[0], rvec[1], rvec[2], tvec[0], tvec[1], tvec[2]};
+			PnpResult r = pnp_ransac(obj.data(), img.data(), nm, cam, iterations, reproj, min_inliers, refine_iterations, 3.0f, guess);
+			memcpy(rvec, r.rvec, sizeof(r.rvec));
+			memcpy(tvec, r.tvec, sizeof(r.tvec));
+			*n_inliers = (int)r.inliers.size();
+			for (size_t i = 0; i < r.inliers.size(); ++i) inlier_ids[i] = ids[r.inliers[i]];
+			if ((int)r.inliers.size() >= min_inliers)
+			{
+				double R[9];
+				rodrigues_v2m(r.rvec, R, nullptr);
+				float Rf[9], tf[3];
+				for (int i = 0; i < 9; ++i) Rf[i] = (float)R[i];
+				for (int i = 0; i < 3; ++i) tf[i] = (float)r.tvec[i];
+				for (int i = 0; i < 3; ++i)
+				{
+					for (int j = 0; j < 3; ++j) transform[4 * i + j] = Rf[3 * j + i];
+					transform[4 * i + 3] = -(Rf[0 + i] * tf[0] + Rf[3 + i] * tf[1] + Rf[6 + i] * tf[2]);
+				}
+				ok = orcv_covariance(obj.data(), img.data(), xyz_to ? objt.data() : nullptr, nm, r.inliers.data(), (int)r.inliers.size(), transform, rvec, tvec,
+				                     K, img_w, img_h, var_median_ratio, max_variance, split_linear, cov);
+				if (!ok)
+					for (int i = 0; i < 12; ++i) transform[i] = 0;
+			}
+		}
+	}
+	covariance_floor(cov);
 	return ok;
 }
 

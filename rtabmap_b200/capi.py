@@ -70,6 +70,8 @@ class VerifyParams(C.Structure):
         ("split_linear_cov", C.c_int),
         ("image_width", C.c_int),
         ("image_height", C.c_int),
+        ("repeat_once", C.c_int),
+        ("guess_win_size", C.c_int),
     ]
 
 
@@ -518,14 +520,15 @@ class Engine:
 
     def verify_batch(self, desc_from, xyz_from, desc_to, uv_to, K4, n_from=None, n_to=None, nndr: float = 0.8, min_inliers: int = 20,
                      iterations: int = 300, reproj_error: float = 2.0, refine_iterations: int = 1, refine_sigma: float = 3.0, xyz_to=None,
-                     var_median_ratio: int = 4, max_variance: float = 0.0, split_linear_cov: bool = False, image_size=(0, 0)):
+                     var_median_ratio: int = 4, max_variance: float = 0.0, split_linear_cov: bool = False, image_size=(0, 0),
+                     repeat_once: bool = False, guess_win_size: int = 40):
         """Memory::computeTransform for a batch of (FROM, TO) pairs; returns a list of dicts."""
         a, b, nf, nt, n_pairs, cap = self._pairs(desc_from, desc_to, n_from, n_to)
         xyz = np.ascontiguousarray(xyz_from, np.float32).reshape(n_pairs, cap, 3)
         uv = np.ascontiguousarray(uv_to, np.float32).reshape(n_pairs, cap, 2)
         xt = None if xyz_to is None else np.ascontiguousarray(xyz_to, np.float32).reshape(n_pairs, cap, 3)
         prm = self.verify_params(K4, nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, var_median_ratio, max_variance,
-                                 split_linear_cov, image_size)
+                                 split_linear_cov, image_size, repeat_once, guess_win_size)
         res = (VerifyResult * n_pairs)()
         mids = np.zeros((n_pairs, cap), np.int32)
         iids = np.zeros((n_pairs, cap), np.int32)
@@ -614,9 +617,10 @@ class Engine:
 
     @staticmethod
     def verify_params(K4, nndr=0.8, min_inliers=20, iterations=300, reproj_error=2.0, refine_iterations=1, refine_sigma=3.0, var_median_ratio=4,
-                      max_variance=0.0, split_linear_cov=False, image_size=(0, 0)):
+                      max_variance=0.0, split_linear_cov=False, image_size=(0, 0), repeat_once=False, guess_win_size=40):
         return VerifyParams(nndr, min_inliers, iterations, reproj_error, refine_iterations, refine_sigma, *[float(k) for k in K4],
-                            int(var_median_ratio), float(max_variance), int(bool(split_linear_cov)), int(image_size[0]), int(image_size[1]))
+                            int(var_median_ratio), float(max_variance), int(bool(split_linear_cov)), int(image_size[0]), int(image_size[1]),
+                            int(bool(repeat_once)), int(guess_win_size))
 
     @staticmethod
     def _results(res, n):
@@ -718,7 +722,7 @@ class Engine:
     def map_frame(self, sig_id: int, wm_sig_ids=None, n_total: int = 0, incremental: bool = True, nndr: float = 0.8, cmp_new: bool = True,
                   want_features: bool = False):
         """Memory::update + computeLikelihood of the oldest detected frame: (n_kp, word ids [n_kp], n_new, likelihood or None[, kp, desc, xyz])."""
-        cap = self._map_cap
+        cap = getattr(self, "_map_cap", 1)
         words = np.zeros(cap, np.int32)
         n_kp = C.c_int(0)
         n_new = C.c_int(0)

@@ -2492,6 +2492,81 @@ static int launch_pnp(lcd_engine * e, int n_pairs, int cap, const lcd_verify_par
 	return LCD_OK;
 }
 
+// Reg/RepeatOnce: the second registration pass of the pairs whose first pass succeeded (guess_match_kernel), then PnP again on all pairs
+// (pairs that keep their first-pass correspondences reproduce their first-pass result).  src as in launch_match.
+static int launch_second_pass(lcd_engine * e, int n_pairs, int cap, const lcd_verify_params * p, cudaStream_t s, const MatchSrc * src)
+{
+	if (!p->repeat_once || p->guess_win_size <= 0 || p->image_width <= 0 || p->image_height <= 0) return LCD_OK;
+	GuessMatchArgs a{};
+	if (src)
+	{
+		a.desc_from = src->desc_from;
+		a.xyz_from = src->xyz_from;
+		a.n_from = src->n_from;
+		a.from_slot = src->from_slot;
+		a.cap_from = src->cap_from;
+		a.desc_to = src->desc_to;
+		a.uv_to = src->uv_to;
+		a.xyz_to = src->xyz_to;
+		a.n_to = src->n_to;
+		a.n_to_all = src->n_to_all;
+		a.cap_to = src->cap_to;
+	}
+	else
+	{
+		a.desc_from = e->v_df.p;
+		a.xyz_from = e->v_xyz.p;
+		a.n_from = e->v_nf.p;
+		a.from_slot = nullptr;
+		a.cap_from = cap;
+		a.desc_to = e->v_dt.p;
+		a.uv_to = e->v_uv.p;
+		a.xyz_to = e->match_has_xyz_to ? e->v_xyz_to.p : nullptr;
+		a.n_to = e->v_nt.p;
+		a.n_to_all = 0;
+		a.cap_to = cap;
+	}
+	a.cap = cap;
+	a.ok1 = e->v_ok.p;
+	a.rvec = e->v_rvec.p;
+	a.tvec = e->v_tvec.p;
+	a.cam = CamK{p->fx, p->fy, p->cx, p->cy};
+	a.img_w = p->image_width;
+	a.img_h = p->image_height;
+	a.win = static_cast<float>(p->guess_win_size);
+	a.nndr = p->nndr;
+	a.obj = e->v_obj.p;
+	a.img = e->v_img.p;
+	a.obj_to = e->pnp_has_obj_to ? e->v_obj_to.p : nullptr;
+	a.match_id = e->v_mid.p;
+	a.match_from = e->v_mfrom.p;
+	a.match_to = e->v_mto.p;
+	a.n_match = e->v_nm.p;
+	const size_t smem = guess_smem_bytes(cap);
+	if (smem > static_cast<size_t>(e->smem_optin)) LCD_FAIL(e, LCD_ERR_CAPACITY, "cap %d needs %zu B of shared memory", cap, smem);
+#define LCD_GUESS_CASE(NW_)                                                                                              \
+	case NW_:                                                                                                            \
+	{                                                                                                                    \
+		auto kern = guess_match_kernel<NW_>;                                                                             \
+		if (smem > 48 * 1024)                                                                                            \
+			LCD_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+		prof_mark(e, LCD_PROF_MATCH, s);                                                                                 \
+		kern<<<n_pairs, 256, smem, s>>>(a);                                                                              \
+		prof_mark(e, LCD_PROF_MATCH, s);                                                                                 \
+		break;                                                                                                           \
+	}
+	switch (e->nw)
+	{
+		LCD_GUESS_CASE(4)
+		LCD_GUESS_CASE(8)
+		LCD_GUESS_CASE(16)
+	default: LCD_FAIL(e, LCD_ERR_INVALID, "unsupported descriptor size");
+	}
+#undef LCD_GUESS_CASE
+	LCD_CHECK_LAUNCH(e);
+	return launch_pnp(e, n_pairs, cap, p, s);
+}
+
 // copy the per-pair verification outputs back (cap = 0: skip the id arrays)
 static int verify_download(lcd_engine * e, int n_pairs, int cap, lcd_verify_result * results, int * match_ids, int * inlier_ids, cudaStream_t s)
 {
@@ -2556,6 +2631,7 @@ int lcd_verify_batch(lcd_engine * e, int n_pairs, int cap, const void * desc_fro
 	e->match_has_xyz_to = xyz_to != nullptr;
 	LCD_TRY(launch_match(e, n_pairs, cap, params->nndr, false, s));
 	LCD_TRY(launch_pnp(e, n_pairs, cap, params, s));
+	LCD_TRY(launch_second_pass(e, n_pairs, cap, params, s, nullptr));
 	return verify_download(e, n_pairs, cap, results, match_ids, inlier_ids, s);
 }
 
@@ -2870,7 +2946,7 @@ static int verify_top_dev(lcd_engine * e, const uint32_t * d_q, const float * d_
 	MatchSrc src{e->st_desc.p, e->st_xyz.p, e->st_n.p, e->d_hyp_slot.p, e->st_cap, d_q, d_uv, d_nq_frame, nq, nq, d_xyz_to};
 	LCD_TRY(launch_match(e, n_frames, cap, vp->nndr, false, s, &src));
 	LCD_TRY(launch_pnp(e, n_frames, cap, vp, s));
-	return LCD_OK;
+	return launch_second_pass(e, n_frames, cap, vp, s, &src);
 }
 
 int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * d_uv, int n_frames, int nq_per_frame, int incremental, float nndr,

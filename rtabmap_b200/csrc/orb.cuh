@@ -304,7 +304,8 @@ orb_fast_kernel(const uint8_t * __restrict__ gray_all, const uint8_t * __restric
 // (VABSDIFF4 / VSETGTU4): ~5 instead of ~25 instructions per pixel for the two full-tile passes.  Results are the same candidate
 // SET (the selection kernel sorts it), bit for bit.
 constexpr int kFastTmaTW = 64, kFastTmaTH = 32;
-constexpr int kFastTmaGW = 80, kFastTmaGH = 40;   // staged box: x0-8 .. x0+72, y0-4 .. y0+36 (inner extent a multiple of 16 bytes)
+constexpr int kFastTmaGW = 96, kFastTmaGH = 40;   // staged box: x0-16 .. x0+80, y0-4 .. y0+36: the TMA needs a 16-byte aligned row start
+                                                  // (x0 is a multiple of 64) and an inner extent that is a multiple of 16 bytes
 constexpr int kFastTmaSW = 72, kFastTmaSH = 34;   // score plane: x0-4 .. x0+68, y0-1 .. y0+33
 
 __device__ __forceinline__ void tma_load_3d(void * smem_dst, const void * tmap, int x, int y, int z, uint64_t * bar)
@@ -344,20 +345,22 @@ orb_fast_tma_kernel(const __grid_constant__ OrbTensorMap tmap, const uint8_t * _
 	if (tid == 0)
 	{
 		mbar_arrive_expect_tx(&s_bar, GW * GH);
-		tma_load_3d(s_gray, &tmap, x0 - 8, y0 - 4, frame, &s_bar);
+		tma_load_3d(s_gray, &tmap, x0 - 16, y0 - 4, frame, &s_bar);
 	}
 	mbar_wait(&s_bar, 0);
 	const int thr = g.fast_thr;
 	const uint32_t thr4 = static_cast<uint32_t>(thr) * 0x01010101u;
-	const uint32_t * W = reinterpret_cast<const uint32_t *>(s_gray); // 20 words per staged row
+	constexpr int WR = GW / 4;                                        // words per staged row
+	const uint32_t * W = reinterpret_cast<const uint32_t *>(s_gray);
 	// compass test (every 9-arc holds ring pixel 0 or 8, and 4 or 12), 4 pixels per item over the score plane
 	for (int it = tid; it < SH * (SW / 4); it += 256)
 	{
 		const int r = it / (SW / 4), k = it % (SW / 4); // score row r = image row y0 - 1 + r; pixels x0 - 4 + 4k .. +3
 		const int gy = r + 3;                           // staged row of the centre
 		const int y = y0 - 1 + r, xb = x0 - 4 + 4 * k;
-		const uint32_t wc = W[gy * 20 + k + 1], wl = W[gy * 20 + k], wr = W[gy * 20 + k + 2];
-		const uint32_t up = W[(gy - 3) * 20 + k + 1], dn = W[(gy + 3) * 20 + k + 1];
+		// pixel x0 - 4 + 4k sits at staged column 4k + 12 = word k + 3
+		const uint32_t wc = W[gy * WR + k + 3], wl = W[gy * WR + k + 2], wr = W[gy * WR + k + 4];
+		const uint32_t up = W[(gy - 3) * WR + k + 3], dn = W[(gy + 3) * WR + k + 3];
 		const uint32_t lf = __byte_perm(wl, wc, 0x4321), rt = __byte_perm(wc, wr, 0x6543);
 		const uint32_t g0 = __vcmpgtu4(__vabsdiffu4(wc, dn), thr4), g8 = __vcmpgtu4(__vabsdiffu4(wc, up), thr4);
 		const uint32_t g4 = __vcmpgtu4(__vabsdiffu4(wc, rt), thr4), g12 = __vcmpgtu4(__vabsdiffu4(wc, lf), thr4);
@@ -381,7 +384,7 @@ orb_fast_tma_kernel(const __grid_constant__ OrbTensorMap tmap, const uint8_t * _
 	{
 		const int i = s_list[q];
 		const int r = i / SW, c = i % SW;
-		s_score[i] = static_cast<uint8_t>(fast_score(s_gray + (r + 3) * GW + c + 4, GW, thr));
+		s_score[i] = static_cast<uint8_t>(fast_score(s_gray + (r + 3) * GW + c + 12, GW, thr));
 	}
 	__syncthreads();
 	// 3x3 strict non-max suppression + border / mask filters, 4 pixels per item over the tile

@@ -230,6 +230,167 @@ pair_match_kernel(const MatchArgs a)
 	MATCH_PHASE(5);
 }
 
+// ------------------------------------------------------------------- second pass: matching with a guess
+// Reg/RepeatOnce (Registration.cpp:221-229): when the first registration succeeded, RegistrationVis runs again with that transform
+// as the guess (RegistrationVis.cpp:1017-1070, :1225-1370, Vis/CorGuessMatchToProjection = false): the 3-D points of FROM are
+// projected into TO's image, the TO keypoints within Vis/CorGuessWinSize pixels of a projection are its candidates, ranked by
+// cv::BFMatcher::knnMatch(k = 2) + the strict Vis/CorNNDR test (a single candidate is accepted as it is); a TO keypoint goes to the
+// first FROM point (ascending index) that selects it; correspondences in ascending FROM index.  The reference finds the candidates
+// with a randomised kd-tree limited to 32 checks — approximate and unordered; this kernel does the EXACT radius
+// search (squared distance < r^2, rtflann/util/result_set.h:475-479) with candidates in ascending TO index, like the oracle.
+// Pairs whose first pass failed (or whose pose is the identity: "guess not set") keep their first-pass correspondences.
+struct GuessMatchArgs
+{
+	const uint32_t * desc_from;
+	const float * xyz_from;
+	const int * n_from;
+	const int * from_slot;
+	int cap_from;
+	const uint32_t * desc_to;
+	const float * uv_to;
+	const float * xyz_to;
+	const int * n_to;
+	int n_to_all;
+	int cap_to;
+	int cap;
+	const int * ok1;        // [n_pairs] first pass accepted
+	const double * rvec;    // [n_pairs][3] first-pass pose
+	const double * tvec;
+	CamK cam;
+	int img_w, img_h;
+	float win;              // Vis/CorGuessWinSize
+	float nndr;
+	// outputs (overwritten only for pairs that run the second pass)
+	float * obj;
+	float * img;
+	float * obj_to;
+	int * match_id;         // FROM index of every correspondence (the reference's ids of this pass)
+	int * match_from;
+	int * match_to;
+	int * n_match;
+};
+
+__host__ __device__ inline size_t guess_smem_bytes(int cap) { return static_cast<size_t>(cap) * (8 + 4 + 4 + 2 + 2 + 1) + 64; }
+
+template <int NW>
+__global__ void __launch_bounds__(256)
+guess_match_kernel(const GuessMatchArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int cap = a.cap;
+	float * s_uv = reinterpret_cast<float *>(smem_raw);            // [cap][2] TO keypoints
+	int * sel = reinterpret_cast<int *>(s_uv + 2 * cap);           // [cap] TO index chosen by FROM i
+	int * claim = sel + cap;                                       // [cap] smallest FROM index that chose TO j
+	uint16_t * L = reinterpret_cast<uint16_t *>(claim + cap);      // [cap]
+	uint16_t * rank = L + cap;                                     // [cap]
+	uint8_t * flag = reinterpret_cast<uint8_t *>(rank + cap);      // [cap]
+	__shared__ double s_R[9], s_t[3];
+	__shared__ int s_n;
+	const int tid = threadIdx.x, pair = blockIdx.x;
+	if (!a.ok1[pair]) return;
+	const double * rv = a.rvec + pair * 3;
+	const double * tv = a.tvec + pair * 3;
+	if (rv[0] == 0.0 && rv[1] == 0.0 && rv[2] == 0.0 && tv[0] == 0.0 && tv[1] == 0.0 && tv[2] == 0.0) return; // guess.isIdentity(): global matching again
+	const int frow = a.from_slot ? a.from_slot[pair] : pair;
+	if (frow < 0) return;
+	const int nf = min(a.n_from[frow], min(cap, a.cap_from));
+	const int nt = min(a.n_to ? a.n_to[pair] : a.n_to_all, min(cap, a.cap_to));
+	const size_t base = static_cast<size_t>(pair) * cap;
+	const size_t fbase = static_cast<size_t>(frow) * a.cap_from, tbase = static_cast<size_t>(pair) * a.cap_to;
+	if (tid == 0)
+	{
+		rodrigues_v2m(rv, s_R, nullptr);
+		s_t[0] = tv[0];
+		s_t[1] = tv[1];
+		s_t[2] = tv[2];
+	}
+	for (int j = tid; j < nt; j += blockDim.x)
+	{
+		s_uv[2 * j] = a.uv_to[(tbase + j) * 2];
+		s_uv[2 * j + 1] = a.uv_to[(tbase + j) * 2 + 1];
+		claim[j] = 0x7FFFFFFF;
+	}
+	__syncthreads();
+	const float r2 = __fmul_rn(a.win, a.win);
+	const float wmax = static_cast<float>(a.img_w - 1), hmax = static_cast<float>(a.img_h - 1);
+	for (int i = tid; i < nf; i += blockDim.x)
+	{
+		int m = -1;
+		const float * X = a.xyz_from + (fbase + i) * 3;
+		double pu, pv;
+		project_point(s_R, s_t, a.cam, X, pu, pv);
+		const float px = static_cast<float>(pu), py = static_cast<float>(pv);
+		const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(static_cast<float>(s_R[6]), X[0]), __fmul_rn(static_cast<float>(s_R[7]), X[1])),
+		                                     __fmul_rn(static_cast<float>(s_R[8]), X[2])), static_cast<float>(s_t[2]));
+		const bool inb = isfinite(px) && !(px < 0.0f) && !(px >= wmax) && isfinite(py) && !(py < 0.0f) && !(py >= hmax);
+		if (inb && zc > 0.0f && isfinite(X[0]) && isfinite(X[1]) && isfinite(X[2]))
+		{
+			uint32_t q[NW];
+			load_desc<NW>(a.desc_from + fbase * NW, i, q);
+			int cnt = 0, b1 = -1;
+			uint32_t d1 = 0xFFFFFFFFu, d2 = 0xFFFFFFFFu;
+			for (int j = 0; j < nt; ++j)
+			{
+				const float dx = __fsub_rn(px, s_uv[2 * j]), dy = __fsub_rn(py, s_uv[2 * j + 1]);
+				const float dist = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+				if (!(dist < r2)) continue;
+				++cnt;
+				uint32_t w[NW];
+				load_desc<NW>(a.desc_to + tbase * NW, j, w);
+				const uint32_t d = hamming<NW, 0>(q, w);
+				if (d < d1)
+				{
+					d2 = d1;
+					d1 = d;
+					b1 = j;
+				}
+				else if (d < d2) d2 = d;
+			}
+			if (cnt >= 2)
+			{
+				if (static_cast<float>(d1) < __fmul_rn(a.nndr, static_cast<float>(d2))) m = b1;
+			}
+			else if (cnt == 1) m = b1;
+			if (m >= 0) atomicMin(&claim[m], i);
+		}
+		sel[i] = m;
+	}
+	__syncthreads();
+	for (int i = tid; i < nf; i += blockDim.x) flag[i] = (sel[i] >= 0 && claim[sel[i]] == i) ? 1 : 0;
+	__syncthreads();
+	if (tid < 32)
+	{
+		const int n = warp0_compact(flag, nf, L, rank);
+		if (tid == 0)
+		{
+			s_n = n;
+			a.n_match[pair] = n;
+		}
+	}
+	__syncthreads();
+	const int nm = s_n;
+	for (int m = tid; m < nm; m += blockDim.x)
+	{
+		const int fi = L[m], ti = sel[fi];
+		const float * p = a.xyz_from + (fbase + fi) * 3;
+		a.obj[(base + m) * 3 + 0] = p[0];
+		a.obj[(base + m) * 3 + 1] = p[1];
+		a.obj[(base + m) * 3 + 2] = p[2];
+		a.img[(base + m) * 2 + 0] = s_uv[2 * ti];
+		a.img[(base + m) * 2 + 1] = s_uv[2 * ti + 1];
+		if (a.obj_to)
+		{
+			const float * r = a.xyz_to + (tbase + ti) * 3;
+			a.obj_to[(base + m) * 3 + 0] = r[0];
+			a.obj_to[(base + m) * 3 + 1] = r[1];
+			a.obj_to[(base + m) * 3 + 2] = r[2];
+		}
+		a.match_id[base + m] = fi;
+		a.match_from[base + m] = fi;
+		a.match_to[base + m] = ti;
+	}
+}
+
 // ------------------------------------------------------------------------------------ PnP RANSAC
 struct PnpArgs
 {
@@ -968,7 +1129,13 @@ __global__ void pack_verify_results_kernel(int n_pairs, const int * __restrict__
 	}
 	for (int k = 0; k < 12; ++k) r.transform[k] = T[12 * i + k];
 	for (int k = 0; k < 36; ++k) r.covariance[k] = 0.0;
-	for (int k = 0; k < 6; ++k) r.covariance[7 * k] = cov6 ? cov6[6 * i + k] : 1.0;
+	for (int k = 0; k < 6; ++k)
+	{
+		// Registration::computeTransformationMod floors the diagonal (COVARIANCE_LINEAR / ANGULAR_EPSILON, Registration.cpp:36-37, :239-250)
+		const double floor_v = k < 3 ? 0.00000001 : 0.00000003;
+		const double c = cov6 ? cov6[6 * i + k] : 1.0;
+		r.covariance[7 * k] = c <= floor_v ? floor_v : c;
+	}
 	out[i] = r;
 }
 

@@ -304,3 +304,49 @@ def test_orb_detection_runs_beside_dictionary_update():
     q = words[59000:59010]
     i1, dd1, _, _ = eng.knn2(q)
     assert (dd1 == 0).all()
+
+
+def test_second_registration_pass_matches_oracle():
+    """Reg/RepeatOnce (default true in the reference, Registration.cpp:221-229): after a successful global-matching pass the pair is
+    registered again with that transform as the guess — projection of FROM's 3-D points, exact radius search among TO's keypoints,
+    knn + strict NNDR among the candidates (RegistrationVis.cpp:1017-1070, :1225-1370).  Correspondence sets and inlier sets exact,
+    pose and covariance 1e-4 against the oracle (which, like the kernel, searches the window exactly: see oracle_verify.cpp)."""
+    rng = np.random.default_rng(51)
+    eng = Engine()
+    cap = 800
+    specs = [(800, 0.3, 0.04), (500, 0.5, 0.1), (300, 0.1, 0.12), (60, 0.0, 0.02), (25, 0.9, 0.02)]
+    pairs = [make_pair(rng, n, flip=f, outlier_frac=o, nan_every=40) for n, o, f in specs]
+    B = len(pairs)
+    F = np.zeros((B, cap, 32), np.uint8)
+    T = np.zeros((B, cap, 32), np.uint8)
+    X = np.full((B, cap, 3), np.nan, np.float32)
+    UV = np.zeros((B, cap, 2), np.float32)
+    n = []
+    for i, (df, x, dt, uv) in enumerate(pairs):
+        m = len(df)
+        F[i, :m], T[i, :m], X[i, :m], UV[i, :m] = df, dt, x, uv
+        n.append(m)
+    res = eng.verify_batch(F, X, T, UV, K4, n, n, image_size=(640, 480), repeat_once=True, guess_win_size=40)
+    res1 = eng.verify_batch(F, X, T, UV, K4, n, n, image_size=(640, 480), repeat_once=False)
+    n_second = 0
+    for i in range(B):
+        m = n[i]
+        o = orc.verify_pair_repeat(F[i, :m], X[i, :m], T[i, :m], UV[i, :m], K4, image_size=(640, 480), repeat_once=True, guess_win_size=40)
+        g = res[i]
+        assert g["ok"] == o["ok"], i
+        assert np.array_equal(g["matches"], o["matches"]), i       # ids of the second pass: FROM indices, ascending
+        assert np.array_equal(g["inliers"], o["inliers"]), i
+        if o["ok"]:
+            assert np.allclose(g["rvec"], o["rvec"], atol=1e-4) and np.allclose(g["tvec"], o["tvec"], atol=1e-4)
+            assert np.allclose(g["covariance"], o["covariance"], rtol=1e-4, atol=1e-9)
+            assert np.allclose(g["transform"], o["transform"], atol=1e-4)
+        if o["second_pass"]:
+            n_second += 1
+            assert not np.array_equal(g["matches"], res1[i]["matches"])   # a different correspondence set than the global matching
+        else:
+            assert np.array_equal(g["matches"], res1[i]["matches"]) and g["ok"] == res1[i]["ok"]
+    assert n_second >= 3
+    # without an image size the projection cannot be bounded: the second pass is skipped, as in the reference (isCalibrated = false)
+    res0 = eng.verify_batch(F, X, T, UV, K4, n, n, image_size=(0, 0), repeat_once=True)
+    for a, b in zip(res0, eng.verify_batch(F, X, T, UV, K4, n, n, image_size=(0, 0), repeat_once=False)):
+        assert np.array_equal(a["matches"], b["matches"]) and np.array_equal(a["inliers"], b["inliers"])
