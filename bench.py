@@ -700,20 +700,24 @@ def run_extras(eng, world, op, vp, d_sig, imgs_all, deps_all, args):
     wm = np.ascontiguousarray(sm.sig_ids)
     n_sigs = int(sm.sig_ids.max())
     eng.map_detect_async(imgs[0], deps[0], op)
-    t_frames = []
+    t_frames, t_detect = [], []
     new_words = 0
     for t in range(n_map + 4):
         if t == 4:
             t0 = time.perf_counter()
+        tb = time.perf_counter()
         if t + 1 < n_map + 4:
             eng.map_detect_async(imgs[t + 1], deps[t + 1], op)
         ta = time.perf_counter()
         n_kp, words, n_new, like = eng.map_frame(n_sigs + 1 + t, wm, n_sigs + 1 + t, True, NNDR, True)
         if t >= 4:
             t_frames.append((time.perf_counter() - ta) * 1e3)
+            t_detect.append((ta - tb) * 1e3)
             new_words += n_new
     dt = time.perf_counter() - t0
     out["mapping_mode"] = {"value": n_map / dt, "unit": "frames/s", "frames": n_map, "ms_per_frame_median": float(np.median(t_frames)),
+                           "ms_map_frame_max": float(np.max(t_frames)), "ms_detect_submit_median": float(np.median(t_detect)),
+                           "ms_detect_submit_max": float(np.max(t_detect)),
                            "new_words_per_frame": new_words / n_map, "dictionary_words_after": eng.size(),
                            "api": "lcd_map_detect_async (frame t+1) overlapped with lcd_map_frame (update + quantise with mutation + references + TF-IDF over "
                                   "10k signatures) of frame t; host images in, word ids + likelihood out, wall clock",
