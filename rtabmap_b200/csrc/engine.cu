@@ -280,7 +280,8 @@ struct lcd_engine
 	// --- scratch
 	DevBuf<uint32_t> d_queries;
 	DevBuf<uint2> d_partial;
-	DevBuf<uint4> tc_words, tc_queries; // int8 operand images of the tensor-core 2-NN
+	DevBuf<uint4> tc_words;             // cached +-1 byte image of the vocabulary rows [0, tc_rows) for the tensor-core 2-NN
+	int tc_rows = 0;
 	DevBuf<uint32_t> d_keys;
 	DevBuf<int> d_word_ids, d_n_new, d_in_ids;
 	DevBuf<int> uq_count, uq_word, uq_prefix;
@@ -545,7 +546,11 @@ int launch_knn_nw(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows
 
 // ---- float descriptors on the tensor cores ------------------------------------------------------------------------
 // rows of the vocabulary changed from `row` on (compaction, re-sorted tail): their image is stale
-void tf_invalidate_from(lcd_engine * e, int row) { e->tf_rows = std::min(e->tf_rows, std::max(row, 0)); }
+void tf_invalidate_from(lcd_engine * e, int row)
+{
+	e->tf_rows = std::min(e->tf_rows, std::max(row, 0));
+	e->tc_rows = std::min(e->tc_rows, std::max(row, 0));
+}
 
 // (1) the cached word image: only rows that are new since the last search are converted.  When rows were converted, the "does not
 // fit fp16" flag is read back at once (a synchronisation that only happens right after the dictionary changed): such a dictionary
@@ -714,21 +719,26 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 			}
 		}
 		const int tps = (n_wtiles + best_split - 1) / best_split;
-		LCD_CUDA(e, e->tc_words.reserve(static_cast<size_t>(n_wtiles) * kTcBN * 16, 0, false, s));
-		LCD_CUDA(e, e->tc_queries.reserve(static_cast<size_t>(n_qtiles) * kTcBM * 16, 0, false, s));
 		LCD_CUDA(e, e->d_partial.reserve(static_cast<size_t>(best_split) * kTcEpiGroups * nq_total, 0, false, s));
+		if (e->tc_rows < n_rows)
 		{
-			const size_t tw = static_cast<size_t>(n_wtiles) * kTcBN * 16, tq = static_cast<size_t>(n_qtiles) * kTcBM * 16;
-			tc_expand_kernel<<<static_cast<unsigned>((tw + 255) / 256), 256, 0, s>>>(e->vocab.p, n_rows, kTcBN, n_wtiles, e->tc_words.p);
-			tc_expand_kernel<<<static_cast<unsigned>((tq + 255) / 256), 256, 0, s>>>(d_q, nq_total, kTcBM, n_qtiles, e->tc_queries.p);
+			// the +-1 byte image of the words is cached with the dictionary: only tiles that gained rows since the last search are written
+			const int t0 = e->tc_rows / kTcBN;
+			const size_t tile16 = static_cast<size_t>(kTcBN) * 16;
+			const int old_tiles = static_cast<int>(e->tc_words.cap / tile16);
+			if (n_wtiles > old_tiles)
+				LCD_CUDA(e, e->tc_words.reserve(static_cast<size_t>(std::max(n_wtiles, old_tiles + old_tiles / 2 + 16)) * tile16, static_cast<size_t>(t0) * tile16, false, s));
+			const size_t todo = static_cast<size_t>(n_wtiles - t0) * tile16;
+			tc_expand_kernel<<<static_cast<unsigned>((todo + 255) / 256), 256, 0, s>>>(e->vocab.p, n_rows, kTcBN, t0, n_wtiles, e->tc_words.p);
+			LCD_CHECK_LAUNCH(e);
+			e->tc_rows = n_rows;
 		}
 		LCD_CUDA(e, cudaFuncSetAttribute(knn2_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
 		prof_mark(e, LCD_PROF_NN, s);
-		knn2_tensor_kernel<<<dim3(n_qtiles, best_split), kTcThreads, kTcSmemBytes, s>>>(e->tc_words.p, n_rows, e->row_offset, e->tc_queries.p, nq_total,
-		                                                                               e->d_partial.p, tps, static_cast<uint32_t>(-32));
+		knn2_tensor_kernel<<<dim3(n_qtiles, best_split), kTcThreads, kTcSmemBytes, s>>>(e->tc_words.p, n_rows, e->row_offset, d_q, nq_total, e->d_partial.p, tps,
+		                                                                               static_cast<uint32_t>(-32));
 		prof_mark(e, LCD_PROF_NN, s);
 		LCD_CHECK_LAUNCH(e);
-		e->launches += 2; // the two expand kernels (LCD_CHECK_LAUNCH counted the 2-NN kernel)
 		e->nn_last_tensor = 1;
 		*n_chunks_out = best_split * kTcEpiGroups;
 		return LCD_OK;
@@ -1392,6 +1402,7 @@ int lcd_dict_clear(lcd_engine * e)
 	e->sig_words.clear();
 	e->total_refs = 0;
 	e->tf_rows = 0;
+	e->tc_rows = 0;
 	e->tf_disabled = false;
 	if (e->tf_wmax2.p) LCD_CUDA(e, cudaMemsetAsync(e->tf_wmax2.p, 0, sizeof(uint32_t), e->stream));
 	if (e->tf_flags.p) LCD_CUDA(e, cudaMemsetAsync(e->tf_flags.p, 0, 4 * sizeof(int), e->stream));

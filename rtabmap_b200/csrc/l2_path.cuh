@@ -139,14 +139,35 @@ __device__ __forceinline__ bool nndr_decide64(unsigned long long a1, unsigned lo
 // inside the chunk by fixed-point iteration over a ballot mask; (C) the chunk's new words join the list.
 // sa1 / sa2: each descriptor's two best index hits (64-bit keys).  Returns the number of created words; flag / rank / L / res as in
 // resolve_rounds.
+// exact rtflann-order distance between a descriptor held in registers and a vector streamed with 16-byte loads (all lanes of a
+// warp read the same address: one transaction per load)
+template <int DIM>
+__device__ __forceinline__ float l2_reg_vs_stream(const float (&a)[DIM], const float * __restrict__ b)
+{
+	const float4 * b4 = reinterpret_cast<const float4 *>(b);
+	float result = 0.0f;
+#pragma unroll
+	for (int i = 0; i < DIM; i += 4)
+	{
+		const float4 v = b4[i >> 2];
+		const float d0 = __fsub_rn(a[i], v.x), d1 = __fsub_rn(a[i + 1], v.y), d2 = __fsub_rn(a[i + 2], v.z), d3 = __fsub_rn(a[i + 3], v.w);
+		float g = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
+		g = __fadd_rn(g, __fmul_rn(d2, d2));
+		g = __fadd_rn(g, __fmul_rn(d3, d3));
+		result = __fadd_rn(result, g);
+	}
+	return result;
+}
+
 template <int DIM>
 __device__ int resolve_rounds_l2(const float * __restrict__ fq, int nq, const unsigned long long * sa1, const unsigned long long * sa2, int * res,
                                  uint16_t * L, uint16_t * rank, uint8_t * flag, int * s_nL, float nndr, int cmp_new)
 {
-	__shared__ unsigned long long s_ext[64];
-	__shared__ float s_dl[32][33]; // s_dl[e][j] = distance between descriptors c0+e and c0+j of the current chunk
+	constexpr int kWarps = kL2ResolveThreads / 32;
+	__shared__ unsigned long long s_wk[kWarps][32][2]; // per warp, per descriptor of the chunk: best two among the created words it scanned
+	__shared__ float s_dl[32][33];                     // s_dl[e][j] = distance between descriptors c0+e and c0+j of the current chunk
 	const int tid = threadIdx.x;
-	const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+	const int warp = tid >> 5, lane = tid & 31;
 	if (!cmp_new)
 	{
 		if (tid < 32)
@@ -162,35 +183,34 @@ __device__ int resolve_rounds_l2(const float * __restrict__ fq, int nq, const un
 	for (int c0 = 0; c0 < nq; c0 += 32)
 	{
 		const int nL = *s_nL;
-		for (int e = warp; e < 32; e += nwarps)
+		// (A) lane j of EVERY warp holds descriptor c0 + j in registers; the warps share out the vectors it is compared with (the 32
+		// chunk-mates and the nL words created so far), each streamed once per warp with broadcast loads
 		{
-			const int i = c0 + e;
-			if (i >= nq) continue;
-			const float * qi = fq + static_cast<size_t>(i) * DIM;
-			const int jm = c0 + lane;
-			s_dl[e][lane] = jm < nq ? l2_rtflann<DIM>(qi, fq + static_cast<size_t>(jm) * DIM) : INFINITY;
-			unsigned long long k1 = kKey64None, k2 = kKey64None;
-			if (nL > 0)
-			{
-				for (int k = lane; k < nL; k += 32)
-				{
-					const float d = l2_rtflann<DIM>(qi, fq + static_cast<size_t>(L[k]) * DIM);
-					top2_insert64(k1, k2, pack64(d, static_cast<uint32_t>(k)));
-				}
+			const int i = min(c0 + lane, nq - 1);
+			float q[DIM];
+			const float4 * q4 = reinterpret_cast<const float4 *>(fq + static_cast<size_t>(i) * DIM);
 #pragma unroll
-				for (int o = 16; o > 0; o >>= 1)
-				{
-					const unsigned long long o1 = __shfl_down_sync(0xFFFFFFFFu, k1, o);
-					const unsigned long long o2 = __shfl_down_sync(0xFFFFFFFFu, k2, o);
-					top2_insert64(k1, k2, o1);
-					top2_insert64(k1, k2, o2);
-				}
-			}
-			if (lane == 0)
+			for (int v = 0; v < DIM / 4; ++v)
 			{
-				s_ext[2 * e] = k1;
-				s_ext[2 * e + 1] = k2;
+				const float4 x = q4[v];
+				q[4 * v] = x.x;
+				q[4 * v + 1] = x.y;
+				q[4 * v + 2] = x.z;
+				q[4 * v + 3] = x.w;
 			}
+			for (int e = warp; e < 32; e += kWarps)
+			{
+				const int m = c0 + e;
+				s_dl[e][lane] = m < nq ? l2_reg_vs_stream<DIM>(q, fq + static_cast<size_t>(m) * DIM) : INFINITY;
+			}
+			unsigned long long k1 = kKey64None, k2 = kKey64None;
+			for (int k = warp; k < nL; k += kWarps)
+			{
+				const float d = l2_reg_vs_stream<DIM>(q, fq + static_cast<size_t>(L[k]) * DIM);
+				top2_insert64(k1, k2, pack64(d, static_cast<uint32_t>(k)));
+			}
+			s_wk[warp][lane][0] = k1;
+			s_wk[warp][lane][1] = k2;
 		}
 		__syncthreads();
 		if (warp == 0)
@@ -199,9 +219,15 @@ __device__ int resolve_rounds_l2(const float * __restrict__ fq, int nq, const un
 			const bool valid = i < nq;
 			float dl[32];
 #pragma unroll
-			for (int jl = 0; jl < 32; ++jl) dl[jl] = s_dl[lane][jl];
+			for (int jl = 0; jl < 32; ++jl) dl[jl] = s_dl[jl][lane]; // the matrix is symmetric; this read is conflict-free
 			const unsigned long long a1 = valid ? sa1[i] : kKey64None, a2 = valid ? sa2[i] : kKey64None;
-			const unsigned long long e1 = s_ext[2 * lane], e2 = s_ext[2 * lane + 1];
+			unsigned long long e1 = kKey64None, e2 = kKey64None;
+#pragma unroll
+			for (int w = 0; w < kWarps; ++w)
+			{
+				top2_insert64(e1, e2, s_wk[w][lane][0]);
+				top2_insert64(e1, e2, s_wk[w][lane][1]);
+			}
 			int bt;
 			bool bad = valid && nndr_decide64(a1, a2, e1, e2, nndr, bt);
 			unsigned long long n1 = e1;

@@ -11,7 +11,8 @@
 // One CTA owns a tile of 128 queries (the M dimension; the tile's accumulator rows are the 128 TMEM lanes, so
 // each epilogue thread owns one query and keeps its running top-2 in registers) and a contiguous range of
 // 256-word tiles (N).  Roles:
-//   warp 0  producer  : cp.async.bulk (TMA engine) of the pre-tiled, pre-swizzled operand images into smem
+//   warp 0  producer  : cp.async.bulk (TMA engine) of the pre-tiled, pre-swizzled word image into smem (the image is cached with the
+//                       dictionary); the query tile is expanded in place by the epilogue warps from its packed form
 //   warp 1  MMA       : one thread issues 8 x tcgen05.mma (M128 N256 K32) per word tile into one of two TMEM
 //                       accumulator stages, then tcgen05.commit to the smem-empty and accumulator-full barriers
 //   warp 2  TMEM alloc/dealloc (512 columns)
@@ -50,9 +51,11 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nibble)
 	return (~m) | t;                                         // 0 -> 0xFF (-1), 1 -> 0x01 (+1)
 }
 
-__global__ void tc_expand_kernel(const uint32_t * __restrict__ src /* [n_rows][8] */, int n_rows, int tile_rows, int n_tiles, uint4 * __restrict__ dst)
+__global__ void tc_expand_kernel(const uint32_t * __restrict__ src /* [n_rows][8] */, int n_rows, int tile_rows, int tile0, int n_tiles,
+                                 uint4 * __restrict__ dst)
 {
-	const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	// tiles [tile0, n_tiles): the image of a frozen dictionary is built once and kept; only tiles that gained rows are rewritten
+	const size_t gid = static_cast<size_t>(tile0) * tile_rows * 16 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	const size_t total = static_cast<size_t>(n_tiles) * tile_rows * 16;
 	if (gid >= total) return;
 	const int chunk = static_cast<int>(gid & 15);           // 16-byte chunk of the 256-byte expanded row
@@ -144,7 +147,7 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // grid = (query tiles, word splits).  partial[(split * kTcEpiGroups + column group) * nq + query] = (best key, second key)
 // over the rows of that split that fall in that column group of their tile.
 __global__ void __launch_bounds__(kTcThreads, 1)
-knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offset, const uint4 * __restrict__ query_img, int nq,
+knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offset, const uint32_t * __restrict__ queries /* [nq][8] packed */, int nq,
                    uint2 * __restrict__ partial, int tiles_per_split, uint32_t neg32)
 {
 	extern __shared__ unsigned char smem_dyn[];
@@ -178,7 +181,7 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 			mbar_init(&tfull[s], 1);
 			mbar_init(&tempty[s], 4 * kTcEpiGroups); // one arrival per epilogue warp
 		}
-		mbar_init(afull, 1);
+		mbar_init(afull, 4 * kTcEpiGroups); // the epilogue warps expand the query tile in place (one arrival per warp)
 		mbar_fence_init();
 	}
 	if (warp == 2) tc_alloc(tmem_slot, 512);
@@ -191,8 +194,6 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 	{
 		if (lane == 0 && n_tiles > 0)
 		{
-			mbar_arrive_expect_tx(afull, kTcABytes);
-			bulk_g2s(sA, reinterpret_cast<const unsigned char *>(query_img) + static_cast<size_t>(qtile) * kTcABytes, kTcABytes, afull);
 			for (int t = 0; t < n_tiles; ++t)
 			{
 				const int s = t % kTcStages;
@@ -234,6 +235,32 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 	}
 	else if (warp >= 4)
 	{
+		// The query tile goes from its packed form (32 B per descriptor) straight into the swizzled +-1 byte image in shared memory:
+		// no expanded copy of the queries ever touches HBM.  One 16-byte chunk (16 descriptor bits) per thread and step.
+		{
+			const int et = tid - 128;
+			uint4 * sA4 = reinterpret_cast<uint4 *>(sA);
+			for (int i = et; i < kTcBM * 16; i += 128 * kTcEpiGroups)
+			{
+				const int r = i >> 4, chunk = i & 15;
+				const int q = qtile * kTcBM + r;
+				uint4 v = make_uint4(0, 0, 0, 0);
+				if (q < nq)
+				{
+					const uint32_t w = queries[static_cast<size_t>(q) * 8 + (chunk >> 1)];
+					const uint32_t bits = (w >> ((chunk & 1) * 16)) & 0xFFFFu;
+					v.x = expand4(bits & 15u);
+					v.y = expand4((bits >> 4) & 15u);
+					v.z = expand4((bits >> 8) & 15u);
+					v.w = expand4((bits >> 12) & 15u);
+				}
+				const int atom = chunk >> 3, c = chunk & 7;
+				sA4[atom * (kTcBM * 8) + r * 8 + (c ^ (r & 7))] = v;
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
+			__syncwarp();
+			if (lane == 0) mbar_arrive(afull);
+		}
 		const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp id % 4)
 		const int cg = (warp - 4) >> 2;               // column group
 		const int qi = qtile * kTcBM + quarter * 32 + lane;

@@ -363,7 +363,8 @@ knn2_tensor_f32_kernel(const TfArgs a)
 				for (int j = 0; j < kTfEpiCols; ++j)
 				{
 					const float x = __int_as_float(v[j]);
-					if (x <= t2 + margin && x < INFINITY)
+					// rows past n_rows of the cached image are words that are not searchable in this call (not indexed yet)
+					if (x <= t2 + margin && x < INFINITY && row0 + j < a.n_rows)
 					{
 						if (emit)
 						{

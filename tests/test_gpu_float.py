@@ -191,7 +191,11 @@ def test_tensor_filter_incremental_stream_matches_oracle():
             eng.remove_words(victims)
             o.remove_words(victims)
     q = noisy(vocab[rng.integers(0, 6000, 50)], 0.05, rng)
+    q[:10] = frame[150:160]                                  # descriptors that became words in the last frame (still not indexed)
     assert np.array_equal(eng.find_nn(q, True, 0.8), o.find_nn(q))
+    # findNN searched the not-indexed words too (their rows are in the cached image now); the index-only search must not see them
+    for a, b in zip(eng.knn2(q), o.knn2(q)):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     eng.update()
     o.update()
     assert np.array_equal(eng.find_nn(q, True, 0.8), o.find_nn(q))
