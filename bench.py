@@ -275,9 +275,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world_size > 1:
         # NCCL's communicator lines (rank count, transport) go to stderr for the driver to read; stdout carries exactly one JSON line
+        # (NCCL would print them to stdout; a file per process keeps stdout clean, rank 0 copies the lines to stderr at the end)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        nccl_log = os.path.join(tempfile.gettempdir(), f"lcd_nccl_{os.getpid()}.log")
+        os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # weak scaling: every GPU brings its own --batch frames per step (a relocalisation service adds cameras with GPUs); the
     # dictionary and the inverted index are sharded by word range, so each rank still searches ALL frames' descriptors.
@@ -644,6 +646,13 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.destroy_process_group()
+        try:
+            with open(os.environ.get("NCCL_DEBUG_FILE", "")) as f:
+                keep = [ln.rstrip() for ln in f if "Init COMPLETE" in ln or "nranks" in ln or "NCCL version" in ln or "Using network" in ln or "NVLS" in ln]
+            for ln in keep[:24]:
+                log("[nccl] " + ln)
+        except OSError:
+            pass
     return 0
 
 
