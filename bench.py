@@ -276,10 +276,10 @@ def run_b200(args):
     if world_size > 1:
         # NCCL's communicator lines (rank count, transport) go to stderr for the driver to read; stdout carries exactly one JSON line
         # (NCCL would print them to stdout; a file per process keeps stdout clean, rank 0 copies the lines to stderr at the end)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        nccl_log = os.path.join(tempfile.gettempdir(), f"lcd_nccl_{os.getpid()}.log")
-        os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(tempfile.gettempdir(), f"lcd_nccl_{os.getpid()}.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # weak scaling: every GPU brings its own --batch frames per step (a relocalisation service adds cameras with GPUs); the
     # dictionary and the inverted index are sharded by word range, so each rank still searches ALL frames' descriptors.

@@ -373,6 +373,8 @@ struct lcd_engine
 	int sh_rank = 0, sh_ranks = 1;
 	cudaStream_t comm_stream = nullptr;
 	cudaEvent_t sh_ev[2][8] = {};
+	cudaEvent_t sh_tr[2] = {};         // LCD_SHARD_TRACE=1: first / last kernel of the step on the compute stream
+	bool sh_trace = false, sh_trace_armed = false;
 	DevBuf<uint8_t> sh_desc_all[2];
 	DevBuf<int> sh_n_all, sh_words_loc[2], sh_words_all[2];
 	DevBuf<uint32_t> sh_keys[2], sh_keys_mine[2];
@@ -1152,6 +1154,8 @@ void lcd_destroy(lcd_engine * e)
 		for (auto & half : e->sh_ev)
 			for (cudaEvent_t ev : half)
 				if (ev) cudaEventDestroy(ev);
+		for (cudaEvent_t ev : e->sh_tr)
+			if (ev) cudaEventDestroy(ev);
 		if (e->orb_stream)
 		{
 			cudaStreamSynchronize(e->orb_stream);
@@ -3497,9 +3501,12 @@ int lcd_shard_unique_id(char id_out[128])
 static int shard_comm_common(lcd_engine * e, int rank, int n_ranks)
 {
 	if (!e->comm_stream) LCD_CUDA(e, cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
+	e->sh_trace = env_int("LCD_SHARD_TRACE", 0) != 0;
 	for (auto & half : e->sh_ev)
 		for (cudaEvent_t & ev : half)
-			if (!ev) LCD_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+			if (!ev) LCD_CUDA(e, cudaEventCreateWithFlags(&ev, e->sh_trace ? cudaEventDefault : cudaEventDisableTiming));
+	for (cudaEvent_t & ev : e->sh_tr)
+		if (e->sh_trace && !ev) LCD_CUDA(e, cudaEventCreate(&ev));
 	e->sh_rank = rank;
 	e->sh_ranks = n_ranks;
 	return LCD_OK;
@@ -3587,7 +3594,22 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		LCD_CUDA(e, e->sh_scores[h].reserve(static_cast<size_t>(part_frames[h]) * G * ns, 0, false, s));
 		LCD_CUDA(e, e->sh_scores_loc[h].reserve(static_cast<size_t>(part_frames[h]) * ns, 0, false, s));
 	}
+	if (e->sh_trace && e->sh_trace_armed)
+	{
+		// timeline of the PREVIOUS step, in ms after its first kernel: per half, the end of each compute stage (s) and exchange (c)
+		LCD_CUDA(e, cudaEventSynchronize(e->sh_tr[1]));
+		LCD_CUDA(e, cudaStreamSynchronize(c));
+		static const char * names[8] = {"orb", "ag_desc", "nn", "a2a_keys", "resolve", "ag_words", "score", "rs_scores"};
+		float ms = 0.f;
+		fprintf(stderr, "[lcd shard trace rank %d]", R);
+		for (int h = 0; h < n_parts; ++h)
+			for (int k = 0; k < 8; ++k)
+				if (cudaEventElapsedTime(&ms, e->sh_tr[0], e->sh_ev[h][k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
+		if (cudaEventElapsedTime(&ms, e->sh_tr[0], e->sh_tr[1]) == cudaSuccess) fprintf(stderr, " end=%.3f", ms);
+		fprintf(stderr, "\n");
+	}
 	LCD_CUDA(e, zero_fill_async(e->o_desc.p, rows * 32, s)); // padding rows of short frames must hold defined bytes
+	if (e->sh_trace) LCD_CUDA(e, cudaEventRecord(e->sh_tr[0], s));
 	// the communication stream starts behind everything already queued on the compute stream
 	LCD_CUDA(e, cudaEventRecord(e->sh_ev[0][7], s));
 	LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[0][7], 0));
@@ -3689,7 +3711,11 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 	if (vp)
 		LCD_TRY(verify_top_dev(e, reinterpret_cast<const uint32_t *>(e->o_desc.p), e->o_uv.p, n_frames, cap, d_likelihood_out, d_sig_ids, ns, vp, s, e->o_n.p,
 		                       e->o_xyz.p));
-	(void)R;
+	if (e->sh_trace)
+	{
+		LCD_CUDA(e, cudaEventRecord(e->sh_tr[1], s));
+		e->sh_trace_armed = true;
+	}
 	return LCD_OK;
 }
 
