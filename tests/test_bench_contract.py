@@ -21,7 +21,9 @@ def test_reference_arm_prints_one_json_line():
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 4 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" when the NN leg is the reference's own rtflann compiled into oracle/_ref, "port" when only the restatement exists
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] == 4 and d["cpu_baseline"]["value"] == d["value"]
+    assert isinstance(d["cpu_baseline"].get("legs"), dict) and d["cpu_baseline"]["legs"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["top1_place_hit_rate"] == 1.0       # the CPU path finds the revisited place of every sampled frame
 
