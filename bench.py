@@ -390,10 +390,13 @@ def run_b200(args):
     barrier()
     torch.cuda.cudart().cudaProfilerStart()  # lets `ncu --profile-from-start off` see exactly the timed region
     t_wall0 = time.perf_counter()
+    host_enqueue_s = 0.0
     for k in range(args.steps):
         flush.fill_(k & 0xFF)  # L2 flush, outside the timed events
         ev[k][0].record(ext)
+        th = time.perf_counter()
         step_dev(k)
+        host_enqueue_s += time.perf_counter() - th
         ev[k][1].record(ext)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -641,7 +644,8 @@ def run_b200(args):
                 "api": "lcd_process_frames_submit/_wait (pinned host buffers, 2 batches in flight, L2 flush between steps inside the timed region)" if world_size == 1 else "lcd_shard_process_frames_dev (exchanges inside the library), double-buffered pinned uploads on a side stream, results copied back every step",
                 "top1_place_hit_rate": e2e_hit, "verified_rate": e2e_verified},
         "roofline": roofline, "cpu_baseline": cpu, "top1_place_hit_rate": hit, "verified_rate": verified, "ransac_iterations_hist_50": iters_hist,
-        "wall_s_timed_region": t_wall, "frames_pool": f"{n_pool} batches of {BL} frames cycled", "oracle_check": sharded_check, **extra,
+        "wall_s_timed_region": t_wall, "host_enqueue_ms_per_step": host_enqueue_s * 1e3 / args.steps,
+        "frames_pool": f"{n_pool} batches of {BL} frames cycled", "oracle_check": sharded_check, **extra,
     }
     print(json.dumps(line), flush=True)
     if world_size > 1:
@@ -727,6 +731,8 @@ def run_extras(eng, world, op, vp, d_sig, imgs_all, deps_all, args):
     out["mapping_mode"] = {"value": n_map / dt, "unit": "frames/s", "frames": n_map, "ms_per_frame_median": float(np.median(t_frames)),
                            "ms_map_frame_max": float(np.max(t_frames)), "ms_detect_submit_median": float(np.median(t_detect)),
                            "ms_detect_submit_max": float(np.max(t_detect)),
+                           "ms_per_frame_p90": float(np.percentile(t_frames, 90)),
+                           "slowest_frames_ms": [[int(i), round(float(t_frames[i]), 2)] for i in np.argsort(t_frames)[::-1][:6]],
                            "new_words_per_frame": new_words / n_map, "dictionary_words_after": eng.size(),
                            "api": "lcd_map_detect_async (frame t+1) overlapped with lcd_map_frame (update + quantise with mutation + references + TF-IDF over "
                                   "10k signatures) of frame t; host images in, word ids + likelihood out, wall clock",

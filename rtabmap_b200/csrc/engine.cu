@@ -37,6 +37,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #include <utility>
+#include <chrono>
 #include <vector>
 
 using namespace lcd;
@@ -374,7 +375,9 @@ struct lcd_engine
 	cudaStream_t comm_stream = nullptr;
 	cudaEvent_t sh_ev[2][8] = {};
 	cudaEvent_t sh_tr[2] = {};         // LCD_SHARD_TRACE=1: first / last kernel of the step on the compute stream
-	bool sh_trace = false, sh_trace_armed = false;
+	int sh_trace = 0, sh_ring_step = 0;
+	bool sh_trace_armed = false;
+	std::vector<cudaEvent_t> sh_ring;  // [step][half][8 stage events + 1 begin/end]
 	DevBuf<uint8_t> sh_desc_all[2];
 	DevBuf<int> sh_n_all, sh_words_loc[2], sh_words_all[2];
 	DevBuf<uint32_t> sh_keys[2], sh_keys_mine[2];
@@ -1155,6 +1158,8 @@ void lcd_destroy(lcd_engine * e)
 			for (cudaEvent_t ev : half)
 				if (ev) cudaEventDestroy(ev);
 		for (cudaEvent_t ev : e->sh_tr)
+			if (ev) cudaEventDestroy(ev);
+		for (cudaEvent_t ev : e->sh_ring)
 			if (ev) cudaEventDestroy(ev);
 		if (e->orb_stream)
 		{
@@ -3498,10 +3503,23 @@ int lcd_shard_unique_id(char id_out[128])
 	return LCD_OK;
 }
 
+// LCD_SHARD_TRACE=2: sixteen steps of per-stage events recorded without any synchronisation, printed after the sixteenth
+static int shard_record(lcd_engine * e, int h, int k, cudaStream_t st)
+{
+	LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][k], st));
+	if (e->sh_trace == 2 && e->sh_ring_step < 16) LCD_CUDA(e, cudaEventRecord(e->sh_ring[(e->sh_ring_step * 2 + h) * 9 + k], st));
+	return LCD_OK;
+}
+
 static int shard_comm_common(lcd_engine * e, int rank, int n_ranks)
 {
 	if (!e->comm_stream) LCD_CUDA(e, cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
-	e->sh_trace = env_int("LCD_SHARD_TRACE", 0) != 0;
+	e->sh_trace = env_int("LCD_SHARD_TRACE", 0);
+	if (e->sh_trace == 2 && e->sh_ring.empty())
+	{
+		e->sh_ring.assign(16 * 2 * 9, nullptr);
+		for (cudaEvent_t & ev : e->sh_ring) LCD_CUDA(e, cudaEventCreate(&ev));
+	}
 	for (auto & half : e->sh_ev)
 		for (cudaEvent_t & ev : half)
 			if (!ev) LCD_CUDA(e, cudaEventCreateWithFlags(&ev, e->sh_trace ? cudaEventDefault : cudaEventDisableTiming));
@@ -3594,7 +3612,9 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		LCD_CUDA(e, e->sh_scores[h].reserve(static_cast<size_t>(part_frames[h]) * G * ns, 0, false, s));
 		LCD_CUDA(e, e->sh_scores_loc[h].reserve(static_cast<size_t>(part_frames[h]) * ns, 0, false, s));
 	}
-	if (e->sh_trace && e->sh_trace_armed)
+	std::chrono::steady_clock::time_point host_t[6];
+	const auto host_begin = std::chrono::steady_clock::now();
+	if (e->sh_trace == 1 && e->sh_trace_armed)
 	{
 		// timeline of the PREVIOUS step, in ms after its first kernel: per half, the end of each compute stage (s) and exchange (c)
 		LCD_CUDA(e, cudaEventSynchronize(e->sh_tr[1]));
@@ -3610,24 +3630,28 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 	}
 	LCD_CUDA(e, zero_fill_async(e->o_desc.p, rows * 32, s)); // padding rows of short frames must hold defined bytes
 	if (e->sh_trace) LCD_CUDA(e, cudaEventRecord(e->sh_tr[0], s));
+	if (e->sh_trace == 2 && e->sh_ring_step < 16) LCD_CUDA(e, cudaEventRecord(e->sh_ring[(e->sh_ring_step * 2 + 0) * 9 + 8], s));
 	// the communication stream starts behind everything already queued on the compute stream
 	LCD_CUDA(e, cudaEventRecord(e->sh_ev[0][7], s));
 	LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[0][7], 0));
 
-	// phase 1: detect + describe the part, all-gather its descriptors (and the keypoint counts)
+	host_t[0] = std::chrono::steady_clock::now();
+	// phase 1: detect + describe the local frames in one pass (splitting detection costs more than the 30-50 us all-gather it would hide),
+	// then all-gather the descriptors part by part (and the keypoint counts): the second part's exchange runs under the first part's search
+	LCD_TRY(orb_run(e, n_frames, d_images, width, height, channels, d_depth, depth_type, op, cap, e->o_kp.p, e->o_desc.p, e->o_xyz.p, e->o_uv.p, e->o_n.p, s, 0,
+	                n_frames));
 	for (int h = 0; h < n_parts; ++h)
 	{
-		LCD_TRY(orb_run(e, part_frames[h], d_images, width, height, channels, d_depth, depth_type, op, cap, e->o_kp.p, e->o_desc.p, e->o_xyz.p, e->o_uv.p,
-		                e->o_n.p, s, part_f0[h], n_frames));
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][0], s));
+		LCD_TRY(shard_record(e, h, 0, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][0], 0));
 		const size_t pr = static_cast<size_t>(part_frames[h]) * cap;
 		LCD_NCCL(e, nc.GroupStart());
 		LCD_NCCL(e, nc.AllGather(e->o_desc.p + static_cast<size_t>(part_f0[h]) * cap * 32, e->sh_desc_all[h].p, pr * 32, ncclUint8, e->comm, c));
 		if (h == n_parts - 1) LCD_NCCL(e, nc.AllGather(e->o_n.p, e->sh_n_all.p, n_frames, ncclInt32, e->comm, c));
 		LCD_NCCL(e, nc.GroupEnd());
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][1], c));
+		LCD_TRY(shard_record(e, h, 1, c));
 	}
+	host_t[1] = std::chrono::steady_clock::now();
 	// phase 2: top-2 keys of every rank's descriptors over the local word range; every rank gets back the keys of ITS frames
 	for (int h = 0; h < n_parts; ++h)
 	{
@@ -3638,7 +3662,7 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		LCD_TRY(run_knn(e, reinterpret_cast<const uint32_t *>(e->sh_desc_all[h].p), nq_all, e->n_indexed, &n_chunks, s));
 		knn2_merge_kernel<<<(nq_all + 255) / 256, 256, 0, s>>>(e->d_partial.p, n_chunks, nq_all, e->sh_keys[h].p);
 		LCD_CHECK_LAUNCH(e);
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][2], s));
+		LCD_TRY(shard_record(e, h, 2, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][2], 0));
 		LCD_NCCL(e, nc.GroupStart());
 		for (int p = 0; p < G; ++p)
@@ -3647,8 +3671,9 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 			LCD_NCCL(e, nc.Recv(e->sh_keys_mine[h].p + static_cast<size_t>(p) * pr * 2, pr * 2, ncclUint32, p, e->comm, c));
 		}
 		LCD_NCCL(e, nc.GroupEnd());
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][3], c));
+		LCD_TRY(shard_record(e, h, 3, c));
 	}
+	host_t[2] = std::chrono::steady_clock::now();
 	// phase 3: merge + NNDR / new-word pass of the local frames, all-gather of their word ids
 	for (int h = 0; h < n_parts; ++h)
 	{
@@ -3670,11 +3695,12 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		LCD_TRY(launch_resolve(e, a, part_frames[h], s));
 		if (d_word_ids_out)
 			LCD_CUDA(e, cudaMemcpyAsync(d_word_ids_out + static_cast<size_t>(part_f0[h]) * cap, e->sh_words_loc[h].p, pr * sizeof(int), cudaMemcpyDeviceToDevice, s));
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][4], s));
+		LCD_TRY(shard_record(e, h, 4, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][4], 0));
 		LCD_NCCL(e, nc.AllGather(e->sh_words_loc[h].p, e->sh_words_all[h].p, pr, ncclInt32, e->comm, c));
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][5], c));
+		LCD_TRY(shard_record(e, h, 5, c));
 	}
+	host_t[3] = std::chrono::steady_clock::now();
 	// phase 4: TF-IDF of every rank's frames over the local word range, reduce-scatter of the exact fixed-point sums
 	for (int h = 0; h < n_parts; ++h)
 	{
@@ -3689,17 +3715,18 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		int nq_pad = 32;
 		while (nq_pad < cap) nq_pad <<= 1;
 		prof_mark(e, LCD_PROF_RESOLVE, s);
-		prep_from_ids_kernel<<<nf_all, kResolveThreads, nq_pad * sizeof(uint32_t), s>>>(e->sh_words_all[h].p, a);
+		prep_local_ids_kernel<<<nf_all, kResolveThreads, nq_pad * sizeof(uint32_t), s>>>(e->sh_words_all[h].p, a);
 		prof_mark(e, LCD_PROF_RESOLVE, s);
 		LCD_CHECK_LAUNCH(e);
 		LCD_TRY(launch_score(e, nf_all, cap, s));
 		gather_fixed_kernel<<<dim3((ns + 255) / 256, nf_all), 256, 0, s>>>(e->acc.p, e->acc_stride, static_cast<int>(e->h_ni.size()), d_sig_ids, ns, e->sh_scores[h].p);
 		LCD_CHECK_LAUNCH(e);
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][6], s));
+		LCD_TRY(shard_record(e, h, 6, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][6], 0));
 		LCD_NCCL(e, nc.ReduceScatter(e->sh_scores[h].p, e->sh_scores_loc[h].p, static_cast<size_t>(part_frames[h]) * ns, ncclInt64, ncclSum, e->comm, c));
-		LCD_CUDA(e, cudaEventRecord(e->sh_ev[h][7], c));
+		LCD_TRY(shard_record(e, h, 7, c));
 	}
+	host_t[4] = std::chrono::steady_clock::now();
 	// phase 5: likelihood of the local frames, verification of their top hypothesis
 	for (int h = 0; h < n_parts; ++h)
 	{
@@ -3715,6 +3742,38 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 	{
 		LCD_CUDA(e, cudaEventRecord(e->sh_tr[1], s));
 		e->sh_trace_armed = true;
+	}
+	host_t[5] = std::chrono::steady_clock::now();
+	if (e->sh_trace == 2 && e->sh_ring_step == 9)
+	{
+		auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+			return std::chrono::duration<double, std::micro>(b - a).count();
+		};
+		fprintf(stderr, "[lcd shard host rank %d] us: reserve=%.0f orb+ag_desc=%.0f nn+a2a=%.0f resolve+ag_words=%.0f score+rs=%.0f verify=%.0f\n", R,
+		        us(host_begin, host_t[0]), us(host_t[0], host_t[1]), us(host_t[1], host_t[2]), us(host_t[2], host_t[3]), us(host_t[3], host_t[4]),
+		        us(host_t[4], host_t[5]));
+	}
+	if (e->sh_trace == 2 && e->sh_ring_step < 16)
+	{
+		LCD_CUDA(e, cudaEventRecord(e->sh_ring[(e->sh_ring_step * 2 + 1) * 9 + 8], s));
+		if (++e->sh_ring_step == 16)
+		{
+			LCD_CUDA(e, cudaStreamSynchronize(s));
+			LCD_CUDA(e, cudaStreamSynchronize(c));
+			static const char * names[8] = {"orb", "ag_desc", "nn", "a2a_keys", "resolve", "ag_words", "score", "rs_scores"};
+			const cudaEvent_t origin = e->sh_ring[(8 * 2 + 0) * 9 + 8]; // begin of step 8
+			for (int st = 8; st < 12; ++st)
+			{
+				float ms = 0.f;
+				fprintf(stderr, "[lcd shard ring rank %d step %d]", R, st);
+				if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + 0) * 9 + 8]) == cudaSuccess) fprintf(stderr, " begin=%.3f", ms);
+				for (int h = 0; h < n_parts; ++h)
+					for (int k = 0; k < 8; ++k)
+						if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + h) * 9 + k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
+				if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + 1) * 9 + 8]) == cudaSuccess) fprintf(stderr, " end=%.3f", ms);
+				fprintf(stderr, "\n");
+			}
+		}
 	}
 	return LCD_OK;
 }

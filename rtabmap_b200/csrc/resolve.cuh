@@ -476,4 +476,39 @@ prep_from_ids_kernel(const int * __restrict__ word_ids, const ResolveArgs a)
 	score_prep(sbuf, nq_pad, nq, a, frame);
 }
 
+// Sharded scoring (lcd_shard_process_frames_dev): a rank scores EVERY rank's frames over its own word range, so only the ids that have
+// postings on this rank matter (no postings = nothing added to any sum).  They are compacted before the sort, which keeps the preparation
+// of G ranks' frames at the cost of one rank's frames unsharded instead of growing with G.
+__global__ void __launch_bounds__(kResolveThreads)
+prep_local_ids_kernel(const int * __restrict__ word_ids, const ResolveArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	__shared__ int s_n;
+	const int nq = a.nq;
+	int nq_pad = 32;
+	while (nq_pad < nq) nq_pad <<= 1;
+	uint32_t * sbuf = reinterpret_cast<uint32_t *>(smem_raw);
+	const int frame = blockIdx.x;
+	const int lane = threadIdx.x & 31;
+	if (threadIdx.x == 0) s_n = 0;
+	__syncthreads();
+	for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) // nq_pad and blockDim are multiples of 32: whole warps iterate together
+	{
+		const int w = i < nq ? word_ids[static_cast<size_t>(frame) * nq + i] : 0;
+		const bool keep = w > 0 && w < a.id_cap && a.post_len[w] > 0;
+		const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
+		int base = 0;
+		if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (keep) sbuf[base + __popc(m & ((1u << lane) - 1u))] = static_cast<uint32_t>(w);
+	}
+	__syncthreads();
+	const int n = s_n;
+	int n_pad = 32;
+	while (n_pad < n) n_pad <<= 1;
+	for (int i = n + threadIdx.x; i < n_pad; i += blockDim.x) sbuf[i] = kSortNone;
+	__syncthreads();
+	score_prep(sbuf, n_pad, nq, a, frame);
+}
+
 } // namespace lcd
