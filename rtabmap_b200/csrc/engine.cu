@@ -3589,10 +3589,16 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
 	cudaStream_t c = e->comm_stream;
 	const int G = e->sh_ranks, R = e->sh_rank;
-	// the local batch is processed as two halves so that the exchanges of one half run under the kernels of the other
-	const int n_parts = n_frames >= 2 ? 2 : 1;
+	// The dictionary search runs on two halves of the local batch, so that the descriptor all-gather of the second half and the key
+	// exchange of the first run under a search kernel.  The stages after it (merge + NNDR, TF-IDF) are one-CTA-per-frame kernels that
+	// take as long for half a batch as for a whole one, so they run once on the whole batch by default and their exchanges (word ids,
+	// score rows) are exposed: measured cheaper than splitting (LCD_SHARD_TAIL_PARTS=2 restores the split).
+	const int n_parts = n_frames >= 2 && env_int("LCD_SHARD_NN_PARTS", 2) >= 2 ? 2 : 1;
 	const int part_frames[2] = {n_parts == 2 ? (n_frames + 1) / 2 : n_frames, n_parts == 2 ? n_frames / 2 : 0};
 	const int part_f0[2] = {0, part_frames[0]};
+	const int t_parts = n_parts == 2 && env_int("LCD_SHARD_TAIL_PARTS", 1) >= 2 ? 2 : 1;
+	const int tail_frames[2] = {t_parts == 2 ? part_frames[0] : n_frames, t_parts == 2 ? part_frames[1] : 0};
+	const int tail_f0[2] = {0, tail_frames[0]};
 	const size_t rows = static_cast<size_t>(n_frames) * cap;
 	LCD_CUDA(e, e->o_kp.reserve(rows, 0, false, s));
 	LCD_CUDA(e, e->o_desc.reserve(rows * 32, 0, false, s));
@@ -3606,11 +3612,15 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		const size_t pr = static_cast<size_t>(part_frames[h]) * cap; // descriptor rows of this part on one rank
 		LCD_CUDA(e, e->sh_desc_all[h].reserve(pr * 32 * G, 0, false, s));
 		LCD_CUDA(e, e->sh_keys[h].reserve(pr * 2 * G, 0, false, s));
-		LCD_CUDA(e, e->sh_keys_mine[h].reserve(pr * 2 * G, 0, false, s));
+	}
+	LCD_CUDA(e, e->sh_keys_mine[0].reserve(rows * 2 * G, 0, false, s)); // [rank][local frame][feature]: both halves land in one array
+	for (int h = 0; h < t_parts; ++h)
+	{
+		const size_t pr = static_cast<size_t>(tail_frames[h]) * cap;
 		LCD_CUDA(e, e->sh_words_loc[h].reserve(pr, 0, false, s));
 		LCD_CUDA(e, e->sh_words_all[h].reserve(pr * G, 0, false, s));
-		LCD_CUDA(e, e->sh_scores[h].reserve(static_cast<size_t>(part_frames[h]) * G * ns, 0, false, s));
-		LCD_CUDA(e, e->sh_scores_loc[h].reserve(static_cast<size_t>(part_frames[h]) * ns, 0, false, s));
+		LCD_CUDA(e, e->sh_scores[h].reserve(static_cast<size_t>(tail_frames[h]) * G * ns, 0, false, s));
+		LCD_CUDA(e, e->sh_scores_loc[h].reserve(static_cast<size_t>(tail_frames[h]) * ns, 0, false, s));
 	}
 	std::chrono::steady_clock::time_point host_t[6];
 	const auto host_begin = std::chrono::steady_clock::now();
@@ -3623,7 +3633,7 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		float ms = 0.f;
 		fprintf(stderr, "[lcd shard trace rank %d]", R);
 		for (int h = 0; h < n_parts; ++h)
-			for (int k = 0; k < 8; ++k)
+			for (int k = 0; k < (h < t_parts ? 8 : 4); ++k)
 				if (cudaEventElapsedTime(&ms, e->sh_tr[0], e->sh_ev[h][k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
 		if (cudaEventElapsedTime(&ms, e->sh_tr[0], e->sh_tr[1]) == cudaSuccess) fprintf(stderr, " end=%.3f", ms);
 		fprintf(stderr, "\n");
@@ -3668,22 +3678,22 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		for (int p = 0; p < G; ++p)
 		{
 			LCD_NCCL(e, nc.Send(e->sh_keys[h].p + static_cast<size_t>(p) * pr * 2, pr * 2, ncclUint32, p, e->comm, c));
-			LCD_NCCL(e, nc.Recv(e->sh_keys_mine[h].p + static_cast<size_t>(p) * pr * 2, pr * 2, ncclUint32, p, e->comm, c));
+			LCD_NCCL(e, nc.Recv(e->sh_keys_mine[0].p + (static_cast<size_t>(p) * rows + static_cast<size_t>(part_f0[h]) * cap) * 2, pr * 2, ncclUint32, p, e->comm, c));
 		}
 		LCD_NCCL(e, nc.GroupEnd());
 		LCD_TRY(shard_record(e, h, 3, c));
 	}
 	host_t[2] = std::chrono::steady_clock::now();
 	// phase 3: merge + NNDR / new-word pass of the local frames, all-gather of their word ids
-	for (int h = 0; h < n_parts; ++h)
+	for (int h = 0; h < t_parts; ++h)
 	{
-		const size_t pr = static_cast<size_t>(part_frames[h]) * cap;
-		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][3], 0));
+		const size_t pr = static_cast<size_t>(tail_frames[h]) * cap;
+		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[t_parts == 2 ? h : n_parts - 1][3], 0));
 		ResolveArgs a{};
-		a.queries = reinterpret_cast<const uint32_t *>(e->o_desc.p) + static_cast<size_t>(part_f0[h]) * cap * e->nw;
+		a.queries = reinterpret_cast<const uint32_t *>(e->o_desc.p) + static_cast<size_t>(tail_f0[h]) * cap * e->nw;
 		a.nq = cap;
-		a.nq_total = static_cast<int>(pr);                         // stride between the G key sets
-		a.partial = reinterpret_cast<const uint2 *>(e->sh_keys_mine[h].p);
+		a.nq_total = static_cast<int>(rows);                       // stride between the G key sets
+		a.partial = reinterpret_cast<const uint2 *>(e->sh_keys_mine[0].p) + static_cast<size_t>(tail_f0[h]) * cap;
 		a.n_chunks = G;
 		a.row_ids = d_row_ids_global;
 		a.incremental = incremental;
@@ -3691,10 +3701,10 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		a.cmp_new = new_words_compared_together;
 		a.last_word_id = last_word_id;
 		a.word_ids_out = e->sh_words_loc[h].p;
-		a.nq_frame = e->o_n.p + part_f0[h];
-		LCD_TRY(launch_resolve(e, a, part_frames[h], s));
+		a.nq_frame = e->o_n.p + tail_f0[h];
+		LCD_TRY(launch_resolve(e, a, tail_frames[h], s));
 		if (d_word_ids_out)
-			LCD_CUDA(e, cudaMemcpyAsync(d_word_ids_out + static_cast<size_t>(part_f0[h]) * cap, e->sh_words_loc[h].p, pr * sizeof(int), cudaMemcpyDeviceToDevice, s));
+			LCD_CUDA(e, cudaMemcpyAsync(d_word_ids_out + static_cast<size_t>(tail_f0[h]) * cap, e->sh_words_loc[h].p, pr * sizeof(int), cudaMemcpyDeviceToDevice, s));
 		LCD_TRY(shard_record(e, h, 4, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][4], 0));
 		LCD_NCCL(e, nc.AllGather(e->sh_words_loc[h].p, e->sh_words_all[h].p, pr, ncclInt32, e->comm, c));
@@ -3702,9 +3712,9 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 	}
 	host_t[3] = std::chrono::steady_clock::now();
 	// phase 4: TF-IDF of every rank's frames over the local word range, reduce-scatter of the exact fixed-point sums
-	for (int h = 0; h < n_parts; ++h)
+	for (int h = 0; h < t_parts; ++h)
 	{
-		const int nf_all = part_frames[h] * G;
+		const int nf_all = tail_frames[h] * G;
 		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][5], 0));
 		LCD_TRY(ensure_uq(e, nf_all, cap, s));
 		LCD_TRY(ensure_acc(e, nf_all));
@@ -3723,16 +3733,16 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		LCD_CHECK_LAUNCH(e);
 		LCD_TRY(shard_record(e, h, 6, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][6], 0));
-		LCD_NCCL(e, nc.ReduceScatter(e->sh_scores[h].p, e->sh_scores_loc[h].p, static_cast<size_t>(part_frames[h]) * ns, ncclInt64, ncclSum, e->comm, c));
+		LCD_NCCL(e, nc.ReduceScatter(e->sh_scores[h].p, e->sh_scores_loc[h].p, static_cast<size_t>(tail_frames[h]) * ns, ncclInt64, ncclSum, e->comm, c));
 		LCD_TRY(shard_record(e, h, 7, c));
 	}
 	host_t[4] = std::chrono::steady_clock::now();
 	// phase 5: likelihood of the local frames, verification of their top hypothesis
-	for (int h = 0; h < n_parts; ++h)
+	for (int h = 0; h < t_parts; ++h)
 	{
-		const int n = part_frames[h] * ns;
+		const int n = tail_frames[h] * ns;
 		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][7], 0));
-		fixed_to_float_kernel<<<(n + 255) / 256, 256, 0, s>>>(e->sh_scores_loc[h].p, n, d_likelihood_out + static_cast<size_t>(part_f0[h]) * ns);
+		fixed_to_float_kernel<<<(n + 255) / 256, 256, 0, s>>>(e->sh_scores_loc[h].p, n, d_likelihood_out + static_cast<size_t>(tail_f0[h]) * ns);
 		LCD_CHECK_LAUNCH(e);
 	}
 	if (vp)
@@ -3768,7 +3778,7 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 				fprintf(stderr, "[lcd shard ring rank %d step %d]", R, st);
 				if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + 0) * 9 + 8]) == cudaSuccess) fprintf(stderr, " begin=%.3f", ms);
 				for (int h = 0; h < n_parts; ++h)
-					for (int k = 0; k < 8; ++k)
+					for (int k = 0; k < (h < t_parts ? 8 : 4); ++k)
 						if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + h) * 9 + k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
 				if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + 1) * 9 + 8]) == cudaSuccess) fprintf(stderr, " end=%.3f", ms);
 				fprintf(stderr, "\n");
