@@ -2099,8 +2099,18 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		a.gray = w_gray;
 		a.mask = w_mask;
 		a.g = g;
-		dim3 blk(32, 8), grd(((width + 1) / 2 + 31) / 32, ((height + 1) / 2 + 7) / 8, n_frames);
-		orb_prepare_kernel<<<grd, blk, 0, s>>>(a);
+		const bool aligned = ((reinterpret_cast<uintptr_t>(d_images) | reinterpret_cast<uintptr_t>(a.depth) | reinterpret_cast<uintptr_t>(w_gray) |
+		                       reinterpret_cast<uintptr_t>(w_mask)) & 15u) == 0 && g.frame_stride % 16 == 0;
+		if (width % 8 == 0 && height % 2 == 0 && aligned && env_int("LCD_ORB_PREP_VEC", 1) != 0)
+		{
+			dim3 blk(16, 16), grd((width / 8 + 15) / 16, (height / 2 + 15) / 16, n_frames);
+			orb_prepare_vec_kernel<<<grd, blk, 0, s>>>(a);
+		}
+		else
+		{
+			dim3 blk(32, 8), grd(((width + 1) / 2 + 31) / 32, ((height + 1) / 2 + 7) / 8, n_frames);
+			orb_prepare_kernel<<<grd, blk, 0, s>>>(a);
+		}
 		LCD_CHECK_LAUNCH(e);
 	}
 	for (int l = 2; l < g.n_levels; ++l)
@@ -2119,38 +2129,34 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 			LCD_CUDA(e, cudaEventCreateWithFlags(&e->aux_join[i], cudaEventDisableTiming));
 		}
 	}
+	// one tensor map per pyramid level ([frame][y][x], 96 x 40 boxes): shared by the FAST and the blur kernels
+	static const int orb_tma = env_int("LCD_ORB_TMA", 1);
+	OrbTensorMap tmaps[kOrbMaxLevels];
+	bool tma_ok = orb_tma != 0;
+	for (int l = 0; l < g.n_levels && tma_ok; ++l)
+		tma_ok = make_plane_tensor_map(&tmaps[l], w_gray + g.off[l], g.w[l], g.h[l], n_frames, static_cast<size_t>(g.frame_stride), kFastTmaGW, kFastTmaGH);
+	e->orb_tma_used = tma_ok ? 1 : 0;
+	LCD_CUDA(e, cudaEventRecord(e->aux_fork, s));
 	if (d_desc)
 	{
 		// the blurred pyramid only feeds the descriptors: it runs on a side stream under FAST and the (latency-bound) selection
-		LCD_CUDA(e, cudaEventRecord(e->aux_fork, s));
 		cudaStream_t bs = e->aux_stream[3];
 		LCD_CUDA(e, cudaStreamWaitEvent(bs, e->aux_fork, 0));
 		for (int l = 0; l < g.n_levels; ++l)
 		{
-			dim3 grd((g.w[l] + kBlurTW - 1) / kBlurTW, (g.h[l] + kBlurTH - 1) / kBlurTH, n_frames);
-			orb_blur_kernel<<<grd, 256, 0, bs>>>(w_gray, w_blur, g, l);
+			if (tma_ok)
+			{
+				dim3 grd((g.w[l] + kFastTmaTW - 1) / kFastTmaTW, (g.h[l] + kFastTmaTH - 1) / kFastTmaTH, n_frames);
+				orb_blur_tma_kernel<<<grd, 256, 0, bs>>>(tmaps[l], w_blur, g, l);
+			}
+			else
+			{
+				dim3 grd((g.w[l] + kBlurTW - 1) / kBlurTW, (g.h[l] + kBlurTH - 1) / kBlurTH, n_frames);
+				orb_blur_kernel<<<grd, 256, 0, bs>>>(w_gray, w_blur, g, l);
+			}
 			LCD_CHECK_LAUNCH(e);
 		}
 		LCD_CUDA(e, cudaEventRecord(e->aux_blur_done, bs));
-	}
-	static const int orb_tma = env_int("LCD_ORB_TMA", 1);
-	for (int l = 0; l < g.n_levels; ++l)
-	{
-		OrbTensorMap tm;
-		if (orb_tma && make_plane_tensor_map(&tm, w_gray + g.off[l], g.w[l], g.h[l], n_frames, static_cast<size_t>(g.frame_stride), kFastTmaGW, kFastTmaGH))
-		{
-			// gray tile + halo staged by the TMA engine (one cp.async.bulk.tensor per CTA), byte-SIMD compass test and suppression
-			dim3 grd((g.w[l] + kFastTmaTW - 1) / kFastTmaTW, (g.h[l] + kFastTmaTH - 1) / kFastTmaTH, n_frames);
-			orb_fast_tma_kernel<<<grd, 256, 0, s>>>(tm, w_mask, g, l, w_cand, w_cand_count);
-			e->orb_tma_used = 1;
-		}
-		else
-		{
-			dim3 grd((g.w[l] + kFastTW - 1) / kFastTW, (g.h[l] + kFastTH - 1) / kFastTH, n_frames);
-			orb_fast_kernel<<<grd, 256, 0, s>>>(w_gray, w_mask, g, l, w_cand, w_cand_count);
-			e->orb_tma_used = 0;
-		}
-		LCD_CHECK_LAUNCH(e);
 	}
 	{
 		OrbSelectArgs a{};
@@ -2162,24 +2168,34 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		a.level_n = w_level_n;
 		a.level_cap = level_cap;
 		a.overflow = e->o_overflow.p;
-		// one launch per level: level l holds at most kOrbCandCap >> l candidates in shared memory (192 KB, 96 KB, 48 KB, ...), so
-		// the coarse levels run several CTAs per SM and level 0 (n_frames CTAs) is a single wave for up to 148 frames
-		// The levels are independent and latency-bound: level 0 stays on the caller's stream, the coarser ones fork onto side
-		// streams and join before the merge.
+		// The levels are independent: level 0 (the long one) stays on the caller's stream, the coarser ones run FAST + selection on side
+		// streams beside it and join before the merge.  Selection is one CTA per (frame, level), latency-bound: level l holds at most
+		// kOrbCandCap >> l candidates in shared memory (192 KB, 96 KB, 48 KB, ...), so the FAST / blur CTAs of other levels share its SMs.
 		LCD_CUDA(e, cudaFuncSetAttribute(orb_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                                 static_cast<int>(static_cast<size_t>(kOrbCandCap) * (4 + 4 + 2 + 2))));
-		LCD_CUDA(e, cudaEventRecord(e->aux_fork, s));
 		for (int l = g.n_levels - 1; l >= 0; --l)
 		{
-			a.level = l;
-			a.cand_cap = std::max(2048, kOrbCandCap >> l);
-			const size_t smem = static_cast<size_t>(a.cand_cap) * (4 + 4 + 2 + 2);
 			cudaStream_t ls = s;
 			if (l > 0)
 			{
 				ls = e->aux_stream[(l - 1) % 3];
 				LCD_CUDA(e, cudaStreamWaitEvent(ls, e->aux_fork, 0));
 			}
+			if (tma_ok)
+			{
+				// gray tile + halo staged by the TMA engine (one cp.async.bulk.tensor per CTA), byte-SIMD compass test and suppression
+				dim3 grd((g.w[l] + kFastTmaTW - 1) / kFastTmaTW, (g.h[l] + kFastTmaTH - 1) / kFastTmaTH, n_frames);
+				orb_fast_tma_kernel<<<grd, 256, 0, ls>>>(tmaps[l], w_mask, g, l, w_cand, w_cand_count);
+			}
+			else
+			{
+				dim3 grd((g.w[l] + kFastTW - 1) / kFastTW, (g.h[l] + kFastTH - 1) / kFastTH, n_frames);
+				orb_fast_kernel<<<grd, 256, 0, ls>>>(w_gray, w_mask, g, l, w_cand, w_cand_count);
+			}
+			LCD_CHECK_LAUNCH(e);
+			a.level = l;
+			a.cand_cap = std::max(2048, kOrbCandCap >> l);
+			const size_t smem = static_cast<size_t>(a.cand_cap) * (4 + 4 + 2 + 2);
 			orb_select_kernel<<<n_frames, kOrbSelectThreads, smem, ls>>>(a);
 			LCD_CHECK_LAUNCH(e);
 			if (l > 0 && l <= 3) LCD_CUDA(e, cudaEventRecord(e->aux_join[l - 1], ls));
@@ -2197,7 +2213,12 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 	{
 		LCD_CUDA(e, cudaStreamWaitEvent(s, e->aux_blur_done, 0));
 		dim3 grd((cap + kOrbDescribeKp - 1) / kOrbDescribeKp, n_frames);
-		orb_describe_kernel<<<grd, 256, 0, s>>>(w_gray, w_blur, g, d_kp, d_n, cap, d_desc);
+		bool patch_ok = g.edge >= kOrbPatchR && env_int("LCD_ORB_PATCH", 1) != 0;
+		for (int l = 0; l < g.n_levels; ++l) patch_ok = patch_ok && g.w[l] % 4 == 0;
+		if (patch_ok)
+			orb_describe_patch_kernel<<<grd, 256, 0, s>>>(w_blur, g, d_kp, d_n, cap, d_desc);
+		else
+			orb_describe_kernel<<<grd, 256, 0, s>>>(w_gray, w_blur, g, d_kp, d_n, cap, d_desc);
 		LCD_CHECK_LAUNCH(e);
 	}
 	if (d_xyz || d_uv)
