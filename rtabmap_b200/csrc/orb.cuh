@@ -781,7 +781,6 @@ orb_select_kernel(const OrbSelectArgs a)
 	__shared__ int s_warp_tot[32], s_cut;
 	const SelectScratch sc{perm + ccap, s_warp_tot, &s_cut};
 	__shared__ int s_umax[20];
-	__shared__ int s_seg[kOrbCandCap / 8]; // exclusive popcount prefix of every 8-word segment of the position bitmap
 
 	const int tid = threadIdx.x;
 	const int level = a.level, frame = blockIdx.x;
@@ -814,15 +813,19 @@ orb_select_kernel(const OrbSelectArgs a)
 	// of candidates at smaller positions: a position bitmap (in the not yet used response array) + one block-wide prefix sum of its
 	// popcounts replaces a 105-stage bitonic sort of 16k keys.
 	{
-		uint32_t * bits = reinterpret_cast<uint32_t *>(resp);   // ccap words = 32 * ccap positions per pass
+		// (a static array for the segment prefixes would push the CTA past the 196 KB shared-memory carve-out and halve the L1 left for
+		// the Harris / angle patches: everything lives in the dynamic allocation)
+		const int nw_max = ccap - ccap / 8;
+		uint32_t * bits = reinterpret_cast<uint32_t *>(resp);   // 7/8 of the response array: 32 * nw_max positions per pass
+		int * s_seg = reinterpret_cast<int *>(bits + nw_max);   // exclusive popcount prefix of every 8-word segment of the bitmap
 		uint32_t * sorted = reinterpret_cast<uint32_t *>(perm); // perm + rpos: ccap words
 		const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 		constexpr int kSegPerThread = kOrbCandCap / 8 / kOrbSelectThreads; // 8-word segments owned by a thread
 		const int n_pos = w * h;
 		int base = 0;
-		for (int p0 = 0; p0 < n_pos; p0 += 32 * ccap)
+		for (int p0 = 0; p0 < n_pos; p0 += 32 * nw_max)
 		{
-			const int nw = min(ccap, (n_pos - p0 + 31) >> 5);
+			const int nw = min(nw_max, (n_pos - p0 + 31) >> 5);
 			for (int i = tid; i < nw; i += blockDim.x) bits[i] = 0u;
 			__syncthreads();
 			for (int i = tid; i < n; i += blockDim.x)
@@ -861,7 +864,7 @@ orb_select_kernel(const OrbSelectArgs a)
 #pragma unroll
 			for (int k = 0; k < kSegPerThread; ++k)
 			{
-				s_seg[tid * kSegPerThread + k] = ex;
+				if ((tid * kSegPerThread + k) * 8 < nw) s_seg[tid * kSegPerThread + k] = ex;
 				ex += tot[k];
 			}
 			__syncthreads();
@@ -947,58 +950,47 @@ orb_select_kernel(const OrbSelectArgs a)
 		a.level_n[slot] = m;
 		if (kept > a.level_cap) atomicExch(a.overflow, 1);
 	}
-	// IC angle + output
+	// IC angle + output: one warp per keypoint, lane = column of the circular patch, so that a row of the patch is one coalesced load and
+	// the 31 rows are independent loads in flight (a thread per keypoint walked ~700 dependent byte loads).  The moments are integer sums:
+	// any summation order gives the reference's value.
 	const int half = a.g.patch / 2;
 	const float sf = static_cast<float>(1 << level);
-	for (int i = tid; i < m; i += blockDim.x)
+	const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+	for (int i = warp; i < m; i += nwarps)
 	{
-		const int pos = static_cast<int>(keys[perm[i]] >> 8);
+		const uint32_t key = keys[perm[i]];
+		const int pos = static_cast<int>(key >> 8);
 		const int x0 = pos % w, y0 = pos / w;
 		int m01 = 0, m10 = 0;
-		if (x0 >= half && x0 < w - half && y0 >= half && y0 < h - half)
+		for (int ub = -half; ub <= half; ub += 32) // one trip for the default 31-pixel patch
 		{
-			const uint8_t * c = img + y0 * w + x0;
-			for (int u = -half; u <= half; ++u) m10 += u * c[u];
-			for (int v = 1; v <= half; ++v)
+			const int u = ub + lane;
+			const int xx = reflect101(x0 + u, w);
+#pragma unroll 4
+			for (int v = -half; v <= half; ++v)
 			{
-				int vsum = 0;
-				const int d = s_umax[v];
-				const uint8_t * rp = c + v * w, * rm = c - v * w;
-				for (int u = -d; u <= d; ++u)
+				const int d = v == 0 ? half : s_umax[v < 0 ? -v : v];
+				if (u <= half && u >= -d && u <= d)
 				{
-					const int vp = rp[u], vm = rm[u];
-					vsum += vp - vm;
-					m10 += u * (vp + vm);
+					const int val = img[reflect101(y0 + v, h) * w + xx];
+					m10 += u * val;
+					m01 += v * val;
 				}
-				m01 += v * vsum;
 			}
 		}
-		else
+		m10 = __reduce_add_sync(0xFFFFFFFFu, m10);
+		m01 = __reduce_add_sync(0xFFFFFFFFu, m01);
+		if (lane == 0)
 		{
-			for (int u = -half; u <= half; ++u) m10 += u * img[reflect101(y0, h) * w + reflect101(x0 + u, w)];
-			for (int v = 1; v <= half; ++v)
-			{
-				int vsum = 0;
-				const int d = s_umax[v];
-				const int yp = reflect101(y0 + v, h), ym = reflect101(y0 - v, h);
-				for (int u = -d; u <= d; ++u)
-				{
-					const int xx = reflect101(x0 + u, w);
-					const int vp = img[yp * w + xx], vm = img[ym * w + xx];
-					vsum += vp - vm;
-					m10 += u * (vp + vm);
-				}
-				m01 += v * vsum;
-			}
+			OrbKeypoint kp;
+			kp.x = __fmul_rn(static_cast<float>(x0), sf);
+			kp.y = __fmul_rn(static_cast<float>(y0), sf);
+			kp.size = __fmul_rn(static_cast<float>(a.g.patch), sf);
+			kp.angle = fast_atan2_deg(static_cast<float>(m01), static_cast<float>(m10));
+			kp.response = resp[perm[i]];
+			kp.octave = level;
+			a.level_kp[static_cast<size_t>(slot) * a.level_cap + i] = kp;
 		}
-		OrbKeypoint kp;
-		kp.x = __fmul_rn(static_cast<float>(x0), sf);
-		kp.y = __fmul_rn(static_cast<float>(y0), sf);
-		kp.size = __fmul_rn(static_cast<float>(a.g.patch), sf);
-		kp.angle = fast_atan2_deg(static_cast<float>(m01), static_cast<float>(m10));
-		kp.response = resp[perm[i]];
-		kp.octave = level;
-		a.level_kp[static_cast<size_t>(slot) * a.level_cap + i] = kp;
 	}
 }
 
@@ -1300,6 +1292,8 @@ orb_describe_patch_kernel(const uint8_t * __restrict__ blur_all, const OrbGeom g
 {
 	__shared__ float4 s_pat[256];
 	__shared__ __align__(16) uint8_t s_patch[8][(2 * kOrbPatchR + 1) * kOrbPatchPitch];
+	__shared__ float s_ca[kOrbDescribeKp], s_sa[kOrbDescribeKp];
+	__shared__ int s_cx[kOrbDescribeKp], s_cy[kOrbDescribeKp], s_level[kOrbDescribeKp];
 	const int frame = blockIdx.y;
 	const int kp0 = blockIdx.x * kOrbDescribeKp;
 	const int n = min(n_kp[frame] - kp0, kOrbDescribeKp);
@@ -1307,17 +1301,27 @@ orb_describe_patch_kernel(const uint8_t * __restrict__ blur_all, const OrbGeom g
 	for (int i = threadIdx.x; i < 256; i += blockDim.x)
 		s_pat[i] = make_float4(static_cast<float>(kOrbPattern31[4 * i]), static_cast<float>(kOrbPattern31[4 * i + 1]),
 		                       static_cast<float>(kOrbPattern31[4 * i + 2]), static_cast<float>(kOrbPattern31[4 * i + 3]));
+	// the rotation of each keypoint once per keypoint, 32 keypoints per warp instruction (double-precision cos / sin: computed by every
+	// lane of the keypoint's warp it would be the whole cost of the kernel)
+	for (int i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const OrbKeypoint kp = kps[static_cast<size_t>(frame) * cap + kp0 + i];
+		const float scale = __fdiv_rn(1.f, static_cast<float>(1 << kp.octave));
+		const float angle = __fmul_rn(kp.angle, static_cast<float>(3.141592653589793238462643383279502884197169399375 / 180.0));
+		s_ca[i] = static_cast<float>(cos(static_cast<double>(angle)));
+		s_sa[i] = static_cast<float>(sin(static_cast<double>(angle)));
+		s_cx[i] = __float2int_rn(__fmul_rn(kp.x, scale));
+		s_cy[i] = __float2int_rn(__fmul_rn(kp.y, scale));
+		s_level[i] = kp.octave;
+	}
 	__syncthreads();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint8_t * patch = s_patch[warp];
 	for (int ki = warp; ki < n; ki += 8)
 	{
-		const OrbKeypoint kp = kps[static_cast<size_t>(frame) * cap + kp0 + ki];
-		const float scale = __fdiv_rn(1.f, static_cast<float>(1 << kp.octave));
-		const float angle = __fmul_rn(kp.angle, static_cast<float>(3.141592653589793238462643383279502884197169399375 / 180.0));
-		const float ca = static_cast<float>(cos(static_cast<double>(angle))), sa = static_cast<float>(sin(static_cast<double>(angle)));
-		const int cx = __float2int_rn(__fmul_rn(kp.x, scale)), cy = __float2int_rn(__fmul_rn(kp.y, scale));
-		const int level = kp.octave;
+		const float ca = s_ca[ki], sa = s_sa[ki];
+		const int cx = s_cx[ki], cy = s_cy[ki];
+		const int level = s_level[ki];
 		const int w = g.w[level];
 		const uint8_t * blr = blur_all + static_cast<size_t>(frame) * g.frame_stride + g.off[level];
 		const int xa = (cx - kOrbPatchR) & ~3;                 // aligned column of the first staged word
