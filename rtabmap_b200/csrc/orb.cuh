@@ -421,6 +421,22 @@ __device__ __forceinline__ void tma_load_3d(void * smem_dst, const void * tmap, 
 	             : "memory");
 }
 
+// Every lane reserves `cnt` consecutive slots of a shared-memory list: one atomic per warp.  All 32 lanes must call.
+__device__ __forceinline__ int warp_reserve(int * counter, int cnt, int lane)
+{
+	int incl = cnt;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += t;
+	}
+	int base = 0;
+	if (lane == 31 && incl) base = atomicAdd(counter, incl);
+	base = __shfl_sync(0xFFFFFFFFu, base, 31);
+	return base + incl - cnt;
+}
+
 struct alignas(64) OrbTensorMap
 {
 	unsigned long long opaque[16]; // CUtensorMap (128 bytes), filled by cuTensorMapEncodeTiled on the host
@@ -433,7 +449,7 @@ orb_fast_tma_kernel(const __grid_constant__ OrbTensorMap tmap, const uint8_t * _
 	constexpr int GW = kFastTmaGW, GH = kFastTmaGH, SW = kFastTmaSW, SH = kFastTmaSH;
 	__shared__ __align__(128) uint8_t s_gray[GH * GW];
 	__shared__ __align__(16) uint8_t s_score[SH * SW];
-	__shared__ uint16_t s_list[SH * (SW - 6)];
+	__shared__ __align__(16) uint16_t s_list[SH * (SW - 6)]; // compass survivors, then (as 32-bit words) the tile's output keys
 	__shared__ int s_n;
 	__shared__ __align__(8) uint64_t s_bar;
 	const int tid = threadIdx.x, lane = tid & 31;
@@ -459,30 +475,37 @@ orb_fast_tma_kernel(const __grid_constant__ OrbTensorMap tmap, const uint8_t * _
 	constexpr int WR = GW / 4;                                        // words per staged row
 	const uint32_t * W = reinterpret_cast<const uint32_t *>(s_gray);
 	// compass test (every 9-arc holds ring pixel 0 or 8, and 4 or 12), 4 pixels per item over the score plane
-	for (int it = tid; it < SH * (SW / 4); it += 256)
+	for (int it0 = 0; it0 < SH * (SW / 4); it0 += 256) // whole warps iterate together: the list slots are reserved once per warp
 	{
-		const int r = it / (SW / 4), k = it % (SW / 4); // score row r = image row y0 - 1 + r; pixels x0 - 4 + 4k .. +3
-		const int gy = r + 3;                           // staged row of the centre
-		const int y = y0 - 1 + r, xb = x0 - 4 + 4 * k;
-		// pixel x0 - 4 + 4k sits at staged column 4k + 12 = word k + 3
-		const uint32_t wc = W[gy * WR + k + 3], wl = W[gy * WR + k + 2], wr = W[gy * WR + k + 4];
-		const uint32_t up = W[(gy - 3) * WR + k + 3], dn = W[(gy + 3) * WR + k + 3];
-		const uint32_t lf = __byte_perm(wl, wc, 0x4321), rt = __byte_perm(wc, wr, 0x6543);
-		const uint32_t g0 = __vcmpgtu4(__vabsdiffu4(wc, dn), thr4), g8 = __vcmpgtu4(__vabsdiffu4(wc, up), thr4);
-		const uint32_t g4 = __vcmpgtu4(__vabsdiffu4(wc, rt), thr4), g12 = __vcmpgtu4(__vabsdiffu4(wc, lf), thr4);
-		uint32_t maybe = (g0 | g8) & (g4 | g12);
-		if (y < 3 || y >= h - 3) maybe = 0u;
-		if (maybe)
+		const int it = it0 + tid;
+		uint32_t maybe = 0u;
+		int r = 0, k = 0;
+		if (it < SH * (SW / 4))
 		{
+			r = it / (SW / 4), k = it % (SW / 4); // score row r = image row y0 - 1 + r; pixels x0 - 4 + 4k .. +3
+			const int gy = r + 3;                 // staged row of the centre
+			const int y = y0 - 1 + r, xb = x0 - 4 + 4 * k;
+			// pixel x0 - 4 + 4k sits at staged column 4k + 12 = word k + 3
+			const uint32_t wc = W[gy * WR + k + 3], wl = W[gy * WR + k + 2], wr = W[gy * WR + k + 4];
+			const uint32_t up = W[(gy - 3) * WR + k + 3], dn = W[(gy + 3) * WR + k + 3];
+			const uint32_t lf = __byte_perm(wl, wc, 0x4321), rt = __byte_perm(wc, wr, 0x6543);
+			const uint32_t g0 = __vcmpgtu4(__vabsdiffu4(wc, dn), thr4), g8 = __vcmpgtu4(__vabsdiffu4(wc, up), thr4);
+			const uint32_t g4 = __vcmpgtu4(__vabsdiffu4(wc, rt), thr4), g12 = __vcmpgtu4(__vabsdiffu4(wc, lf), thr4);
+			maybe = (g0 | g8) & (g4 | g12);
+			if (y < 3 || y >= h - 3) maybe = 0u;
+			// only the tile and its 1-pixel ring are scored (x0 - 1 .. x0 + 64), inside the 3-pixel image margin of FAST
 #pragma unroll
 			for (int b = 0; b < 4; ++b)
 			{
 				const int x = xb + b;
-				// only the tile and its 1-pixel ring are scored (x0 - 1 .. x0 + 64), inside the 3-pixel image margin of FAST
-				if (((maybe >> (8 * b)) & 0xFFu) && x >= 3 && x < w - 3 && x >= x0 - 1 && x <= x0 + kFastTmaTW)
-					s_list[atomicAdd(&s_n, 1)] = static_cast<uint16_t>(r * SW + 4 * k + b);
+				if (!(x >= 3 && x < w - 3 && x >= x0 - 1 && x <= x0 + kFastTmaTW)) maybe &= ~(0xFFu << (8 * b));
 			}
 		}
+		const int cnt = __popc(maybe) >> 3; // the comparison masks are 0x00 / 0xFF per byte
+		int at = warp_reserve(&s_n, cnt, lane);
+#pragma unroll
+		for (int b = 0; b < 4; ++b)
+			if ((maybe >> (8 * b)) & 0xFFu) s_list[at++] = static_cast<uint16_t>(r * SW + 4 * k + b);
 	}
 	__syncthreads();
 	const int n_list = s_n;
@@ -497,8 +520,15 @@ orb_fast_tma_kernel(const __grid_constant__ OrbTensorMap tmap, const uint8_t * _
 	const int slot = frame * g.n_levels + level;
 	const size_t plane = static_cast<size_t>(frame) * g.frame_stride + g.off[level];
 	const uint32_t * S = reinterpret_cast<const uint32_t *>(s_score); // 18 words per score row
-	for (int it = tid; it < kFastTmaTH * (kFastTmaTW / 4); it += 256)
+	// survivors of the tile go to a shared list first (slots reserved once per warp), the mask test and the reservation in the frame's
+	// global list then run over that list: one global atomic per 32 survivors instead of one per survivor, mask bytes loaded in parallel
+	__syncthreads();
+	if (tid == 0) s_n = 0;
+	__syncthreads();
+	uint32_t * s_out = reinterpret_cast<uint32_t *>(s_list); // <= 512 strict 3x3 maxima in a 64 x 32 tile; s_list holds 2244 u16
+	for (int it0 = 0; it0 < kFastTmaTH * (kFastTmaTW / 4); it0 += 256)
 	{
+		const int it = it0 + tid;
 		const int ty = it / (kFastTmaTW / 4), k = it % (kFastTmaTW / 4); // pixels x0 + 4k .. +3 of row y0 + ty
 		const int y = y0 + ty, xb = x0 + 4 * k;
 		const int sr = ty + 1;
@@ -515,25 +545,38 @@ orb_fast_tma_kernel(const __grid_constant__ OrbTensorMap tmap, const uint8_t * _
 				keep &= __vcmpgtu4(c, __byte_perm(a1, a2, 0x4321)); // right neighbours
 				if (dr != 0) keep &= __vcmpgtu4(c, a1);
 			}
-		}
-		if (keep)
-		{
 #pragma unroll
 			for (int b = 0; b < 4; ++b)
 			{
 				const int x = xb + b;
-				bool ok = ((keep >> (8 * b)) & 0xFFu) && x >= g.edge && x < w - g.edge && x >= 3 && x < w - 3;
-				if (ok && mask_all && mask_all[plane + static_cast<size_t>(y) * w + x] == 0) ok = false;
-				if (ok)
-				{
-					const int pos = atomicAdd(&cand_count[slot], 1);
-					if (pos < kOrbCandCap)
-						cand[static_cast<size_t>(slot) * kOrbCandCap + pos] = (static_cast<uint32_t>(y * w + x) << 8) | ((c >> (8 * b)) & 0xFFu);
-				}
+				if (!(x >= g.edge && x < w - g.edge && x >= 3 && x < w - 3)) keep &= ~(0xFFu << (8 * b));
 			}
 		}
+		const int cnt = __popc(keep) >> 3;
+		int at = warp_reserve(&s_n, cnt, lane);
+#pragma unroll
+		for (int b = 0; b < 4; ++b)
+			if ((keep >> (8 * b)) & 0xFFu) s_out[at++] = (static_cast<uint32_t>(y * w + xb + b) << 8) | ((c >> (8 * b)) & 0xFFu);
 	}
-	(void)lane;
+	__syncthreads();
+	const int n_out = s_n;
+	for (int q0 = 0; q0 < n_out; q0 += 256)
+	{
+		const int q = q0 + tid;
+		uint32_t key = 0u;
+		bool ok = q < n_out;
+		if (ok)
+		{
+			key = s_out[q];
+			if (mask_all && mask_all[plane + (key >> 8)] == 0) ok = false;
+		}
+		const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+		int base = 0;
+		if (lane == 0 && m) base = atomicAdd(&cand_count[slot], __popc(m));
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		const int pos = base + __popc(m & ((1u << lane) - 1u));
+		if (ok && pos < kOrbCandCap) cand[static_cast<size_t>(slot) * kOrbCandCap + pos] = key;
+	}
 }
 
 // ---- K3: per (frame, level) selection: raster order, retainBest(2N) on FAST score, Harris, retainBest(N),
@@ -956,12 +999,34 @@ orb_select_kernel(const OrbSelectArgs a)
 	const int half = a.g.patch / 2;
 	const float sf = static_cast<float>(1 << level);
 	const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+	// rows of the circular patch that hold column u = lane - half: |v| <= vlim (umax is non-increasing in v); -1 = column outside the patch
+	const int u_lane = lane - half;
+	int vlim = -1;
+	if (u_lane <= half)
+		for (int v = 0; v <= half; ++v)
+			if ((v == 0 ? half : s_umax[v]) >= (u_lane < 0 ? -u_lane : u_lane)) vlim = v;
 	for (int i = warp; i < m; i += nwarps)
 	{
 		const uint32_t key = keys[perm[i]];
 		const int pos = static_cast<int>(key >> 8);
 		const int x0 = pos % w, y0 = pos / w;
 		int m01 = 0, m10 = 0;
+		if (half <= 15 && x0 >= half && x0 < w - half && y0 >= half && y0 < h - half)
+		{
+			// default patch, keypoint away from the border (always, with the default edge threshold): lane = column u, rows |v| <= vlim(u)
+			const uint8_t * col = img + y0 * w + x0 + u_lane;
+			int sum = 0;
+#pragma unroll
+			for (int v = -15; v <= 15; ++v)
+				if ((v < 0 ? -v : v) <= vlim)
+				{
+					const int val = col[v * w];
+					sum += val;
+					m01 += v * val;
+				}
+			m10 = u_lane * sum;
+		}
+		else
 		for (int ub = -half; ub <= half; ub += 32) // one trip for the default 31-pixel patch
 		{
 			const int u = ub + lane;
@@ -1298,9 +1363,10 @@ orb_describe_patch_kernel(const uint8_t * __restrict__ blur_all, const OrbGeom g
 	const int kp0 = blockIdx.x * kOrbDescribeKp;
 	const int n = min(n_kp[frame] - kp0, kOrbDescribeKp);
 	if (n <= 0) return;
+	// test t = 8 * byte + bit is kept at [bit * 32 + byte]: the 32 lanes of a warp (lane = descriptor byte) read consecutive float4
 	for (int i = threadIdx.x; i < 256; i += blockDim.x)
-		s_pat[i] = make_float4(static_cast<float>(kOrbPattern31[4 * i]), static_cast<float>(kOrbPattern31[4 * i + 1]),
-		                       static_cast<float>(kOrbPattern31[4 * i + 2]), static_cast<float>(kOrbPattern31[4 * i + 3]));
+		s_pat[(i & 7) * 32 + (i >> 3)] = make_float4(static_cast<float>(kOrbPattern31[4 * i]), static_cast<float>(kOrbPattern31[4 * i + 1]),
+		                                             static_cast<float>(kOrbPattern31[4 * i + 2]), static_cast<float>(kOrbPattern31[4 * i + 3]));
 	// the rotation of each keypoint once per keypoint, 32 keypoints per warp instruction (double-precision cos / sin: computed by every
 	// lane of the keypoint's warp it would be the whole cost of the kernel)
 	for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -1340,7 +1406,7 @@ orb_describe_patch_kernel(const uint8_t * __restrict__ blur_all, const OrbGeom g
 #pragma unroll
 		for (int b = 0; b < 8; ++b)
 		{
-			const float4 p = s_pat[lane * 8 + b];
+			const float4 p = s_pat[b * 32 + lane];
 			const int x0 = __float2int_rn(__fsub_rn(__fmul_rn(p.x, ca), __fmul_rn(p.y, sa)));
 			const int y0 = __float2int_rn(__fadd_rn(__fmul_rn(p.x, sa), __fmul_rn(p.y, ca)));
 			const int x1 = __float2int_rn(__fsub_rn(__fmul_rn(p.z, ca), __fmul_rn(p.w, sa)));
