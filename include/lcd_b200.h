@@ -469,8 +469,9 @@ int lcd_shard_comm_destroy(lcd_engine * e);
  * descriptors, top-2 keys of every rank's descriptors over the local word range (lcd_shard_set_row_offset), all-to-all so that every rank
  * receives the keys of ITS frames, merge + NNDR / new-word pass of the local frames, all-gather of their word ids, TF-IDF of all frames
  * over the local word range, reduce-scatter of the exact 64-bit fixed-point sums, likelihood + verification of the local frames'
- * top hypotheses (results through lcd_process_fetch).  The local batch runs as two halves so that the exchanges of one half (on the
- * engine's communication stream) overlap the kernels of the other.  d_row_ids_global: global row -> word id of the WHOLE dictionary
+ * top hypotheses (results through lcd_process_fetch).  The dictionary search runs as two halves of the local batch so that the
+ * descriptor and key exchanges (on the engine's communication stream) overlap a search kernel; the later stages run once on the whole
+ * batch.  LCD_SHARD_TRACE=1|2 (environment) prints a per-stage timeline of the step to stderr.  d_row_ids_global: global row -> word id of the WHOLE dictionary
  * (rows of all ranks in ascending id order); d_word_ids_out[n_frames * n_features] (may be NULL), d_likelihood_out[n_frames * ns].
  * Every rank must call it with the same n_frames.  Results equal the unsharded engine's: word ids bit for bit, likelihood from the same
  * exact sums. */

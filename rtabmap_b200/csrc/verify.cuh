@@ -748,10 +748,16 @@ pnp_ransac_kernel(const PnpArgs a)
 			cnt[tid] = c;
 		}
 		__syncthreads();
-		// inlier counts: every hypothesis is counted by blockDim.x / kPnpChunk threads, each over a slice of the points
+		// Inlier counts + the sequential bookkeeping, in two sub-chunks (16 hypotheses, then the other 112).  The adaptive iteration
+		// count of the reference usually ends the run within the first few hypotheses (a 90 % inlier ratio needs 7 iterations at 0.99
+		// confidence), so counting the inliers of all 128 poses first was mostly wasted fp64 work; the replay is the same sequential
+		// loop either way.  Every hypothesis of a sub-chunk is counted by blockDim.x / size threads, each over a slice of the points.
+		for (int sub0 = 0; sub0 < kPnpChunk;)
 		{
-			const int h = tid % kPnpChunk, part = tid / kPnpChunk, parts = blockDim.x / kPnpChunk;
-			if (cnt[h] >= 0)
+			const int sub1 = sub0 == 0 ? 16 : kPnpChunk;
+			const int nh = sub1 - sub0, parts = blockDim.x / nh;
+			const int h = sub0 + tid % nh, part = tid / nh;
+			if (part < parts && cnt[h] >= 0)
 			{
 				double R[9];
 				rodrigues_v2m(h_rt + h * 6, R, nullptr);
@@ -772,42 +778,45 @@ pnp_ransac_kernel(const PnpArgs a)
 				for (; i < i1; ++i) c += reproj_err(R, tv, cam, X + 3 * i, uv + 2 * i) <= thr2 ? 1 : 0;
 				if (c) atomicAdd(&cnt[h], c);
 			}
-			if (a.phase_clk && tid == 0 && chunk0 == 0) a.phase_clk[pair * 16 + 8 + 5] = clock64();
-		}
-		__syncthreads();
-		if (chunk0 == 0) PNP_PHASE(2);
-		if (tid == 0)
-		{
-			int it0 = s_it, niters = s_niters, maxGood = s_maxgood;
-			const int chunk_end = chunk0 + kPnpChunk;
-			if (n == 6)
+			if (a.phase_clk && tid == 0 && chunk0 == 0 && sub0 == 0) a.phase_clk[pair * 16 + 8 + 5] = clock64();
+			__syncthreads();
+			if (tid == 0)
 			{
-				if (cnt[0] >= 0)
+				int it0 = s_it, niters = s_niters, maxGood = s_maxgood;
+				const int chunk_end = chunk0 + sub1;
+				if (n == 6)
 				{
-					s_best = 0;
-					for (int k = 0; k < 6; ++k) lm.param[k] = h_rt[k];
-				}
-				it0 = 0;
-			}
-			else
-			{
-				for (; it0 < niters && it0 < chunk_end; ++it0)
-				{
-					const int c = cnt[it0 - chunk0];
-					if (c < 0) continue;
-					if (c > max(maxGood, 5))
+					if (cnt[0] >= 0)
 					{
-						s_best = it0;
-						maxGood = c;
-						for (int k = 0; k < 6; ++k) lm.param[k] = h_rt[(it0 - chunk0) * 6 + k];
-						niters = ransac_update_num_iters(0.99, static_cast<double>(n - c) / n, 6, niters);
+						s_best = 0;
+						for (int k = 0; k < 6; ++k) lm.param[k] = h_rt[k];
+					}
+					it0 = 0;
+				}
+				else
+				{
+					for (; it0 < niters && it0 < chunk_end; ++it0)
+					{
+						const int c = cnt[it0 - chunk0];
+						if (c < 0) continue;
+						if (c > max(maxGood, 5))
+						{
+							s_best = it0;
+							maxGood = c;
+							for (int k = 0; k < 6; ++k) lm.param[k] = h_rt[(it0 - chunk0) * 6 + k];
+							niters = ransac_update_num_iters(0.99, static_cast<double>(n - c) / n, 6, niters);
+						}
 					}
 				}
+				s_it = it0;
+				s_niters = niters;
+				s_maxgood = maxGood;
 			}
-			s_it = it0;
-			s_niters = niters;
-			s_maxgood = maxGood;
+			__syncthreads();
+			if (s_niters <= chunk0 + sub1) break; // the run ended inside this sub-chunk (uniform: shared state read after the barrier)
+			sub0 = sub1;
 		}
+		if (chunk0 == 0) PNP_PHASE(2);
 		__syncthreads();
 	}
 	const int best = s_best;
