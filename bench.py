@@ -287,7 +287,9 @@ def run_b200(args):
     B = BL * world_size            # frames per step of the whole job
     n_pool = 3
 
-    eng = Engine(device=local, desc_dim=DESC_BYTES, max_words=W_WORDS, max_signatures=S_SIGS + 2, max_queries=F_FEATS, max_batch=B)
+    # capacity hints with the headroom the mapping-mode extra needs (52 more signatures, ~30k more words): growing a 440 MB signature
+    # store in the middle of a stream costs one cudaMalloc + copy (300 ms measured); a mapping session sizes its engine for the session
+    eng = Engine(device=local, desc_dim=DESC_BYTES, max_words=W_WORDS + 65536, max_signatures=S_SIGS + 128, max_queries=F_FEATS, max_batch=B)
     op = Engine.orb_params(KCAM, n_features=F_FEATS)
     vp = Engine.verify_params(KCAM, image_size=(IMG_W, IMG_H))
 

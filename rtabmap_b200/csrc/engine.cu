@@ -725,6 +725,8 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 		}
 		const int tps = (n_wtiles + best_split - 1) / best_split;
 		LCD_CUDA(e, e->d_partial.reserve(static_cast<size_t>(best_split) * kTcEpiGroups * nq_total, 0, false, s));
+		static const int tc_recache = env_int("LCD_TC_RECACHE", 0); // experiment: rebuild the word image on every search (as r01 did)
+		if (tc_recache) e->tc_rows = 0;
 		if (e->tc_rows < n_rows)
 		{
 			// the +-1 byte image of the words is cached with the dictionary: only tiles that gained rows since the last search are written
