@@ -3613,15 +3613,21 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 	cudaStream_t c = e->comm_stream;
 	const int G = e->sh_ranks, R = e->sh_rank;
 	// The dictionary search runs on two halves of the local batch, so that the descriptor all-gather of the second half and the key
-	// exchange of the first run under a search kernel.  The stages after it (merge + NNDR, TF-IDF) are one-CTA-per-frame kernels that
-	// take as long for half a batch as for a whole one, so they run once on the whole batch by default and their exchanges (word ids,
-	// score rows) are exposed: measured cheaper than splitting (LCD_SHARD_TAIL_PARTS=2 restores the split).
+	// exchange of the first run under a search kernel.  The merge + NNDR stage is a one-CTA-per-frame kernel that takes as long for half a
+	// batch as for a whole one, so it runs once on the whole batch and its exchange (word ids) is exposed: measured cheaper than splitting.
 	const int n_parts = n_frames >= 2 && env_int("LCD_SHARD_NN_PARTS", 2) >= 2 ? 2 : 1;
 	const int part_frames[2] = {n_parts == 2 ? (n_frames + 1) / 2 : n_frames, n_parts == 2 ? n_frames / 2 : 0};
 	const int part_f0[2] = {0, part_frames[0]};
-	const int t_parts = n_parts == 2 && env_int("LCD_SHARD_TAIL_PARTS", 1) >= 2 ? 2 : 1;
-	const int tail_frames[2] = {t_parts == 2 ? part_frames[0] : n_frames, t_parts == 2 ? part_frames[1] : 0};
-	const int tail_f0[2] = {0, tail_frames[0]};
+	// merge + NNDR always runs on the whole batch; the TF-IDF stage scores G x n_frames frames, so from 4 ranks on it is no longer a
+	// single-wave kernel and is split in two halves of every rank's frames: the reduce-scatter of the first half runs under the scoring of
+	// the second (LCD_SHARD_SCORE_PARTS=1|2 overrides)
+	const int t_parts = 1;
+	const int tail_frames[2] = {n_frames, 0};
+	const int tail_f0[2] = {0, n_frames};
+	const int s_parts_env = env_int("LCD_SHARD_SCORE_PARTS", 0);
+	const int s_parts = n_frames >= 2 && (s_parts_env ? s_parts_env >= 2 : G >= 4) ? 2 : 1;
+	const int score_frames[2] = {s_parts == 2 ? (n_frames + 1) / 2 : n_frames, s_parts == 2 ? n_frames / 2 : 0};
+	const int score_f0[2] = {0, score_frames[0]};
 	const size_t rows = static_cast<size_t>(n_frames) * cap;
 	LCD_CUDA(e, e->o_kp.reserve(rows, 0, false, s));
 	LCD_CUDA(e, e->o_desc.reserve(rows * 32, 0, false, s));
@@ -3637,13 +3643,12 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		LCD_CUDA(e, e->sh_keys[h].reserve(pr * 2 * G, 0, false, s));
 	}
 	LCD_CUDA(e, e->sh_keys_mine[0].reserve(rows * 2 * G, 0, false, s)); // [rank][local frame][feature]: both halves land in one array
-	for (int h = 0; h < t_parts; ++h)
+	LCD_CUDA(e, e->sh_words_loc[0].reserve(rows, 0, false, s));
+	LCD_CUDA(e, e->sh_words_all[0].reserve(rows * G, 0, false, s));
+	for (int h = 0; h < s_parts; ++h)
 	{
-		const size_t pr = static_cast<size_t>(tail_frames[h]) * cap;
-		LCD_CUDA(e, e->sh_words_loc[h].reserve(pr, 0, false, s));
-		LCD_CUDA(e, e->sh_words_all[h].reserve(pr * G, 0, false, s));
-		LCD_CUDA(e, e->sh_scores[h].reserve(static_cast<size_t>(tail_frames[h]) * G * ns, 0, false, s));
-		LCD_CUDA(e, e->sh_scores_loc[h].reserve(static_cast<size_t>(tail_frames[h]) * ns, 0, false, s));
+		LCD_CUDA(e, e->sh_scores[h].reserve(static_cast<size_t>(score_frames[h]) * G * ns, 0, false, s));
+		LCD_CUDA(e, e->sh_scores_loc[h].reserve(static_cast<size_t>(score_frames[h]) * ns, 0, false, s));
 	}
 	std::chrono::steady_clock::time_point host_t[6];
 	const auto host_begin = std::chrono::steady_clock::now();
@@ -3656,8 +3661,8 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		float ms = 0.f;
 		fprintf(stderr, "[lcd shard trace rank %d]", R);
 		for (int h = 0; h < n_parts; ++h)
-			for (int k = 0; k < (h < t_parts ? 8 : 4); ++k)
-				if (cudaEventElapsedTime(&ms, e->sh_tr[0], e->sh_ev[h][k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
+			for (int k = 0; k < 8; ++k)
+				if ((k < 4 || (k < 6 ? h < t_parts : h < s_parts)) && cudaEventElapsedTime(&ms, e->sh_tr[0], e->sh_ev[h][k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
 		if (cudaEventElapsedTime(&ms, e->sh_tr[0], e->sh_tr[1]) == cudaSuccess) fprintf(stderr, " end=%.3f", ms);
 		fprintf(stderr, "\n");
 	}
@@ -3735,10 +3740,10 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 	}
 	host_t[3] = std::chrono::steady_clock::now();
 	// phase 4: TF-IDF of every rank's frames over the local word range, reduce-scatter of the exact fixed-point sums
-	for (int h = 0; h < t_parts; ++h)
+	for (int h = 0; h < s_parts; ++h)
 	{
-		const int nf_all = tail_frames[h] * G;
-		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][5], 0));
+		const int nf_all = score_frames[h] * G; // frames [score_f0, +score_frames) of every rank, rank-major
+		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[0][5], 0));
 		LCD_TRY(ensure_uq(e, nf_all, cap, s));
 		LCD_TRY(ensure_acc(e, nf_all));
 		LCD_CUDA(e, zero_fill_async(e->acc.p, static_cast<size_t>(e->acc_stride) * nf_all * sizeof(long long), s));
@@ -3748,7 +3753,7 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		int nq_pad = 32;
 		while (nq_pad < cap) nq_pad <<= 1;
 		prof_mark(e, LCD_PROF_RESOLVE, s);
-		prep_local_ids_kernel<<<nf_all, kResolveThreads, nq_pad * sizeof(uint32_t), s>>>(e->sh_words_all[h].p, a);
+		prep_local_ids_kernel<<<nf_all, kResolveThreads, nq_pad * sizeof(uint32_t), s>>>(e->sh_words_all[0].p, a, n_frames, score_f0[h], score_frames[h]);
 		prof_mark(e, LCD_PROF_RESOLVE, s);
 		LCD_CHECK_LAUNCH(e);
 		LCD_TRY(launch_score(e, nf_all, cap, s));
@@ -3756,16 +3761,16 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 		LCD_CHECK_LAUNCH(e);
 		LCD_TRY(shard_record(e, h, 6, s));
 		LCD_CUDA(e, cudaStreamWaitEvent(c, e->sh_ev[h][6], 0));
-		LCD_NCCL(e, nc.ReduceScatter(e->sh_scores[h].p, e->sh_scores_loc[h].p, static_cast<size_t>(tail_frames[h]) * ns, ncclInt64, ncclSum, e->comm, c));
+		LCD_NCCL(e, nc.ReduceScatter(e->sh_scores[h].p, e->sh_scores_loc[h].p, static_cast<size_t>(score_frames[h]) * ns, ncclInt64, ncclSum, e->comm, c));
 		LCD_TRY(shard_record(e, h, 7, c));
 	}
 	host_t[4] = std::chrono::steady_clock::now();
 	// phase 5: likelihood of the local frames, verification of their top hypothesis
-	for (int h = 0; h < t_parts; ++h)
+	for (int h = 0; h < s_parts; ++h)
 	{
-		const int n = tail_frames[h] * ns;
+		const int n = score_frames[h] * ns;
 		LCD_CUDA(e, cudaStreamWaitEvent(s, e->sh_ev[h][7], 0));
-		fixed_to_float_kernel<<<(n + 255) / 256, 256, 0, s>>>(e->sh_scores_loc[h].p, n, d_likelihood_out + static_cast<size_t>(tail_f0[h]) * ns);
+		fixed_to_float_kernel<<<(n + 255) / 256, 256, 0, s>>>(e->sh_scores_loc[h].p, n, d_likelihood_out + static_cast<size_t>(score_f0[h]) * ns);
 		LCD_CHECK_LAUNCH(e);
 	}
 	if (vp)
@@ -3801,8 +3806,8 @@ int lcd_shard_process_frames_dev(lcd_engine * e, int n_frames, const uint8_t * d
 				fprintf(stderr, "[lcd shard ring rank %d step %d]", R, st);
 				if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + 0) * 9 + 8]) == cudaSuccess) fprintf(stderr, " begin=%.3f", ms);
 				for (int h = 0; h < n_parts; ++h)
-					for (int k = 0; k < (h < t_parts ? 8 : 4); ++k)
-						if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + h) * 9 + k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
+					for (int k = 0; k < 8; ++k)
+						if ((k < 4 || (k < 6 ? h < t_parts : h < s_parts)) && cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + h) * 9 + k]) == cudaSuccess) fprintf(stderr, " %s%d=%.3f", names[k], h, ms);
 				if (cudaEventElapsedTime(&ms, origin, e->sh_ring[(st * 2 + 1) * 9 + 8]) == cudaSuccess) fprintf(stderr, " end=%.3f", ms);
 				fprintf(stderr, "\n");
 			}

@@ -480,8 +480,9 @@ prep_from_ids_kernel(const int * __restrict__ word_ids, const ResolveArgs a)
 // postings on this rank matter (no postings = nothing added to any sum).  They are compacted before the sort, which keeps the preparation
 // of G ranks' frames at the cost of one rank's frames unsharded instead of growing with G.
 __global__ void __launch_bounds__(kResolveThreads)
-prep_local_ids_kernel(const int * __restrict__ word_ids, const ResolveArgs a)
+prep_local_ids_kernel(const int * __restrict__ word_ids, const ResolveArgs a, int frames_per_rank, int part_f0, int part_frames)
 {
+	// block b prepares frame part_f0 + b % part_frames of rank b / part_frames; word_ids is [rank][frames_per_rank][nq]
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	__shared__ int s_n;
 	const int nq = a.nq;
@@ -489,12 +490,13 @@ prep_local_ids_kernel(const int * __restrict__ word_ids, const ResolveArgs a)
 	while (nq_pad < nq) nq_pad <<= 1;
 	uint32_t * sbuf = reinterpret_cast<uint32_t *>(smem_raw);
 	const int frame = blockIdx.x;
+	const int src_frame = (frame / part_frames) * frames_per_rank + part_f0 + frame % part_frames;
 	const int lane = threadIdx.x & 31;
 	if (threadIdx.x == 0) s_n = 0;
 	__syncthreads();
 	for (int i = threadIdx.x; i < nq_pad; i += blockDim.x) // nq_pad and blockDim are multiples of 32: whole warps iterate together
 	{
-		const int w = i < nq ? word_ids[static_cast<size_t>(frame) * nq + i] : 0;
+		const int w = i < nq ? word_ids[static_cast<size_t>(src_frame) * nq + i] : 0;
 		const bool keep = w > 0 && w < a.id_cap && a.post_len[w] > 0;
 		const uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
 		int base = 0;
