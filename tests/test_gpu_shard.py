@@ -115,12 +115,15 @@ def test_two_word_range_shards_equal_one_engine(by_frame):
             assert not got_w[b, n_valid[b]:].any()
 
 
-def test_fused_sharded_step_with_a_single_rank_communicator_equals_the_unsharded_call():
-    """lcd_shard_process_frames_dev (the exchanges inside the library, NCCL loaded at run time) on a communicator of ONE rank: every
+@pytest.mark.parametrize("score_parts", [1, 2])
+def test_fused_sharded_step_with_a_single_rank_communicator_equals_the_unsharded_call(score_parts, monkeypatch):
+    """score_parts: the TF-IDF stage whole (what 1-2 ranks run) or in two halves with a reduce-scatter each (what 4+ ranks run).
+    lcd_shard_process_frames_dev (the exchanges inside the library, NCCL loaded at run time) on a communicator of ONE rank: every
     collective degenerates to a copy, the two-half pipeline and all the bookkeeping still run, and the result must equal
     lcd_process_frames_dev on the same engine — word ids, likelihood, hypotheses, verification."""
     import torch
 
+    monkeypatch.setenv("LCD_SHARD_SCORE_PARTS", str(score_parts))
     eng = Engine(max_words=8192, max_signatures=400)
     op = Engine.orb_params(synth.CAMERA_K4, n_features=300)
     world = synth.make_place_world(lambda im, dp: eng.orb_detect_describe(im[None], dp[None], op, cap=300)[0], 6, 1500, 120, 300, 240, 320)
