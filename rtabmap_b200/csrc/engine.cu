@@ -742,8 +742,12 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 		}
 		LCD_CUDA(e, cudaFuncSetAttribute(knn2_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
 		prof_mark(e, LCD_PROF_NN, s);
-		knn2_tensor_kernel<<<dim3(n_qtiles, best_split), kTcThreads, kTcSmemBytes, s>>>(e->tc_words.p, n_rows, e->row_offset, d_q, nq_total, e->d_partial.p, tps,
-		                                                                               static_cast<uint32_t>(-32));
+		// persistent grid: one CTA per SM walks the (query tile, word split) items (LCD_NN_PERSIST=0: one CTA per item, as r01)
+		static const int nn_persist = env_int("LCD_NN_PERSIST", 1);
+		const int n_items = n_qtiles * best_split;
+		const int grid = nn_persist ? std::min(n_items, e->sm_count) : n_items;
+		knn2_tensor_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(e->tc_words.p, n_rows, e->row_offset, d_q, nq_total, e->d_partial.p, tps,
+		                                                        static_cast<uint32_t>(-32), n_qtiles, best_split);
 		prof_mark(e, LCD_PROF_NN, s);
 		LCD_CHECK_LAUNCH(e);
 		e->nn_last_tensor = 1;

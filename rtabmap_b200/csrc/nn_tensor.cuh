@@ -144,11 +144,17 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // ---- the kernel ------------------------------------------------------------------------------------
 // neg32 = (uint32_t)-32, passed as an argument so that the key arithmetic stays an IMAD on the FMA pipe instead of being
 // strength-reduced to a shift-add on the ALU pipe, which the min/max network needs.
-// grid = (query tiles, word splits).  partial[(split * kTcEpiGroups + column group) * nq + query] = (best key, second key)
-// over the rows of that split that fall in that column group of their tile.
+// Work items = (query tile, word split) pairs, item = split * n_qtiles + qtile.  The grid is PERSISTENT: CTA b runs items b, b + gridDim.x,
+// ... with one TMEM allocation and one set of barriers; the word-tile stream, the MMA issue and the two accumulator stages run on across
+// item boundaries (all barrier phases are functions of a CTA-wide running tile count), and the epilogue warps write the next item's query
+// tile into shared memory as soon as the last MMA of the current item has completed, before they read that last accumulator out.  What
+// an item boundary costs is that expansion (a few hundred cycles) instead of a CTA launch, a TMEM allocation and a pipeline fill — which
+// is what a word-range shard with few tiles per item was paying (24 tiles per item at 8 ranks).
+// partial[(split * kTcEpiGroups + column group) * nq + query] = (best key, second key) over the rows of that split that fall in that
+// column group of their tile.
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offset, const uint32_t * __restrict__ queries /* [nq][8] packed */, int nq,
-                   uint2 * __restrict__ partial, int tiles_per_split, uint32_t neg32)
+                   uint2 * __restrict__ partial, int tiles_per_split, uint32_t neg32, int n_qtiles, int n_splits)
 {
 	extern __shared__ unsigned char smem_dyn[];
 	unsigned char * smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -159,15 +165,17 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 	uint64_t * empty = bars + kTcStages;       // [kTcStages] word tile consumed by the MMAs
 	uint64_t * tfull = bars + 2 * kTcStages;   // [2] accumulator stage complete
 	uint64_t * tempty = tfull + 2;             // [2] accumulator stage drained by the epilogue
-	uint64_t * afull = tempty + 2;             // [1] query tile landed
+	uint64_t * afull = tempty + 2;             // [1] query tile of the item written (phase = item count of this CTA)
 	uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(afull + 1);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int n_tiles_total = (n_rows + kTcBN - 1) / kTcBN;
-	const int tile_begin = blockIdx.y * tiles_per_split;
-	const int tile_end = min(n_tiles_total, tile_begin + tiles_per_split);
-	const int n_tiles = max(0, tile_end - tile_begin);
-	const int qtile = blockIdx.x;
+	const int n_items = n_qtiles * n_splits;
+	// tiles of an item (every role walks the same item sequence and keeps the same running tile count)
+	auto item_tiles = [&](int item, int & tile_begin) {
+		tile_begin = (item / n_qtiles) * tiles_per_split;
+		return max(0, min(n_tiles_total, tile_begin + tiles_per_split) - tile_begin);
+	};
 
 	if (tid == 0)
 	{
@@ -192,44 +200,57 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 
 	if (warp == 0)
 	{
-		if (lane == 0 && n_tiles > 0)
+		if (lane == 0)
 		{
-			for (int t = 0; t < n_tiles; ++t)
+			int g = 0; // running tile count of this CTA
+			for (int item = blockIdx.x; item < n_items; item += gridDim.x)
 			{
-				const int s = t % kTcStages;
-				if (t >= kTcStages) mbar_wait(&empty[s], ((t / kTcStages) - 1) & 1);
-				mbar_arrive_expect_tx(&full[s], kTcBBytes);
-				const unsigned char * src = reinterpret_cast<const unsigned char *>(word_img) + static_cast<size_t>(tile_begin + t) * kTcBBytes;
-				bulk_g2s(sB + s * kTcBBytes, src, kTcBBytes / 2, &full[s]);
-				bulk_g2s(sB + s * kTcBBytes + kTcBBytes / 2, src + kTcBBytes / 2, kTcBBytes / 2, &full[s]);
+				int tile_begin;
+				const int n_tiles = item_tiles(item, tile_begin);
+				for (int t = 0; t < n_tiles; ++t, ++g)
+				{
+					const int s = g % kTcStages;
+					if (g >= kTcStages) mbar_wait(&empty[s], ((g / kTcStages) - 1) & 1);
+					mbar_arrive_expect_tx(&full[s], kTcBBytes);
+					const unsigned char * src = reinterpret_cast<const unsigned char *>(word_img) + static_cast<size_t>(tile_begin + t) * kTcBBytes;
+					bulk_g2s(sB + s * kTcBBytes, src, kTcBBytes / 2, &full[s]);
+					bulk_g2s(sB + s * kTcBBytes + kTcBBytes / 2, src + kTcBBytes / 2, kTcBBytes / 2, &full[s]);
+				}
 			}
 		}
 	}
 	else if (warp == 1)
 	{
-		if (lane == 0 && n_tiles > 0)
+		if (lane == 0)
 		{
 			constexpr uint32_t idesc = tc_idesc_i8(kTcBM, kTcBN);
 			const uint32_t a_base = smem_u32(sA);
-			mbar_wait(afull, 0);
-			for (int t = 0; t < n_tiles; ++t)
+			int g = 0, k = 0;
+			for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k)
 			{
-				const int s = t % kTcStages, acc = t & 1;
-				if (t >= 2) mbar_wait(&tempty[acc], ((t >> 1) - 1) & 1);
-				mbar_wait(&full[s], (t / kTcStages) & 1);
+				int tile_begin;
+				const int n_tiles = item_tiles(item, tile_begin);
+				mbar_wait(afull, k & 1);
 				tc_fence_after();
-				const uint32_t b_base = smem_u32(sB + s * kTcBBytes);
-				const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kTcBN);
-#pragma unroll
-				for (int ks = 0; ks < kTcK / 32; ++ks)
+				for (int t = 0; t < n_tiles; ++t, ++g)
 				{
-					const uint32_t atom = ks >> 2, koff = (ks & 3) * 32;
-					const uint64_t ad = tc_smem_desc(a_base + atom * (kTcBM * 128) + koff);
-					const uint64_t bd = tc_smem_desc(b_base + atom * (kTcBN * 128) + koff);
-					tc_mma_i8(d_addr, ad, bd, idesc, ks > 0 ? 1u : 0u);
+					const int s = g % kTcStages, acc = g & 1;
+					if (g >= 2) mbar_wait(&tempty[acc], ((g >> 1) - 1) & 1);
+					mbar_wait(&full[s], (g / kTcStages) & 1);
+					tc_fence_after();
+					const uint32_t b_base = smem_u32(sB + s * kTcBBytes);
+					const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * kTcBN);
+#pragma unroll
+					for (int ks = 0; ks < kTcK / 32; ++ks)
+					{
+						const uint32_t atom = ks >> 2, koff = (ks & 3) * 32;
+						const uint64_t ad = tc_smem_desc(a_base + atom * (kTcBM * 128) + koff);
+						const uint64_t bd = tc_smem_desc(b_base + atom * (kTcBN * 128) + koff);
+						tc_mma_i8(d_addr, ad, bd, idesc, ks > 0 ? 1u : 0u);
+					}
+					tc_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+					tc_commit(&tfull[acc]); // accumulator stage complete
 				}
-				tc_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
-				tc_commit(&tfull[acc]); // accumulator stage complete
 			}
 		}
 	}
@@ -237,18 +258,29 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 	{
 		// The query tile goes from its packed form (32 B per descriptor) straight into the swizzled +-1 byte image in shared memory:
 		// no expanded copy of the queries ever touches HBM.  One 16-byte chunk (16 descriptor bits) per thread and step.
-		{
-			const int et = tid - 128;
-			uint4 * sA4 = reinterpret_cast<uint4 *>(sA);
-			for (int i = et; i < kTcBM * 16; i += 128 * kTcEpiGroups)
+		const int et = tid - 128;
+		uint4 * sA4 = reinterpret_cast<uint4 *>(sA);
+		constexpr int kItems = kTcBM * 16 / (128 * kTcEpiGroups); // chunks per thread: same chunk column, rows 32 apart
+		constexpr int kRowStep = 128 * kTcEpiGroups / 16;
+		const int chunk = et & 15, r0 = et >> 4;
+		uint32_t w[kItems];
+		auto load_packed = [&](int qtile) { // all loads in flight before the first use: one memory round trip
+#pragma unroll
+			for (int j = 0; j < kItems; ++j)
 			{
-				const int r = i >> 4, chunk = i & 15;
-				const int q = qtile * kTcBM + r;
+				const int q = qtile * kTcBM + r0 + j * kRowStep;
+				w[j] = q < nq ? __ldg(queries + static_cast<size_t>(q) * 8 + (chunk >> 1)) : 0u;
+			}
+		};
+		auto expand_tile = [&](int qtile) {
+#pragma unroll
+			for (int j = 0; j < kItems; ++j)
+			{
+				const int r = r0 + j * kRowStep;
 				uint4 v = make_uint4(0, 0, 0, 0);
-				if (q < nq)
+				if (qtile * kTcBM + r < nq)
 				{
-					const uint32_t w = queries[static_cast<size_t>(q) * 8 + (chunk >> 1)];
-					const uint32_t bits = (w >> ((chunk & 1) * 16)) & 0xFFFFu;
+					const uint32_t bits = (w[j] >> ((chunk & 1) * 16)) & 0xFFFFu;
 					v.x = expand4(bits & 15u);
 					v.y = expand4((bits >> 4) & 15u);
 					v.z = expand4((bits >> 8) & 15u);
@@ -260,77 +292,96 @@ knn2_tensor_kernel(const uint4 * __restrict__ word_img, int n_rows, int row_offs
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the tensor core's async proxy
 			__syncwarp();
 			if (lane == 0) mbar_arrive(afull);
-		}
+		};
 		const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp id % 4)
 		const int cg = (warp - 4) >> 2;               // column group
-		const int qi = qtile * kTcBM + quarter * 32 + lane;
-		uint32_t k1 = kKeyNone, k2 = kKeyNone;
-		int thr = -100000;                            // accumulator value a candidate has to exceed to enter the top-2
-		for (int t = 0; t < n_tiles; ++t)
+		int g = 0;
+		if (static_cast<int>(blockIdx.x) < n_items)
 		{
-			const int acc = t & 1;
-			mbar_wait(&tfull[acc], (t >> 1) & 1);
-			tc_fence_after();
-			const int row0 = (tile_begin + t) * kTcBN + cg * kTcEpiCols;
-			const int valid = n_rows - row0;              // columns of this group that are real words (may be <= 0)
-			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTcBN + cg * kTcEpiCols);
-			int v[kTcEpiCols];
-#pragma unroll
-			for (int c0 = 0; c0 < kTcEpiCols; c0 += 32) tc_ld32(taddr + c0, *reinterpret_cast<int(*)[32]>(&v[c0]));
-			tc_wait_ld();
-			// the accumulator stage is free as soon as the values are in registers
-			tc_fence_before();
-			__syncwarp();
-			if (lane == 0) mbar_arrive(&tempty[acc]);
-			if (valid >= kTcEpiCols)
+			load_packed(static_cast<int>(blockIdx.x) % n_qtiles);
+			expand_tile(static_cast<int>(blockIdx.x) % n_qtiles);
+		}
+		for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+		{
+			int tile_begin;
+			const int n_tiles = item_tiles(item, tile_begin);
+			const int qtile = item % n_qtiles, split = item / n_qtiles;
+			const int next = item + static_cast<int>(gridDim.x);
+			const bool has_next = next < n_items;
+			if (has_next) load_packed(next % n_qtiles); // in registers long before the boundary
+			const int qi = qtile * kTcBM + quarter * 32 + lane;
+			uint32_t k1 = kKeyNone, k2 = kKeyNone;
+			int thr = -100000;                            // accumulator value a candidate has to exceed to enter the top-2
+			for (int t = 0; t < n_tiles; ++t, ++g)
 			{
-				// Branch-free top-2 over the 64 columns with 16-bit keys, two columns per register:
-				//   key16 = distance * 64 + j = acc * (-32) + (8192 + j)   (distance = (256 - acc) / 2 <= 256, j < 32)
-				// The low half-word carries column j, the high half-word column j + 32; S = acc_hi * 65536 + acc_lo and
-				// K = S * (-32) + (8192 + j) * 65537 is that pair of keys exactly (every field stays in [0, 65536), so no
-				// carry crosses the halves).  Two IMADs (FMA pipe) and three VIMNMX.U16x2 (ALU pipe) per column pair.
-				uint32_t p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
+				const int acc = g & 1;
+				mbar_wait(&tfull[acc], (g >> 1) & 1);
+				tc_fence_after();
+				// last tile of the item: every MMA that reads the query tile has completed -> write the next item's tile now, so that its
+				// first MMAs run while this accumulator is read out
+				if (t == n_tiles - 1 && has_next) expand_tile(next % n_qtiles);
+				const int row0 = (tile_begin + t) * kTcBN + cg * kTcEpiCols;
+				const int valid = n_rows - row0;              // columns of this group that are real words (may be <= 0)
+				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTcBN + cg * kTcEpiCols);
+				int v[kTcEpiCols];
 #pragma unroll
-				for (int j = 0; j < 32; ++j)
+				for (int c0 = 0; c0 < kTcEpiCols; c0 += 32) tc_ld32(taddr + c0, *reinterpret_cast<int(*)[32]>(&v[c0]));
+				tc_wait_ld();
+				// the accumulator stage is free as soon as the values are in registers
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&tempty[acc]);
+				if (valid >= kTcEpiCols)
 				{
-					const uint32_t sp = static_cast<uint32_t>(v[j + 32]) * 65536u + static_cast<uint32_t>(v[j]);
-					const uint32_t kp = sp * neg32 + static_cast<uint32_t>(8192 + j) * 65537u;
-					const uint32_t mx = __vmaxu2(p1, kp);
-					p1 = __vminu2(p1, kp);
-					p2 = __vminu2(p2, mx);
-				}
-				// the four survivors (two per half) go into the running packed keys only if they can improve them
-				const uint32_t best16 = min(p1 & 0xFFFFu, p1 >> 16);
-				if (static_cast<int>(best16 >> 6) * 2 < kTcK - thr)
-				{
-					const uint32_t base = static_cast<uint32_t>(row_offset + row0);
-					const uint32_t c[4] = {p1 & 0xFFFFu, p2 & 0xFFFFu, p1 >> 16, p2 >> 16};
+					// Branch-free top-2 over the 64 columns with 16-bit keys, two columns per register:
+					//   key16 = distance * 64 + j = acc * (-32) + (8192 + j)   (distance = (256 - acc) / 2 <= 256, j < 32)
+					// The low half-word carries column j, the high half-word column j + 32; S = acc_hi * 65536 + acc_lo and
+					// K = S * (-32) + (8192 + j) * 65537 is that pair of keys exactly (every field stays in [0, 65536), so no
+					// carry crosses the halves).  Two IMADs (FMA pipe) and three VIMNMX.U16x2 (ALU pipe) per column pair.
+					uint32_t p1 = 0xFFFFFFFFu, p2 = 0xFFFFFFFFu;
 #pragma unroll
-					for (int u = 0; u < 4; ++u)
+					for (int j = 0; j < 32; ++j)
 					{
-						const uint32_t key = ((c[u] >> 6) << kKeyShift) + base + (c[u] & 63u) + (u >= 2 ? 32u : 0u);
-						top2_insert(k1, k2, key);
+						const uint32_t sp = static_cast<uint32_t>(v[j + 32]) * 65536u + static_cast<uint32_t>(v[j]);
+						const uint32_t kp = sp * neg32 + static_cast<uint32_t>(8192 + j) * 65537u;
+						const uint32_t mx = __vmaxu2(p1, kp);
+						p1 = __vminu2(p1, kp);
+						p2 = __vminu2(p2, mx);
+					}
+					// the four survivors (two per half) go into the running packed keys only if they can improve them
+					const uint32_t best16 = min(p1 & 0xFFFFu, p1 >> 16);
+					if (static_cast<int>(best16 >> 6) * 2 < kTcK - thr)
+					{
+						const uint32_t base = static_cast<uint32_t>(row_offset + row0);
+						const uint32_t c[4] = {p1 & 0xFFFFu, p2 & 0xFFFFu, p1 >> 16, p2 >> 16};
+#pragma unroll
+						for (int u = 0; u < 4; ++u)
+						{
+							const uint32_t key = ((c[u] >> 6) << kKeyShift) + base + (c[u] & 63u) + (u >= 2 ? 32u : 0u);
+							top2_insert(k1, k2, key);
+						}
+						thr = k2 == kKeyNone ? -100000 : kTcK - 2 * static_cast<int>(k2 >> kKeyShift);
+					}
+				}
+				else if (valid > 0)
+				{
+					// last, partly filled tile: plain insertion of the real columns
+#pragma unroll
+					for (int j = 0; j < kTcEpiCols; ++j)
+					{
+						if (j < valid)
+						{
+							const uint32_t key = (static_cast<uint32_t>(kTcK - v[j]) << (kKeyShift - 1)) + static_cast<uint32_t>(row_offset + row0 + j);
+							top2_insert(k1, k2, key);
+						}
 					}
 					thr = k2 == kKeyNone ? -100000 : kTcK - 2 * static_cast<int>(k2 >> kKeyShift);
 				}
+				__syncwarp();
 			}
-			else if (valid > 0)
-			{
-				// last, partly filled tile: plain insertion of the real columns
-#pragma unroll
-				for (int j = 0; j < kTcEpiCols; ++j)
-				{
-					if (j < valid)
-					{
-						const uint32_t key = (static_cast<uint32_t>(kTcK - v[j]) << (kKeyShift - 1)) + static_cast<uint32_t>(row_offset + row0 + j);
-						top2_insert(k1, k2, key);
-					}
-				}
-				thr = k2 == kKeyNone ? -100000 : kTcK - 2 * static_cast<int>(k2 >> kKeyShift);
-			}
-			__syncwarp();
+			if (n_tiles == 0 && has_next) expand_tile(next % n_qtiles); // (an item without tiles: nothing reads the query tile)
+			if (qi < nq) partial[(static_cast<size_t>(split) * kTcEpiGroups + cg) * nq + qi] = make_uint2(k1, k2);
 		}
-		if (qi < nq) partial[(static_cast<size_t>(blockIdx.y) * kTcEpiGroups + cg) * nq + qi] = make_uint2(k1, k2);
 	}
 
 	tc_fence_before();
