@@ -47,13 +47,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    tmp = LIB.with_name(f".{LIB.name}.{os.getpid()}.tmp")  # written beside the target and renamed: readers never see a partial file
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(tmp), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     res = subprocess.run(cmd, capture_output=True, text=True, cwd=str(CSRC))
     if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB)
     if verbose:
         print(res.stderr)
     return LIB

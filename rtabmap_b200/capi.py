@@ -8,6 +8,8 @@ if the library is missing it is built (nvcc); if no CUDA device is present ``Eng
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -186,7 +188,11 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         return _lib
     path = library_path()
     if build_if_missing and _build.needs_build():
-        _build.build()
+        # one process may rebuild a stale library in place; the ranks of a multi-process job must not race each other on the same file
+        if not path.exists() or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+            _build.build()
+        else:
+            print(f"rtabmap_b200: {path} is older than its sources; not rebuilding inside a {os.environ.get('WORLD_SIZE')}-process job", file=sys.stderr)
     if not path.exists():
         raise LcdError(-2, f"{path} is missing: the CUDA extension must be built (python -m rtabmap_b200.build)")
     lib = C.CDLL(str(path))

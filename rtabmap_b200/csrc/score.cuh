@@ -48,24 +48,34 @@ score_kernel(const ScoreArgs a)
 	if (nuq == 0) return;
 	const int * uqp = a.uq_prefix + static_cast<size_t>(frame) * (a.nq + 1);
 	const int total = uqp[nuq];
-	const int first = blockIdx.x * kScoreThreads;
-	if (first >= total) return;
+	// every block takes one contiguous slice of the frame's postings, its threads consecutive postings: a thread's next posting is 256
+	// further on, i.e. in the same or one of the next few words, so ONE binary search per thread and then a short forward walk replaces
+	// a 10-step search per posting (59 % of the kernel's instructions before).  Integer atomics: the result does not depend on the order.
+	const int chunk = (total + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+	const int begin = blockIdx.x * chunk, end = min(total, begin + chunk);
+	if (begin >= end) return;
 	for (int i = threadIdx.x; i <= nuq; i += kScoreThreads) s_prefix[i] = uqp[i];
 	__syncthreads();
 	const int * uqw = a.uq_word + static_cast<size_t>(frame) * a.nq;
 	const float * uqi = a.uq_idf + static_cast<size_t>(frame) * a.nq;
 	long long * acc = a.acc + static_cast<size_t>(frame) * a.acc_stride;
 
-	for (int p = first + threadIdx.x; p < total; p += gridDim.x * kScoreThreads)
+	int p = begin + threadIdx.x;
+	if (p >= end) return;
+	int lo = 0;
 	{
 		// largest k with prefix[k] <= p
-		int lo = 0, hi = nuq;
+		int hi = nuq;
 		while (hi - lo > 1)
 		{
 			const int mid = (lo + hi) >> 1;
 			if (s_prefix[mid] <= p) lo = mid;
 			else hi = mid;
 		}
+	}
+	for (; p < end; p += kScoreThreads)
+	{
+		while (s_prefix[lo + 1] <= p) ++lo; // p < total = prefix[nuq]: stops at lo < nuq
 		const int word = uqw[lo];
 		const float idf = uqi[lo];
 		const int2 ref = a.postings[static_cast<size_t>(a.post_off[word]) + (p - s_prefix[lo])];
