@@ -123,6 +123,10 @@ int lcd_orb_detect_describe_dev(lcd_engine * e, int n_frames, const uint8_t * d_
  * level 0, half as many per further level), else 0; synchronises the device.  The host-buffer entry points report the condition
  * themselves (LCD_ERR_CAPACITY); the *_dev variants return before the kernels ran, so their callers ask here. */
 int lcd_orb_overflow(lcd_engine * e);
+/* Which kernels the last detection used (bit flags; diagnostics for tests and benchmarks): 1 = FAST and blur tiles staged by TMA with a
+ * tensor map (rows a multiple of 16 bytes), 2 = descriptors from shared-memory patches (rows a multiple of 4 bytes on every level, edge
+ * threshold >= 19), 4 = vectorised gray / mask preparation (rows a multiple of 8 pixels, even height).  0 = the general kernels. */
+int lcd_orb_last_path(const lcd_engine * e);
 
 /* ---- dictionary: VWDictionary ------------------------------------------------ */
 /* replaces: VWDictionary::addWord (VWDictionary.cpp:1554-1580) for n words whose ids

@@ -111,6 +111,7 @@ SIGNATURES = {
     "lcd_orb_detect_describe": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
     "lcd_orb_detect_describe_dev": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "lcd_orb_overflow": (_I, [_P]),
+    "lcd_orb_last_path": (_I, [_P]),
     "lcd_dict_add_words": (_I, [_P, _P, _P, _I]),
     "lcd_dict_remove_words": (_I, [_P, _P, _I]),
     "lcd_dict_update": (_I, [_P]),
@@ -614,6 +615,11 @@ class Engine:
 
     def sig_slots(self) -> int:
         return self._lib.lcd_sig_slots(self._h)
+
+    @property
+    def orb_last_path(self) -> int:
+        """bit flags of the kernels the last detection used: 1 TMA tiles, 2 shared-memory patches, 4 vectorised preparation"""
+        return self._lib.lcd_orb_last_path(self._h)
 
     def orb_overflow(self) -> bool:
         r = self._lib.lcd_orb_overflow(self._h)

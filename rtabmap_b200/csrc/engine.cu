@@ -326,6 +326,7 @@ struct lcd_engine
 	DevBuf<float> o_xyz, o_uv;
 	float gauss_sigma_loaded = -1.f;
 	int orb_tma_used = 0; // the last FAST launch staged its tiles through a tensor map
+	int orb_path = 0;     // lcd_orb_last_path flags of the last detection
 	DevBuf<float> d_uv;
 
 	// measurement hooks (lcd_profile_*)
@@ -2107,8 +2108,10 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		a.g = g;
 		const bool aligned = ((reinterpret_cast<uintptr_t>(d_images) | reinterpret_cast<uintptr_t>(a.depth) | reinterpret_cast<uintptr_t>(w_gray) |
 		                       reinterpret_cast<uintptr_t>(w_mask)) & 15u) == 0 && g.frame_stride % 16 == 0;
+		e->orb_path = 0;
 		if (width % 8 == 0 && height % 2 == 0 && aligned && env_int("LCD_ORB_PREP_VEC", 1) != 0)
 		{
+			e->orb_path |= 4;
 			dim3 blk(16, 16), grd((width / 8 + 15) / 16, (height / 2 + 15) / 16, n_frames);
 			orb_prepare_vec_kernel<<<grd, blk, 0, s>>>(a);
 		}
@@ -2136,12 +2139,13 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		}
 	}
 	// one tensor map per pyramid level ([frame][y][x], 96 x 40 boxes): shared by the FAST and the blur kernels
-	static const int orb_tma = env_int("LCD_ORB_TMA", 1);
+	const int orb_tma = env_int("LCD_ORB_TMA", 1);
 	OrbTensorMap tmaps[kOrbMaxLevels];
 	bool tma_ok = orb_tma != 0;
 	for (int l = 0; l < g.n_levels && tma_ok; ++l)
 		tma_ok = make_plane_tensor_map(&tmaps[l], w_gray + g.off[l], g.w[l], g.h[l], n_frames, static_cast<size_t>(g.frame_stride), kFastTmaGW, kFastTmaGH);
 	e->orb_tma_used = tma_ok ? 1 : 0;
+	if (tma_ok) e->orb_path |= 1;
 	LCD_CUDA(e, cudaEventRecord(e->aux_fork, s));
 	if (d_desc)
 	{
@@ -2221,6 +2225,7 @@ static int orb_run(lcd_engine * e, int n_frames, const uint8_t * d_images, int w
 		dim3 grd((cap + kOrbDescribeKp - 1) / kOrbDescribeKp, n_frames);
 		bool patch_ok = g.edge >= kOrbPatchR && env_int("LCD_ORB_PATCH", 1) != 0;
 		for (int l = 0; l < g.n_levels; ++l) patch_ok = patch_ok && g.w[l] % 4 == 0;
+		if (patch_ok) e->orb_path |= 2;
 		if (patch_ok)
 			orb_describe_patch_kernel<<<grd, 256, 0, s>>>(w_blur, g, d_kp, d_n, cap, d_desc);
 		else
@@ -2320,6 +2325,11 @@ int lcd_orb_overflow(lcd_engine * e)
 	LCD_CUDA(e, cudaDeviceSynchronize());
 	LCD_CUDA(e, cudaMemcpy(&flag, e->o_overflow.p, sizeof(int), cudaMemcpyDeviceToHost));
 	return flag ? 1 : 0;
+}
+
+int lcd_orb_last_path(const lcd_engine * e)
+{
+	return e ? e->orb_path : LCD_ERR_INVALID;
 }
 
 long long lcd_debug_orb_buffer(lcd_engine * e, int which, void * out, long long cap_bytes)

@@ -130,3 +130,36 @@ def test_orb_1280x720():
     want = f2d.detect_describe(img, depth, k4, f2d.OrbParams())
     assert len(want[0]) == 1000
     check_frame(got, want)
+
+
+def test_orb_general_kernels_equal_the_fast_paths(monkeypatch):
+    """Every specialised kernel (TMA-staged FAST / blur, patch-staged descriptors, vectorised preparation) keeps its general predecessor
+    as the fallback for shapes it does not cover; with the specialisations switched off the output must not change by a bit."""
+    imgs = np.stack([synth.make_image(480, 640, 40 + i, bgr=True) for i in range(2)])
+    depth = np.stack([synth.make_depth(480, 640, 50 + i) for i in range(2)])
+    eng = Engine()
+    op = Engine.orb_params(K4)
+    fast = eng.orb_detect_describe(imgs, depth, op)
+    assert eng.orb_last_path == 7
+    for name in ("LCD_ORB_TMA", "LCD_ORB_PATCH", "LCD_ORB_PREP_VEC"):
+        monkeypatch.setenv(name, "0")
+    general = eng.orb_detect_describe(imgs, depth, op)
+    assert eng.orb_last_path == 0
+    for a, b in zip(fast, general):
+        for x, y in zip(a, b):
+            assert np.array_equal(np.nan_to_num(x).view(np.uint8), np.nan_to_num(y).view(np.uint8))
+
+
+@pytest.mark.parametrize("hw", [(250, 332), (243, 325)])
+def test_orb_sizes_the_specialised_kernels_do_not_cover(hw):
+    """Rows that are not a multiple of 16 bytes (no tensor map), of 8 pixels (no vector loads) or, on a coarser level, of 4 bytes
+    (no aligned patch loads): the general kernels run, same bar against cv::ORB."""
+    h, w = hw
+    img = synth.make_image(h, w, 61)
+    depth = synth.make_depth(h, w, 62)
+    eng = Engine()
+    got = eng.orb_detect_describe(img[None], depth[None], Engine.orb_params(K4, n_features=400))[0]
+    want = f2d.detect_describe(img, depth, K4, f2d.OrbParams(n_features=400))
+    assert len(want[0]) > 100
+    check_frame(got, want)
+    assert eng.orb_last_path == 0
