@@ -743,10 +743,20 @@ int run_knn(lcd_engine * e, const uint32_t * d_q, int nq_total, int n_rows, int 
 		}
 		LCD_CUDA(e, cudaFuncSetAttribute(knn2_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
 		prof_mark(e, LCD_PROF_NN, s);
-		// persistent grid: one CTA per SM walks the (query tile, word split) items (LCD_NN_PERSIST=0: one CTA per item, as r01)
+		// A CTA walks several (query tile, word split) items with one TMEM allocation and a running pipeline (LCD_NN_PERSIST=0: one CTA
+		// per item, as r01).  Unsharded: one CTA per SM takes them all.  Inside the sharded step the search runs beside NCCL kernels that
+		// need a few SMs now and then: a grid that holds every SM until the end starves them and then waits for them (measured at 4 ranks:
+		// 1.35 -> 1.48 ms), so there a CTA takes only enough items for ~96 word tiles and the grid stays several waves deep.
 		static const int nn_persist = env_int("LCD_NN_PERSIST", 1);
 		const int n_items = n_qtiles * best_split;
-		const int grid = nn_persist ? std::min(n_items, e->sm_count) : n_items;
+		int grid = n_items;
+		if (nn_persist && e->comm)
+		{
+			const int per_cta = std::max(1, std::min(8, (96 + tps - 1) / std::max(tps, 1))); // items per CTA: 1 / 2 / 4 at 2 / 4 / 8 ranks of C2
+			grid = (n_items + per_cta - 1) / per_cta;
+		}
+		else if (nn_persist)
+			grid = std::min(n_items, e->sm_count);
 		knn2_tensor_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(e->tc_words.p, n_rows, e->row_offset, d_q, nq_total, e->d_partial.p, tps,
 		                                                        static_cast<uint32_t>(-32), n_qtiles, best_split);
 		prof_mark(e, LCD_PROF_NN, s);
