@@ -376,6 +376,10 @@ int lcd_process_batch_dev(lcd_engine * e, const void * d_queries, const float * 
                           const int * d_sig_ids, int ns, int n_total, const lcd_verify_params * vp,
                           int * d_word_ids_out, float * d_likelihood_out, void * stream);
 int lcd_process_fetch(lcd_engine * e, int n_frames, int * hypothesis_out, lcd_verify_result * results);
+/* The same download queued on `stream` (NULL: the engine's stream) behind the step that produced the results, without any
+ * synchronisation: a caller that keeps steps in flight (pinned output buffers, one set per step in flight) reads them after its own
+ * event / stream synchronisation, while the next step already runs. */
+int lcd_process_fetch_async(lcd_engine * e, int n_frames, int * hypothesis_out, lcd_verify_result * results, void * stream);
 /* The whole hot path for n_frames frames: Memory::update (detect + quantise, Rtabmap.cpp:1470) ->
  * Memory::computeLikelihood (:2117) -> Memory::computeTransform of the top hypothesis (:3143), as
  * independent localisation queries (no mutation).  Host buffers in, host results out: n_kp_out[n_frames]

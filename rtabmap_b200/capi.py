@@ -155,6 +155,7 @@ SIGNATURES = {
     "lcd_process_batch": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "lcd_process_batch_dev": (_I, [_P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
     "lcd_process_fetch": (_I, [_P, _I, _P, _P]),
+    "lcd_process_fetch_async": (_I, [_P, _I, _P, _P, _P]),
     "lcd_process_frames": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "lcd_process_frames_submit": (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _F, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "lcd_process_frames_wait": (_I, [_P]),
@@ -759,6 +760,17 @@ class Engine:
         res = (VerifyResult * n_frames)()
         self._check(self._lib.lcd_process_fetch(self._h, n_frames, _ptr(hyp), res))
         return hyp, self._results(res, n_frames)
+
+    def process_fetch_async(self, n_frames: int, hyp_ptr: int, res_ptr: int, stream: int = 0):
+        """queue the download of the last step's hypotheses (int32[n]) and results (lcd_verify_result[n]) into pinned host memory at the given
+        addresses, behind that step on `stream`; nothing is synchronised — read them after an event recorded behind this call"""
+        self._check(self._lib.lcd_process_fetch_async(self._h, n_frames, C.c_void_p(hyp_ptr), C.c_void_p(res_ptr), C.c_void_p(stream)))
+
+    @staticmethod
+    def results_from_buffer(buf: np.ndarray, n_frames: int):
+        """lcd_verify_result records written by process_fetch_async into a uint8 array -> the dictionaries process_fetch returns"""
+        res = (VerifyResult * n_frames).from_buffer_copy(buf[: n_frames * C.sizeof(VerifyResult)].tobytes())
+        return Engine._results(res, n_frames)
 
     # -- word-range sharding ----------------------------------------------------------------------
     @staticmethod

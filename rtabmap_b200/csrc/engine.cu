@@ -3303,6 +3303,25 @@ int lcd_process_fetch(lcd_engine * e, int n_frames, int * hypothesis_out, lcd_ve
 	return LCD_OK;
 }
 
+int lcd_process_fetch_async(lcd_engine * e, int n_frames, int * hypothesis_out, lcd_verify_result * results, void * stream)
+{
+	if (!e) return LCD_ERR_INVALID;
+	LCD_TRY(set_device(e));
+	if (n_frames <= 0) return LCD_OK;
+	cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+	if (hypothesis_out) LCD_CUDA(e, cudaMemcpyAsync(hypothesis_out, e->d_hyp_id.p, n_frames * sizeof(int), cudaMemcpyDeviceToHost, s));
+	if (results)
+	{
+		static_assert(sizeof(PackedVerifyResult) == sizeof(lcd_verify_result), "packed result layout");
+		LCD_CUDA(e, e->v_packed.reserve(n_frames, 0, false, s));
+		pack_verify_results_kernel<<<(n_frames + 127) / 128, 128, 0, s>>>(n_frames, e->v_ok.p, e->v_nm.p, e->v_ninl.p, e->v_iters.p, e->v_rvec.p, e->v_tvec.p,
+		                                                                 e->v_T.p, e->v_cov6.p, e->v_packed.p);
+		LCD_CHECK_LAUNCH(e);
+		LCD_CUDA(e, cudaMemcpyAsync(results, e->v_packed.p, n_frames * sizeof(PackedVerifyResult), cudaMemcpyDeviceToHost, s));
+	}
+	return LCD_OK;
+}
+
 int lcd_process_batch(lcd_engine * e, const void * queries, const float * uv, int n_frames, int nq_per_frame, int incremental, float nndr,
                       int new_words_compared_together, const int * sig_ids, int ns, int n_total, const lcd_verify_params * vp,
                       int * word_ids_out, float * likelihood_out, int * hypothesis_out, lcd_verify_result * results)
