@@ -1017,6 +1017,18 @@ def main():
         return run_reference(args)
     if args.config == "c4":
         return run_c4(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # a rank that dies with the process group and the library's communicator still alive can hang in their teardown (and the other
+        # ranks in a collective) until the launcher's timeout: report the error and leave without running any destructor
+        try:
+            return run_b200(args)
+        except BaseException:
+            import traceback
+
+            traceback.print_exc()
+            sys.stderr.flush()
+            sys.stdout.flush()
+            os._exit(1)
     return run_b200(args)
 
 
