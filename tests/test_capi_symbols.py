@@ -47,3 +47,24 @@ def test_engine_fails_loudly_without_gpu(has_gpu):
         pytest.skip("a GPU is present")
     with pytest.raises(rtabmap_b200.LcdError):
         rtabmap_b200.Engine()
+
+
+def test_verify_result_records_round_trip_through_a_byte_buffer():
+    """lcd_process_fetch_async writes lcd_verify_result records into caller memory; the binding reads them back from a byte buffer.
+    The record is 400 bytes (4 ints, 2 x 3 doubles, 12 floats, 36 doubles), the size the library's static_assert pins."""
+    import ctypes
+
+    import numpy as np
+
+    n = 3
+    assert ctypes.sizeof(capi.VerifyResult) == 400
+    arr = (capi.VerifyResult * n)()
+    for i in range(n):
+        arr[i].ok, arr[i].n_matches, arr[i].n_inliers, arr[i].iterations_run = i % 2, 10 + i, 5 + i, 7
+        for k in range(3):
+            arr[i].rvec[k], arr[i].tvec[k] = 0.1 * k + i, 1.0 * k - i
+        for k in range(36):
+            arr[i].covariance[k] = 0.5 * k
+    res = rtabmap_b200.Engine.results_from_buffer(np.frombuffer(bytes(arr), dtype=np.uint8), n)
+    assert [r["ok"] for r in res] == [False, True, False] and res[2]["n_matches"] == 12 and res[1]["n_inliers"] == 6
+    assert np.allclose(res[2]["tvec"], [-2, -1, 0]) and res[0]["covariance"].shape == (6, 6) and res[0]["covariance"][1, 0] == 3.0
