@@ -3313,6 +3313,7 @@ int lcd_process_fetch_async(lcd_engine * e, int n_frames, int * hypothesis_out, 
 	if (results)
 	{
 		static_assert(sizeof(PackedVerifyResult) == sizeof(lcd_verify_result), "packed result layout");
+		if (!e->v_ok.p || !e->d_hyp_id.p) LCD_FAIL(e, LCD_ERR_STATE, "no verification results on the device: run a step with verify parameters first");
 		LCD_CUDA(e, e->v_packed.reserve(n_frames, 0, false, s));
 		pack_verify_results_kernel<<<(n_frames + 127) / 128, 128, 0, s>>>(n_frames, e->v_ok.p, e->v_nm.p, e->v_ninl.p, e->v_iters.p, e->v_rvec.p, e->v_tvec.p,
 		                                                                 e->v_T.p, e->v_cov6.p, e->v_packed.p);
