@@ -475,50 +475,77 @@ def run_b200(args):
             if trace:
                 print("e2e trace (t_submit_ms, submit_call_ms, collect_call_ms):", trace[:10], file=sys.stderr)
     else:
-        # sharded job: the public calls are the *_dev entry points, so the caller owns the copies.  Two steps in flight: the upload of
-        # step k+1 (this rank's frames, pinned host memory) runs on a side stream under the kernels and collectives of step k, and
-        # every step's word ids, likelihood rows, hypotheses and verification results are queued behind it (lcd_process_fetch_async)
-        # into one of two pinned result sets; the host reads the set of step k-1 while step k runs.
-        from rtabmap_b200.capi import VerifyResult
         up = torch.cuda.Stream()
         up_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        done_ev = [torch.cuda.Event(), torch.cuda.Event()]
-        res_bytes = ctypes.sizeof(VerifyResult) * nf
-        sets = [dict(words=torch.zeros((nf, F_FEATS), dtype=torch.int32).pin_memory(), like=torch.zeros((nf, S_SIGS), dtype=torch.float32).pin_memory(),
-                     hyp=torch.zeros(nf, dtype=torch.int32).pin_memory(), res=torch.zeros(res_bytes, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        if os.environ.get("LCD_BENCH_PIPELINED_E2E", "0") != "1":
+            # sharded job: the public calls are the *_dev entry points, so the caller owns the copies.  Double-buffered: the upload of
+            # step k+1 (this rank's frames, pinned host memory) runs on a side stream under the kernels and collectives of step k;
+            # every step's word ids, likelihood rows, hypotheses and verification results are copied back inside the timed region
+            # (lcd_process_fetch: one device-wide synchronisation per step).  This is the loop every committed N>1 line was measured with.
+            def prefetch(k):
+                with torch.cuda.stream(up):
+                    d_img[k & 1].copy_(h_img[k % n_pool], non_blocking=True)
+                    d_dep[k & 1].copy_(h_dep[k % n_pool], non_blocking=True)
+                    up_ev[k & 1].record(up)
 
-        def prefetch(k):
-            with torch.cuda.stream(up):
-                if k >= 2:
-                    up.wait_event(done_ev[k & 1])  # step k-2 read this device buffer
-                d_img[k & 1].copy_(h_img[k % n_pool], non_blocking=True)
-                d_dep[k & 1].copy_(h_dep[k % n_pool], non_blocking=True)
-                up_ev[k & 1].record(up)
+            barrier()
+            t0 = time.perf_counter()
+            prefetch(0)
+            for k in range(args.steps):
+                flush.fill_(k & 0xFF)
+                ext.wait_event(up_ev[k & 1])
+                sharded_step(d_img[k & 1], d_dep[k & 1])
+                h_words.view(-1).copy_(d_words, non_blocking=True)
+                h_like.view(-1).copy_(d_like, non_blocking=True)
+                if k + 1 < args.steps:
+                    prefetch(k + 1)
+                hyp_h, res_h = eng.process_fetch(nf)  # device-wide synchronisation + results of this rank's frames
+            e2e_s = time.perf_counter() - t0
+            e2e_api = "lcd_shard_process_frames_dev (exchanges inside the library), double-buffered pinned uploads on a side stream, results copied back every step"
+        else:
+            # sharded job: the public calls are the *_dev entry points, so the caller owns the copies.  Two steps in flight: the upload of
+            # step k+1 (this rank's frames, pinned host memory) runs on a side stream under the kernels and collectives of step k, and
+            # every step's word ids, likelihood rows, hypotheses and verification results are queued behind it (lcd_process_fetch_async)
+            # into one of two pinned result sets; the host reads the set of step k-1 while step k runs.
+            from rtabmap_b200.capi import VerifyResult
+            done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            res_bytes = ctypes.sizeof(VerifyResult) * nf
+            sets = [dict(words=torch.zeros((nf, F_FEATS), dtype=torch.int32).pin_memory(), like=torch.zeros((nf, S_SIGS), dtype=torch.float32).pin_memory(),
+                         hyp=torch.zeros(nf, dtype=torch.int32).pin_memory(), res=torch.zeros(res_bytes, dtype=torch.uint8).pin_memory()) for _ in range(2)]
 
-        def consume(k):
-            done_ev[k & 1].synchronize()
-            o = sets[k & 1]
-            return o["hyp"].numpy().copy(), Engine.results_from_buffer(o["res"].numpy(), nf)
+            def prefetch(k):
+                with torch.cuda.stream(up):
+                    if k >= 2:
+                        up.wait_event(done_ev[k & 1])  # step k-2 read this device buffer
+                    d_img[k & 1].copy_(h_img[k % n_pool], non_blocking=True)
+                    d_dep[k & 1].copy_(h_dep[k % n_pool], non_blocking=True)
+                    up_ev[k & 1].record(up)
 
-        barrier()
-        t0 = time.perf_counter()
-        prefetch(0)
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)
-            ext.wait_event(up_ev[k & 1])
-            sharded_step(d_img[k & 1], d_dep[k & 1])
-            o = sets[k & 1]
-            o["words"].view(-1).copy_(d_words, non_blocking=True)
-            o["like"].view(-1).copy_(d_like, non_blocking=True)
-            eng.process_fetch_async(nf, o["hyp"].data_ptr(), o["res"].data_ptr(), eng.stream)
-            done_ev[k & 1].record(ext)
-            if k + 1 < args.steps:
-                prefetch(k + 1)
-            if k > 0:
-                hyp_h, res_h = consume(k - 1)
-        hyp_h, res_h = consume(args.steps - 1)
-        e2e_s = time.perf_counter() - t0
-        h_words, h_like = sets[(args.steps - 1) & 1]["words"], sets[(args.steps - 1) & 1]["like"]  # what the oracle check below reads
+            def consume(k):
+                done_ev[k & 1].synchronize()
+                o = sets[k & 1]
+                return o["hyp"].numpy().copy(), Engine.results_from_buffer(o["res"].numpy(), nf)
+
+            barrier()
+            t0 = time.perf_counter()
+            prefetch(0)
+            for k in range(args.steps):
+                flush.fill_(k & 0xFF)
+                ext.wait_event(up_ev[k & 1])
+                sharded_step(d_img[k & 1], d_dep[k & 1])
+                o = sets[k & 1]
+                o["words"].view(-1).copy_(d_words, non_blocking=True)
+                o["like"].view(-1).copy_(d_like, non_blocking=True)
+                eng.process_fetch_async(nf, o["hyp"].data_ptr(), o["res"].data_ptr(), eng.stream)
+                done_ev[k & 1].record(ext)
+                if k + 1 < args.steps:
+                    prefetch(k + 1)
+                if k > 0:
+                    hyp_h, res_h = consume(k - 1)
+            hyp_h, res_h = consume(args.steps - 1)
+            e2e_s = time.perf_counter() - t0
+            h_words, h_like = sets[(args.steps - 1) & 1]["words"], sets[(args.steps - 1) & 1]["like"]  # what the oracle check below reads
+            e2e_api = "lcd_shard_process_frames_dev (exchanges inside the library) + lcd_process_fetch_async: two steps in flight, pinned uploads on a side stream, every step's word ids / likelihood / hypotheses / results copied back"
     barrier()
     clocks = sampler.stop() if sampler else None
     if world_size > 1:
@@ -668,7 +695,7 @@ def run_b200(args):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * (img_bytes + dep_bytes) + S_SIGS * 4),
                 "d2h_bytes_per_step": int(nq * 4 + B * S_SIGS * 4 + B * (4 + 4 + 124 + 288)),
-                "api": "lcd_process_frames_submit/_wait (pinned host buffers, 2 batches in flight, L2 flush between steps inside the timed region)" if world_size == 1 else "lcd_shard_process_frames_dev (exchanges inside the library) + lcd_process_fetch_async: two steps in flight, pinned uploads on a side stream, every step's word ids / likelihood / hypotheses / results copied back",
+                "api": "lcd_process_frames_submit/_wait (pinned host buffers, 2 batches in flight, L2 flush between steps inside the timed region)" if world_size == 1 else e2e_api,
                 "top1_place_hit_rate": e2e_hit, "verified_rate": e2e_verified},
         "roofline": roofline, "cpu_baseline": cpu, "top1_place_hit_rate": hit, "verified_rate": verified, "ransac_iterations_hist_50": iters_hist,
         "wall_s_timed_region": t_wall, "host_enqueue_ms_per_step": host_enqueue_s * 1e3 / args.steps,
