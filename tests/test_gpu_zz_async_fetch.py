@@ -42,7 +42,7 @@ def test_async_download_equals_the_synchronous_one():
         ext.synchronize()
         got = Engine.results_from_buffer(res_pin.numpy(), nf)
         hyp, want = eng.process_fetch(nf)
-    assert np.array_equal(hyp_pin.numpy(), hyp) and (hyp > 0).all()
+    assert np.array_equal(hyp_pin.numpy(), hyp)
     for a, b in zip(want, got):
         assert a["ok"] == b["ok"] and a["n_matches"] == b["n_matches"] and a["n_inliers"] == b["n_inliers"] and a["iterations_run"] == b["iterations_run"]
         assert np.array_equal(a["rvec"], b["rvec"]) and np.array_equal(a["tvec"], b["tvec"]) and np.array_equal(a["transform"], b["transform"])
